@@ -1,0 +1,227 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference in the build container.
+
+Run:  python oracle/gen_golden.py            (needs /root/reference; CPU only)
+
+The reference cannot travel to the GPU box, so its outputs are committed as small fixtures.
+What is executed (all from /root/reference, loaded by path, nothing copied):
+  * selective_scan_ref, mamba_inner_ref          requirements/Mamba/mamba/mamba_ssm/ops/selective_scan_interface.py
+  * causal_conv1d_ref                            requirements/Mamba/causal-conv1d/causal_conv1d/causal_conv1d_interface.py
+  * TFM Mamba (v3 forward+backward)              requirements/mamba_simple.py
+  * MMConv.two_row_columnwise_flatten_grad_safe / inverse   src/UM_Net/MMUNet.py
+Harness-side patches only: stub modules `causal_conv1d_cuda` / `selective_scan_cuda`,
+a stub `timm`, and a `mamba_ssm` namespace whose fused-op names are bound to the reference's own
+*_ref functions (the reference has no CPU implementation of the fused ops other than those refs).
+Input distributions follow the reference tests (tests/ops/test_selective_scan.py:58-88,
+tests/test_causal_conv1d.py:39-50), seed 0.
+"""
+import importlib.util
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+warnings.filterwarnings("ignore")
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def load_reference():
+    for n in ("causal_conv1d_cuda", "selective_scan_cuda", "timm"):
+        sys.modules[n] = types.ModuleType(n)
+    sys.path.insert(0, f"{REF}/requirements/Mamba/causal-conv1d")
+    import causal_conv1d.causal_conv1d_interface as cci
+    spec = importlib.util.spec_from_file_location(
+        "ref_ssi", f"{REF}/requirements/Mamba/mamba/mamba_ssm/ops/selective_scan_interface.py")
+    ssi = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ssi)
+    # CPU stand-ins for the fused ops = the reference's own refs
+    ssi.causal_conv1d_fn = cci.causal_conv1d_ref
+    ssi.selective_scan_fn = ssi.selective_scan_ref
+
+    def inner_no_out_proj(xz, cw, cb, xw, dw, A, B=None, C=None, D=None, delta_bias=None,
+                          B_proj_bias=None, C_proj_bias=None, delta_softplus=True):
+        d_inner = xz.shape[1] // 2
+        eye = torch.eye(d_inner, dtype=xz.dtype)
+        return ssi.mamba_inner_ref(xz, cw, cb, xw, dw, eye, None, A, B, C, D, delta_bias).transpose(1, 2)
+
+    pkg = types.ModuleType("mamba_ssm")
+    pkg.__path__ = []
+    ops = types.ModuleType("mamba_ssm.ops")
+    ops.__path__ = []
+    iface = types.ModuleType("mamba_ssm.ops.selective_scan_interface")
+    iface.selective_scan_fn = ssi.selective_scan_ref
+    iface.mamba_inner_fn = ssi.mamba_inner_ref
+    iface.bimamba_inner_fn = ssi.bimamba_inner_ref
+    iface.mamba_inner_fn_no_out_proj = inner_no_out_proj
+    sys.modules.update({"mamba_ssm": pkg, "mamba_ssm.ops": ops,
+                        "mamba_ssm.ops.selective_scan_interface": iface})
+    cpkg = sys.modules["causal_conv1d"]
+    cpkg.causal_conv1d_fn = cci.causal_conv1d_ref
+    cpkg.causal_conv1d_update = None
+    spec = importlib.util.spec_from_file_location("ref_mamba_simple", f"{REF}/requirements/mamba_simple.py")
+    ms = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ms)
+    pkg.Mamba = ms.Mamba
+    spec = importlib.util.spec_from_file_location("ref_mmunet", f"{REF}/src/UM_Net/MMUNet.py")
+    mm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mm)
+    return cci, ssi, ms, mm
+
+
+def npy(t):
+    return None if t is None else t.detach().cpu().numpy()
+
+
+def gen_scan(ssi):
+    cases = {}
+    for name, (B, D, L, N, G, has_z, has_D, has_bias, softplus) in {
+        "ref128": (2, 4, 128, 8, 1, True, True, True, True),      # reference test shape
+        "odd37": (2, 3, 37, 4, 1, True, True, True, True),        # ragged L
+        "groups2": (2, 4, 64, 8, 2, True, True, True, True),      # varBC_groups=2
+        "plain": (1, 2, 50, 16, 1, False, False, False, False),   # no z / D / bias / softplus
+        "n16_l300": (2, 6, 300, 16, 1, True, True, True, True),   # MMConv-like D=6, N=16
+    }.items():
+        torch.manual_seed(0)
+        A = (-0.5 * torch.rand(D, N)).requires_grad_()
+        shp = (B, N, L) if G == 1 else (B, G, N, L)
+        Bm = torch.randn(*shp, requires_grad=True)
+        Cm = torch.randn(*shp, requires_grad=True)
+        Dp = torch.randn(D, requires_grad=True) if has_D else None
+        z = torch.randn(B, D, L, requires_grad=True) if has_z else None
+        bias = (0.5 * torch.rand(D)).requires_grad_() if has_bias else None
+        u = torch.randn(B, D, L, requires_grad=True)
+        delta = (0.5 * torch.rand(B, D, L)).requires_grad_()
+        out, last = ssi.selective_scan_ref(u, delta, A, Bm, Cm, Dp, z, bias, softplus, True)
+        g = torch.randn_like(out)
+        out.backward(g)
+        rec = dict(u=u, delta=delta, A=A, B=Bm, C=Cm, D=Dp, z=z, delta_bias=bias, dout=g, out=out,
+                   last_state=last, du=u.grad, ddelta=delta.grad, dA=A.grad, dB=Bm.grad, dC=Cm.grad,
+                   dD=None if Dp is None else Dp.grad, dz=None if z is None else z.grad,
+                   ddelta_bias=None if bias is None else bias.grad)
+        for k, v in rec.items():
+            if v is not None:
+                cases[f"{name}.{k}"] = npy(v)
+        cases[f"{name}.softplus"] = np.array(int(softplus))
+    np.savez_compressed(os.path.join(OUT, "selective_scan.npz"), **cases)
+
+
+def gen_conv(cci):
+    cases = {}
+    for name, (B, D, L, W, silu, has_bias) in {
+        "w4_silu": (2, 8, 151, 4, True, True),
+        "w3_plain": (2, 8, 64, 3, False, True),
+        "w2_nobias": (1, 5, 8, 2, True, False),
+        "w4_short": (2, 4, 3, 4, True, True),          # L < width
+    }.items():
+        torch.manual_seed(0)
+        x = torch.randn(B, D, L, requires_grad=True)
+        w = torch.randn(D, W, requires_grad=True)
+        b = torch.randn(D, requires_grad=True) if has_bias else None
+        out = cci.causal_conv1d_ref(x, w, b, "silu" if silu else None)
+        g = torch.randn_like(out)
+        out.backward(g)
+        rec = dict(x=x, w=w, bias=b, dout=g, out=out, dx=x.grad, dw=w.grad, dbias=None if b is None else b.grad)
+        for k, v in rec.items():
+            if v is not None:
+                cases[f"{name}.{k}"] = npy(v)
+        cases[f"{name}.silu"] = np.array(int(silu))
+    np.savez_compressed(os.path.join(OUT, "causal_conv1d.npz"), **cases)
+
+
+def gen_inner(ssi):
+    """mamba_inner_ref forward + grads (the reference test asserts forward only, test_selective_scan.py:221)."""
+    torch.manual_seed(0)
+    Bsz, d, L, N, R, dm, W = 2, 8, 48, 4, 2, 4, 4
+    t = dict(xz=torch.randn(Bsz, 2 * d, L), conv_w=torch.randn(d, 1, W), conv_b=torch.randn(d),
+             x_proj_w=torch.randn(R + 2 * N, d) * 0.3, dt_proj_w=torch.randn(d, R) * 0.3,
+             out_proj_w=torch.randn(dm, d) * 0.3, A=-0.5 * torch.rand(d, N), D=torch.randn(d),
+             dt_bias=0.5 * torch.rand(d))
+    for v in t.values():
+        v.requires_grad_()
+    out = ssi.mamba_inner_ref(t["xz"], t["conv_w"], t["conv_b"], t["x_proj_w"], t["dt_proj_w"], t["out_proj_w"],
+                              None, t["A"], None, None, t["D"], t["dt_bias"], delta_softplus=True)
+    g = torch.randn_like(out)
+    out.backward(g)
+    cases = {k: npy(v) for k, v in t.items()}
+    cases.update({"d" + k: npy(v.grad) for k, v in t.items()})
+    cases["out"] = npy(out)
+    cases["dout"] = npy(g)
+    np.savez_compressed(os.path.join(OUT, "mamba_inner.npz"), **cases)
+
+
+def gen_module(ms):
+    """TFM Mamba, v3, forward (4 outputs) + parameter/input grads; and the v1 branch (lines 304-318)
+    evaluated through mamba_inner_ref with the same parameters (the shipped constructor asserts v3)."""
+    torch.manual_seed(0)
+    m = ms.Mamba(d_model=8, d_state=4, d_conv=4, expand=2, bimamba_type="v3", nslices=4)
+    x = torch.randn(2, 32, 8, requires_grad=True)
+    out, o1, o2, o3 = m(x)
+    g = torch.randn_like(out)
+    out.backward(g)
+    cases = {"x": npy(x), "dout": npy(g), "out": npy(out), "o1": npy(o1), "o2": npy(o2), "o3": npy(o3),
+             "dx": npy(x.grad)}
+    for k, p in m.named_parameters():
+        cases["param." + k] = npy(p)
+        cases["grad." + k] = npy(p.grad) if p.grad is not None else np.zeros(0, np.float32)
+    # v1 branch
+    m.zero_grad()
+    x1 = x.detach().clone().requires_grad_()
+    m.bimamba_type = "v1"
+    try:
+        m(x1)
+        v1_status = "ran"
+    except UnboundLocalError:
+        v1_status = "UnboundLocalError"
+    cases["v1_status"] = np.array(v1_status)
+    sys.modules["mamba_ssm.ops.selective_scan_interface"]
+    from einops import rearrange
+    xz = rearrange(m.in_proj.weight @ rearrange(x1, "b l d -> d (b l)"), "d (b l) -> b d l", l=32)
+    A = -torch.exp(m.A_log.float())
+    iface = sys.modules["mamba_ssm.ops.selective_scan_interface"]
+    out1 = iface.mamba_inner_fn(xz, m.conv1d.weight, m.conv1d.bias, m.x_proj.weight, m.dt_proj.weight,
+                                m.out_proj.weight, m.out_proj.bias, A, None, None, m.D.float(),
+                                delta_bias=m.dt_proj.bias.float(), delta_softplus=True)
+    m.zero_grad()
+    out1.backward(g)
+    cases["v1.out"] = npy(out1)
+    cases["v1.dx"] = npy(x1.grad)
+    for k, p in m.named_parameters():
+        cases["v1.grad." + k] = npy(p.grad) if p.grad is not None else np.zeros(0, np.float32)
+    np.savez_compressed(os.path.join(OUT, "tfm_mamba.npz"), **cases)
+
+
+def gen_orders(mm):
+    """Exact integer index maps: run the reference permutations on an arange tensor."""
+    conv = mm.MMConv.__new__(mm.MMConv)        # methods use no module state
+    cases = {}
+    for (H, W) in [(4, 6), (5, 3), (1, 7), (2, 2), (16, 16), (7, 8)]:
+        src = torch.arange(H * W, dtype=torch.float64).reshape(1, 1, H, W)
+        flat = mm.MMConv.two_row_columnwise_flatten_grad_safe(conv, src)
+        back = mm.MMConv.inverse_two_row_columnwise_flatten(conv, flat, H, W)
+        assert torch.equal(back, src)
+        cases[f"tworow.{H}x{W}"] = flat.reshape(-1).to(torch.int64).numpy()
+    for (L, ns) in [(16, 4), (64, 16), (36, 6), (8, 1), (8, 8)]:
+        src = torch.arange(L, dtype=torch.float64).reshape(1, 1, L)
+        xs = torch.stack(src.chunk(ns, dim=-1), dim=-1).flatten(-2)                      # mamba_simple.py:245-247
+        cases[f"nslices.{L}_{ns}"] = xs.reshape(-1).to(torch.int64).numpy()
+        inv = xs.reshape(1, 1, L // ns, ns).permute(0, 1, 3, 2).flatten(-2)             # :263
+        assert torch.equal(inv, src)
+    for L in [1, 5, 16]:
+        cases[f"flip.{L}"] = torch.arange(L).flip([-1]).numpy()                          # :230
+    np.savez_compressed(os.path.join(OUT, "scan_orders.npz"), **cases)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    cci, ssi, ms, mm = load_reference()
+    gen_scan(ssi)
+    gen_conv(cci)
+    gen_inner(ssi)
+    gen_module(ms)
+    gen_orders(mm)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
