@@ -1,0 +1,166 @@
+/*
+ * mmunet_b200 — C-ABI of the B200-native (sm_100a) Mamba-block hot path of MM-UNet.
+ *
+ * Drop-in boundary: these entry points replace the reference's two pybind11/torch-C++ extension
+ * modules (which are torch-ABI, not C-ABI):
+ *
+ *   selective_scan_cuda.fwd / .bwd        requirements/Mamba/mamba/csrc/selective_scan/selective_scan.cpp:226-232, 338-349, 494-497
+ *   causal_conv1d_cuda.causal_conv1d_fwd / _bwd
+ *                                         requirements/Mamba/causal-conv1d/csrc/causal_conv1d.cpp:130-133, 191-196, 329-333
+ *   (parameter blocks mirror SSMParamsBase/SSMParamsBwd  selective_scan.h:26-101  and
+ *    ConvParamsBase/ConvParamsBwd  causal_conv1d.h:9-52)
+ *
+ * plus the scan-order gather/scatter that the reference expresses as torch view/permute/flip/stack
+ * copies (src/UM_Net/MMUNet.py:68-121, requirements/mamba_simple.py:230,245-247,263).
+ *
+ * Conventions
+ *   - plain pointers + sizes + element strides; no torch types.  All pointers are DEVICE pointers.
+ *   - the caller allocates every output and workspace (the library never owns memory).
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns without
+ *     synchronising.  Re-entrant: no global scratch.
+ *   - return value: 0 on success; MMU_ERR_* (<0) for argument errors, or a positive cudaError_t
+ *     for launch failures.  mmu_last_error() gives a thread-local human readable message.
+ *   - the innermost (sequence) stride of every activation tensor must be 1 (same rule as the
+ *     reference: selective_scan.cpp:252-253, causal_conv1d.cpp:151).  Batch / channel strides are
+ *     free, which is what the (L, B*L, 1)-strided `xz` produced by in_proj needs.
+ *
+ * Supported subset (everything MM-UNet uses; the rest is rejected with MMU_ERR_UNSUPPORTED):
+ *   real A (fp32), input-dependent B and C of shape (batch, 1, dstate, L) [n_groups == 1],
+ *   dstate <= 256, activations fp32 / bf16 / fp16, conv width 2..4.
+ */
+#ifndef MMUNET_B200_H
+#define MMUNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMU_VERSION 100
+
+enum mmu_dtype { MMU_F32 = 0, MMU_BF16 = 1, MMU_F16 = 2 };
+
+enum mmu_error {
+    MMU_OK = 0,
+    MMU_ERR_INVALID = -1,      /* bad shape / null pointer / bad stride */
+    MMU_ERR_UNSUPPORTED = -2,  /* valid for the reference, not implemented here */
+    MMU_ERR_WORKSPACE = -3     /* workspace too small */
+};
+
+/* x[b][d][k][n] holds the scan state h after token (k+1)*MMU_STATE_STRIDE-1 (fp32).  It plays the role of
+ * the reference's `x` / scan_intermediates tensor (selective_scan.cpp:313) at a finer grain. */
+#define MMU_STATE_STRIDE 64
+
+/* ---------------------------------------------------------------------------------------------
+ * selective scan.  replaces selective_scan_cuda.fwd  (selective_scan.cpp:226-336)
+ *   u, delta, z, out : (batch, dim, seqlen)   dtype `dtype`, seqlen-stride 1
+ *   A               : (dim, dstate) fp32 contiguous
+ *   B, C            : (batch, 1, dstate, seqlen) dtype `dtype`; strides (B_bs, B_ns, 1)
+ *   D, delta_bias   : (dim) fp32 or NULL;  z / out_z NULL when there is no gate
+ *   out             : y*silu(z) when z != NULL, else y.  (The reference's separate pre-gate `out`
+ *                     tensor is not produced: the backward recomputes it.)
+ *   x               : (batch, dim, ceil(seqlen/MMU_STATE_STRIDE), dstate) fp32, contiguous; NULL allowed
+ *                     for inference (no backward).
+ *   last_state      : (batch, dim, dstate) fp32 or NULL
+ *   workspace       : mmu_selective_scan_fwd_workspace() bytes (may be NULL when that is 0)
+ * --------------------------------------------------------------------------------------------- */
+typedef struct mmu_scan_fwd_params {
+    int32_t batch, dim, seqlen, dstate;
+    int32_t dtype;           /* enum mmu_dtype */
+    int32_t delta_softplus;  /* 0/1 */
+    int32_t reverse;         /* 0: scan l = 0..L-1.  1: scan l = L-1..0 (fused flip, mamba_simple.py:230) */
+    int32_t reserved;
+    const void *u, *delta, *z, *B, *C;
+    const float *A, *D, *delta_bias;
+    void *out;
+    float *x;
+    float *last_state;
+    int64_t u_bs, u_ds, delta_bs, delta_ds, z_bs, z_ds, out_bs, out_ds;   /* element strides */
+    int64_t B_bs, B_ns, C_bs, C_ns;
+    void *workspace;
+    size_t workspace_bytes;
+} mmu_scan_fwd_params;
+
+size_t mmu_selective_scan_fwd_workspace(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate);
+int mmu_selective_scan_fwd(const mmu_scan_fwd_params *p, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * selective scan backward.  replaces selective_scan_cuda.bwd  (selective_scan.cpp:338-492)
+ *   inputs as forward + dout (batch, dim, seqlen) and x from the forward.
+ *   du, ddelta, dz : (batch, dim, seqlen) dtype `dtype` (dz NULL iff z NULL)
+ *   dA (dim,dstate), dD (dim), ddelta_bias (dim), dB, dC (batch,1,dstate,seqlen contiguous): fp32,
+ *   ACCUMULATED INTO (atomics) — the caller zero-fills them, as the reference does
+ *   (selective_scan.cpp:458-466).  dD / ddelta_bias may be NULL when D / delta_bias are NULL.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct mmu_scan_bwd_params {
+    mmu_scan_fwd_params f;   /* f.out, f.last_state unused */
+    const void *dout;
+    int64_t dout_bs, dout_ds;
+    void *du, *ddelta, *dz;
+    int64_t du_bs, du_ds, ddelta_bs, ddelta_ds, dz_bs, dz_ds;
+    float *dA, *dB, *dC, *dD, *ddelta_bias;
+} mmu_scan_bwd_params;
+
+size_t mmu_selective_scan_bwd_workspace(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate);
+int mmu_selective_scan_bwd(const mmu_scan_bwd_params *p, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * causal depthwise conv1d.  replaces causal_conv1d_cuda.causal_conv1d_fwd/_bwd
+ *   (causal_conv1d.cpp:130-268)
+ *   x, out, dout, dx : (batch, dim, seqlen) dtype `dtype`, seqlen-stride 1
+ *   weight (dim, width) fp32 with strides (w_ds, w_ws); bias (dim) fp32 or NULL
+ *   dweight (dim, width) fp32 contiguous, dbias (dim) fp32: accumulated into (caller zero-fills)
+ * --------------------------------------------------------------------------------------------- */
+typedef struct mmu_conv_params {
+    int32_t batch, dim, seqlen, width;
+    int32_t dtype;
+    int32_t silu;            /* 0/1 */
+    int32_t reverse;         /* 1: anti-causal == conv of the flipped sequence, stored un-flipped (mamba_simple.py:230) */
+    int32_t reserved;
+    const void *x;
+    const float *weight, *bias;
+    void *out;               /* fwd */
+    int64_t x_bs, x_ds, out_bs, out_ds, w_ds, w_ws;
+    /* backward only */
+    const void *dout;
+    void *dx;
+    float *dweight, *dbias;
+    int64_t dout_bs, dout_ds, dx_bs, dx_ds;
+} mmu_conv_params;
+
+int mmu_causal_conv1d_fwd(const mmu_conv_params *p, void *stream);
+int mmu_causal_conv1d_bwd(const mmu_conv_params *p, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * scan-order gather / scatter over the last (token) axis of a (rows, L) matrix with row stride.
+ *   order: MMU_ORDER_*;  gather:  dst[r][l] = src[r][idx(l)];  scatter: dst[r][idx(l)] = src[r][l]
+ *   idx(l) is the closed form of the reference permutations (bit-exact):
+ *     FLIP      idx = L-1-l                                   mamba_simple.py:230
+ *     NSLICES   idx(j*ns+s) = s*(L/ns)+j     (L % ns == 0)    mamba_simple.py:245-247 (scatter = :263)
+ *     TWOROW    rows of an (H, W) map taken in pairs, column-interleaved, odd last row appended
+ *                                                             MMUNet.py:68-93 (scatter = :95-121)
+ *   rows = product of leading dims; src/dst row strides in elements; L = H*W.
+ *   mmu_scan_order_index writes idx as int64 (for tests and host-side index building).
+ * --------------------------------------------------------------------------------------------- */
+enum mmu_order { MMU_ORDER_ROWMAJOR = 0, MMU_ORDER_FLIP = 1, MMU_ORDER_NSLICES = 2, MMU_ORDER_TWOROW = 3 };
+
+int mmu_scan_order_gather(const void *src, void *dst, int32_t dtype, int64_t rows, int64_t src_rs, int64_t dst_rs,
+                          int32_t order, int32_t H, int32_t W, int32_t nslices, void *stream);
+int mmu_scan_order_scatter(const void *src, void *dst, int32_t dtype, int64_t rows, int64_t src_rs, int64_t dst_rs,
+                           int32_t order, int32_t H, int32_t W, int32_t nslices, void *stream);
+int mmu_scan_order_index(int64_t *idx_dev, int32_t order, int32_t H, int32_t W, int32_t nslices, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * misc
+ * --------------------------------------------------------------------------------------------- */
+int mmu_version(void);
+const char *mmu_last_error(void);
+/* number of kernel launches issued through this library by the calling process (bench.py's gpu_launches) */
+uint64_t mmu_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMUNET_B200_H */

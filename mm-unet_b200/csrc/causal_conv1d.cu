@@ -1,0 +1,214 @@
+// Depthwise causal conv1d (width 2..4) forward / backward for sm_100a.
+//
+// Replaces causal_conv1d_fwd_kernel / causal_conv1d_bwd_kernel
+// (requirements/Mamba/causal-conv1d/csrc/causal_conv1d_fwd.cu:39-130, causal_conv1d_bwd.cu:46-240).
+// The reference walks one (batch, channel) row per CTA, chunk after chunk; a conv has no long-range dependency, so
+// here the grid is (token-blocks, channel, batch): MM-UNet's D=6 / L=65536 rows spread over all SMs.
+// Each thread owns VT = 8 consecutive tokens (one or two 16-byte vectors) plus a 3-token halo that hits L1.
+//   fwd : out[l]  = act(bias + sum_k w[k] x[l-(W-1-k)])
+//   bwd : dpre[l] = dout[l] * silu'(pre[l]) (pre recomputed, causal_conv1d_bwd.cu:153-164)
+//         dx[l]   = sum_k w[k] dpre[l+(W-1-k)]        dw[k] = sum_{b,l} x[l-(W-1-k)] dpre[l]       db = sum dpre
+// Widths < 4 are handled as width 4 with zero leading taps.
+#include "scan_tiles.cuh"
+
+namespace mmu {
+
+struct ConvArgs {
+    const void *x, *dout;
+    const float *w, *bias;
+    void *out, *dx;
+    float *dw, *db;
+    int64_t x_bs, x_ds, o_bs, o_ds, w_ds, w_ws, g_bs, g_ds, dx_bs, dx_ds;
+    int B, D, L, W;
+    int silu, reverse;
+    unsigned vec_mask;   // bit0 x, bit1 out/dx, bit2 dout
+};
+
+constexpr int kConvVT = 8, kConvNT = 128;
+
+// logical token t lives at memory position t (forward) or L-1-t (reverse)
+__device__ __forceinline__ int mpos(int t, int L, bool rev) { return rev ? L - 1 - t : t; }
+
+template <typename IN_T>
+__device__ __forceinline__ void load8(const IN_T *rp, int t, int L, bool vec, bool rev, float v[kConvVT]) {
+    if (vec && t + kConvVT <= L) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const Quad<IN_T> q = *reinterpret_cast<const Quad<IN_T> *>(rp + (rev ? L - 4 - (t + 4 * h) : t + 4 * h));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[4 * h + k] = Elem<IN_T>::to_f(q.v[rev ? 3 - k : k]);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kConvVT; ++k) v[k] = (t + k < L) ? Elem<IN_T>::to_f(rp[mpos(t + k, L, rev)]) : 0.f;
+    }
+}
+
+template <typename OUT_T>
+__device__ __forceinline__ void store8(OUT_T *rp, int t, int L, bool vec, bool rev, const float v[kConvVT]) {
+    if (vec && t + kConvVT <= L) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            Quad<OUT_T> q;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q.v[rev ? 3 - k : k] = Elem<OUT_T>::from_f(v[4 * h + k]);
+            *reinterpret_cast<Quad<OUT_T> *>(rp + (rev ? L - 4 - (t + 4 * h) : t + 4 * h)) = q;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kConvVT; ++k)
+            if (t + k < L) rp[mpos(t + k, L, rev)] = Elem<OUT_T>::from_f(v[k]);
+    }
+}
+
+__device__ __forceinline__ void load_taps(const ConvArgs &p, int d, float w4[4], float &bias) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int kk = k - (4 - p.W);
+        w4[k] = kk >= 0 ? p.w[(int64_t)d * p.w_ds + (int64_t)kk * p.w_ws] : 0.f;
+    }
+    bias = p.bias != nullptr ? p.bias[d] : 0.f;
+}
+
+template <typename IN_T> __global__ void __launch_bounds__(kConvNT) conv1d_fwd_kernel(const __grid_constant__ ConvArgs p) {
+    const int d = blockIdx.y, b = blockIdx.z;
+    const int t = (blockIdx.x * kConvNT + threadIdx.x) * kConvVT;
+    if (t >= p.L) return;
+    float w4[4], bias;
+    load_taps(p, d, w4, bias);
+    const IN_T *xr = reinterpret_cast<const IN_T *>(p.x) + (int64_t)b * p.x_bs + (int64_t)d * p.x_ds;
+    float xv[kConvVT + 3];
+    const bool rev = p.reverse != 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) xv[k] = (t - 3 + k >= 0) ? Elem<IN_T>::to_f(xr[mpos(t - 3 + k, p.L, rev)]) : 0.f;
+    load8<IN_T>(xr, t, p.L, p.vec_mask & 1u, rev, xv + 3);
+    float o[kConvVT];
+#pragma unroll
+    for (int i = 0; i < kConvVT; ++i) {
+        float acc = bias;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc = fmaf(w4[k], xv[i + k], acc);
+        o[i] = p.silu ? acc * sigmoid_f(acc) : acc;
+    }
+    store8<IN_T>(reinterpret_cast<IN_T *>(p.out) + (int64_t)b * p.o_bs + (int64_t)d * p.o_ds, t, p.L, p.vec_mask & 2u,
+                 rev, o);
+}
+
+template <typename IN_T> __global__ void __launch_bounds__(kConvNT) conv1d_bwd_kernel(const __grid_constant__ ConvArgs p) {
+    const int d = blockIdx.y, b = blockIdx.z;
+    const int t = (blockIdx.x * kConvNT + threadIdx.x) * kConvVT;
+    float w4[4], bias;
+    load_taps(p, d, w4, bias);
+    float part[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // dw4[0..3], dbias
+    const bool rev = p.reverse != 0;
+    if (t < p.L) {
+        const IN_T *xr = reinterpret_cast<const IN_T *>(p.x) + (int64_t)b * p.x_bs + (int64_t)d * p.x_ds;
+        const IN_T *gr = reinterpret_cast<const IN_T *>(p.dout) + (int64_t)b * p.g_bs + (int64_t)d * p.g_ds;
+        float xv[kConvVT + 6], gv[kConvVT + 3];   // x[t-3 .. t+10], dout[t .. t+10]
+#pragma unroll
+        for (int k = 0; k < 3; ++k) xv[k] = (t - 3 + k >= 0) ? Elem<IN_T>::to_f(xr[mpos(t - 3 + k, p.L, rev)]) : 0.f;
+        load8<IN_T>(xr, t, p.L, p.vec_mask & 1u, rev, xv + 3);
+        load8<IN_T>(gr, t, p.L, p.vec_mask & 4u, rev, gv);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int tt = t + kConvVT + k;
+            xv[3 + kConvVT + k] = tt < p.L ? Elem<IN_T>::to_f(xr[mpos(tt, p.L, rev)]) : 0.f;
+            gv[kConvVT + k] = tt < p.L ? Elem<IN_T>::to_f(gr[mpos(tt, p.L, rev)]) : 0.f;
+        }
+        float dpre[kConvVT + 3];
+#pragma unroll
+        for (int i = 0; i < kConvVT + 3; ++i) {
+            float g = gv[i];
+            if (p.silu) {
+                float pre = bias;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) pre = fmaf(w4[k], xv[i + k], pre);
+                const float s = sigmoid_f(pre);
+                g *= s * fmaf(pre, 1.f - s, 1.f);
+            }
+            dpre[i] = g;   // zero beyond L because dout is zero there
+        }
+        float dxv[kConvVT];
+#pragma unroll
+        for (int i = 0; i < kConvVT; ++i) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc = fmaf(w4[k], dpre[i + 3 - k], acc);
+            dxv[i] = acc;
+            part[4] += dpre[i];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) part[k] = fmaf(xv[i + k], dpre[i], part[k]);
+        }
+        store8<IN_T>(reinterpret_cast<IN_T *>(p.dx) + (int64_t)b * p.dx_bs + (int64_t)d * p.dx_ds, t, p.L, p.vec_mask & 2u,
+                     rev, dxv);
+    }
+    // block reduce -> one atomic per (channel, tap) per CTA
+    __shared__ float red[kConvNT / 32][5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        float v = part[k];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        float v = 0.f;
+#pragma unroll
+        for (int wdx = 0; wdx < kConvNT / 32; ++wdx) v += red[wdx][threadIdx.x];
+        if (threadIdx.x == 4) {
+            if (p.db != nullptr) atomicAdd(p.db + d, v);
+        } else {
+            const int kk = (int)threadIdx.x - (4 - p.W);
+            if (kk >= 0) atomicAdd(p.dw + (int64_t)d * p.W + kk, v);
+        }
+    }
+}
+
+namespace {
+template <typename IN_T> int run_conv(const mmu_conv_params *p, bool bwd, cudaStream_t st) {
+    ConvArgs a{};
+    a.x = p->x, a.dout = p->dout, a.w = p->weight, a.bias = p->bias, a.out = p->out, a.dx = p->dx;
+    a.dw = p->dweight, a.db = p->dbias;
+    a.x_bs = p->x_bs, a.x_ds = p->x_ds, a.o_bs = p->out_bs, a.o_ds = p->out_ds, a.w_ds = p->w_ds, a.w_ws = p->w_ws;
+    a.g_bs = p->dout_bs, a.g_ds = p->dout_ds, a.dx_bs = p->dx_bs, a.dx_ds = p->dx_ds;
+    a.B = p->batch, a.D = p->dim, a.L = p->seqlen, a.W = p->width, a.silu = p->silu, a.reverse = p->reverse;
+    const int L = p->seqlen;
+    const bool rv = p->reverse != 0;
+    a.vec_mask = quad_ok<IN_T>(p->x, p->x_bs, p->x_ds, L, rv) ? 1u : 0u;
+    if (!bwd) {
+        a.vec_mask |= quad_ok<IN_T>(p->out, p->out_bs, p->out_ds, L, rv) ? 2u : 0u;
+    } else {
+        a.vec_mask |= quad_ok<IN_T>(p->dx, p->dx_bs, p->dx_ds, L, rv) ? 2u : 0u;
+        a.vec_mask |= quad_ok<IN_T>(p->dout, p->dout_bs, p->dout_ds, L, rv) ? 4u : 0u;
+    }
+    const int per_block = kConvNT * kConvVT;
+    dim3 grid((L + per_block - 1) / per_block, p->dim, p->batch);
+    if (grid.y > 65535 || grid.z > 65535) return set_error(MMU_ERR_UNSUPPORTED, "causal_conv1d: dim/batch > 65535");
+    if (bwd) conv1d_bwd_kernel<IN_T><<<grid, kConvNT, 0, st>>>(a);
+    else conv1d_fwd_kernel<IN_T><<<grid, kConvNT, 0, st>>>(a);
+    count_launch();
+    return check_launch(bwd ? "causal_conv1d_bwd" : "causal_conv1d_fwd");
+}
+
+int conv_entry(const mmu_conv_params *p, bool bwd, void *stream) {
+    if (p == nullptr) return set_error(MMU_ERR_INVALID, "causal_conv1d: null params");
+    if (p->batch <= 0 || p->dim <= 0 || p->seqlen <= 0) return set_error(MMU_ERR_INVALID, "causal_conv1d: empty shape");
+    if (p->width < 2 || p->width > 4) return set_error(MMU_ERR_INVALID, "causal_conv1d only supports width between 2 and 4");
+    if (!p->x || !p->weight) return set_error(MMU_ERR_INVALID, "causal_conv1d: null tensor pointer");
+    if (!bwd && !p->out) return set_error(MMU_ERR_INVALID, "causal_conv1d_fwd: null out");
+    if (bwd && (!p->dout || !p->dx || !p->dweight)) return set_error(MMU_ERR_INVALID, "causal_conv1d_bwd: null tensor pointer");
+    if (bwd && p->bias != nullptr && !p->dbias) return set_error(MMU_ERR_INVALID, "causal_conv1d_bwd: dbias missing");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (p->dtype) {
+        case MMU_F32: return run_conv<float>(p, bwd, st);
+        case MMU_BF16: return run_conv<__nv_bfloat16>(p, bwd, st);
+        case MMU_F16: return run_conv<__half>(p, bwd, st);
+        default: return set_error(MMU_ERR_UNSUPPORTED, "causal_conv1d: dtype %d", p->dtype);
+    }
+}
+}  // namespace
+}  // namespace mmu
+
+extern "C" int mmu_causal_conv1d_fwd(const mmu_conv_params *p, void *stream) { return mmu::conv_entry(p, false, stream); }
+extern "C" int mmu_causal_conv1d_bwd(const mmu_conv_params *p, void *stream) { return mmu::conv_entry(p, true, stream); }

@@ -1,0 +1,102 @@
+// Scan-order gather / scatter (bit-exact index maps) for sm_100a.
+//
+// The reference expresses these as torch view/permute/flip/stack copies:
+//   two-row column-interleaved "morph" order   src/UM_Net/MMUNet.py:68-93 (flatten), :95-121 (inverse)
+//   flip                                       requirements/mamba_simple.py:230
+//   nslices interleave                         requirements/mamba_simple.py:245-247 (gather), :263 (scatter)
+// Here idx(l) is evaluated in closed form per element; the kernel is a pure HBM-bound permutation:
+//   gather : dst[r][l]      = src[r][idx(l)]
+//   scatter: dst[r][idx(l)] = src[r][l]
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace mmu {
+
+struct OrderMap {
+    int order, W, ns, L, Ls, even_tokens;   // Ls = L / ns, even_tokens = 2*(H/2)*W
+    __device__ __forceinline__ int operator()(int l) const {
+        switch (order) {
+            case MMU_ORDER_FLIP: return L - 1 - l;
+            case MMU_ORDER_NSLICES: {
+                const int jj = l / ns, s = l - jj * ns;
+                return s * Ls + jj;
+            }
+            case MMU_ORDER_TWOROW: {
+                if (l >= even_tokens) return l;   // odd tail row, appended row-major
+                const int pair = l / (2 * W), rem = l - pair * 2 * W;
+                return (2 * pair + (rem & 1)) * W + (rem >> 1);
+            }
+            default: return l;
+        }
+    }
+};
+
+template <typename T, bool SCATTER>
+__global__ void __launch_bounds__(256) scan_order_kernel(const T *__restrict__ src, T *__restrict__ dst, int64_t rows,
+                                                         int64_t src_rs, int64_t dst_rs, OrderMap m) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= m.L) return;
+    const int k = m(l);
+    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+        if (SCATTER) dst[r * dst_rs + k] = src[r * src_rs + l];
+        else dst[r * dst_rs + l] = src[r * src_rs + k];
+    }
+}
+
+__global__ void scan_order_index_kernel(int64_t *idx, OrderMap m) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < m.L) idx[l] = m(l);
+}
+
+namespace {
+int make_map(OrderMap &m, int order, int H, int W, int ns) {
+    if (H <= 0 || W <= 0) return set_error(MMU_ERR_INVALID, "scan_order: empty map %dx%d", H, W);
+    if ((int64_t)H * W > INT32_MAX) return set_error(MMU_ERR_UNSUPPORTED, "scan_order: H*W exceeds int32");
+    if (order < MMU_ORDER_ROWMAJOR || order > MMU_ORDER_TWOROW) return set_error(MMU_ERR_INVALID, "scan_order: order %d", order);
+    m.order = order, m.W = W, m.L = H * W, m.ns = 1, m.Ls = m.L, m.even_tokens = 2 * (H / 2) * W;
+    if (order == MMU_ORDER_NSLICES) {
+        if (ns <= 0 || m.L % ns != 0) return set_error(MMU_ERR_INVALID, "scan_order: L=%d not divisible by nslices=%d", m.L, ns);
+        m.ns = ns, m.Ls = m.L / ns;
+    }
+    return MMU_OK;
+}
+
+template <bool SCATTER>
+int run_order(const void *src, void *dst, int dtype, int64_t rows, int64_t src_rs, int64_t dst_rs, int order, int H, int W,
+              int ns, void *stream) {
+    OrderMap m;
+    if (int rc = make_map(m, order, H, W, ns)) return rc;
+    if (rows <= 0) return set_error(MMU_ERR_INVALID, "scan_order: rows=%lld", (long long)rows);
+    if (!src || !dst) return set_error(MMU_ERR_INVALID, "scan_order: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid((m.L + 255) / 256, (unsigned)std::min<int64_t>(rows, 65535));
+    if (dtype == MMU_F32)
+        scan_order_kernel<float, SCATTER><<<grid, 256, 0, st>>>((const float *)src, (float *)dst, rows, src_rs, dst_rs, m);
+    else if (dtype == MMU_BF16 || dtype == MMU_F16)
+        scan_order_kernel<uint16_t, SCATTER><<<grid, 256, 0, st>>>((const uint16_t *)src, (uint16_t *)dst, rows, src_rs, dst_rs, m);
+    else
+        return set_error(MMU_ERR_UNSUPPORTED, "scan_order: dtype %d", dtype);
+    count_launch();
+    return check_launch("scan_order");
+}
+}  // namespace
+}  // namespace mmu
+
+extern "C" int mmu_scan_order_gather(const void *src, void *dst, int32_t dtype, int64_t rows, int64_t src_rs, int64_t dst_rs,
+                                     int32_t order, int32_t H, int32_t W, int32_t nslices, void *stream) {
+    return mmu::run_order<false>(src, dst, dtype, rows, src_rs, dst_rs, order, H, W, nslices, stream);
+}
+extern "C" int mmu_scan_order_scatter(const void *src, void *dst, int32_t dtype, int64_t rows, int64_t src_rs, int64_t dst_rs,
+                                      int32_t order, int32_t H, int32_t W, int32_t nslices, void *stream) {
+    return mmu::run_order<true>(src, dst, dtype, rows, src_rs, dst_rs, order, H, W, nslices, stream);
+}
+extern "C" int mmu_scan_order_index(int64_t *idx_dev, int32_t order, int32_t H, int32_t W, int32_t nslices, void *stream) {
+    using namespace mmu;
+    OrderMap m;
+    if (int rc = make_map(m, order, H, W, nslices)) return rc;
+    if (!idx_dev) return set_error(MMU_ERR_INVALID, "scan_order_index: null pointer");
+    scan_order_index_kernel<<<(m.L + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(idx_dev, m);
+    count_launch();
+    return check_launch("scan_order_index");
+}

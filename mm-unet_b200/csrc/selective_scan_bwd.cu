@@ -1,0 +1,590 @@
+// Selective scan backward for sm_100a (recompute-based; never materialises the L x N state in HBM).
+//
+// Replaces selective_scan_bwd_kernel (requirements/Mamba/mamba/csrc/selective_scan/selective_scan_bwd_kernel.cuh:75-489).
+// Math: SURVEY.md Appendix A.  Decomposition (DESIGN.md "scan backward"):
+//
+//   * chunks of 64 tokens are walked last -> first; the forward state entering a chunk comes from the x buffer
+//     the forward kernel saved every MMU_STATE_STRIDE tokens, the reverse state dh is carried in shared memory;
+//   * a warp owns 4 channel rows x 8 token-lanes x 8 tokens; both in-chunk scans (forward recompute, reverse dh)
+//     are 3-step 8-lane shuffle scans; the dstate axis is split over NGW warps and walked two states at a time
+//     with packed FFMA2;
+//   * dB/dC (sums over channels) are reduced across the 4 rows of a warp with a select/shuffle butterfly, across
+//     the row-warps of the CTA in shared memory, and only then added to global memory - (D / rows-per-CTA)
+//     atomics per element instead of the reference's D (selective_scan_bwd_kernel.cuh:306-315);
+//   * the pre-gate output y is recomputed (one extra FFMA2 per state pair), so `out` is never read;
+//   * like the forward, the sequence can be split over CTAs: an aggregate pass yields per-segment
+//     (dh at segment start | zero inflow, sum(delta), delta_first), a tiny kernel chains them right-to-left.
+#include <algorithm>
+#include <cstdlib>
+
+#include "scan_tiles.cuh"
+
+namespace mmu {
+
+struct BwdArgs {
+    const void *u, *delta, *z, *dout, *Bm, *Cm;
+    const float *A, *Dv, *dbias, *x;
+    void *du, *ddelta, *dz;
+    float *dA, *dB, *dC, *dD, *ddbias;
+    float *seg_dh, *seg_dsum, *seg_dfirst;
+    const float *dhin;
+    int64_t u_bs, u_ds, dl_bs, dl_ds, z_bs, z_ds, g_bs, g_ds, B_bs, B_ns, C_bs, C_ns;
+    int64_t du_bs, du_ds, ddl_bs, ddl_ds, dz_bs, dz_ds;
+    int B, D, L, N, Ne;
+    int nseg, cps, nchunks, nx;
+    int softplus, reverse;
+    unsigned vec_mask;   // bit0 u, 1 delta, 2 z, 3 dout, 4 B, 5 C, 6 du, 7 ddelta, 8 dz
+};
+
+template <int RQ, int NGW> struct BwdCfg {
+    static constexpr int T = 8, LS = 8, RG = 4;
+    static constexpr int R = RQ * RG, TL = LS * T, NT = 32 * RQ * NGW, NW = RQ * NGW;
+    static_assert(TL == MMU_STATE_STRIDE, "backward chunk == saved-state stride");
+    static size_t smem_floats(int Ne) {
+        return (size_t)4 * R * TL + 2 * (size_t)Ne * TL + (size_t)NGW * 3 * R * TL + (size_t)RQ * (Ne / 2) * 4 * TL +
+               (size_t)5 * R * Ne + (size_t)R * Ne * 8 + 4 * R;
+    }
+};
+
+template <typename IN_T, int RQ, int NGW, bool AGG>
+__global__ void __launch_bounds__(32 * RQ * NGW, (AGG ? 512 : 384) / (32 * RQ * NGW)) scan_bwd_kernel(const __grid_constant__ BwdArgs p) {
+    using Cfg = BwdCfg<RQ, NGW>;
+    constexpr int T = Cfg::T, R = Cfg::R, TL = Cfg::TL, NT = Cfg::NT, NW = Cfg::NW;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wq = warp / NGW, g = warp % NGW, rg = lane >> 3, j = lane & 7;
+    const int b = blockIdx.y, row0 = blockIdx.x * R, seg = blockIdx.z;
+    const int N = p.N, Ne = p.Ne, NP = Ne >> 1, D = p.D, L = p.L;
+    const bool has_z = p.z != nullptr, rev = p.reverse != 0, sp = p.softplus != 0;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *s_u = reinterpret_cast<float *>(smem_raw);   // [R][TL]  u, later du
+    float *s_dl = s_u + R * TL;                          // [R][TL]  softplus(delta+bias), later ddelta
+    float *s_z = s_dl + R * TL;                          // [R][TL]  z -> dz factor -> dz
+    float *s_g = s_z + R * TL;                           // [R][TL]  dout -> dy
+    float *s_B = s_g + R * TL;                           // [Ne][TL]
+    float *s_C = s_B + Ne * TL;                          // [Ne][TL]
+    float *s_part = s_C + Ne * TL;                       // [NGW][3][R][TL]  partial S1, S2, y
+    float *s_dbc = s_part + NGW * 3 * R * TL;            // [RQ][NP][4][TL]  row-reduced dB.x dB.y dC.x dC.y
+    float *s_A2 = s_dbc + RQ * NP * 4 * TL;              // [R][Ne]  A*log2e
+    float *s_A = s_A2 + R * Ne;                          // [R][Ne]
+    float *s_hin = s_A + R * Ne;                         // [R][Ne]  forward state entering the chunk
+    float *s_dhc = s_hin + R * Ne;                       // [R][Ne]  dh at the first token of the next chunk
+    float *s_an = s_dhc + R * Ne;                        // [R][Ne]  a at the first token of the next chunk
+    float *s_dA = s_an + R * Ne;                         // [R][NP][8 lanes][2]
+    float *s_bias = s_dA + R * Ne * 8;                   // [R]
+    float *s_D = s_bias + R;                             // [R]
+    float *s_dD = s_D + R;                               // [R]
+    float *s_db = s_dD + R;                              // [R]
+
+    const int c_begin = seg * p.cps, c_end = min(p.nchunks, c_begin + p.cps);
+    const IN_T *dl_b = reinterpret_cast<const IN_T *>(p.delta) + (int64_t)b * p.dl_bs;
+
+    for (int r = tid; r < R; r += NT) {
+        const int row = row0 + r;
+        s_bias[r] = (row < D && p.dbias != nullptr) ? p.dbias[row] : 0.f;
+        s_D[r] = (row < D && p.Dv != nullptr) ? p.Dv[row] : 0.f;
+        s_dD[r] = 0.f;
+        s_db[r] = 0.f;
+    }
+    __syncthreads();
+    for (int i = tid; i < R * Ne; i += NT) {
+        const int r = i / Ne, n = i - r * Ne, row = row0 + r;
+        const bool ok = row < D && n < N;
+        const float A = ok ? p.A[(int64_t)row * N + n] : 0.f;
+        s_A[i] = A;
+        s_A2[i] = A * kLog2e;
+        float dh0 = 0.f, an = 1.f;
+        const int tn = c_end * TL;   // first logical token of the next segment
+        if (ok && tn < L) {
+            const float raw = Elem<IN_T>::to_f(dl_b[(int64_t)row * p.dl_ds + (rev ? L - 1 - tn : tn)]) + s_bias[r];
+            an = ex2(A * kLog2e * (sp ? softplus_f(raw) : raw));
+            if (!AGG && p.dhin != nullptr) dh0 = p.dhin[(((int64_t)b * D + row) * p.nseg + seg) * Ne + n];
+        }
+        s_dhc[i] = dh0;
+        s_an[i] = an;
+    }
+    for (int i = tid; i < R * Ne * 8; i += NT) s_dA[i] = 0.f;
+
+    const IN_T *u_b = reinterpret_cast<const IN_T *>(p.u) + (int64_t)b * p.u_bs;
+    const IN_T *z_b = has_z ? reinterpret_cast<const IN_T *>(p.z) + (int64_t)b * p.z_bs : nullptr;
+    const IN_T *g_b = reinterpret_cast<const IN_T *>(p.dout) + (int64_t)b * p.g_bs;
+    const IN_T *B_b = reinterpret_cast<const IN_T *>(p.Bm) + (int64_t)b * p.B_bs;
+    const IN_T *C_b = reinterpret_cast<const IN_T *>(p.Cm) + (int64_t)b * p.C_bs;
+
+    const int npw = (NP + NGW - 1) / NGW;
+    const int pair0 = g * npw, pair1 = min(NP, pair0 + npw);
+    const int lr = wq * 4 + rg;
+    const bool hi = (rg & 2) != 0, lo = (rg & 1) != 0;
+    float dsum = 0.f, dfirst = 0.f;
+
+    for (int c = c_end - 1; c >= c_begin; --c) {
+        const int t0 = c * TL;
+        __syncthreads();
+        load_tile<IN_T, T, TL, NT>(s_dl, dl_b, p.dl_ds, row0, R, D, t0, L, rev, p.vec_mask & 2u, tid, 0.f,
+                                   [&](int r, float v) {
+                                       const float xx = v + s_bias[r];
+                                       return sp ? softplus_f(xx) : xx;
+                                   });
+        load_tile<IN_T, T, TL, NT>(s_g, g_b, p.g_ds, row0, R, D, t0, L, rev, p.vec_mask & 8u, tid, 0.f,
+                                   [](int, float v) { return v; });
+        load_tile<IN_T, T, TL, NT>(s_C, C_b, p.C_ns, 0, Ne, N, t0, L, rev, p.vec_mask & 32u, tid, 0.f,
+                                   [](int, float v) { return v; });
+        if (has_z) {
+            load_tile<IN_T, T, TL, NT>(s_z, z_b, p.z_ds, row0, R, D, t0, L, rev, p.vec_mask & 4u, tid, 0.f,
+                                       [](int, float v) { return v; });
+            // same thread, same elements as the two loads above: dy = dout*silu(z); s_z <- d(out)/dy-independent dz factor
+            for (int idx = tid; idx < R * (TL / 4); idx += NT) {
+                const int rr = idx / (TL / 4), ch = idx - rr * (TL / 4);
+                const int zoff = rr * TL + 4 * swz_chunk<T>(ch);   // exactly the chunk this thread just wrote
+                float4 z4 = *reinterpret_cast<const float4 *>(s_z + zoff);
+                float4 g4 = *reinterpret_cast<const float4 *>(s_g + zoff);
+                float *zz = reinterpret_cast<float *>(&z4), *gg = reinterpret_cast<float *>(&g4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float s = sigmoid_f(zz[k]);
+                    const float gz = gg[k] * s;
+                    gg[k] = gz * zz[k];                               // dy   (bwd_kernel.cuh:186-191)
+                    zz[k] = gz * fmaf(zz[k], 1.f - s, 1.f);           // dz = y * this
+                }
+                *reinterpret_cast<float4 *>(s_z + zoff) = z4;
+                *reinterpret_cast<float4 *>(s_g + zoff) = g4;
+            }
+        }
+        if (!AGG) {
+            load_tile<IN_T, T, TL, NT>(s_u, u_b, p.u_ds, row0, R, D, t0, L, rev, p.vec_mask & 1u, tid, 0.f,
+                                       [](int, float v) { return v; });
+            load_tile<IN_T, T, TL, NT>(s_B, B_b, p.B_ns, 0, Ne, N, t0, L, rev, p.vec_mask & 16u, tid, 0.f,
+                                       [](int, float v) { return v; });
+            for (int i = tid; i < R * Ne; i += NT) {
+                const int r = i / Ne, n = i - r * Ne, row = row0 + r;
+                s_hin[i] = (c > 0 && row < D && n < N) ? p.x[(((int64_t)b * D + row) * p.nx + (c - 1)) * N + n] : 0.f;
+            }
+        }
+        __syncthreads();
+
+        float dl[T], dlu[T], dy[T];
+        {
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int off = lr * TL + 4 * swz_chunk<T>(j * 2 + cc);
+                const float4 d4 = *reinterpret_cast<const float4 *>(s_dl + off);
+                const float4 g4 = *reinterpret_cast<const float4 *>(s_g + off);
+                float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!AGG) u4 = *reinterpret_cast<const float4 *>(s_u + off);
+                dl[4 * cc] = d4.x, dl[4 * cc + 1] = d4.y, dl[4 * cc + 2] = d4.z, dl[4 * cc + 3] = d4.w;
+                dy[4 * cc] = g4.x, dy[4 * cc + 1] = g4.y, dy[4 * cc + 2] = g4.z, dy[4 * cc + 3] = g4.w;
+                dlu[4 * cc] = d4.x * u4.x, dlu[4 * cc + 1] = d4.y * u4.y, dlu[4 * cc + 2] = d4.z * u4.z,
+                         dlu[4 * cc + 3] = d4.w * u4.w;
+            }
+        }
+        if (AGG) {
+#pragma unroll
+            for (int i = 0; i < T; ++i) dsum += dl[i];
+            if (c == c_begin) dfirst = dl[0];   // meaningful in lane j == 0
+        }
+        float2 S1[T], S2[T], yv[T];
+#pragma unroll
+        for (int i = 0; i < T; ++i) S1[i] = S2[i] = yv[i] = make_float2(0.f, 0.f);
+
+        for (int pr = pair0; pr < pair1; ++pr) {
+            const float2 A2 = *reinterpret_cast<const float2 *>(s_A2 + lr * Ne + 2 * pr);
+            float2 a[T], Cv[T], Bv[T];
+            {
+                const float *sC0 = s_C + (2 * pr) * TL, *sC1 = sC0 + TL;
+                const float *sB0 = s_B + (2 * pr) * TL, *sB1 = sB0 + TL;
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int off = 4 * swz_chunk<T>(j * 2 + cc);
+                    const float4 c0 = *reinterpret_cast<const float4 *>(sC0 + off);
+                    const float4 c1 = *reinterpret_cast<const float4 *>(sC1 + off);
+                    Cv[4 * cc] = make_float2(c0.x, c1.x), Cv[4 * cc + 1] = make_float2(c0.y, c1.y);
+                    Cv[4 * cc + 2] = make_float2(c0.z, c1.z), Cv[4 * cc + 3] = make_float2(c0.w, c1.w);
+                    if (!AGG) {
+                        const float4 b0 = *reinterpret_cast<const float4 *>(sB0 + off);
+                        const float4 b1 = *reinterpret_cast<const float4 *>(sB1 + off);
+                        Bv[4 * cc] = make_float2(b0.x, b1.x), Bv[4 * cc + 1] = make_float2(b0.y, b1.y);
+                        Bv[4 * cc + 2] = make_float2(b0.z, b1.z), Bv[4 * cc + 3] = make_float2(b0.w, b1.w);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < T; ++i) a[i] = ex2(fmul2(splat(dl[i]), A2));
+
+            // ---- forward recompute: state before my first token ------------------------------------------
+            float2 hs = make_float2(0.f, 0.f);
+            if (!AGG) {
+                float2 P = make_float2(1.f, 1.f), hl = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < T; ++i) {
+                    hl = ffma2(a[i], hl, fmul2(splat(dlu[i]), Bv[i]));
+                    P = fmul2(P, a[i]);
+                }
+#pragma unroll
+                for (int k = 1; k < 8; k <<= 1) {
+                    const float2 Pn = shfl_up2(P, k, 8), Hn = shfl_up2(hl, k, 8);
+                    if (j >= k) {
+                        hl = ffma2(P, Hn, hl);
+                        P = fmul2(P, Pn);
+                    }
+                }
+                const float2 hc = *reinterpret_cast<const float2 *>(s_hin + lr * Ne + 2 * pr);
+                const float2 send = ffma2(P, hc, hl);
+                hs = shfl_up2(send, 1, 8);
+                if (j == 0) hs = hc;
+            }
+            // ---- reverse: dh at the first token of the lane to my right ---------------------------------------
+            float *dhc_p = s_dhc + lr * Ne + 2 * pr, *an_p = s_an + lr * Ne + 2 * pr;
+            float2 a_nl = shfl_down2(a[0], 1, 8);   // a of the first token of the next lane
+            if (j == 7) a_nl = *reinterpret_cast<const float2 *>(an_p);
+            float2 dhn;
+            {
+                float2 Pr = a_nl, dhl = fmul2(Cv[T - 1], splat(dy[T - 1]));
+#pragma unroll
+                for (int i = T - 2; i >= 0; --i) {
+                    dhl = ffma2(a[i + 1], dhl, fmul2(Cv[i], splat(dy[i])));
+                    Pr = fmul2(Pr, a[i + 1]);
+                }
+#pragma unroll
+                for (int k = 1; k < 8; k <<= 1) {
+                    const float2 Pn = shfl_down2(Pr, k, 8), Hn = shfl_down2(dhl, k, 8);
+                    if (j + k < 8) {
+                        dhl = ffma2(Pr, Hn, dhl);
+                        Pr = fmul2(Pr, Pn);
+                    }
+                }
+                const float2 dhc = *reinterpret_cast<const float2 *>(dhc_p);
+                const float2 dfirst_tok = ffma2(Pr, dhc, dhl);   // dh at my first token
+                dhn = shfl_down2(dfirst_tok, 1, 8);
+                if (j == 7) dhn = dhc;
+                __syncwarp();
+                if (j == 0) {
+                    *reinterpret_cast<float2 *>(dhc_p) = dfirst_tok;
+                    *reinterpret_cast<float2 *>(an_p) = a[0];
+                }
+            }
+            if (AGG) continue;
+
+            // ---- forward states of my tokens -------------------------------------------------------------------
+            float2 h[T];
+            {
+                float2 hp = hs;
+#pragma unroll
+                for (int i = 0; i < T; ++i) {
+                    hp = ffma2(a[i], hp, fmul2(splat(dlu[i]), Bv[i]));
+                    h[i] = hp;
+                }
+            }
+            // ---- reverse sweep: consume -----------------------------------------------------------------------------
+            const float2 Av = *reinterpret_cast<const float2 *>(s_A + lr * Ne + 2 * pr);
+            float2 e = fmul2(a_nl, dhn);   // a_{t+1} * dh_{t+1} for my last token
+            float2 dAacc = make_float2(0.f, 0.f);
+            float red[T];
+#pragma unroll
+            for (int i = T - 1; i >= 0; --i) {
+                const float2 dh = ffma2(Cv[i], splat(dy[i]), e);
+                const float2 hprev = i > 0 ? h[i - 1] : hs;
+                e = fmul2(a[i], dh);
+                const float2 q = fmul2(e, hprev);                    // dh * a_t * h_{t-1}
+                S1[i] = ffma2(dh, Bv[i], S1[i]);
+                S2[i] = ffma2(Av, q, S2[i]);
+                dAacc = ffma2(splat(dl[i]), q, dAacc);
+                yv[i] = ffma2(Cv[i], h[i], yv[i]);
+                const float2 dBv = fmul2(dh, splat(dlu[i]));
+                const float2 dCv = fmul2(h[i], splat(dy[i]));
+                // butterfly over the 4 rows of the warp: (dB.x dB.y dC.x dC.y) x 4 lanes -> 1 value per lane
+                float2 keep = hi ? dCv : dBv;
+                const float2 snd = hi ? dBv : dCv;
+                keep.x += __shfl_xor_sync(0xffffffffu, snd.x, 16);
+                keep.y += __shfl_xor_sync(0xffffffffu, snd.y, 16);
+                const float k1 = lo ? keep.y : keep.x, s1 = lo ? keep.x : keep.y;
+                red[i] = k1 + __shfl_xor_sync(0xffffffffu, s1, 8);
+            }
+            {
+                float *dst = s_dbc + ((wq * NP + pr) * 4 + rg) * TL + j * T;
+                *reinterpret_cast<float4 *>(dst) = make_float4(red[0], red[1], red[2], red[3]);
+                *reinterpret_cast<float4 *>(dst + 4) = make_float4(red[4], red[5], red[6], red[7]);
+                float2 *dAp = reinterpret_cast<float2 *>(s_dA) + (lr * NP + pr) * 8 + j;
+                *dAp = fadd2(*dAp, dAacc);
+            }
+        }
+        if (AGG) continue;
+
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            const int off = lr * TL + 4 * swz_chunk<T>(j * 2 + cc);
+            float *pp = s_part + (g * 3) * R * TL + off;
+            *reinterpret_cast<float4 *>(pp) = make_float4(S1[4 * cc].x + S1[4 * cc].y, S1[4 * cc + 1].x + S1[4 * cc + 1].y,
+                                                          S1[4 * cc + 2].x + S1[4 * cc + 2].y, S1[4 * cc + 3].x + S1[4 * cc + 3].y);
+            *reinterpret_cast<float4 *>(pp + R * TL) =
+                make_float4(S2[4 * cc].x + S2[4 * cc].y, S2[4 * cc + 1].x + S2[4 * cc + 1].y,
+                            S2[4 * cc + 2].x + S2[4 * cc + 2].y, S2[4 * cc + 3].x + S2[4 * cc + 3].y);
+            *reinterpret_cast<float4 *>(pp + 2 * R * TL) =
+                make_float4(yv[4 * cc].x + yv[4 * cc].y, yv[4 * cc + 1].x + yv[4 * cc + 1].y,
+                            yv[4 * cc + 2].x + yv[4 * cc + 2].y, yv[4 * cc + 3].x + yv[4 * cc + 3].y);
+        }
+        __syncthreads();
+
+        // ---- epilogue A: per-(row,token) gradients; one warp per row, two tokens per lane ---------------------------
+        for (int r = warp; r < R; r += NW) {
+            const int off = r * TL + 2 * lane;   // raw position
+            float2 s1 = make_float2(0.f, 0.f), s2 = s1, yy = s1;
+#pragma unroll
+            for (int gg = 0; gg < NGW; ++gg) {
+                const float *pp = s_part + (gg * 3) * R * TL + off;
+                s1 = fadd2(s1, *reinterpret_cast<const float2 *>(pp));
+                s2 = fadd2(s2, *reinterpret_cast<const float2 *>(pp + R * TL));
+                yy = fadd2(yy, *reinterpret_cast<const float2 *>(pp + 2 * R * TL));
+            }
+            const float2 u2 = *reinterpret_cast<const float2 *>(s_u + off);
+            const float2 d2 = *reinterpret_cast<const float2 *>(s_dl + off);
+            const float2 g2 = *reinterpret_cast<const float2 *>(s_g + off);
+            const float Dk = s_D[r];
+            float2 du = ffma2(d2, s1, fmul2(splat(Dk), g2));         // D*dy + delta*S1   (bwd_kernel.cuh:211,280-281)
+            float2 dd = ffma2(u2, s1, s2);                           // u*S1 + S2         (:282-283)
+            if (sp) {                                                // d softplus = sigmoid(x) = 1 - exp(-softplus(x))
+                dd.x *= 1.f - __expf(-d2.x);
+                dd.y *= 1.f - __expf(-d2.y);
+            }
+            float pdD = g2.x * u2.x + g2.y * u2.y, pdb = dd.x + dd.y;
+#pragma unroll
+            for (int k = 16; k > 0; k >>= 1) {
+                pdD += __shfl_xor_sync(0xffffffffu, pdD, k);
+                pdb += __shfl_xor_sync(0xffffffffu, pdb, k);
+            }
+            if (lane == 0) {
+                s_dD[r] += pdD;
+                s_db[r] += pdb;
+            }
+            *reinterpret_cast<float2 *>(s_u + off) = du;
+            *reinterpret_cast<float2 *>(s_dl + off) = dd;
+            if (has_z) {
+                const float2 zf = *reinterpret_cast<const float2 *>(s_z + off);
+                yy = ffma2(splat(Dk), u2, yy);
+                *reinterpret_cast<float2 *>(s_z + off) = fmul2(yy, zf);
+            }
+        }
+        // ---- epilogue B: dB / dC -> global (sum over the CTA's row-warps, then one atomic per element) ---------------
+        {
+            float *dB_b = p.dB + (int64_t)b * N * L, *dC_b = p.dC + (int64_t)b * N * L;
+            for (int idx = tid; idx < NP * 4 * TL; idx += NT) {
+                const int tok = idx % TL, kind = (idx / TL) & 3, pr = idx / (4 * TL);
+                float v = s_dbc[idx];
+#pragma unroll
+                for (int q = 1; q < RQ; ++q) v += s_dbc[q * NP * 4 * TL + idx];
+                const int n = 2 * pr + (kind & 1), t = t0 + tok;
+                if (n < N && t < L) atomicAdd(((kind & 2) ? dC_b : dB_b) + (int64_t)n * L + (rev ? L - 1 - t : t), v);
+            }
+        }
+        __syncthreads();
+        store_tile<IN_T, T, TL, NT>(s_u, reinterpret_cast<IN_T *>(p.du) + (int64_t)b * p.du_bs, p.du_ds, row0, R, D, t0, L,
+                                    rev, p.vec_mask & 64u, tid);
+        store_tile<IN_T, T, TL, NT>(s_dl, reinterpret_cast<IN_T *>(p.ddelta) + (int64_t)b * p.ddl_bs, p.ddl_ds, row0, R, D,
+                                    t0, L, rev, p.vec_mask & 128u, tid);
+        if (has_z)
+            store_tile<IN_T, T, TL, NT>(s_z, reinterpret_cast<IN_T *>(p.dz) + (int64_t)b * p.dz_bs, p.dz_ds, row0, R, D, t0,
+                                        L, rev, p.vec_mask & 256u, tid);
+    }
+
+    __syncthreads();
+    if (AGG) {
+        for (int i = tid; i < R * Ne; i += NT) {
+            const int r = i / Ne, n = i - r * Ne, row = row0 + r;
+            if (row < D) p.seg_dh[(((int64_t)b * D + row) * p.nseg + seg) * Ne + n] = s_dhc[i];
+        }
+        if (g == 0) {
+            float s = dsum;
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            const int row = row0 + lr;
+            if (j == 0 && row < D) {
+                p.seg_dsum[((int64_t)b * D + row) * p.nseg + seg] = s;
+                p.seg_dfirst[((int64_t)b * D + row) * p.nseg + seg] = dfirst;
+            }
+        }
+    } else {
+        for (int i = tid; i < R * Ne; i += NT) {
+            const int r = i / Ne, n = i - r * Ne, row = row0 + r;
+            if (row < D && n < N) {
+                const float *src = s_dA + ((r * NP + (n >> 1)) * 8) * 2 + (n & 1);
+                float v = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v += src[2 * k];
+                atomicAdd(p.dA + (int64_t)row * N + n, v);           // sum over batch and segments
+            }
+        }
+        for (int r = tid; r < R; r += NT) {
+            const int row = row0 + r;
+            if (row < D) {
+                if (p.dD != nullptr) atomicAdd(p.dD + row, s_dD[r]);
+                if (p.ddbias != nullptr) atomicAdd(p.ddbias + row, s_db[r]);
+            }
+        }
+    }
+}
+
+// chain reverse aggregates right-to-left: dhin[s] = dh at the first token of segment s+1
+__global__ void scan_bwd_chain_kernel(const float *__restrict__ A, const float *__restrict__ seg_dh,
+                                      const float *__restrict__ seg_dsum, const float *__restrict__ seg_dfirst,
+                                      float *__restrict__ dhin, int B, int D, int N, int Ne, int nseg) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * D * Ne) return;
+    const int n = (int)(i % Ne);
+    const int64_t bd = i / Ne;
+    const int row = (int)(bd % D);
+    const float a2 = n < N ? A[(int64_t)row * N + n] * kLog2e : 0.f;
+    float carry = 0.f;
+    for (int s = nseg - 1; s >= 0; --s) {
+        dhin[(bd * nseg + s) * Ne + n] = carry;
+        // product of a_{t+1} over the tokens t of segment s
+        const float dnext = s + 1 < nseg ? seg_dfirst[bd * nseg + s + 1] : 0.f;
+        const float P = ex2(a2 * (seg_dsum[bd * nseg + s] - seg_dfirst[bd * nseg + s] + dnext));
+        carry = fmaf(P, carry, seg_dh[(bd * nseg + s) * Ne + n]);
+    }
+}
+
+namespace {
+
+int env_int(const char *name, int dflt) {
+    const char *s = getenv(name);
+    return s ? atoi(s) : dflt;
+}
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+constexpr int kNumBwdCfg = 3;
+constexpr int kBwdCfg[kNumBwdCfg][2] = {{2, 2}, {1, 4}, {2, 4}};   // {RQ, NGW}
+
+struct BwdPlan {
+    int cfg, R, nseg, cps, nchunks;
+};
+
+BwdPlan plan_bwd(int B, int D, int L) {
+    BwdPlan pl;
+    pl.cfg = D <= 4 ? 1 : 0;
+    pl.cfg = env_int("MMU_BWD_CFG", pl.cfg);
+    if (pl.cfg < 0 || pl.cfg >= kNumBwdCfg) pl.cfg = 0;
+    const int RQ = kBwdCfg[pl.cfg][0], NGW = kBwdCfg[pl.cfg][1];
+    pl.R = 4 * RQ;
+    pl.nchunks = (L + 63) / 64;
+    const int warps = B * ((D + pl.R - 1) / pl.R) * RQ * NGW;
+    const int target = 148 * 12;
+    int nseg = (target + warps - 1) / warps;
+    nseg = std::min(nseg, std::max(1, pl.nchunks / 8));
+    nseg = std::max(1, std::min(nseg, 64));
+    nseg = env_int("MMU_BWD_NSEG", nseg);
+    nseg = std::max(1, std::min(nseg, pl.nchunks));
+    pl.cps = (pl.nchunks + nseg - 1) / nseg;
+    pl.nseg = (pl.nchunks + pl.cps - 1) / pl.cps;
+    return pl;
+}
+
+template <typename IN_T, int RQ, int NGW> int launch_bwd(const BwdArgs &a, bool agg, cudaStream_t st) {
+    using Cfg = BwdCfg<RQ, NGW>;
+    const size_t smem = Cfg::smem_floats(a.Ne) * sizeof(float);
+    if (smem > 227 * 1024) return set_error(MMU_ERR_UNSUPPORTED, "selective_scan_bwd: dstate %d needs %zu B smem", a.N, smem);
+    dim3 grid((a.D + Cfg::R - 1) / Cfg::R, a.B, a.nseg), block(Cfg::NT);
+    if (agg) {
+        auto k = scan_bwd_kernel<IN_T, RQ, NGW, true>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, block, smem, st>>>(a);
+    } else {
+        auto k = scan_bwd_kernel<IN_T, RQ, NGW, false>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, block, smem, st>>>(a);
+    }
+    count_launch();
+    return check_launch("selective_scan_bwd");
+}
+
+template <typename IN_T> int dispatch_bwd(int cfg, const BwdArgs &a, bool agg, cudaStream_t st) {
+    switch (cfg) {
+        case 0: return launch_bwd<IN_T, 2, 2>(a, agg, st);
+        case 1: return launch_bwd<IN_T, 1, 4>(a, agg, st);
+        default: return launch_bwd<IN_T, 2, 4>(a, agg, st);
+    }
+}
+
+template <typename IN_T> int run_bwd(const mmu_scan_bwd_params *p, cudaStream_t st) {
+    const mmu_scan_fwd_params &f = p->f;
+    const BwdPlan pl = plan_bwd(f.batch, f.dim, f.seqlen);
+    BwdArgs a{};
+    a.u = f.u, a.delta = f.delta, a.z = f.z, a.dout = p->dout, a.Bm = f.B, a.Cm = f.C;
+    a.A = f.A, a.Dv = f.D, a.dbias = f.delta_bias, a.x = f.x;
+    a.du = p->du, a.ddelta = p->ddelta, a.dz = p->dz;
+    a.dA = p->dA, a.dB = p->dB, a.dC = p->dC, a.dD = p->dD, a.ddbias = p->ddelta_bias;
+    a.u_bs = f.u_bs, a.u_ds = f.u_ds, a.dl_bs = f.delta_bs, a.dl_ds = f.delta_ds, a.z_bs = f.z_bs, a.z_ds = f.z_ds;
+    a.g_bs = p->dout_bs, a.g_ds = p->dout_ds, a.B_bs = f.B_bs, a.B_ns = f.B_ns, a.C_bs = f.C_bs, a.C_ns = f.C_ns;
+    a.du_bs = p->du_bs, a.du_ds = p->du_ds, a.ddl_bs = p->ddelta_bs, a.ddl_ds = p->ddelta_ds;
+    a.dz_bs = p->dz_bs, a.dz_ds = p->dz_ds;
+    a.B = f.batch, a.D = f.dim, a.L = f.seqlen, a.N = f.dstate, a.Ne = (f.dstate + 1) & ~1;
+    a.nseg = pl.nseg, a.cps = pl.cps, a.nchunks = pl.nchunks;
+    a.nx = (f.seqlen + MMU_STATE_STRIDE - 1) / MMU_STATE_STRIDE;
+    a.softplus = f.delta_softplus, a.reverse = f.reverse;
+    const bool rev = f.reverse != 0;
+    const int L = f.seqlen;
+    a.vec_mask = (quad_ok<IN_T>(f.u, f.u_bs, f.u_ds, L, rev) ? 1u : 0u) |
+                 (quad_ok<IN_T>(f.delta, f.delta_bs, f.delta_ds, L, rev) ? 2u : 0u) |
+                 ((f.z && quad_ok<IN_T>(f.z, f.z_bs, f.z_ds, L, rev)) ? 4u : 0u) |
+                 (quad_ok<IN_T>(p->dout, p->dout_bs, p->dout_ds, L, rev) ? 8u : 0u) |
+                 (quad_ok<IN_T>(f.B, f.B_bs, f.B_ns, L, rev) ? 16u : 0u) |
+                 (quad_ok<IN_T>(f.C, f.C_bs, f.C_ns, L, rev) ? 32u : 0u) |
+                 (quad_ok<IN_T>(p->du, p->du_bs, p->du_ds, L, rev) ? 64u : 0u) |
+                 (quad_ok<IN_T>(p->ddelta, p->ddelta_bs, p->ddelta_ds, L, rev) ? 128u : 0u) |
+                 ((p->dz && quad_ok<IN_T>(p->dz, p->dz_bs, p->dz_ds, L, rev)) ? 256u : 0u);
+    if (pl.nseg > 1) {
+        const size_t n_state = (size_t)a.B * a.D * pl.nseg * a.Ne, n_row = (size_t)a.B * a.D * pl.nseg;
+        const size_t need = 2 * align256(n_state * 4) + 2 * align256(n_row * 4);
+        if (f.workspace == nullptr || f.workspace_bytes < need)
+            return set_error(MMU_ERR_WORKSPACE, "selective_scan_bwd: workspace %zu < %zu", f.workspace_bytes, need);
+        char *w = static_cast<char *>(f.workspace);
+        a.seg_dh = reinterpret_cast<float *>(w);
+        float *dhin = reinterpret_cast<float *>(w + align256(n_state * 4));
+        a.seg_dsum = reinterpret_cast<float *>(w + 2 * align256(n_state * 4));
+        a.seg_dfirst = reinterpret_cast<float *>(w + 2 * align256(n_state * 4) + align256(n_row * 4));
+        a.dhin = nullptr;
+        int rc = dispatch_bwd<IN_T>(pl.cfg, a, true, st);
+        if (rc) return rc;
+        const int64_t tot = (int64_t)a.B * a.D * a.Ne;
+        scan_bwd_chain_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(a.A, a.seg_dh, a.seg_dsum, a.seg_dfirst, dhin,
+                                                                             a.B, a.D, a.N, a.Ne, pl.nseg);
+        count_launch();
+        rc = check_launch("scan_bwd_chain");
+        if (rc) return rc;
+        a.dhin = dhin;
+    }
+    return dispatch_bwd<IN_T>(pl.cfg, a, false, st);
+}
+
+}  // namespace
+}  // namespace mmu
+
+extern "C" size_t mmu_selective_scan_bwd_workspace(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate) {
+    const int Ne = (dstate + 1) & ~1;
+    const int nchunks = (seqlen + 63) / 64;
+    const size_t nseg = (size_t)std::max(1, std::min(nchunks, std::max(64, mmu::env_int("MMU_BWD_NSEG", 1))));
+    const size_t n_state = (size_t)batch * dim * nseg * Ne, n_row = (size_t)batch * dim * nseg;
+    return 2 * mmu::align256(n_state * 4) + 2 * mmu::align256(n_row * 4);
+}
+
+extern "C" int mmu_selective_scan_bwd(const mmu_scan_bwd_params *p, void *stream) {
+    using namespace mmu;
+    if (p == nullptr) return set_error(MMU_ERR_INVALID, "selective_scan_bwd: null params");
+    const mmu_scan_fwd_params &f = p->f;
+    if (f.batch <= 0 || f.dim <= 0 || f.seqlen <= 0 || f.dstate <= 0)
+        return set_error(MMU_ERR_INVALID, "selective_scan_bwd: empty shape");
+    if (f.dstate > 256) return set_error(MMU_ERR_INVALID, "selective_scan only supports state dimension <= 256");
+    if (!f.u || !f.delta || !f.A || !f.B || !f.C || !p->dout || !p->du || !p->ddelta || !p->dA || !p->dB || !p->dC)
+        return set_error(MMU_ERR_INVALID, "selective_scan_bwd: null tensor pointer");
+    if (f.seqlen > MMU_STATE_STRIDE && !f.x)
+        return set_error(MMU_ERR_INVALID, "selective_scan_bwd: x (saved states from the forward) is required");
+    if ((f.z != nullptr) != (p->dz != nullptr)) return set_error(MMU_ERR_INVALID, "selective_scan_bwd: dz must be given iff z is");
+    if ((f.D != nullptr && !p->dD) || (f.delta_bias != nullptr && !p->ddelta_bias))
+        return set_error(MMU_ERR_INVALID, "selective_scan_bwd: dD / ddelta_bias missing");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (f.dtype) {
+        case MMU_F32: return run_bwd<float>(p, st);
+        case MMU_BF16: return run_bwd<__nv_bfloat16>(p, st);
+        case MMU_F16: return run_bwd<__half>(p, st);
+        default: return set_error(MMU_ERR_UNSUPPORTED, "selective_scan_bwd: dtype %d", f.dtype);
+    }
+}

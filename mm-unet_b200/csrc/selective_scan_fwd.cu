@@ -1,0 +1,446 @@
+// Selective scan forward for sm_100a.
+//
+// Replaces selective_scan_fwd_kernel (requirements/Mamba/mamba/csrc/selective_scan/selective_scan_fwd_kernel.cuh:67-303)
+// with a different decomposition (see DESIGN.md "scan forward"):
+//
+//   * a warp owns 4 channel rows x 8 token-lanes; a lane owns T consecutive tokens of RD rows, so the cross-lane
+//     prefix combination is a 3-step shuffle scan (8 lanes) instead of a 128-thread CUB BlockScan;
+//   * the dstate axis is split over NGW warps of the CTA and walked two states at a time with packed
+//     FFMA2/FMUL2 (Blackwell issues two fp32 lanes per slot); partial y's meet in shared memory;
+//   * B/C chunks are staged once per CTA and shared by all its rows (the reference re-reads them per channel);
+//   * the recurrence is applied in "correction form": y_t += C_t*(hloc_t + Pcum_t*h_start), which needs one
+//     MUFU.EX2 per (token,state) and no second serial pass;
+//   * the sequence can be split over CTAs (grid.z segments): an aggregate pass produces per-segment
+//     (sum(delta), h_end), a tiny kernel chains them, the main pass starts each segment from its true state.
+//     This is what fills the GPU for MM-UNet's D=6 / L=65536 scans (hard part 1).
+//
+// The state h is fp32 in registers; chunk-to-chunk carries live in shared memory (dstate is a runtime value).
+#include <algorithm>
+#include <cstdlib>
+
+#include "scan_tiles.cuh"
+
+namespace mmu {
+
+struct FwdArgs {
+    const void *u, *delta, *z, *Bm, *Cm;
+    const float *A, *Dv, *dbias;
+    void *out;
+    float *x, *last_state;
+    float *seg_hend, *seg_dsum;
+    const float *hin;
+    int64_t u_bs, u_ds, dl_bs, dl_ds, z_bs, z_ds, o_bs, o_ds, B_bs, B_ns, C_bs, C_ns;
+    int B, D, L, N, Ne;
+    int nseg, cps, nchunks, nx;
+    int softplus, reverse;
+    unsigned vec_mask;   // bit0 u, 1 delta, 2 z, 3 out, 4 B, 5 C
+};
+
+template <int T, int RD, int RQ, int NGW> struct FwdCfg {
+    static constexpr int LS = 8, RG = 4;
+    static constexpr int WROWS = RG * RD, R = RQ * WROWS, TL = LS * T, NT = 32 * RQ * NGW, CPT = T / 4;
+    static size_t smem_bytes(int Ne) {
+        return sizeof(float) * ((size_t)3 * R * TL + 2 * (size_t)Ne * TL + (size_t)NGW * R * TL + 2 * (size_t)R * Ne +
+                                2 * R);
+    }
+};
+
+template <typename IN_T, int T, int RD, int RQ, int NGW, bool AGG>
+__global__ void __launch_bounds__(32 * RQ * NGW) scan_fwd_kernel(const __grid_constant__ FwdArgs p) {
+    using Cfg = FwdCfg<T, RD, RQ, NGW>;
+    constexpr int R = Cfg::R, TL = Cfg::TL, NT = Cfg::NT, CPT = Cfg::CPT, WROWS = Cfg::WROWS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wq = warp / NGW, g = warp % NGW, rg = lane >> 3, j = lane & 7;
+    const int b = blockIdx.y, row0 = blockIdx.x * R, seg = blockIdx.z;
+    const int N = p.N, Ne = p.Ne, NP = Ne >> 1, D = p.D, L = p.L;
+    const bool has_z = p.z != nullptr;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *s_u = reinterpret_cast<float *>(smem_raw);   // [R][TL]
+    float *s_dl = s_u + R * TL;                          // [R][TL]  softplus(delta + bias)
+    float *s_z = s_dl + R * TL;                          // [R][TL]  z, then the gated output
+    float *s_B = s_z + R * TL;                           // [Ne][TL]
+    float *s_C = s_B + Ne * TL;                          // [Ne][TL]
+    float *s_yp = s_C + Ne * TL;                         // [NGW][R][TL] partial y per dstate group
+    float *s_A2 = s_yp + NGW * R * TL;                   // [R][Ne]  A * log2(e)
+    float *s_carry = s_A2 + R * Ne;                      // [R][Ne]  state entering the next chunk
+    float *s_bias = s_carry + R * Ne;                    // [R]
+    float *s_D = s_bias + R;                             // [R]
+
+    for (int i = tid; i < R * Ne; i += NT) {
+        const int r = i / Ne, n = i - r * Ne, row = row0 + r;
+        const bool ok = row < D && n < N;
+        s_A2[i] = ok ? p.A[(int64_t)row * N + n] * kLog2e : 0.f;
+        float h0 = 0.f;
+        if (!AGG && ok && p.hin != nullptr && seg > 0) h0 = p.hin[(((int64_t)b * D + row) * p.nseg + seg) * Ne + n];
+        s_carry[i] = h0;
+    }
+    for (int r = tid; r < R; r += NT) {
+        const int row = row0 + r;
+        s_bias[r] = (row < D && p.dbias != nullptr) ? p.dbias[row] : 0.f;
+        s_D[r] = (row < D && p.Dv != nullptr) ? p.Dv[row] : 0.f;
+    }
+
+    const IN_T *u_b = reinterpret_cast<const IN_T *>(p.u) + (int64_t)b * p.u_bs;
+    const IN_T *dl_b = reinterpret_cast<const IN_T *>(p.delta) + (int64_t)b * p.dl_bs;
+    const IN_T *z_b = has_z ? reinterpret_cast<const IN_T *>(p.z) + (int64_t)b * p.z_bs : nullptr;
+    const IN_T *B_b = reinterpret_cast<const IN_T *>(p.Bm) + (int64_t)b * p.B_bs;
+    const IN_T *C_b = reinterpret_cast<const IN_T *>(p.Cm) + (int64_t)b * p.C_bs;
+    IN_T *o_b = AGG ? nullptr : reinterpret_cast<IN_T *>(p.out) + (int64_t)b * p.o_bs;
+    const bool rev = p.reverse != 0, sp = p.softplus != 0;
+
+    const int npw = (NP + NGW - 1) / NGW;
+    const int pair0 = g * npw, pair1 = min(NP, pair0 + npw);
+    int lr[RD];
+#pragma unroll
+    for (int r = 0; r < RD; ++r) lr[r] = wq * WROWS + rg * RD + r;
+
+    float dsum[RD];
+#pragma unroll
+    for (int r = 0; r < RD; ++r) dsum[r] = 0.f;
+
+    const int c_begin = seg * p.cps, c_end = min(p.nchunks, c_begin + p.cps);
+    for (int c = c_begin; c < c_end; ++c) {
+        const int t0 = c * TL;
+        __syncthreads();   // tiles free (previous store finished), tables initialised
+        load_tile<IN_T, T, TL, NT>(s_u, u_b, p.u_ds, row0, R, D, t0, L, rev, p.vec_mask & 1u, tid, 0.f,
+                                   [](int, float v) { return v; });
+        load_tile<IN_T, T, TL, NT>(s_dl, dl_b, p.dl_ds, row0, R, D, t0, L, rev, p.vec_mask & 2u, tid, 0.f,
+                                   [&](int r, float v) {
+                                       const float xx = v + s_bias[r];
+                                       return sp ? softplus_f(xx) : xx;
+                                   });
+        load_tile<IN_T, T, TL, NT>(s_B, B_b, p.B_ns, 0, Ne, N, t0, L, rev, p.vec_mask & 16u, tid, 0.f,
+                                   [](int, float v) { return v; });
+        if (!AGG) {
+            if (has_z)
+                load_tile<IN_T, T, TL, NT>(s_z, z_b, p.z_ds, row0, R, D, t0, L, rev, p.vec_mask & 4u, tid, 0.f,
+                                           [](int, float v) { return v; });
+            load_tile<IN_T, T, TL, NT>(s_C, C_b, p.C_ns, 0, Ne, N, t0, L, rev, p.vec_mask & 32u, tid, 0.f,
+                                       [](int, float v) { return v; });
+        }
+        __syncthreads();
+
+        // ---- per-(token,row) registers: delta and delta*u of my T tokens -------------------------------
+        float dl[RD][T], dlu[RD][T];
+#pragma unroll
+        for (int r = 0; r < RD; ++r) {
+#pragma unroll
+            for (int cc = 0; cc < CPT; ++cc) {
+                const int off = lr[r] * TL + 4 * swz_chunk<T>(j * CPT + cc);
+                const float4 d4 = *reinterpret_cast<const float4 *>(s_dl + off);
+                const float4 u4 = *reinterpret_cast<const float4 *>(s_u + off);
+                dl[r][4 * cc + 0] = d4.x, dl[r][4 * cc + 1] = d4.y, dl[r][4 * cc + 2] = d4.z, dl[r][4 * cc + 3] = d4.w;
+                dlu[r][4 * cc + 0] = d4.x * u4.x, dlu[r][4 * cc + 1] = d4.y * u4.y;
+                dlu[r][4 * cc + 2] = d4.z * u4.z, dlu[r][4 * cc + 3] = d4.w * u4.w;
+            }
+            if (AGG) {
+#pragma unroll
+                for (int i = 0; i < T; ++i) dsum[r] += dl[r][i];
+            }
+        }
+        float2 y2[RD][T];
+#pragma unroll
+        for (int r = 0; r < RD; ++r)
+#pragma unroll
+            for (int i = 0; i < T; ++i) y2[r][i] = make_float2(0.f, 0.f);
+
+        for (int pr = pair0; pr < pair1; ++pr) {
+            float2 A2[RD], P[RD], hl[RD];
+            float2 cp[RD][T];
+#pragma unroll
+            for (int r = 0; r < RD; ++r) {
+                A2[r] = *reinterpret_cast<const float2 *>(s_A2 + lr[r] * Ne + 2 * pr);
+                P[r] = make_float2(1.f, 1.f);
+                hl[r] = make_float2(0.f, 0.f);
+            }
+            const float *sB0 = s_B + (2 * pr) * TL, *sB1 = sB0 + TL;
+            const float *sC0 = s_C + (2 * pr) * TL, *sC1 = sC0 + TL;
+#pragma unroll
+            for (int cc = 0; cc < CPT; ++cc) {
+                const int off = 4 * swz_chunk<T>(j * CPT + cc);
+                const float4 b0 = *reinterpret_cast<const float4 *>(sB0 + off);
+                const float4 b1 = *reinterpret_cast<const float4 *>(sB1 + off);
+                float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+                if (!AGG) {
+                    c0 = *reinterpret_cast<const float4 *>(sC0 + off);
+                    c1 = *reinterpret_cast<const float4 *>(sC1 + off);
+                }
+                const float2 Bv[4] = {{b0.x, b1.x}, {b0.y, b1.y}, {b0.z, b1.z}, {b0.w, b1.w}};
+                const float2 Cv[4] = {{c0.x, c1.x}, {c0.y, c1.y}, {c0.z, c1.z}, {c0.w, c1.w}};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = 4 * cc + k;
+#pragma unroll
+                    for (int r = 0; r < RD; ++r) {
+                        const float2 a = ex2(fmul2(splat(dl[r][i]), A2[r]));
+                        const float2 bb = fmul2(splat(dlu[r][i]), Bv[k]);
+                        hl[r] = ffma2(a, hl[r], bb);
+                        P[r] = fmul2(P[r], a);
+                        if (!AGG) {
+                            y2[r][i] = ffma2(Cv[k], hl[r], y2[r][i]);
+                            cp[r][i] = fmul2(Cv[k], P[r]);
+                        }
+                    }
+                }
+            }
+            // ---- 8-lane inclusive scan of (P, hl), then apply the chunk carry -------------------------------
+#pragma unroll
+            for (int r = 0; r < RD; ++r) {
+                float2 Pi = P[r], Hi = hl[r];
+#pragma unroll
+                for (int k = 1; k < 8; k <<= 1) {
+                    const float2 Pn = shfl_up2(Pi, k, 8), Hn = shfl_up2(Hi, k, 8);
+                    if (j >= k) {
+                        Hi = ffma2(Pi, Hn, Hi);
+                        Pi = fmul2(Pi, Pn);
+                    }
+                }
+                float *cptr = s_carry + lr[r] * Ne + 2 * pr;
+                const float2 hc = *reinterpret_cast<const float2 *>(cptr);
+                const float2 send = ffma2(Pi, hc, Hi);   // state after my last token
+                float2 hs = shfl_up2(send, 1, 8);        // state before my first token
+                if (j == 0) hs = hc;
+                __syncwarp();
+                if (j == 7) *reinterpret_cast<float2 *>(cptr) = send;
+                if (!AGG) {
+                    if (p.x != nullptr && (((j + 1) * T) % MMU_STATE_STRIDE) == 0) {
+                        const int kk = (t0 + (j + 1) * T) / MMU_STATE_STRIDE - 1;
+                        const int row = row0 + lr[r];
+                        if (kk < p.nx && row < D) {
+                            float *xp = p.x + (((int64_t)b * D + row) * p.nx + kk) * N + 2 * pr;
+                            xp[0] = send.x;
+                            if (2 * pr + 1 < N) xp[1] = send.y;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < T; ++i) y2[r][i] = ffma2(cp[r][i], hs, y2[r][i]);
+                }
+            }
+        }
+        if (AGG) continue;
+
+        // ---- partial y of my dstate group -> shared -----------------------------------------------------------
+#pragma unroll
+        for (int r = 0; r < RD; ++r)
+#pragma unroll
+            for (int cc = 0; cc < CPT; ++cc) {
+                const int off = (g * R + lr[r]) * TL + 4 * swz_chunk<T>(j * CPT + cc);
+                *reinterpret_cast<float4 *>(s_yp + off) =
+                    make_float4(y2[r][4 * cc].x + y2[r][4 * cc].y, y2[r][4 * cc + 1].x + y2[r][4 * cc + 1].y,
+                                y2[r][4 * cc + 2].x + y2[r][4 * cc + 2].y, y2[r][4 * cc + 3].x + y2[r][4 * cc + 3].y);
+            }
+        __syncthreads();
+        // ---- epilogue: sum groups, D skip, SiLU gate (selective_scan_fwd_kernel.cuh:158,280-298) ---------------
+        for (int idx = tid; idx < R * (TL / 4); idx += NT) {
+            const int r = idx / (TL / 4);
+            const int off = idx * 4;   // raw (swizzled) position: all tiles share the layout
+            float4 y = *reinterpret_cast<const float4 *>(s_yp + off);
+#pragma unroll
+            for (int gg = 1; gg < NGW; ++gg) {
+                const float4 t = *reinterpret_cast<const float4 *>(s_yp + gg * R * TL + off);
+                y.x += t.x, y.y += t.y, y.z += t.z, y.w += t.w;
+            }
+            const float4 u4 = *reinterpret_cast<const float4 *>(s_u + off);
+            const float dsk = s_D[r];
+            y.x = fmaf(dsk, u4.x, y.x), y.y = fmaf(dsk, u4.y, y.y), y.z = fmaf(dsk, u4.z, y.z), y.w = fmaf(dsk, u4.w, y.w);
+            if (has_z) {
+                const float4 z4 = *reinterpret_cast<const float4 *>(s_z + off);
+                y.x *= z4.x * sigmoid_f(z4.x), y.y *= z4.y * sigmoid_f(z4.y);
+                y.z *= z4.z * sigmoid_f(z4.z), y.w *= z4.w * sigmoid_f(z4.w);
+            }
+            *reinterpret_cast<float4 *>(s_z + off) = y;
+        }
+        __syncthreads();
+        store_tile<IN_T, T, TL, NT>(s_z, o_b, p.o_ds, row0, R, D, t0, L, rev, p.vec_mask & 8u, tid);
+    }
+
+    __syncthreads();
+    if (AGG) {
+        for (int i = tid; i < R * Ne; i += NT) {
+            const int r = i / Ne, n = i - r * Ne, row = row0 + r;
+            if (row < D) p.seg_hend[(((int64_t)b * D + row) * p.nseg + seg) * Ne + n] = s_carry[i];
+        }
+        if (g == 0) {
+#pragma unroll
+            for (int r = 0; r < RD; ++r) {
+                float s = dsum[r];
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                const int row = row0 + lr[r];
+                if (j == 0 && row < D) p.seg_dsum[((int64_t)b * D + row) * p.nseg + seg] = s;
+            }
+        }
+    } else if (p.last_state != nullptr && seg == p.nseg - 1) {
+        for (int i = tid; i < R * Ne; i += NT) {
+            const int r = i / Ne, n = i - r * Ne, row = row0 + r;
+            if (row < D && n < N) p.last_state[((int64_t)b * D + row) * N + n] = s_carry[i];
+        }
+    }
+}
+
+// chain the per-segment aggregates: hin[s] = state entering segment s
+__global__ void scan_fwd_chain_kernel(const float *__restrict__ A, const float *__restrict__ seg_hend,
+                                      const float *__restrict__ seg_dsum, float *__restrict__ hin, int B, int D, int N,
+                                      int Ne, int nseg) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * D * Ne) return;
+    const int n = (int)(i % Ne);
+    const int64_t bd = i / Ne;
+    const int row = (int)(bd % D);
+    const float a2 = n < N ? A[(int64_t)row * N + n] * kLog2e : 0.f;
+    float h = 0.f;
+    for (int s = 0; s < nseg; ++s) {
+        hin[(bd * nseg + s) * Ne + n] = h;
+        h = fmaf(ex2(a2 * seg_dsum[bd * nseg + s]), h, seg_hend[(bd * nseg + s) * Ne + n]);
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+namespace {
+
+struct FwdPlan {
+    int cfg;    // index into the instantiation table
+    int R, TL;  // rows per CTA, tokens per chunk
+    int nseg, cps, nchunks;
+};
+
+// instantiation table: {T, RD, RQ, NGW}
+constexpr int kNumFwdCfg = 4;
+constexpr int kFwdCfg[kNumFwdCfg][4] = {
+    {16, 1, 2, 4},   // 0: wide default   (8 rows, 8 warps)
+    {16, 1, 4, 2},   // 1: wide, more rows per CTA (16 rows, 8 warps)
+    {16, 1, 1, 4},   // 2: narrow (4 rows, 4 warps)
+    {8, 2, 2, 4},    // 3: two rows per lane (16 rows, 8 warps)
+};
+
+int env_int(const char *name, int dflt) {
+    const char *s = getenv(name);
+    return s ? atoi(s) : dflt;
+}
+
+FwdPlan plan_fwd(int B, int D, int L, int /*N*/) {
+    FwdPlan pl;
+    pl.cfg = D <= 8 ? 2 : 0;
+    pl.cfg = env_int("MMU_FWD_CFG", pl.cfg);
+    if (pl.cfg < 0 || pl.cfg >= kNumFwdCfg) pl.cfg = 0;
+    const int *c = kFwdCfg[pl.cfg];
+    pl.R = c[2] * 4 * c[1];
+    pl.TL = 8 * c[0];
+    pl.nchunks = (L + pl.TL - 1) / pl.TL;
+    const int warps = B * ((D + pl.R - 1) / pl.R) * c[2] * c[3];
+    const int target = 148 * 16;
+    int nseg = (target + warps - 1) / warps;
+    nseg = std::min(nseg, std::max(1, pl.nchunks / 4));   // at least 4 chunks per segment
+    nseg = std::max(1, std::min(nseg, 64));
+    nseg = env_int("MMU_FWD_NSEG", nseg);
+    nseg = std::max(1, std::min(nseg, pl.nchunks));
+    pl.cps = (pl.nchunks + nseg - 1) / nseg;
+    pl.nseg = (pl.nchunks + pl.cps - 1) / pl.cps;
+    return pl;
+}
+
+template <typename IN_T, int T, int RD, int RQ, int NGW>
+int launch_fwd(const FwdArgs &a, bool agg, cudaStream_t st) {
+    using Cfg = FwdCfg<T, RD, RQ, NGW>;
+    const size_t smem = Cfg::smem_bytes(a.Ne);
+    if (smem > 227 * 1024) return set_error(MMU_ERR_UNSUPPORTED, "selective_scan_fwd: dstate %d needs %zu B smem", a.N, smem);
+    dim3 grid((a.D + Cfg::R - 1) / Cfg::R, a.B, a.nseg), block(Cfg::NT);
+    if (agg) {
+        auto k = scan_fwd_kernel<IN_T, T, RD, RQ, NGW, true>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, block, smem, st>>>(a);
+    } else {
+        auto k = scan_fwd_kernel<IN_T, T, RD, RQ, NGW, false>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, block, smem, st>>>(a);
+    }
+    count_launch();
+    return check_launch("selective_scan_fwd");
+}
+
+template <typename IN_T> int dispatch_fwd(int cfg, const FwdArgs &a, bool agg, cudaStream_t st) {
+    switch (cfg) {
+        case 0: return launch_fwd<IN_T, 16, 1, 2, 4>(a, agg, st);
+        case 1: return launch_fwd<IN_T, 16, 1, 4, 2>(a, agg, st);
+        case 2: return launch_fwd<IN_T, 16, 1, 1, 4>(a, agg, st);
+        default: return launch_fwd<IN_T, 8, 2, 2, 4>(a, agg, st);
+    }
+}
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+template <typename IN_T> int run_fwd(const mmu_scan_fwd_params *p, cudaStream_t st) {
+    const FwdPlan pl = plan_fwd(p->batch, p->dim, p->seqlen, p->dstate);
+    FwdArgs a{};
+    a.u = p->u, a.delta = p->delta, a.z = p->z, a.Bm = p->B, a.Cm = p->C;
+    a.A = p->A, a.Dv = p->D, a.dbias = p->delta_bias;
+    a.out = p->out, a.x = p->x, a.last_state = p->last_state;
+    a.u_bs = p->u_bs, a.u_ds = p->u_ds, a.dl_bs = p->delta_bs, a.dl_ds = p->delta_ds;
+    a.z_bs = p->z_bs, a.z_ds = p->z_ds, a.o_bs = p->out_bs, a.o_ds = p->out_ds;
+    a.B_bs = p->B_bs, a.B_ns = p->B_ns, a.C_bs = p->C_bs, a.C_ns = p->C_ns;
+    a.B = p->batch, a.D = p->dim, a.L = p->seqlen, a.N = p->dstate, a.Ne = (p->dstate + 1) & ~1;
+    a.nseg = pl.nseg, a.cps = pl.cps, a.nchunks = pl.nchunks;
+    a.nx = (p->seqlen + MMU_STATE_STRIDE - 1) / MMU_STATE_STRIDE;
+    a.softplus = p->delta_softplus, a.reverse = p->reverse;
+    const bool rev = p->reverse != 0;
+    const int L = p->seqlen;
+    a.vec_mask = (quad_ok<IN_T>(p->u, p->u_bs, p->u_ds, L, rev) ? 1u : 0u) |
+                 (quad_ok<IN_T>(p->delta, p->delta_bs, p->delta_ds, L, rev) ? 2u : 0u) |
+                 ((p->z && quad_ok<IN_T>(p->z, p->z_bs, p->z_ds, L, rev)) ? 4u : 0u) |
+                 (quad_ok<IN_T>(p->out, p->out_bs, p->out_ds, L, rev) ? 8u : 0u) |
+                 (quad_ok<IN_T>(p->B, p->B_bs, p->B_ns, L, rev) ? 16u : 0u) |
+                 (quad_ok<IN_T>(p->C, p->C_bs, p->C_ns, L, rev) ? 32u : 0u);
+    if (pl.nseg > 1) {
+        const size_t n_state = (size_t)a.B * a.D * pl.nseg * a.Ne;
+        const size_t need = 2 * align256(n_state * 4) + align256((size_t)a.B * a.D * pl.nseg * 4);
+        if (p->workspace == nullptr || p->workspace_bytes < need)
+            return set_error(MMU_ERR_WORKSPACE, "selective_scan_fwd: workspace %zu < %zu", p->workspace_bytes, need);
+        char *w = static_cast<char *>(p->workspace);
+        a.seg_hend = reinterpret_cast<float *>(w);
+        float *hin = reinterpret_cast<float *>(w + align256(n_state * 4));
+        a.seg_dsum = reinterpret_cast<float *>(w + 2 * align256(n_state * 4));
+        a.hin = nullptr;
+        int rc = dispatch_fwd<IN_T>(pl.cfg, a, true, st);
+        if (rc) return rc;
+        const int64_t tot = (int64_t)a.B * a.D * a.Ne;
+        scan_fwd_chain_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(a.A, a.seg_hend, a.seg_dsum, hin, a.B, a.D,
+                                                                             a.N, a.Ne, pl.nseg);
+        count_launch();
+        rc = check_launch("scan_fwd_chain");
+        if (rc) return rc;
+        a.hin = hin;
+    }
+    return dispatch_fwd<IN_T>(pl.cfg, a, false, st);
+}
+
+}  // namespace
+}  // namespace mmu
+
+extern "C" size_t mmu_selective_scan_fwd_workspace(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate) {
+    // upper bound over every plan the dispatcher can pick (nseg <= 64 unless forced by MMU_FWD_NSEG)
+    const int Ne = (dstate + 1) & ~1;
+    const int nchunks = (seqlen + 63) / 64;
+    const size_t nseg = (size_t)std::max(1, std::min(nchunks, std::max(64, mmu::env_int("MMU_FWD_NSEG", 1))));
+    const size_t n_state = (size_t)batch * dim * nseg * Ne;
+    return 2 * mmu::align256(n_state * 4) + mmu::align256((size_t)batch * dim * nseg * 4);
+}
+
+extern "C" int mmu_selective_scan_fwd(const mmu_scan_fwd_params *p, void *stream) {
+    using namespace mmu;
+    if (p == nullptr) return set_error(MMU_ERR_INVALID, "selective_scan_fwd: null params");
+    if (p->batch <= 0 || p->dim <= 0 || p->seqlen <= 0 || p->dstate <= 0)
+        return set_error(MMU_ERR_INVALID, "selective_scan_fwd: empty shape (batch=%d dim=%d seqlen=%d dstate=%d)", p->batch,
+                         p->dim, p->seqlen, p->dstate);
+    if (p->dstate > 256) return set_error(MMU_ERR_INVALID, "selective_scan only supports state dimension <= 256");
+    if (!p->u || !p->delta || !p->A || !p->B || !p->C || !p->out)
+        return set_error(MMU_ERR_INVALID, "selective_scan_fwd: null tensor pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (p->dtype) {
+        case MMU_F32: return run_fwd<float>(p, st);
+        case MMU_BF16: return run_fwd<__nv_bfloat16>(p, st);
+        case MMU_F16: return run_fwd<__half>(p, st);
+        default: return set_error(MMU_ERR_UNSUPPORTED, "selective_scan_fwd: dtype %d", p->dtype);
+    }
+}

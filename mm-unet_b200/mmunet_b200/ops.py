@@ -1,0 +1,632 @@
+"""Host-side mirror of the reference's fused-op interface, on top of the C-ABI CUDA library.
+
+Same names, argument meaning and error behaviour as
+  requirements/Mamba/mamba/mamba_ssm/ops/selective_scan_interface.py   (SelectiveScanFn :14-83,
+      MambaInnerFnNoOutProj :155-289, MambaInnerFn :292-434, BiMambaInnerFn :437-603, wrappers :606-633)
+  requirements/Mamba/causal-conv1d/causal_conv1d/causal_conv1d_interface.py  (CausalConv1dFn :10-46)
+
+PyTorch is used for device memory, streams, autograd bookkeeping and the skinny projection GEMMs
+(cuBLAS through F.linear / matmul, exactly where the reference uses them).  Every scan / conv / permutation
+is a call into libmmunet_b200.so; there is no CPU or eager fallback - a missing library or a non-CUDA tensor
+raises RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("mmunet_b200: expected CUDA tensors (there is no CPU path)")
+
+
+# ----------------------------------------------------------------------------------------------------------
+# raw kernels
+# ----------------------------------------------------------------------------------------------------------
+
+def _scan_checks(u, delta, A, B, C, D, z, delta_bias):
+    """Argument validation with the reference's rules (selective_scan.cpp:233-303)."""
+    _require_cuda(u, delta, A, B, C, D, z, delta_bias)
+    if u.dtype not in _DT:
+        raise RuntimeError("selective_scan: input type must be float32, float16 or bfloat16")
+    if A.is_complex():
+        raise RuntimeError("selective_scan: complex A is not supported by mmunet_b200 (MM-UNet uses real A)")
+    if A.dtype != torch.float32:
+        raise RuntimeError("selective_scan: weight_type (A) must be float32")
+    if B.dim() < 3 or C.dim() < 3:
+        raise RuntimeError("selective_scan: constant (non input-dependent) B/C are not supported by mmunet_b200")
+    if delta.dtype != u.dtype or B.dtype != u.dtype or C.dtype != u.dtype:
+        raise RuntimeError("selective_scan: delta, B and C must have the same dtype as u")
+    batch, dim, L = u.shape
+    N = A.shape[1]
+    if N > 256:
+        raise RuntimeError("selective_scan only supports state dimension <= 256")
+    if delta.shape != u.shape:
+        raise RuntimeError(f"selective_scan: delta shape {tuple(delta.shape)} != u shape {tuple(u.shape)}")
+    if A.shape[0] != dim:
+        raise RuntimeError("selective_scan: A must be (dim, dstate)")
+    for name, t in (("B", B), ("C", C)):
+        if t.shape[0] != batch or t.shape[-2] != N or t.shape[-1] != L:
+            raise RuntimeError(f"selective_scan: {name} must be (batch, n_groups, dstate, seqlen)")
+        if dim % t.shape[1] != 0:
+            raise RuntimeError("selective_scan: dim must be divisible by n_groups")
+    for name, t in (("u", u), ("delta", delta), ("B", B), ("C", C), ("z", z)):
+        if t is not None and t.stride(-1) != 1 and t.shape[-1] > 1:
+            raise RuntimeError(f"selective_scan: {name}.stride(-1) must be 1")
+    if D is not None and (D.dtype != torch.float32 or D.shape != (dim,)):
+        raise RuntimeError("selective_scan: D must be float32 of shape (dim,)")
+    if delta_bias is not None and (delta_bias.dtype != torch.float32 or delta_bias.shape != (dim,)):
+        raise RuntimeError("selective_scan: delta_bias must be float32 of shape (dim,)")
+    if z is not None and (z.dtype != u.dtype or z.shape != u.shape):
+        raise RuntimeError("selective_scan: z must match u in dtype and shape")
+    if B.shape[1] != C.shape[1]:
+        raise RuntimeError("selective_scan: B and C must have the same n_groups")
+
+
+def _fill_fwd(p, u, delta, A, B, C, D, z, delta_bias, softplus, reverse, g, G):
+    """Fill a ScanFwdParams for group g of G (rows [g*H, (g+1)*H))."""
+    batch, dim, L = u.shape
+    H = dim // G
+    es = u.element_size()
+    p.batch, p.dim, p.seqlen, p.dstate = batch, H, L, A.shape[1]
+    p.dtype, p.delta_softplus, p.reverse = _DT[u.dtype], int(bool(softplus)), int(bool(reverse))
+    p.u = u.data_ptr() + g * H * u.stride(1) * es
+    p.delta = delta.data_ptr() + g * H * delta.stride(1) * es
+    p.z = None if z is None else z.data_ptr() + g * H * z.stride(1) * es
+    p.B = B.data_ptr() + g * B.stride(1) * es
+    p.C = C.data_ptr() + g * C.stride(1) * es
+    p.A = A.data_ptr() + g * H * A.stride(0) * 4
+    p.D = None if D is None else D.data_ptr() + g * H * 4
+    p.delta_bias = None if delta_bias is None else delta_bias.data_ptr() + g * H * 4
+    p.u_bs, p.u_ds = u.stride(0), u.stride(1)
+    p.delta_bs, p.delta_ds = delta.stride(0), delta.stride(1)
+    if z is not None:
+        p.z_bs, p.z_ds = z.stride(0), z.stride(1)
+    p.B_bs, p.B_ns, p.C_bs, p.C_ns = B.stride(0), B.stride(2), C.stride(0), C.stride(2)
+
+
+def selective_scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, reverse=False,
+                       save_states=True, return_last_state=False):
+    """-> (out, x, last_state).  out is y*silu(z) when z is given.  x: (batch, dim, ceil(L/64), dstate) fp32."""
+    _scan_checks(u, delta, A, B, C, D, z, delta_bias)
+    batch, dim, L = u.shape
+    N = A.shape[1]
+    G = B.shape[1]
+    A = A.contiguous()
+    out = torch.empty_like(u, memory_format=torch.contiguous_format)
+    nx = (L + _lib.STATE_STRIDE - 1) // _lib.STATE_STRIDE
+    x = torch.empty((batch, dim, nx, N), device=u.device, dtype=torch.float32) if save_states else None
+    last = torch.empty((batch, dim, N), device=u.device, dtype=torch.float32) if return_last_state else None
+    H = dim // G
+    L_ = _lib.lib()
+    ws_bytes = L_.mmu_selective_scan_fwd_workspace(batch, H, L, N)
+    ws = torch.empty(ws_bytes, device=u.device, dtype=torch.uint8) if ws_bytes else None
+    with torch.cuda.device(u.device):
+        for g in range(G):
+            p = _lib.ScanFwdParams()
+            _fill_fwd(p, u, delta, A, B, C, D, z, delta_bias, delta_softplus, reverse, g, G)
+            p.out = out.data_ptr() + g * H * out.stride(1) * out.element_size()
+            p.out_bs, p.out_ds = out.stride(0), out.stride(1)
+            p.x = None if x is None else x.data_ptr() + g * H * x.stride(1) * 4
+            p.last_state = None if last is None else last.data_ptr() + g * H * N * 4
+            if G > 1:   # per-group x / last_state slices are not batch-contiguous: run into temporaries
+                xg = torch.empty((batch, H, nx, N), device=u.device, dtype=torch.float32) if save_states else None
+                lg = torch.empty((batch, H, N), device=u.device, dtype=torch.float32) if return_last_state else None
+                p.x, p.last_state = _ptr(xg), _ptr(lg)
+            p.workspace, p.workspace_bytes = _ptr(ws), ws_bytes
+            _lib.check(L_.mmu_selective_scan_fwd(C.byref(p), _stream()), "selective_scan_fwd")
+            if G > 1:
+                if x is not None:
+                    x[:, g * H:(g + 1) * H] = xg
+                if last is not None:
+                    last[:, g * H:(g + 1) * H] = lg
+    return out, x, last
+
+
+def selective_scan_bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softplus=False, reverse=False,
+                       du=None, ddelta=None, dz=None):
+    """-> (du, ddelta, dA, dB, dC, dD, dz, ddelta_bias); dA/dB/dC/dD/ddelta_bias fp32.
+    du / ddelta / dz may be pre-allocated views (e.g. halves of dxz, as selective_scan_interface.py:244-248)."""
+    _scan_checks(u, delta, A, B, C, D, z, delta_bias)
+    _require_cuda(dout, x)
+    batch, dim, L = u.shape
+    N = A.shape[1]
+    G = B.shape[1]
+    H = dim // G
+    A = A.contiguous()
+    if dout.dtype != u.dtype or dout.shape != u.shape:
+        raise RuntimeError("selective_scan_bwd: dout must match u in dtype and shape")
+    if dout.stride(-1) != 1 and L > 1:
+        dout = dout.contiguous()
+    du = torch.empty_like(u, memory_format=torch.contiguous_format) if du is None else du
+    ddelta = torch.empty_like(delta, memory_format=torch.contiguous_format) if ddelta is None else ddelta
+    if z is not None and dz is None:
+        dz = torch.empty_like(z, memory_format=torch.contiguous_format)
+    dA = torch.zeros_like(A)
+    dB = torch.zeros((batch, G, N, L), device=u.device, dtype=torch.float32)
+    dC = torch.zeros((batch, G, N, L), device=u.device, dtype=torch.float32)
+    dD = torch.zeros(dim, device=u.device, dtype=torch.float32) if D is not None else None
+    dbias = torch.zeros(dim, device=u.device, dtype=torch.float32) if delta_bias is not None else None
+    L_ = _lib.lib()
+    ws_bytes = L_.mmu_selective_scan_bwd_workspace(batch, H, L, N)
+    ws = torch.empty(ws_bytes, device=u.device, dtype=torch.uint8) if ws_bytes else None
+    es = u.element_size()
+    with torch.cuda.device(u.device):
+        for g in range(G):
+            p = _lib.ScanBwdParams()
+            _fill_fwd(p.f, u, delta, A, B, C, D, z, delta_bias, delta_softplus, reverse, g, G)
+            xg = x if G == 1 else x[:, g * H:(g + 1) * H].contiguous()
+            p.f.x = xg.data_ptr()
+            p.f.workspace, p.f.workspace_bytes = _ptr(ws), ws_bytes
+            p.dout = dout.data_ptr() + g * H * dout.stride(1) * es
+            p.dout_bs, p.dout_ds = dout.stride(0), dout.stride(1)
+            p.du = du.data_ptr() + g * H * du.stride(1) * es
+            p.du_bs, p.du_ds = du.stride(0), du.stride(1)
+            p.ddelta = ddelta.data_ptr() + g * H * ddelta.stride(1) * es
+            p.ddelta_bs, p.ddelta_ds = ddelta.stride(0), ddelta.stride(1)
+            if dz is not None:
+                p.dz = dz.data_ptr() + g * H * dz.stride(1) * es
+                p.dz_bs, p.dz_ds = dz.stride(0), dz.stride(1)
+            p.dA = dA.data_ptr() + g * H * N * 4
+            if G == 1:
+                p.dB, p.dC = dB.data_ptr(), dC.data_ptr()
+            else:
+                dBg = torch.zeros((batch, 1, N, L), device=u.device, dtype=torch.float32)
+                dCg = torch.zeros_like(dBg)
+                p.dB, p.dC = dBg.data_ptr(), dCg.data_ptr()
+            p.dD = None if dD is None else dD.data_ptr() + g * H * 4
+            p.ddelta_bias = None if dbias is None else dbias.data_ptr() + g * H * 4
+            _lib.check(L_.mmu_selective_scan_bwd(C.byref(p), _stream()), "selective_scan_bwd")
+            if G > 1:
+                dB[:, g:g + 1] = dBg
+                dC[:, g:g + 1] = dCg
+    return du, ddelta, dA, dB, dC, dD, dz, dbias
+
+
+def _conv_params(x, weight, bias, silu, reverse=False):
+    _require_cuda(x, weight, bias)
+    if x.dtype not in _DT:
+        raise RuntimeError("causal_conv1d: input type must be float32, float16 or bfloat16")
+    if x.dim() != 3 or weight.dim() != 2 or weight.shape[0] != x.shape[1]:
+        raise RuntimeError("causal_conv1d: x must be (batch, dim, seqlen) and weight (dim, width)")
+    if not 2 <= weight.shape[1] <= 4:
+        raise RuntimeError("causal_conv1d only supports width between 2 and 4")
+    if bias is not None and bias.shape != (x.shape[1],):
+        raise RuntimeError("causal_conv1d: bias must be (dim,)")
+    p = _lib.ConvParams()
+    p.batch, p.dim, p.seqlen = x.shape
+    p.width, p.dtype, p.silu, p.reverse = weight.shape[1], _DT[x.dtype], int(bool(silu)), int(bool(reverse))
+    p.x, p.weight, p.bias = x.data_ptr(), weight.data_ptr(), _ptr(bias)
+    p.x_bs, p.x_ds, p.w_ds, p.w_ws = x.stride(0), x.stride(1), weight.stride(0), weight.stride(1)
+    return p
+
+
+def causal_conv1d_fwd(x, weight, bias=None, silu=False, reverse=False):
+    """x (B,D,L) with stride(-1)==1; weight (D,W) / bias (D) are used in fp32."""
+    if x.stride(-1) != 1 and x.shape[-1] > 1:
+        x = x.contiguous()
+    weight = weight.float()
+    bias = None if bias is None else bias.float().contiguous()
+    p = _conv_params(x, weight, bias, silu, reverse)
+    out = torch.empty_like(x, memory_format=torch.contiguous_format)
+    p.out, p.out_bs, p.out_ds = out.data_ptr(), out.stride(0), out.stride(1)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().mmu_causal_conv1d_fwd(C.byref(p), _stream()), "causal_conv1d_fwd")
+    return out
+
+
+def causal_conv1d_bwd(x, weight, bias, dout, silu=False, dx=None, reverse=False):
+    """-> (dx, dweight fp32 (D,W), dbias fp32 or None)."""
+    if x.stride(-1) != 1 and x.shape[-1] > 1:
+        x = x.contiguous()
+    if dout.stride(-1) != 1 and dout.shape[-1] > 1:
+        dout = dout.contiguous()
+    _require_cuda(dout)
+    if dout.dtype != x.dtype or dout.shape != x.shape:
+        raise RuntimeError("causal_conv1d_bwd: dout must match x in dtype and shape")
+    weight = weight.float()
+    bias = None if bias is None else bias.float().contiguous()
+    p = _conv_params(x, weight, bias, silu, reverse)
+    dx = torch.empty_like(x, memory_format=torch.contiguous_format) if dx is None else dx
+    dw = torch.zeros(weight.shape, device=x.device, dtype=torch.float32)
+    db = torch.zeros(x.shape[1], device=x.device, dtype=torch.float32) if bias is not None else None
+    p.dout, p.dout_bs, p.dout_ds = dout.data_ptr(), dout.stride(0), dout.stride(1)
+    p.dx, p.dx_bs, p.dx_ds = dx.data_ptr(), dx.stride(0), dx.stride(1)
+    p.dweight, p.dbias = dw.data_ptr(), _ptr(db)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().mmu_causal_conv1d_bwd(C.byref(p), _stream()), "causal_conv1d_bwd")
+    return dx, dw, db
+
+
+# ----------------------------------------------------------------------------------------------------------
+# autograd functions with the reference's signatures
+# ----------------------------------------------------------------------------------------------------------
+
+class SelectiveScanFn(torch.autograd.Function):
+    """selective_scan_interface.py:14-74."""
+
+    @staticmethod
+    def forward(ctx, u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
+                return_last_state=False):
+        if u.stride(-1) != 1:
+            u = u.contiguous()
+        if delta.stride(-1) != 1:
+            delta = delta.contiguous()
+        if D is not None:
+            D = D.contiguous()
+        if B.stride(-1) != 1:
+            B = B.contiguous()
+        if C.stride(-1) != 1:
+            C = C.contiguous()
+        if z is not None and z.stride(-1) != 1:
+            z = z.contiguous()
+        ctx.squeeze_B = B.dim() == 3
+        ctx.squeeze_C = C.dim() == 3
+        if ctx.squeeze_B:
+            B = B.unsqueeze(1)
+        if ctx.squeeze_C:
+            C = C.unsqueeze(1)
+        out, x, last = selective_scan_fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus,
+                                          save_states=True, return_last_state=return_last_state)
+        ctx.delta_softplus = delta_softplus
+        ctx.has_z = z is not None
+        ctx.save_for_backward(u, delta, A, B, C, D, z, delta_bias, x)
+        return out if not return_last_state else (out, last)
+
+    @staticmethod
+    def backward(ctx, dout, *args):
+        u, delta, A, B, C, D, z, delta_bias, x = ctx.saved_tensors
+        du, ddelta, dA, dB, dC, dD, dz, ddelta_bias = selective_scan_bwd(
+            u, delta, A, B, C, D, z, delta_bias, dout, x, ctx.delta_softplus)
+        dB = (dB.squeeze(1) if ctx.squeeze_B else dB).to(B.dtype)
+        dC = (dC.squeeze(1) if ctx.squeeze_C else dC).to(C.dtype)
+        return du, ddelta, dA, dB, dC, dD, dz, ddelta_bias, None, None
+
+
+def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
+                      return_last_state=False):
+    """selective_scan_interface.py:77-83.  With return_last_state=True returns (out, last_state (B,D,N));
+    the gradient of last_state is ignored, as in the reference."""
+    return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state)
+
+
+class CausalConv1dFn(torch.autograd.Function):
+    """causal_conv1d_interface.py:10-34."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias=None, activation=None):
+        if activation not in [None, "silu", "swish"]:
+            raise NotImplementedError("activation must be None, silu, or swish")
+        if x.stride(2) != 1:
+            x = x.contiguous()
+        bias = bias.contiguous() if bias is not None else None
+        ctx.save_for_backward(x, weight, bias)
+        ctx.activation = activation in ["silu", "swish"]
+        return causal_conv1d_fwd(x, weight, bias, ctx.activation)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, bias = ctx.saved_tensors
+        dx, dweight, dbias = causal_conv1d_bwd(x, weight, bias, dout, ctx.activation)
+        return dx, dweight.to(weight.dtype), (dbias.to(bias.dtype) if bias is not None else None), None
+
+
+def causal_conv1d_fn(x, weight, bias=None, activation=None):
+    """x: (batch, dim, seqlen); weight: (dim, width); bias: (dim,); activation None | "silu" | "swish"."""
+    return CausalConv1dFn.apply(x, weight, bias, activation)
+
+
+def _autocast_dtype():
+    return torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else None
+
+
+class _InnerCore:
+    """Shared forward/backward of the fused inner functions (conv -> x_proj -> dt_proj -> scan)."""
+
+    @staticmethod
+    def forward(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C, D, delta_bias,
+                B_proj_bias, C_proj_bias, delta_softplus, reverse=False):
+        if B is not None or C is not None or B_proj_bias is not None or C_proj_bias is not None:
+            raise NotImplementedError("mmunet_b200: only input-dependent B/C without projection bias are supported "
+                                      "(the only form MM-UNet's Mamba uses)")
+        if A.is_complex():
+            raise NotImplementedError("mmunet_b200: complex A is not supported")
+        L = xz.shape[-1]
+        R = delta_proj_weight.shape[1]
+        N = A.shape[-1]
+        if xz.stride(-1) != 1:
+            xz = xz.contiguous()
+        conv_w = conv1d_weight.reshape(conv1d_weight.shape[0], -1)
+        x, z = xz.chunk(2, dim=1)
+        conv_b = conv1d_bias.contiguous() if conv1d_bias is not None else None
+        conv_out = causal_conv1d_fwd(x, conv_w, conv_b, True, reverse=reverse)      # (b, d, l) contiguous
+        batch, d = conv_out.shape[0], conv_out.shape[1]
+        x_dbl = F.linear(conv_out.transpose(1, 2).reshape(batch * L, d), x_proj_weight)      # (b l, R+2N)
+        delta = (delta_proj_weight @ x_dbl[:, :R].t()).view(d, batch, L).transpose(0, 1)      # (b, d, l) view
+        Bm = x_dbl[:, R:R + N].view(batch, L, N).transpose(1, 2).contiguous().unsqueeze(1)    # (b, 1, n, l)
+        Cm = x_dbl[:, R + N:].view(batch, L, N).transpose(1, 2).contiguous().unsqueeze(1)
+        D = D.contiguous() if D is not None else None
+        out_z, xs, _ = selective_scan_fwd(conv_out, delta, A, Bm, Cm, D, z, delta_bias, delta_softplus, reverse=reverse)
+        saved = (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, conv_out, delta, A, Bm, Cm, D, delta_bias, xs)
+        return out_z, saved
+
+    @staticmethod
+    def backward(saved, dout_y, delta_softplus, reverse=False):
+        """dout_y: (b, d, l).  Returns (dxz, dconv_w (d,1,w), dconv_b, dx_proj_w, ddt_proj_w, dA, dD, ddelta_bias)."""
+        (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, conv_out, delta, A, Bm, Cm, D, delta_bias, xs) = saved
+        L = xz.shape[-1]
+        R = delta_proj_weight.shape[1]
+        N = A.shape[-1]
+        x, z = xz.chunk(2, dim=1)
+        batch, d = x.shape[0], x.shape[1]
+        dxz = torch.empty_like(xz)
+        dx, dz = dxz.chunk(2, dim=1)
+        # (d, b, l)-major gradients: their "d (b l)" views feed the projection GEMMs without a transpose copy
+        du_buf = torch.empty((d, batch, L), device=xz.device, dtype=xz.dtype).transpose(0, 1)
+        ddl_buf = torch.empty((d, batch, L), device=xz.device, dtype=xz.dtype).transpose(0, 1)
+        dconv_out, ddelta, dA, dB, dC, dD, dz, ddelta_bias = selective_scan_bwd(
+            conv_out, delta, A, Bm, Cm, D, z, delta_bias, dout_y, xs, delta_softplus, reverse=reverse, dz=dz,
+            du=du_buf, ddelta=ddl_buf)
+        dx_dbl = torch.empty_like(x_dbl)
+        dx_dbl[:, R:R + N] = dB.view(batch, N, L).transpose(1, 2).reshape(batch * L, N)
+        dx_dbl[:, R + N:] = dC.view(batch, N, L).transpose(1, 2).reshape(batch * L, N)
+        ddelta2 = ddelta.transpose(0, 1).reshape(d, batch * L)                      # (d, b l)
+        ddt_proj_w = ddelta2 @ x_dbl[:, :R]                                         # (d, R)
+        dx_dbl[:, :R] = ddelta2.t() @ delta_proj_weight                             # (b l, R)
+        conv_flat = conv_out.transpose(1, 2).reshape(batch * L, d)
+        dx_proj_w = dx_dbl.t() @ conv_flat                                          # (R+2N, d)
+        dconv2 = dconv_out.transpose(0, 1).reshape(d, batch * L)
+        dconv2 = torch.addmm(dconv2, x_proj_weight.t(), dx_dbl.t())                 # (d, b l)
+        dconv_out = dconv2.view(d, batch, L).transpose(0, 1)                        # (b, d, l) view, stride(-1)==1
+        _, dconv_w, dconv_b = causal_conv1d_bwd(x, conv_w, conv_b, dconv_out, True, dx=dx, reverse=reverse)
+        return dxz, dconv_w.unsqueeze(1), dconv_b, dx_proj_w, ddt_proj_w, dA, dD, ddelta_bias
+
+
+def _cast_proj(*ws):
+    dt = _autocast_dtype()
+    return tuple(w.to(dt) if (dt is not None and w is not None) else w for w in ws)
+
+
+class MambaInnerFnNoOutProj(torch.autograd.Function):
+    """selective_scan_interface.py:155-289 (returns out_z (b, d, l))."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B=None, C=None, D=None,
+                delta_bias=None, B_proj_bias=None, C_proj_bias=None, delta_softplus=True, checkpoint_lvl=1,
+                reverse=False):
+        x_proj_weight, delta_proj_weight = _cast_proj(x_proj_weight, delta_proj_weight)
+        out_z, saved = _InnerCore.forward(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C, D,
+                                          delta_bias, B_proj_bias, C_proj_bias, delta_softplus, reverse=reverse)
+        ctx.delta_softplus = delta_softplus
+        ctx.reverse = reverse
+        ctx.save_for_backward(*[t for t in saved if t is not None])
+        ctx.mask = [t is not None for t in saved]
+        return out_z
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        it = iter(ctx.saved_tensors)
+        saved = tuple(next(it) if m else None for m in ctx.mask)
+        dxz, dcw, dcb, dxw, ddw, dA, dD, ddb = _InnerCore.backward(saved, dout, ctx.delta_softplus, reverse=ctx.reverse)
+        return (dxz, dcw, dcb, dxw, ddw, dA, None, None, dD, ddb, None, None, None, None, None)
+
+
+class MambaInnerFn(torch.autograd.Function):
+    """selective_scan_interface.py:292-434 (fused out_proj; returns (b, l, d_model))."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias,
+                A, B=None, C=None, D=None, delta_bias=None, B_proj_bias=None, C_proj_bias=None, delta_softplus=True,
+                checkpoint_lvl=1):
+        x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias = _cast_proj(
+            x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias)
+        out_z, saved = _InnerCore.forward(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C, D,
+                                          delta_bias, B_proj_bias, C_proj_bias, delta_softplus)
+        ctx.delta_softplus = delta_softplus
+        ctx.out_proj_bias_is_None = out_proj_bias is None
+        saved = saved + (out_proj_weight, out_z)
+        ctx.save_for_backward(*[t for t in saved if t is not None])
+        ctx.mask = [t is not None for t in saved]
+        return F.linear(out_z.transpose(1, 2), out_proj_weight, out_proj_bias)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        it = iter(ctx.saved_tensors)
+        saved = tuple(next(it) if m else None for m in ctx.mask)
+        out_proj_weight, out_z = saved[-2], saved[-1]
+        batch, L, e = dout.shape
+        dout2 = dout.reshape(batch * L, e)                                          # (b l, e)
+        d = out_z.shape[1]
+        dout_y = (dout2 @ out_proj_weight).view(batch, L, d).transpose(1, 2)        # (b, d, l), stride(-1) != 1
+        dout_y = dout_y.contiguous()
+        dxz, dcw, dcb, dxw, ddw, dA, dD, ddb = _InnerCore.backward(saved[:-2], dout_y, ctx.delta_softplus)
+        dout_proj_w = dout2.t() @ out_z.transpose(1, 2).reshape(batch * L, d)       # (e, d)
+        dout_proj_b = dout2.sum(0) if not ctx.out_proj_bias_is_None else None
+        return (dxz, dcw, dcb, dxw, ddw, dout_proj_w, dout_proj_b, dA, None, None, dD, ddb, None, None, None, None)
+
+
+class BiMambaInnerFn(torch.autograd.Function):
+    """selective_scan_interface.py:437-603: one conv/projection feeding a forward scan (A) and a scan over the
+    flipped sequence (A_b); the flip is fused into the kernels (`reverse`) instead of materialised."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias,
+                A, A_b, B=None, C=None, D=None, delta_bias=None, B_proj_bias=None, C_proj_bias=None,
+                delta_softplus=True, checkpoint_lvl=1):
+        x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias = _cast_proj(
+            x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias)
+        out_f, saved = _InnerCore.forward(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C, D,
+                                          delta_bias, B_proj_bias, C_proj_bias, delta_softplus)
+        (xz_, conv_w, conv_b, x_dbl, xw, dw, conv_out, delta, A_, Bm, Cm, D_, db_, xs_f) = saved
+        z = xz_.chunk(2, dim=1)[1]
+        out_b, xs_b, _ = selective_scan_fwd(conv_out, delta, A_b, Bm, Cm, D_, z, db_, delta_softplus, reverse=True)
+        out_z = out_f + out_b            # out_b is already stored in un-flipped positions
+        ctx.delta_softplus = delta_softplus
+        ctx.out_proj_bias_is_None = out_proj_bias is None
+        saved = saved + (out_proj_weight, out_z, A_b, xs_b)
+        ctx.save_for_backward(*[t for t in saved if t is not None])
+        ctx.mask = [t is not None for t in saved]
+        return F.linear(out_z.transpose(1, 2), out_proj_weight, out_proj_bias)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        it = iter(ctx.saved_tensors)
+        saved = tuple(next(it) if m else None for m in ctx.mask)
+        out_proj_weight, out_z, A_b, xs_b = saved[-4:]
+        core = saved[:-4]
+        (xz, conv_w, conv_b, x_dbl, xw, dw, conv_out, delta, A, Bm, Cm, D, dbias, xs_f) = core
+        batch, L, e = dout.shape
+        d = out_z.shape[1]
+        R, N = dw.shape[1], A.shape[-1]
+        dout2 = dout.reshape(batch * L, e)
+        dout_y = (dout2 @ out_proj_weight).view(batch, L, d).transpose(1, 2).contiguous()
+        z = xz.chunk(2, dim=1)[1]
+        # reverse-direction scan gradients first (plain tensors), then fold them into the shared backward
+        du_b, ddl_b, dA_b, dB_b, dC_b, dD_b, dz_b, ddb_b = selective_scan_bwd(
+            conv_out, delta, A_b, Bm, Cm, D, z, dbias, dout_y, xs_b, ctx.delta_softplus, reverse=True)
+        x = xz.chunk(2, dim=1)[0]
+        dxz = torch.empty_like(xz)
+        dx, dz = dxz.chunk(2, dim=1)
+        du_f, ddl_f, dA, dB_f, dC_f, dD_f, dz, ddb_f = selective_scan_bwd(
+            conv_out, delta, A, Bm, Cm, D, z, dbias, dout_y, xs_f, ctx.delta_softplus, dz=dz)
+        dz += dz_b
+        dconv_out, ddelta = du_f + du_b, ddl_f + ddl_b
+        dB, dC = dB_f + dB_b, dC_f + dC_b
+        dD = None if D is None else dD_f + dD_b
+        ddb = None if dbias is None else ddb_f + ddb_b
+        dx_dbl = torch.empty_like(x_dbl)
+        dx_dbl[:, R:R + N] = dB.view(batch, N, L).transpose(1, 2).reshape(batch * L, N)
+        dx_dbl[:, R + N:] = dC.view(batch, N, L).transpose(1, 2).reshape(batch * L, N)
+        ddelta2 = ddelta.transpose(0, 1).reshape(d, batch * L)
+        ddw = ddelta2 @ x_dbl[:, :R]
+        dx_dbl[:, :R] = ddelta2.t() @ dw
+        dxw = dx_dbl.t() @ conv_out.transpose(1, 2).reshape(batch * L, d)
+        dconv2 = torch.addmm(dconv_out.transpose(0, 1).reshape(d, batch * L), xw.t(), dx_dbl.t())
+        dconv_out = dconv2.view(d, batch, L).transpose(0, 1)
+        _, dcw, dcb = causal_conv1d_bwd(x, conv_w, conv_b, dconv_out, True, dx=dx)
+        dout_proj_w = dout2.t() @ out_z.transpose(1, 2).reshape(batch * L, d)
+        dout_proj_b = dout2.sum(0) if not ctx.out_proj_bias_is_None else None
+        return (dxz, dcw.unsqueeze(1), dcb, dxw, ddw, dout_proj_w, dout_proj_b, dA, dA_b, None, None, dD, ddb,
+                None, None, None, None)
+
+
+def mamba_inner_fn(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias,
+                   A, B=None, C=None, D=None, delta_bias=None, B_proj_bias=None, C_proj_bias=None,
+                   delta_softplus=True):
+    return MambaInnerFn.apply(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight,
+                              out_proj_bias, A, B, C, D, delta_bias, B_proj_bias, C_proj_bias, delta_softplus)
+
+
+def bimamba_inner_fn(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias,
+                     A, A_b, B=None, C=None, D=None, delta_bias=None, B_proj_bias=None, C_proj_bias=None,
+                     delta_softplus=True):
+    return BiMambaInnerFn.apply(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight,
+                                out_proj_bias, A, A_b, B, C, D, delta_bias, B_proj_bias, C_proj_bias, delta_softplus)
+
+
+def mamba_inner_fn_no_out_proj(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B=None, C=None,
+                               D=None, delta_bias=None, B_proj_bias=None, C_proj_bias=None, delta_softplus=True):
+    return MambaInnerFnNoOutProj.apply(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C, D,
+                                       delta_bias, B_proj_bias, C_proj_bias, delta_softplus)
+
+
+def mamba_inner_fn_no_out_proj_reversed(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, D=None,
+                                        delta_bias=None, delta_softplus=True):
+    """== mamba_inner_fn_no_out_proj(xz.flip(-1), ...).flip(-1) (requirements/mamba_simple.py:229-241,270) without
+    materialising either flip: the conv runs anti-causally and the scan walks l = L-1..0."""
+    return MambaInnerFnNoOutProj.apply(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, None, None,
+                                       D, delta_bias, None, None, delta_softplus, 1, True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# scan-order permutations (bit-exact index maps)
+# ----------------------------------------------------------------------------------------------------------
+
+def _order_call(fn_name, src, order, H, W, nslices):
+    _require_cuda(src)
+    if src.dtype not in _DT:
+        raise RuntimeError("scan_order: dtype must be float32, float16 or bfloat16")
+    L = H * W
+    if src.shape[-1] != L:
+        raise RuntimeError(f"scan_order: last dim {src.shape[-1]} != H*W = {L}")
+    if order == _lib.ORDER_NSLICES and (nslices <= 0 or L % nslices):
+        raise RuntimeError(f"scan_order: sequence length {L} is not divisible by nslices {nslices}")
+    # the (b, 2d, l) view produced by in_proj is (2d, b, l)-contiguous: permute instead of copying
+    swap = src.dim() == 3 and not src.is_contiguous() and src.transpose(0, 1).is_contiguous()
+    base = src.transpose(0, 1) if swap else src
+    src2 = base.reshape(-1, L)
+    if src2.stride(-1) != 1:
+        src2 = src2.contiguous()
+    dst = torch.empty((src2.shape[0], L), device=src.device, dtype=src.dtype)
+    with torch.cuda.device(src.device):
+        rc = getattr(_lib.lib(), fn_name)(src2.data_ptr(), dst.data_ptr(), _DT[src.dtype], src2.shape[0],
+                                          src2.stride(0), dst.stride(0), order, H, W, max(1, nslices), _stream())
+    _lib.check(rc, fn_name)
+    dst = dst.view(*base.shape[:-1], L)
+    return dst.transpose(0, 1) if swap else dst
+
+
+class _ScanOrderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, order, H, W, nslices, scatter):
+        ctx.args = (order, H, W, nslices, scatter)
+        return _order_call("mmu_scan_order_scatter" if scatter else "mmu_scan_order_gather", x, order, H, W, nslices)
+
+    @staticmethod
+    def backward(ctx, g):
+        order, H, W, nslices, scatter = ctx.args
+        # the adjoint of a permutation gather is the scatter with the same index map, and vice versa
+        return (_order_call("mmu_scan_order_gather" if scatter else "mmu_scan_order_scatter", g, order, H, W, nslices),
+                None, None, None, None, None)
+
+
+def scan_order_gather(x, order, H, W, nslices=1):
+    """y[..., l] = x[..., idx(l)]  (x: (..., H*W))."""
+    return _ScanOrderFn.apply(x, order, H, W, nslices, False)
+
+
+def scan_order_scatter(y, order, H, W, nslices=1):
+    """x[..., idx(l)] = y[..., l]."""
+    return _ScanOrderFn.apply(y, order, H, W, nslices, True)
+
+
+def scan_order_index(order, H, W, nslices=1, device="cuda"):
+    idx = torch.empty(H * W, device=device, dtype=torch.int64)
+    with torch.cuda.device(idx.device):
+        _lib.check(_lib.lib().mmu_scan_order_index(idx.data_ptr(), order, H, W, max(1, nslices), _stream()),
+                   "mmu_scan_order_index")
+    return idx
+
+
+def two_row_flatten(x):
+    """(B,C,H,W) -> (B,C,H*W) in MMConv's morph order (MMUNet.py:68-93)."""
+    B, C_, H, W = x.shape
+    return scan_order_gather(x.reshape(B, C_, H * W), _lib.ORDER_TWOROW, H, W)
+
+
+def two_row_unflatten(x_flat, H, W):
+    """inverse (MMUNet.py:95-121): (B,C,L) -> (B,C,H,W)."""
+    B, C_, L = x_flat.shape
+    return scan_order_scatter(x_flat, _lib.ORDER_TWOROW, H, W).view(B, C_, H, W)

@@ -1,0 +1,163 @@
+"""GPU parity of the fused inner functions and the TFM-interface Mamba module against
+(a) golden vectors produced by the unmodified reference module / mamba_inner_ref (oracle/gen_golden.py) and
+(b) the torch oracle (oracle/torch_ref.py) run on CPU with the same parameters."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import torch_ref
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from mmunet_b200 import Mamba, ops
+DEV = "cuda"
+
+
+def close(name, got, ref, rtol=2e-3, atol=2e-3):
+    got = got.detach().float().cpu().numpy().astype(np.float64)
+    ref = np.asarray(ref.detach().cpu().numpy() if torch.is_tensor(ref) else ref, np.float64)
+    assert got.shape == ref.shape, (name, got.shape, ref.shape)
+    atol = atol * max(1.0, float(np.abs(ref).max()))
+    err = np.abs(got - ref)
+    worst = float((err / (atol + rtol * np.abs(ref))).max())
+    assert np.isfinite(got).all() and worst <= 1.0, f"{name}: max|err|={err.max():.3e} worst/bound={worst:.2f}"
+
+
+def test_mamba_inner_fn_golden():
+    c = np.load(os.path.join(GOLDEN, "mamba_inner.npz"))
+    keys = ("xz", "conv_w", "conv_b", "x_proj_w", "dt_proj_w", "out_proj_w", "A", "D", "dt_bias")
+    t = {k: torch.tensor(c[k], device=DEV, requires_grad=True) for k in keys}
+    out = ops.mamba_inner_fn(t["xz"], t["conv_w"], t["conv_b"], t["x_proj_w"], t["dt_proj_w"], t["out_proj_w"], None,
+                             t["A"], None, None, t["D"], t["dt_bias"], delta_softplus=True)
+    close("out", out, c["out"])                       # the only assert the reference's own test makes (:221)
+    out.backward(torch.tensor(c["dout"], device=DEV))
+    for k in keys:
+        close("d" + k, t[k].grad, c["d" + k], 5e-3, 5e-3)
+
+
+@pytest.mark.parametrize("batch,d,L,N,R", [(2, 8, 48, 4, 2), (3, 6, 200, 16, 1), (1, 128, 256, 16, 4)])
+@pytest.mark.parametrize("reverse", [False, True])
+def test_inner_no_out_proj_vs_torch_oracle(batch, d, L, N, R, reverse):
+    g = torch.Generator().manual_seed(1)
+    p = dict(xz=torch.randn(batch, 2 * d, L, generator=g), conv_w=torch.randn(d, 1, 4, generator=g) * 0.5,
+             conv_b=torch.randn(d, generator=g) * 0.5, x_proj_w=torch.randn(R + 2 * N, d, generator=g) * 0.3,
+             dt_proj_w=torch.randn(d, R, generator=g) * 0.3, A=-0.5 * torch.rand(d, N, generator=g),
+             D=torch.randn(d, generator=g), dt_bias=0.5 * torch.rand(d, generator=g))
+    dout = torch.randn(batch, d, L, generator=g)
+    cpu = {k: v.clone().requires_grad_() for k, v in p.items()}
+    xz_in = cpu["xz"].flip(-1) if reverse else cpu["xz"]
+    ref = torch_ref.mamba_inner(xz_in, cpu["conv_w"], cpu["conv_b"], cpu["x_proj_w"], cpu["dt_proj_w"], cpu["A"],
+                                cpu["D"], cpu["dt_bias"], with_out_proj=False)
+    if reverse:
+        ref = ref.flip(-1)
+    ref.backward(dout)
+    gpu = {k: v.to(DEV).requires_grad_() for k, v in p.items()}
+    # give xz the (l, b*l, 1) strides in_proj produces
+    xz = gpu["xz"].detach().transpose(0, 1).contiguous().transpose(0, 1).requires_grad_()
+    if reverse:
+        out = ops.mamba_inner_fn_no_out_proj_reversed(xz, gpu["conv_w"], gpu["conv_b"], gpu["x_proj_w"], gpu["dt_proj_w"],
+                                                      gpu["A"], gpu["D"], gpu["dt_bias"])
+    else:
+        out = ops.mamba_inner_fn_no_out_proj(xz, gpu["conv_w"], gpu["conv_b"], gpu["x_proj_w"], gpu["dt_proj_w"],
+                                             gpu["A"], None, None, gpu["D"], gpu["dt_bias"])
+    close("out", out, ref)
+    out.backward(dout.to(DEV))
+    close("dxz", xz.grad, cpu["xz"].grad, 5e-3, 5e-3)
+    for k in ("conv_w", "conv_b", "x_proj_w", "dt_proj_w", "A", "D", "dt_bias"):
+        close("d" + k, gpu[k].grad, cpu[k].grad, 5e-3, 5e-3)
+
+
+def _load_golden_module(bimamba_type):
+    c = np.load(os.path.join(GOLDEN, "tfm_mamba.npz"))
+    m = Mamba(d_model=8, d_state=4, d_conv=4, expand=2, bimamba_type=bimamba_type, nslices=4)
+    sd = {k[len("param."):]: torch.tensor(c[k]) for k in c.files if k.startswith("param.")}
+    assert set(sd) == set(m.state_dict()), "state_dict names must match the reference module (SURVEY.md section 5)"
+    m.load_state_dict(sd)
+    return c, m.to(DEV)
+
+
+def test_tfm_mamba_v3_golden():
+    c, m = _load_golden_module("v3")
+    x = torch.tensor(c["x"], device=DEV, requires_grad=True)
+    out, o1, o2, o3 = m(x)
+    for name, got in (("out", out), ("o1", o1), ("o2", o2), ("o3", o3)):
+        close(name, got, c[name])
+    out.backward(torch.tensor(c["dout"], device=DEV))
+    close("dx", x.grad, c["dx"], 5e-3, 5e-3)
+    for k, p in m.named_parameters():
+        close("grad." + k, p.grad, c["grad." + k], 5e-3, 5e-3)
+
+
+def test_tfm_mamba_v1_golden():
+    """bimamba_type="v1": mamba_simple.py:304-318 evaluated with the same parameters (the reference module itself
+    raises UnboundLocalError there - recorded in the fixture)."""
+    c, m = _load_golden_module("v1")
+    assert str(c["v1_status"]) == "UnboundLocalError"
+    x = torch.tensor(c["x"], device=DEV, requires_grad=True)
+    out, o1, o2, o3 = m(x)
+    assert o1 is None and o2 is None and o3 is None
+    close("v1.out", out, c["v1.out"])
+    out.backward(torch.tensor(c["dout"], device=DEV))
+    close("v1.dx", x.grad, c["v1.dx"], 5e-3, 5e-3)
+    for k, p in m.named_parameters():
+        ref = c["v1.grad." + k]
+        if ref.size == 0:
+            assert p.grad is None, k            # _b / _s sets are unused by v1
+        else:
+            close("v1.grad." + k, p.grad, ref, 5e-3, 5e-3)
+
+
+@pytest.mark.parametrize("bimamba_type", ["v1", "v2", "v3"])
+@pytest.mark.parametrize("d_model,L,ns", [(3, 256, 8), (64, 512, 16)])
+def test_tfm_mamba_vs_torch_oracle(bimamba_type, d_model, L, ns):
+    torch.manual_seed(3)
+    m = Mamba(d_model=d_model, d_state=16, d_conv=4, expand=2, bimamba_type=bimamba_type, nslices=ns)
+    x = torch.randn(2, L, d_model)
+    xc = x.clone().requires_grad_()
+    ref, r1, r2, r3 = torch_ref.mamba_forward(m, xc)
+    dout = torch.randn_like(ref)
+    ref.backward(dout)
+    ref_grads = {k: (None if p.grad is None else p.grad.clone()) for k, p in m.named_parameters()}
+    m.zero_grad()
+    m = m.to(DEV)
+    xg = x.to(DEV).requires_grad_()
+    out, o1, o2, o3 = m(xg)
+    close("out", out, ref)
+    if bimamba_type == "v3":
+        close("o1", o1, r1), close("o2", o2, r2), close("o3", o3, r3)
+    out.backward(dout.to(DEV))
+    close("dx", xg.grad, xc.grad, 5e-3, 5e-3)
+    for k, p in m.named_parameters():
+        if ref_grads[k] is None:
+            assert p.grad is None, k
+        else:
+            close("grad." + k, p.grad, ref_grads[k], 5e-3, 5e-3)
+
+
+def test_tfm_mamba_bf16_autocast():
+    torch.manual_seed(5)
+    m = Mamba(d_model=64, d_state=16, bimamba_type="v3", nslices=16)
+    x = torch.randn(2, 1024, 64)
+    ref, *_ = torch_ref.mamba_forward(m, x)
+    m = m.to(DEV)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out, *_ = m(x.to(DEV).requires_grad_())
+    assert out.dtype == torch.bfloat16
+    close("out.bf16", out, ref.detach(), 2e-2, 5e-2)
+    out.float().sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+def test_selective_scan_fn_3d_BC_and_slow_path():
+    torch.manual_seed(7)
+    m = Mamba(d_model=8, d_state=4, bimamba_type="v1", use_fast_path=False)
+    m2 = Mamba(d_model=8, d_state=4, bimamba_type="v1")
+    m2.load_state_dict(m.state_dict())
+    x = torch.randn(2, 70, 8, device=DEV)
+    a, *_ = m.to(DEV)(x)
+    b, *_ = m2.to(DEV)(x)
+    close("slow==fast", a, b.detach(), 1e-4, 1e-4)
