@@ -12,7 +12,7 @@ raises RuntimeError.
 """
 from __future__ import annotations
 
-import ctypes as C
+import ctypes as ct
 
 import torch
 import torch.nn.functional as F
@@ -130,7 +130,7 @@ def selective_scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta
                 lg = torch.empty((batch, H, N), device=u.device, dtype=torch.float32) if return_last_state else None
                 p.x, p.last_state = _ptr(xg), _ptr(lg)
             p.workspace, p.workspace_bytes = _ptr(ws), ws_bytes
-            _lib.check(L_.mmu_selective_scan_fwd(C.byref(p), _stream()), "selective_scan_fwd")
+            _lib.check(L_.mmu_selective_scan_fwd(ct.byref(p), _stream()), "selective_scan_fwd")
             if G > 1:
                 if x is not None:
                     x[:, g * H:(g + 1) * H] = xg
@@ -192,7 +192,7 @@ def selective_scan_bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softp
                 p.dB, p.dC = dBg.data_ptr(), dCg.data_ptr()
             p.dD = None if dD is None else dD.data_ptr() + g * H * 4
             p.ddelta_bias = None if dbias is None else dbias.data_ptr() + g * H * 4
-            _lib.check(L_.mmu_selective_scan_bwd(C.byref(p), _stream()), "selective_scan_bwd")
+            _lib.check(L_.mmu_selective_scan_bwd(ct.byref(p), _stream()), "selective_scan_bwd")
             if G > 1:
                 dB[:, g:g + 1] = dBg
                 dC[:, g:g + 1] = dCg
@@ -227,7 +227,7 @@ def causal_conv1d_fwd(x, weight, bias=None, silu=False, reverse=False):
     out = torch.empty_like(x, memory_format=torch.contiguous_format)
     p.out, p.out_bs, p.out_ds = out.data_ptr(), out.stride(0), out.stride(1)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().mmu_causal_conv1d_fwd(C.byref(p), _stream()), "causal_conv1d_fwd")
+        _lib.check(_lib.lib().mmu_causal_conv1d_fwd(ct.byref(p), _stream()), "causal_conv1d_fwd")
     return out
 
 
@@ -250,7 +250,7 @@ def causal_conv1d_bwd(x, weight, bias, dout, silu=False, dx=None, reverse=False)
     p.dx, p.dx_bs, p.dx_ds = dx.data_ptr(), dx.stride(0), dx.stride(1)
     p.dweight, p.dbias = dw.data_ptr(), _ptr(db)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().mmu_causal_conv1d_bwd(C.byref(p), _stream()), "causal_conv1d_bwd")
+        _lib.check(_lib.lib().mmu_causal_conv1d_bwd(ct.byref(p), _stream()), "causal_conv1d_bwd")
     return dx, dw, db
 
 
