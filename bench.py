@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200-native Mamba-block hot path.
+
+Workload (BASELINE.json configs[1]): the isolated Mamba block - causal_conv1d (width 4, SiLU) forward, selective scan
+forward, selective scan backward, causal_conv1d backward - at B=8, D=384, L=4096 (a 64x64 map), d_state=16, with
+z-gate, D-skip, delta-bias and softplus, on synthetic data in the reference tests' distributions.  One "step" is one
+pass of those four kernels over one batch.  The metric is the reference's own: algorithmic HBM bytes of the step per
+second (scan fwd+bwd (11D+6N)BLs, conv fwd+bwd 5BDLs), i.e. GB/s against the HBM roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype fp32|bf16] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU); every rank runs its own batch (weak scaling, no data-path collective:
+every (batch, channel) scan lane is independent - SURVEY.md section 8e); time = max over ranks, value = sum of bytes / time.
+
+`--impl reference` times the reference's own CPU path for the same step - the pure-PyTorch selective_scan_ref /
+causal_conv1d_ref algorithm (restated in oracle/torch_ref.py because /root/reference does not exist on the GPU box) -
+on the host cores, on a bounded sample of the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "mm-unet_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+B, D, L, N, W = 8, 384, 4096, 16, 4
+METRIC = "selective-scan+causal_conv1d fwd+bwd algorithmic HBM GB/s (isolated Mamba block)"
+
+
+def algo_bytes(batch, s):
+    scan_f = (4 * D + 2 * N) * batch * L * s
+    scan_b = (7 * D + 4 * N) * batch * L * s
+    conv_f = 2 * batch * D * L * s
+    conv_b = 3 * batch * D * L * s
+    return dict(scan_fwd=scan_f, scan_bwd=scan_b, conv_fwd=conv_f, conv_bwd=conv_b, step=scan_f + scan_b + conv_f + conv_b)
+
+
+def make_inputs(batch, dtype, device, seed=0, pin=False):
+    """Reference test distributions (tests/ops/test_selective_scan.py:58-88, tests/test_causal_conv1d.py:39-50)."""
+    g = torch.Generator().manual_seed(seed)
+    t = dict(
+        x=torch.randn(batch, D, L, generator=g), delta=0.5 * torch.rand(batch, D, L, generator=g),
+        z=torch.randn(batch, D, L, generator=g), Bm=torch.randn(batch, 1, N, L, generator=g),
+        Cm=torch.randn(batch, 1, N, L, generator=g), dout=torch.randn(batch, D, L, generator=g))
+    w = dict(A=-0.5 * torch.rand(D, N, generator=g), Dp=torch.randn(D, generator=g), dbias=0.5 * torch.rand(D, generator=g),
+             cw=torch.randn(D, W, generator=g), cb=torch.randn(D, generator=g))
+    t = {k: v.to(dtype) for k, v in t.items()}
+    if pin:
+        t = {k: v.pin_memory() for k, v in t.items()}
+    else:
+        t = {k: v.to(device) for k, v in t.items()}
+    w = {k: v.to(device) for k, v in w.items()}
+    return t, w
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu summary (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
+
+
+def cpu_baseline_port(sample_batch=B, min_seconds=10.0, max_reps=8):
+    """The oracle's C port (OpenMP over all host cores) on a bounded sample of the same step: the full batch, repeated
+    until about 10 s of CPU work have been timed."""
+    import oracle
+    t, w = make_inputs(sample_batch, torch.float32, "cpu")
+    n = {k: v.numpy() for k, v in {**t, **w}.items()}
+    reps, t0 = 0, time.perf_counter()
+    while reps < max_reps and (reps == 0 or time.perf_counter() - t0 < min_seconds):
+        u = oracle.causal_conv1d_fwd(n["x"], n["cw"], n["cb"], True)
+        oracle.selective_scan_fwd(u, n["delta"], n["A"], n["Bm"], n["Cm"], n["Dp"], n["z"], n["dbias"], True)
+        g = oracle.selective_scan_bwd(u, n["delta"], n["A"], n["Bm"], n["Cm"], n["Dp"], n["z"], n["dbias"], n["dout"], True)
+        oracle.causal_conv1d_bwd(n["x"], n["cw"], n["cb"], g["du"], True)
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": algo_bytes(sample_batch, 4)["step"] / dt / 1e9, "unit": "GB/s", "cores": oracle.num_threads(),
+            "kind": "port", "sample": f"{reps} x full step (batch {sample_batch}, D={D}, L={L}, N={N}), fp32, "
+            f"oracle/scan_oracle.c (OpenMP), {dt:.2f} s per step", "seconds_per_step": dt}
+
+
+def run_reference(args):
+    """Reference arm: the reference's pure-PyTorch CPU algorithm (selective_scan_ref / causal_conv1d_ref restated in
+    oracle/torch_ref.py), all host threads, bounded sample (batch 1 of 8) per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import torch_ref
+    sample_batch = 1
+    t, w = make_inputs(sample_batch, torch.float32, "cpu")
+    torch.set_num_threads(os.cpu_count() or 1)
+
+    def step():
+        x = t["x"].clone().requires_grad_()
+        delta, z = t["delta"].clone().requires_grad_(), t["z"].clone().requires_grad_()
+        Bm, Cm = t["Bm"].clone().requires_grad_(), t["Cm"].clone().requires_grad_()
+        A, Dp, db = (w[k].clone().requires_grad_() for k in ("A", "Dp", "dbias"))
+        cw, cb = w["cw"].clone().requires_grad_(), w["cb"].clone().requires_grad_()
+        u = torch_ref.causal_conv1d(x, cw, cb, "silu")
+        out = torch_ref.selective_scan(u, delta, A, Bm, Cm, Dp, z, db, True)
+        out.backward(t["dout"])
+        return float(x.grad.sum())
+
+    for _ in range(min(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = algo_bytes(sample_batch, 4)["step"] / dt / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"isolated Mamba block B={B} D={D} L={L} N={N} conv_width={W}; CPU sample = batch {sample_batch}"},
+            "cpu_baseline": {"value": val, "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"batch {sample_batch} of {B} per step; pure-PyTorch selective_scan_ref/causal_conv1d_ref "
+                                       "algorithm (oracle/torch_ref.py), autograd backward"},
+            "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    from mmunet_b200 import _lib, ops
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
+    s = 4 if dtype == torch.float32 else 2
+    nbytes = algo_bytes(B, s)
+    t, w = make_inputs(B, dtype, dev, seed=rank)
+    warm = max(3, args.warmup)
+
+    # ---------------- device-resident arm: raw kernels through the C-ABI, per-kernel CUDA events -------------------
+    du = torch.empty_like(t["x"]); dd = torch.empty_like(t["x"]); dz = torch.empty_like(t["x"]); dx = torch.empty_like(t["x"])
+    names = ("conv_fwd", "scan_fwd", "scan_bwd", "conv_bwd")
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+
+    def step(e=None):
+        if e: e[0].record()
+        u = ops.causal_conv1d_fwd(t["x"], w["cw"], w["cb"], True)
+        if e: e[1].record()
+        out, xs, _ = ops.selective_scan_fwd(u, t["delta"], w["A"], t["Bm"], t["Cm"], w["Dp"], t["z"], w["dbias"], True)
+        if e: e[2].record()
+        g = ops.selective_scan_bwd(u, t["delta"], w["A"], t["Bm"], t["Cm"], w["Dp"], t["z"], w["dbias"], t["dout"], xs, True,
+                                   du=du, ddelta=dd, dz=dz)
+        if e: e[3].record()
+        ops.causal_conv1d_bwd(t["x"], w["cw"], w["cb"], du, True, dx=dx)
+        if e: e[4].record()
+        return g
+
+    for _ in range(warm):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    if dist: dist.barrier()
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    t0 = time.perf_counter()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(args.steps):
+        step(ev[i])
+    stop.record()
+    torch.cuda.synchronize()
+    if dist: dist.barrier()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    launches = _lib.launch_count() - n0
+    dev_ms = start.elapsed_time(stop)
+    tm = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+    if dist: dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    dev_ms = float(tm.item())
+    per_kernel = {n: sum(ev[i][k].elapsed_time(ev[i][k + 1]) for i in range(args.steps)) / args.steps for k, n in enumerate(names)}
+
+    # ---------------- end-to-end arm: public autograd API, pinned host buffers, H2D + D2H inside the timed region ---
+    ht, _ = make_inputs(B, dtype, dev, seed=rank, pin=True)
+    dbuf = {k: torch.empty_like(v, device=dev) for k, v in ht.items()}
+    host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+    params = {k: w[k].clone().requires_grad_() for k in ("A", "Dp", "dbias", "cw", "cb")}
+
+    def e2e_step():
+        for k in ht:
+            dbuf[k].copy_(ht[k], non_blocking=True)
+        x = dbuf["x"].requires_grad_()
+        u = ops.causal_conv1d_fn(x, params["cw"], params["cb"], "silu")
+        out = ops.selective_scan_fn(u, dbuf["delta"], params["A"], dbuf["Bm"], dbuf["Cm"], params["Dp"], dbuf["z"],
+                                    params["dbias"], True)
+        loss = (out.float() * dbuf["dout"].float()).sum()
+        loss.backward()
+        host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+        dbuf["x"] = dbuf["x"].detach()
+        for p_ in params.values():
+            p_.grad = None
+
+    e2e_steps = max(3, args.steps // 3)
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    if dist: dist.barrier()
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s2.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e2.record()
+    torch.cuda.synchronize()
+    tm2 = torch.tensor([s2.elapsed_time(e2)], device=dev, dtype=torch.float64)
+    if dist: dist.all_reduce(tm2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(tm2.item()) / e2e_steps
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join(timeout=3)
+    h2d = sum(v.numel() * v.element_size() for v in ht.values())
+
+    if rank != 0:
+        if dist: dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    ms = dev_ms / args.steps
+    value = world * nbytes["step"] / (ms * 1e-3) / 1e9
+    dom = max(("scan_bwd", "scan_fwd"), key=lambda n: per_kernel[n])
+    ach = nbytes[dom] / (per_kernel[dom] * 1e-3) / 1e9
+    traffic = ncu_traffic().get(f"{dom}_{args.dtype}")
+    line = {
+        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if dtype == torch.float32 else "bf16 I/O, f32 state", "data": "synthetic",
+        "config": {"workload": f"isolated Mamba block: causal_conv1d(w={W},silu) fwd -> selective_scan fwd -> bwd -> conv1d bwd; "
+                               f"B={B} D={D} L={L} d_state={N}, z+D+delta_bias+softplus; per-GPU batch fixed (weak scaling)",
+                   "l2": "inputs (818 MB fp32 / 409 MB bf16 per step) larger than the 126 MB L2", "io_dtype": args.dtype},
+        "e2e": {"value": world * nbytes["step"] / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
+                "api": "causal_conv1d_fn + selective_scan_fn (autograd), pinned host inputs, loss read back"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": nbytes[dom], "avg_launch_us": per_kernel[dom] * 1e3,
+                     "frac_of_nominal_8000": ach / 8000.0},
+        "kernels": {n: {"avg_us": per_kernel[n] * 1e3, "algorithmic_GBps": nbytes[n] / (per_kernel[n] * 1e-3) / 1e9,
+                        "frac_of_peak": nbytes[n] / (per_kernel[n] * 1e-3) / 1e9 / peak} for n in names},
+        "scan_fwd_bwd": {"us": (per_kernel["scan_fwd"] + per_kernel["scan_bwd"]) * 1e3,
+                         "GBps": (nbytes["scan_fwd"] + nbytes["scan_bwd"]) / ((per_kernel["scan_fwd"] + per_kernel["scan_bwd"]) * 1e-3) / 1e9},
+        "clocks": sampler.summary(), "wall_s": wall,
+    }
+    line["scan_fwd_bwd"]["frac_of_peak"] = line["scan_fwd_bwd"]["GBps"] / peak
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline_port()
+        except Exception as exc:  # the oracle is a checker; its absence must not hide the GPU number
+            line["cpu_baseline"] = {"error": repr(exc)}
+    print(json.dumps(line))
+    if dist: dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -52,7 +52,16 @@ __device__ __forceinline__ float ex2(float x) {
 __device__ __forceinline__ float2 ex2(float2 x) { return make_float2(ex2(x.x), ex2(x.y)); }
 
 // softplus with the reference's threshold (selective_scan_fwd_kernel.cuh:153-156; F.softplus default)
-__device__ __forceinline__ float softplus_f(float x) { return x <= 20.f ? log1pf(__expf(x)) : x; }
+// log1p(e^x) without the libm log1pf call: for small e = e^x the alternating series (error < e^5/5), otherwise
+// log(1+e) through MUFU.LG2.  Relative error stays < 1e-5 over the whole range (delta feeds exp(delta*A), so it is the
+// relative error that matters).
+__device__ __forceinline__ float softplus_f(float x) {
+    const float e = __expf(fminf(x, 20.f));
+    const float series = e * fmaf(e, fmaf(e, fmaf(e, -0.25f, 0.33333334f), -0.5f), 1.f);
+    const float lg = __logf(1.f + e);
+    const float r = e < 1.5e-2f ? series : lg;
+    return x <= 20.f ? r : x;
+}
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 __device__ __forceinline__ float2 shfl_up2(float2 v, int delta, int width) {

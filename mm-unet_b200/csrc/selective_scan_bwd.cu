@@ -33,6 +33,7 @@ struct BwdArgs {
     int B, D, L, N, Ne;
     int nseg, cps, nchunks, nx;
     int softplus, reverse;
+    int dbg_no_atomics;   // timing experiments only (MMU_BWD_NOATOM=1): skip the dB/dC atomics, results are wrong
     unsigned vec_mask;   // bit0 u, 1 delta, 2 z, 3 dout, 4 B, 5 C, 6 du, 7 ddelta, 8 dz
 };
 
@@ -61,8 +62,8 @@ __global__ void __launch_bounds__(32 * RQ * NGW, (AGG ? 512 : 384) / (32 * RQ * 
     float *s_dl = s_u + R * TL;                          // [R][TL]  softplus(delta+bias), later ddelta
     float *s_z = s_dl + R * TL;                          // [R][TL]  z -> dz factor -> dz
     float *s_g = s_z + R * TL;                           // [R][TL]  dout -> dy
-    float *s_B = s_g + R * TL;                           // [Ne][TL]
-    float *s_C = s_B + Ne * TL;                          // [Ne][TL]
+    float *s_B = s_g + R * TL;                           // [NP][TL][2]  pair-interleaved
+    float *s_C = s_B + Ne * TL;                          // [NP][TL][2]
     float *s_part = s_C + Ne * TL;                       // [NGW][3][R][TL]  partial S1, S2, y
     float *s_dbc = s_part + NGW * 3 * R * TL;            // [RQ][NP][4][TL]  row-reduced dB.x dB.y dC.x dC.y
     float *s_A2 = s_dbc + RQ * NP * 4 * TL;              // [R][Ne]  A*log2e
@@ -117,25 +118,79 @@ __global__ void __launch_bounds__(32 * RQ * NGW, (AGG ? 512 : 384) / (32 * RQ * 
     const bool hi = (rg & 2) != 0, lo = (rg & 1) != 0;
     float dsum = 0.f, dfirst = 0.f;
 
+    // per-thread constant shared-memory offsets (hoisted out of every loop)
+    const int off_t0 = lr * TL + 4 * swz_chunk<T>(j * 2), off_t1 = lr * TL + 4 * swz_chunk<T>(j * 2 + 1);
+    int off_bc[4];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) off_bc[cc] = bc_off(j * 4 + cc);
+
+    // ---- chunk loop (last -> first) with register prefetch of the next chunk's tiles -----------------------------------
+    constexpr int QT = R * (TL / 4);                      // quads of a row tile
+    constexpr int KR = (QT + NT - 1) / NT;
+    constexpr int K2 = (8 * (TL / 4) + NT - 1) / NT;      // pair-quads per thread of a B / C tile (fast path: dstate <= 16)
+    constexpr int KH = (R * 16 + NT - 1) / NT;
+    const bool fast_all = (p.vec_mask & 0x8000u) != 0;
+    Quad<IN_T> q_u[KR], q_dl[KR], q_z[KR], q_g[KR], q_B[2 * K2], q_C[2 * K2];
+    float q_h[KH];
+    auto ident = [](int, float v) { return v; };
+    auto dl_xf = [&](int r, float v) {
+        const float xx = v + s_bias[r];
+        return sp ? softplus_f(xx) : xx;
+    };
+    auto load_hin = [&](int c, int i) -> float {
+        const int r = i / Ne, n = i - r * Ne, row = row0 + r;
+        return (c > 0 && row < D && n < N) ? p.x[(((int64_t)b * D + row) * p.nx + (c - 1)) * N + n] : 0.f;
+    };
+    auto prefetch = [&](int c) {
+        const int t0 = c * TL;
+        tile_prefetch<IN_T, TL, NT, KR>(q_dl, dl_b, p.dl_ds, row0, D, QT, t0, L, rev, tid);
+        tile_prefetch<IN_T, TL, NT, KR>(q_g, g_b, p.g_ds, row0, D, QT, t0, L, rev, tid);
+        bc_prefetch<IN_T, TL, NT, K2>(q_C, C_b, p.C_ns, N, NP, t0, L, rev, tid);
+        if (has_z) tile_prefetch<IN_T, TL, NT, KR>(q_z, z_b, p.z_ds, row0, D, QT, t0, L, rev, tid);
+        if (!AGG) {
+            tile_prefetch<IN_T, TL, NT, KR>(q_u, u_b, p.u_ds, row0, D, QT, t0, L, rev, tid);
+            bc_prefetch<IN_T, TL, NT, K2>(q_B, B_b, p.B_ns, N, NP, t0, L, rev, tid);
+#pragma unroll
+            for (int k = 0; k < KH; ++k) q_h[k] = (tid + k * NT < R * Ne) ? load_hin(c, tid + k * NT) : 0.f;
+        }
+    };
+    float acc_dD[KR], acc_db[KR];    // per-thread partial dD / ddelta_bias of the row its epilogue quad belongs to
+#pragma unroll
+    for (int k = 0; k < KR; ++k) acc_dD[k] = acc_db[k] = 0.f;
+
+    bool cur_fast = fast_all && c_end * TL <= L;
+    if (cur_fast) prefetch(c_end - 1);
     for (int c = c_end - 1; c >= c_begin; --c) {
         const int t0 = c * TL;
         __syncthreads();
-        load_tile<IN_T, T, TL, NT>(s_dl, dl_b, p.dl_ds, row0, R, D, t0, L, rev, p.vec_mask & 2u, tid, 0.f,
-                                   [&](int r, float v) {
-                                       const float xx = v + s_bias[r];
-                                       return sp ? softplus_f(xx) : xx;
-                                   });
-        load_tile<IN_T, T, TL, NT>(s_g, g_b, p.g_ds, row0, R, D, t0, L, rev, p.vec_mask & 8u, tid, 0.f,
-                                   [](int, float v) { return v; });
-        load_tile<IN_T, T, TL, NT>(s_C, C_b, p.C_ns, 0, Ne, N, t0, L, rev, p.vec_mask & 32u, tid, 0.f,
-                                   [](int, float v) { return v; });
+        if (cur_fast) {
+            tile_commit<IN_T, T, TL, NT, KR>(s_dl, q_dl, QT, rev, tid, dl_xf);
+            tile_commit<IN_T, T, TL, NT, KR>(s_g, q_g, QT, rev, tid, ident);
+            bc_commit<IN_T, TL, NT, K2>(s_C, q_C, NP, rev, tid);
+            if (has_z) tile_commit<IN_T, T, TL, NT, KR>(s_z, q_z, QT, rev, tid, ident);
+            if (!AGG) {
+                tile_commit<IN_T, T, TL, NT, KR>(s_u, q_u, QT, rev, tid, ident);
+                bc_commit<IN_T, TL, NT, K2>(s_B, q_B, NP, rev, tid);
+#pragma unroll
+                for (int k = 0; k < KH; ++k)
+                    if (tid + k * NT < R * Ne) s_hin[tid + k * NT] = q_h[k];
+            }
+        } else {
+            load_tile<IN_T, T, TL, NT>(s_dl, dl_b, p.dl_ds, row0, R, D, t0, L, rev, p.vec_mask & 2u, tid, 0.f, dl_xf);
+            load_tile<IN_T, T, TL, NT>(s_g, g_b, p.g_ds, row0, R, D, t0, L, rev, p.vec_mask & 8u, tid, 0.f, ident);
+            bc_load_generic<IN_T, TL, NT>(s_C, C_b, p.C_ns, N, Ne, t0, L, rev, tid);
+            if (has_z) load_tile<IN_T, T, TL, NT>(s_z, z_b, p.z_ds, row0, R, D, t0, L, rev, p.vec_mask & 4u, tid, 0.f, ident);
+            if (!AGG) {
+                load_tile<IN_T, T, TL, NT>(s_u, u_b, p.u_ds, row0, R, D, t0, L, rev, p.vec_mask & 1u, tid, 0.f, ident);
+                bc_load_generic<IN_T, TL, NT>(s_B, B_b, p.B_ns, N, Ne, t0, L, rev, tid);
+                for (int i = tid; i < R * Ne; i += NT) s_hin[i] = load_hin(c, i);
+            }
+        }
         if (has_z) {
-            load_tile<IN_T, T, TL, NT>(s_z, z_b, p.z_ds, row0, R, D, t0, L, rev, p.vec_mask & 4u, tid, 0.f,
-                                       [](int, float v) { return v; });
-            // same thread, same elements as the two loads above: dy = dout*silu(z); s_z <- d(out)/dy-independent dz factor
-            for (int idx = tid; idx < R * (TL / 4); idx += NT) {
+            // same thread, same elements as it just wrote: dy = dout*silu(z); s_z <- factor such that dz = y * s_z
+            for (int idx = tid; idx < QT; idx += NT) {
                 const int rr = idx / (TL / 4), ch = idx - rr * (TL / 4);
-                const int zoff = rr * TL + 4 * swz_chunk<T>(ch);   // exactly the chunk this thread just wrote
+                const int zoff = rr * TL + 4 * swz_chunk<T>(ch);
                 float4 z4 = *reinterpret_cast<const float4 *>(s_z + zoff);
                 float4 g4 = *reinterpret_cast<const float4 *>(s_g + zoff);
                 float *zz = reinterpret_cast<float *>(&z4), *gg = reinterpret_cast<float *>(&g4);
@@ -150,32 +205,22 @@ __global__ void __launch_bounds__(32 * RQ * NGW, (AGG ? 512 : 384) / (32 * RQ * 
                 *reinterpret_cast<float4 *>(s_g + zoff) = g4;
             }
         }
-        if (!AGG) {
-            load_tile<IN_T, T, TL, NT>(s_u, u_b, p.u_ds, row0, R, D, t0, L, rev, p.vec_mask & 1u, tid, 0.f,
-                                       [](int, float v) { return v; });
-            load_tile<IN_T, T, TL, NT>(s_B, B_b, p.B_ns, 0, Ne, N, t0, L, rev, p.vec_mask & 16u, tid, 0.f,
-                                       [](int, float v) { return v; });
-            for (int i = tid; i < R * Ne; i += NT) {
-                const int r = i / Ne, n = i - r * Ne, row = row0 + r;
-                s_hin[i] = (c > 0 && row < D && n < N) ? p.x[(((int64_t)b * D + row) * p.nx + (c - 1)) * N + n] : 0.f;
-            }
-        }
         __syncthreads();
+        cur_fast = fast_all && c > c_begin;    // every chunk before the last one of the sequence is full
+        if (cur_fast) prefetch(c - 1);
 
         float dl[T], dlu[T], dy[T];
-        {
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const int off = lr * TL + 4 * swz_chunk<T>(j * 2 + cc);
-                const float4 d4 = *reinterpret_cast<const float4 *>(s_dl + off);
-                const float4 g4 = *reinterpret_cast<const float4 *>(s_g + off);
-                float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (!AGG) u4 = *reinterpret_cast<const float4 *>(s_u + off);
-                dl[4 * cc] = d4.x, dl[4 * cc + 1] = d4.y, dl[4 * cc + 2] = d4.z, dl[4 * cc + 3] = d4.w;
-                dy[4 * cc] = g4.x, dy[4 * cc + 1] = g4.y, dy[4 * cc + 2] = g4.z, dy[4 * cc + 3] = g4.w;
-                dlu[4 * cc] = d4.x * u4.x, dlu[4 * cc + 1] = d4.y * u4.y, dlu[4 * cc + 2] = d4.z * u4.z,
-                         dlu[4 * cc + 3] = d4.w * u4.w;
-            }
+        for (int cc = 0; cc < 2; ++cc) {
+            const int off = cc ? off_t1 : off_t0;
+            const float4 d4 = *reinterpret_cast<const float4 *>(s_dl + off);
+            const float4 g4 = *reinterpret_cast<const float4 *>(s_g + off);
+            float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!AGG) u4 = *reinterpret_cast<const float4 *>(s_u + off);
+            dl[4 * cc] = d4.x, dl[4 * cc + 1] = d4.y, dl[4 * cc + 2] = d4.z, dl[4 * cc + 3] = d4.w;
+            dy[4 * cc] = g4.x, dy[4 * cc + 1] = g4.y, dy[4 * cc + 2] = g4.z, dy[4 * cc + 3] = g4.w;
+            dlu[4 * cc] = d4.x * u4.x, dlu[4 * cc + 1] = d4.y * u4.y, dlu[4 * cc + 2] = d4.z * u4.z,
+                     dlu[4 * cc + 3] = d4.w * u4.w;
         }
         if (AGG) {
 #pragma unroll
@@ -186,25 +231,20 @@ __global__ void __launch_bounds__(32 * RQ * NGW, (AGG ? 512 : 384) / (32 * RQ * 
 #pragma unroll
         for (int i = 0; i < T; ++i) S1[i] = S2[i] = yv[i] = make_float2(0.f, 0.f);
 
-        for (int pr = pair0; pr < pair1; ++pr) {
-            const float2 A2 = *reinterpret_cast<const float2 *>(s_A2 + lr * Ne + 2 * pr);
+        const float *pB = s_B + pair0 * 2 * TL, *pC = s_C + pair0 * 2 * TL;
+        int tab = lr * Ne + 2 * pair0;          // offset of my (row, pair) in the [R][Ne] tables
+        float *pdbc = s_dbc + ((wq * NP + pair0) * 4 + rg) * TL + j * T;
+        float2 *pdA = reinterpret_cast<float2 *>(s_dA) + (lr * NP + pair0) * 8 + j;
+        for (int pr = pair0; pr < pair1; ++pr, pB += 2 * TL, pC += 2 * TL, tab += 2, pdbc += 4 * TL, pdA += 8) {
+            const float2 A2 = *reinterpret_cast<const float2 *>(s_A2 + tab);
             float2 a[T], Cv[T], Bv[T];
-            {
-                const float *sC0 = s_C + (2 * pr) * TL, *sC1 = sC0 + TL;
-                const float *sB0 = s_B + (2 * pr) * TL, *sB1 = sB0 + TL;
 #pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int off = 4 * swz_chunk<T>(j * 2 + cc);
-                    const float4 c0 = *reinterpret_cast<const float4 *>(sC0 + off);
-                    const float4 c1 = *reinterpret_cast<const float4 *>(sC1 + off);
-                    Cv[4 * cc] = make_float2(c0.x, c1.x), Cv[4 * cc + 1] = make_float2(c0.y, c1.y);
-                    Cv[4 * cc + 2] = make_float2(c0.z, c1.z), Cv[4 * cc + 3] = make_float2(c0.w, c1.w);
-                    if (!AGG) {
-                        const float4 b0 = *reinterpret_cast<const float4 *>(sB0 + off);
-                        const float4 b1 = *reinterpret_cast<const float4 *>(sB1 + off);
-                        Bv[4 * cc] = make_float2(b0.x, b1.x), Bv[4 * cc + 1] = make_float2(b0.y, b1.y);
-                        Bv[4 * cc + 2] = make_float2(b0.z, b1.z), Bv[4 * cc + 3] = make_float2(b0.w, b1.w);
-                    }
+            for (int cc = 0; cc < 4; ++cc) {
+                const float4 c4 = *reinterpret_cast<const float4 *>(pC + off_bc[cc]);
+                Cv[2 * cc] = make_float2(c4.x, c4.y), Cv[2 * cc + 1] = make_float2(c4.z, c4.w);
+                if (!AGG) {
+                    const float4 b4 = *reinterpret_cast<const float4 *>(pB + off_bc[cc]);
+                    Bv[2 * cc] = make_float2(b4.x, b4.y), Bv[2 * cc + 1] = make_float2(b4.z, b4.w);
                 }
             }
 #pragma unroll
@@ -227,13 +267,13 @@ __global__ void __launch_bounds__(32 * RQ * NGW, (AGG ? 512 : 384) / (32 * RQ * 
                         P = fmul2(P, Pn);
                     }
                 }
-                const float2 hc = *reinterpret_cast<const float2 *>(s_hin + lr * Ne + 2 * pr);
+                const float2 hc = *reinterpret_cast<const float2 *>(s_hin + tab);
                 const float2 send = ffma2(P, hc, hl);
                 hs = shfl_up2(send, 1, 8);
                 if (j == 0) hs = hc;
             }
             // ---- reverse: dh at the first token of the lane to my right ---------------------------------------
-            float *dhc_p = s_dhc + lr * Ne + 2 * pr, *an_p = s_an + lr * Ne + 2 * pr;
+            float *dhc_p = s_dhc + tab, *an_p = s_an + tab;
             float2 a_nl = shfl_down2(a[0], 1, 8);   // a of the first token of the next lane
             if (j == 7) a_nl = *reinterpret_cast<const float2 *>(an_p);
             float2 dhn;
@@ -275,7 +315,7 @@ __global__ void __launch_bounds__(32 * RQ * NGW, (AGG ? 512 : 384) / (32 * RQ * 
                 }
             }
             // ---- reverse sweep: consume -----------------------------------------------------------------------------
-            const float2 Av = *reinterpret_cast<const float2 *>(s_A + lr * Ne + 2 * pr);
+            const float2 Av = *reinterpret_cast<const float2 *>(s_A + tab);
             float2 e = fmul2(a_nl, dhn);   // a_{t+1} * dh_{t+1} for my last token
             float2 dAacc = make_float2(0.f, 0.f);
             float red[T];
@@ -299,20 +339,15 @@ __global__ void __launch_bounds__(32 * RQ * NGW, (AGG ? 512 : 384) / (32 * RQ * 
                 const float k1 = lo ? keep.y : keep.x, s1 = lo ? keep.x : keep.y;
                 red[i] = k1 + __shfl_xor_sync(0xffffffffu, s1, 8);
             }
-            {
-                float *dst = s_dbc + ((wq * NP + pr) * 4 + rg) * TL + j * T;
-                *reinterpret_cast<float4 *>(dst) = make_float4(red[0], red[1], red[2], red[3]);
-                *reinterpret_cast<float4 *>(dst + 4) = make_float4(red[4], red[5], red[6], red[7]);
-                float2 *dAp = reinterpret_cast<float2 *>(s_dA) + (lr * NP + pr) * 8 + j;
-                *dAp = fadd2(*dAp, dAacc);
-            }
+            *reinterpret_cast<float4 *>(pdbc) = make_float4(red[0], red[1], red[2], red[3]);
+            *reinterpret_cast<float4 *>(pdbc + 4) = make_float4(red[4], red[5], red[6], red[7]);
+            *pdA = fadd2(*pdA, dAacc);
         }
         if (AGG) continue;
 
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
-            const int off = lr * TL + 4 * swz_chunk<T>(j * 2 + cc);
-            float *pp = s_part + (g * 3) * R * TL + off;
+            float *pp = s_part + (g * 3) * R * TL + (cc ? off_t1 : off_t0);
             *reinterpret_cast<float4 *>(pp) = make_float4(S1[4 * cc].x + S1[4 * cc].y, S1[4 * cc + 1].x + S1[4 * cc + 1].y,
                                                           S1[4 * cc + 2].x + S1[4 * cc + 2].y, S1[4 * cc + 3].x + S1[4 * cc + 3].y);
             *reinterpret_cast<float4 *>(pp + R * TL) =
@@ -324,47 +359,59 @@ __global__ void __launch_bounds__(32 * RQ * NGW, (AGG ? 512 : 384) / (32 * RQ * 
         }
         __syncthreads();
 
-        // ---- epilogue A: per-(row,token) gradients; one warp per row, two tokens per lane ---------------------------
-        for (int r = warp; r < R; r += NW) {
-            const int off = r * TL + 2 * lane;   // raw position
-            float2 s1 = make_float2(0.f, 0.f), s2 = s1, yy = s1;
+        // ---- epilogue A: per-(row,token) gradients, one quad per thread, stored straight to global ------------------------
+        {
+            IN_T *du_b = reinterpret_cast<IN_T *>(p.du) + (int64_t)b * p.du_bs;
+            IN_T *dd_b = reinterpret_cast<IN_T *>(p.ddelta) + (int64_t)b * p.ddl_bs;
+            IN_T *dz_b = has_z ? reinterpret_cast<IN_T *>(p.dz) + (int64_t)b * p.dz_bs : nullptr;
 #pragma unroll
-            for (int gg = 0; gg < NGW; ++gg) {
-                const float *pp = s_part + (gg * 3) * R * TL + off;
-                s1 = fadd2(s1, *reinterpret_cast<const float2 *>(pp));
-                s2 = fadd2(s2, *reinterpret_cast<const float2 *>(pp + R * TL));
-                yy = fadd2(yy, *reinterpret_cast<const float2 *>(pp + 2 * R * TL));
-            }
-            const float2 u2 = *reinterpret_cast<const float2 *>(s_u + off);
-            const float2 d2 = *reinterpret_cast<const float2 *>(s_dl + off);
-            const float2 g2 = *reinterpret_cast<const float2 *>(s_g + off);
-            const float Dk = s_D[r];
-            float2 du = ffma2(d2, s1, fmul2(splat(Dk), g2));         // D*dy + delta*S1   (bwd_kernel.cuh:211,280-281)
-            float2 dd = ffma2(u2, s1, s2);                           // u*S1 + S2         (:282-283)
-            if (sp) {                                                // d softplus = sigmoid(x) = 1 - exp(-softplus(x))
-                dd.x *= 1.f - __expf(-d2.x);
-                dd.y *= 1.f - __expf(-d2.y);
-            }
-            float pdD = g2.x * u2.x + g2.y * u2.y, pdb = dd.x + dd.y;
+            for (int k = 0; k < KR; ++k) {
+                const int idx = tid + k * NT;
+                if (idx >= QT) continue;
+                const int r = idx / (TL / 4), cs = idx - r * (TL / 4);
+                const int off = idx * 4;   // raw (swizzled) position
+                float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1, yy = s1;
 #pragma unroll
-            for (int k = 16; k > 0; k >>= 1) {
-                pdD += __shfl_xor_sync(0xffffffffu, pdD, k);
-                pdb += __shfl_xor_sync(0xffffffffu, pdb, k);
-            }
-            if (lane == 0) {
-                s_dD[r] += pdD;
-                s_db[r] += pdb;
-            }
-            *reinterpret_cast<float2 *>(s_u + off) = du;
-            *reinterpret_cast<float2 *>(s_dl + off) = dd;
-            if (has_z) {
-                const float2 zf = *reinterpret_cast<const float2 *>(s_z + off);
-                yy = ffma2(splat(Dk), u2, yy);
-                *reinterpret_cast<float2 *>(s_z + off) = fmul2(yy, zf);
+                for (int gg = 0; gg < NGW; ++gg) {
+                    const float *pp = s_part + (gg * 3) * R * TL + off;
+                    const float4 a1 = *reinterpret_cast<const float4 *>(pp);
+                    const float4 a2 = *reinterpret_cast<const float4 *>(pp + R * TL);
+                    const float4 a3 = *reinterpret_cast<const float4 *>(pp + 2 * R * TL);
+                    s1.x += a1.x, s1.y += a1.y, s1.z += a1.z, s1.w += a1.w;
+                    s2.x += a2.x, s2.y += a2.y, s2.z += a2.z, s2.w += a2.w;
+                    yy.x += a3.x, yy.y += a3.y, yy.z += a3.z, yy.w += a3.w;
+                }
+                const float4 u4 = *reinterpret_cast<const float4 *>(s_u + off);
+                const float4 d4 = *reinterpret_cast<const float4 *>(s_dl + off);
+                const float4 g4 = *reinterpret_cast<const float4 *>(s_g + off);
+                const float Dk = s_D[r];
+                const float uu[4] = {u4.x, u4.y, u4.z, u4.w}, dd_[4] = {d4.x, d4.y, d4.z, d4.w};
+                const float gg_[4] = {g4.x, g4.y, g4.z, g4.w}, S1[4] = {s1.x, s1.y, s1.z, s1.w};
+                const float S2[4] = {s2.x, s2.y, s2.z, s2.w}, Y[4] = {yy.x, yy.y, yy.z, yy.w};
+                float du[4], dd[4], dzv[4];
+                float4 zf = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_z) zf = *reinterpret_cast<const float4 *>(s_z + off);
+                const float ZF[4] = {zf.x, zf.y, zf.z, zf.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    du[e] = fmaf(dd_[e], S1[e], Dk * gg_[e]);          // D*dy + delta*S1   (bwd_kernel.cuh:211,280-281)
+                    float t_ = fmaf(uu[e], S1[e], S2[e]);               // u*S1 + S2         (:282-283)
+                    if (sp) t_ *= 1.f - __expf(-dd_[e]);                // softplus' = sigmoid(x) = 1 - exp(-softplus(x))
+                    dd[e] = t_;
+                    dzv[e] = fmaf(Dk, uu[e], Y[e]) * ZF[e];
+                    acc_dD[k] = fmaf(gg_[e], uu[e], acc_dD[k]);
+                    acc_db[k] += t_;
+                }
+                const int row = row0 + r, t = t0 + 4 * swz_chunk<T>(cs);
+                if (row < D && t < L) {
+                    store_quad<IN_T>(du_b + (int64_t)row * p.du_ds, t, L, rev, p.vec_mask & 64u, du);
+                    store_quad<IN_T>(dd_b + (int64_t)row * p.ddl_ds, t, L, rev, p.vec_mask & 128u, dd);
+                    if (has_z) store_quad<IN_T>(dz_b + (int64_t)row * p.dz_ds, t, L, rev, p.vec_mask & 256u, dzv);
+                }
             }
         }
         // ---- epilogue B: dB / dC -> global (sum over the CTA's row-warps, then one atomic per element) ---------------
-        {
+        if (!p.dbg_no_atomics) {
             float *dB_b = p.dB + (int64_t)b * N * L, *dC_b = p.dC + (int64_t)b * N * L;
             for (int idx = tid; idx < NP * 4 * TL; idx += NT) {
                 const int tok = idx % TL, kind = (idx / TL) & 3, pr = idx / (4 * TL);
@@ -375,14 +422,6 @@ __global__ void __launch_bounds__(32 * RQ * NGW, (AGG ? 512 : 384) / (32 * RQ * 
                 if (n < N && t < L) atomicAdd(((kind & 2) ? dC_b : dB_b) + (int64_t)n * L + (rev ? L - 1 - t : t), v);
             }
         }
-        __syncthreads();
-        store_tile<IN_T, T, TL, NT>(s_u, reinterpret_cast<IN_T *>(p.du) + (int64_t)b * p.du_bs, p.du_ds, row0, R, D, t0, L,
-                                    rev, p.vec_mask & 64u, tid);
-        store_tile<IN_T, T, TL, NT>(s_dl, reinterpret_cast<IN_T *>(p.ddelta) + (int64_t)b * p.ddl_bs, p.ddl_ds, row0, R, D,
-                                    t0, L, rev, p.vec_mask & 128u, tid);
-        if (has_z)
-            store_tile<IN_T, T, TL, NT>(s_z, reinterpret_cast<IN_T *>(p.dz) + (int64_t)b * p.dz_bs, p.dz_ds, row0, R, D, t0,
-                                        L, rev, p.vec_mask & 256u, tid);
     }
 
     __syncthreads();
@@ -413,6 +452,15 @@ __global__ void __launch_bounds__(32 * RQ * NGW, (AGG ? 512 : 384) / (32 * RQ * 
                 atomicAdd(p.dA + (int64_t)row * N + n, v);           // sum over batch and segments
             }
         }
+#pragma unroll
+        for (int k = 0; k < KR; ++k) {
+            const int idx = tid + k * NT;
+            if (idx < QT) {
+                atomicAdd(s_dD + idx / (TL / 4), acc_dD[k]);
+                atomicAdd(s_db + idx / (TL / 4), acc_db[k]);
+            }
+        }
+        __syncthreads();
         for (int r = tid; r < R; r += NT) {
             const int row = row0 + r;
             if (row < D) {
@@ -468,7 +516,7 @@ BwdPlan plan_bwd(int B, int D, int L) {
     pl.nchunks = (L + 63) / 64;
     const int warps = B * ((D + pl.R - 1) / pl.R) * RQ * NGW;
     const int target = 148 * 12;
-    int nseg = (target + warps - 1) / warps;
+    int nseg = warps >= 148 * 6 ? 1 : (target + warps - 1) / warps;   // splitting costs a second pass: only when starved
     nseg = std::min(nseg, std::max(1, pl.nchunks / 8));
     nseg = std::max(1, std::min(nseg, 64));
     nseg = env_int("MMU_BWD_NSEG", nseg);
@@ -520,6 +568,7 @@ template <typename IN_T> int run_bwd(const mmu_scan_bwd_params *p, cudaStream_t 
     a.nseg = pl.nseg, a.cps = pl.cps, a.nchunks = pl.nchunks;
     a.nx = (f.seqlen + MMU_STATE_STRIDE - 1) / MMU_STATE_STRIDE;
     a.softplus = f.delta_softplus, a.reverse = f.reverse;
+    a.dbg_no_atomics = env_int("MMU_BWD_NOATOM", 0);
     const bool rev = f.reverse != 0;
     const int L = f.seqlen;
     a.vec_mask = (quad_ok<IN_T>(f.u, f.u_bs, f.u_ds, L, rev) ? 1u : 0u) |
@@ -531,6 +580,8 @@ template <typename IN_T> int run_bwd(const mmu_scan_bwd_params *p, cudaStream_t 
                  (quad_ok<IN_T>(p->du, p->du_bs, p->du_ds, L, rev) ? 64u : 0u) |
                  (quad_ok<IN_T>(p->ddelta, p->ddelta_bs, p->ddelta_ds, L, rev) ? 128u : 0u) |
                  ((p->dz && quad_ok<IN_T>(p->dz, p->dz_bs, p->dz_ds, L, rev)) ? 256u : 0u);
+    const unsigned need = 1u | 2u | 8u | 16u | 32u | (f.z ? 4u : 0u);
+    if ((a.vec_mask & need) == need && a.Ne <= 16 && env_int("MMU_NO_PREFETCH", 0) == 0) a.vec_mask |= 0x8000u;
     if (pl.nseg > 1) {
         const size_t n_state = (size_t)a.B * a.D * pl.nseg * a.Ne, n_row = (size_t)a.B * a.D * pl.nseg;
         const size_t need = 2 * align256(n_state * 4) + 2 * align256(n_row * 4);

@@ -36,19 +36,20 @@ struct FwdArgs {
     unsigned vec_mask;   // bit0 u, 1 delta, 2 z, 3 out, 4 B, 5 C
 };
 
-template <int T, int RD, int RQ, int NGW> struct FwdCfg {
-    static constexpr int LS = 8, RG = 4;
+template <int RD, int RQ, int NGW> struct FwdCfg {
+    static constexpr int T = 8, LS = 8, RG = 4;
     static constexpr int WROWS = RG * RD, R = RQ * WROWS, TL = LS * T, NT = 32 * RQ * NGW, CPT = T / 4;
+    static_assert(TL == MMU_STATE_STRIDE, "one saved state per chunk");
     static size_t smem_bytes(int Ne) {
         return sizeof(float) * ((size_t)3 * R * TL + 2 * (size_t)Ne * TL + (size_t)NGW * R * TL + 2 * (size_t)R * Ne +
                                 2 * R);
     }
 };
 
-template <typename IN_T, int T, int RD, int RQ, int NGW, bool AGG>
-__global__ void __launch_bounds__(32 * RQ * NGW) scan_fwd_kernel(const __grid_constant__ FwdArgs p) {
-    using Cfg = FwdCfg<T, RD, RQ, NGW>;
-    constexpr int R = Cfg::R, TL = Cfg::TL, NT = Cfg::NT, CPT = Cfg::CPT, WROWS = Cfg::WROWS;
+template <typename IN_T, int RD, int RQ, int NGW, bool AGG>
+__global__ void __launch_bounds__(32 * RQ * NGW, 512 / (32 * RQ * NGW)) scan_fwd_kernel(const __grid_constant__ FwdArgs p) {
+    using Cfg = FwdCfg<RD, RQ, NGW>;
+    constexpr int T = Cfg::T, R = Cfg::R, TL = Cfg::TL, NT = Cfg::NT, CPT = Cfg::CPT, WROWS = Cfg::WROWS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wq = warp / NGW, g = warp % NGW, rg = lane >> 3, j = lane & 7;
     const int b = blockIdx.y, row0 = blockIdx.x * R, seg = blockIdx.z;
@@ -58,9 +59,9 @@ __global__ void __launch_bounds__(32 * RQ * NGW) scan_fwd_kernel(const __grid_co
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *s_u = reinterpret_cast<float *>(smem_raw);   // [R][TL]
     float *s_dl = s_u + R * TL;                          // [R][TL]  softplus(delta + bias)
-    float *s_z = s_dl + R * TL;                          // [R][TL]  z, then the gated output
-    float *s_B = s_z + R * TL;                           // [Ne][TL]
-    float *s_C = s_B + Ne * TL;                          // [Ne][TL]
+    float *s_z = s_dl + R * TL;                          // [R][TL]
+    float *s_B = s_z + R * TL;                           // [NP][TL][2]  pair-interleaved
+    float *s_C = s_B + Ne * TL;                          // [NP][TL][2]
     float *s_yp = s_C + Ne * TL;                         // [NGW][R][TL] partial y per dstate group
     float *s_A2 = s_yp + NGW * R * TL;                   // [R][Ne]  A * log2(e)
     float *s_carry = s_A2 + R * Ne;                      // [R][Ne]  state entering the next chunk
@@ -91,35 +92,69 @@ __global__ void __launch_bounds__(32 * RQ * NGW) scan_fwd_kernel(const __grid_co
 
     const int npw = (NP + NGW - 1) / NGW;
     const int pair0 = g * npw, pair1 = min(NP, pair0 + npw);
-    int lr[RD];
+
+    // per-thread constant shared-memory offsets (hoisted out of every loop)
+    int off_t[RD][CPT];            // my T tokens inside a row tile
 #pragma unroll
-    for (int r = 0; r < RD; ++r) lr[r] = wq * WROWS + rg * RD + r;
+    for (int r = 0; r < RD; ++r)
+#pragma unroll
+        for (int cc = 0; cc < CPT; ++cc) off_t[r][cc] = (wq * WROWS + rg * RD + r) * TL + 4 * swz_chunk<T>(j * CPT + cc);
+    int off_bc[T / 2];             // my T tokens inside a pair-row of a B / C tile
+#pragma unroll
+    for (int cc = 0; cc < T / 2; ++cc) off_bc[cc] = bc_off(j * (T / 2) + cc);
+    const int lr0 = wq * WROWS + rg * RD;
 
     float dsum[RD];
 #pragma unroll
     for (int r = 0; r < RD; ++r) dsum[r] = 0.f;
 
+    // ---- chunk loop with register prefetch: the global loads of chunk c+1 are in flight while chunk c is scanned ----
+    constexpr int QT = R * (TL / 4);                      // quads of a row tile
+    constexpr int KR = (QT + NT - 1) / NT;
+    constexpr int K2 = (8 * (TL / 4) + NT - 1) / NT;      // pair-quads per thread of a B / C tile (fast path: dstate <= 16)
+    const bool fast_all = (p.vec_mask & 0x80u) != 0;      // every tensor vector-accessible and dstate <= 16 (host-checked)
+    Quad<IN_T> q_u[KR], q_dl[KR], q_z[KR], q_B[2 * K2], q_C[2 * K2];
+    auto ident = [](int, float v) { return v; };
+    auto dl_xf = [&](int r, float v) {
+        const float xx = v + s_bias[r];
+        return sp ? softplus_f(xx) : xx;
+    };
+    auto prefetch = [&](int c) {
+        const int t0 = c * TL;
+        tile_prefetch<IN_T, TL, NT, KR>(q_u, u_b, p.u_ds, row0, D, QT, t0, L, rev, tid);
+        tile_prefetch<IN_T, TL, NT, KR>(q_dl, dl_b, p.dl_ds, row0, D, QT, t0, L, rev, tid);
+        bc_prefetch<IN_T, TL, NT, K2>(q_B, B_b, p.B_ns, N, NP, t0, L, rev, tid);
+        if (!AGG) {
+            if (has_z) tile_prefetch<IN_T, TL, NT, KR>(q_z, z_b, p.z_ds, row0, D, QT, t0, L, rev, tid);
+            bc_prefetch<IN_T, TL, NT, K2>(q_C, C_b, p.C_ns, N, NP, t0, L, rev, tid);
+        }
+    };
     const int c_begin = seg * p.cps, c_end = min(p.nchunks, c_begin + p.cps);
+    bool cur_fast = fast_all && (c_begin + 1) * TL <= L;
+    if (cur_fast) prefetch(c_begin);
     for (int c = c_begin; c < c_end; ++c) {
         const int t0 = c * TL;
-        __syncthreads();   // tiles free (previous store finished), tables initialised
-        load_tile<IN_T, T, TL, NT>(s_u, u_b, p.u_ds, row0, R, D, t0, L, rev, p.vec_mask & 1u, tid, 0.f,
-                                   [](int, float v) { return v; });
-        load_tile<IN_T, T, TL, NT>(s_dl, dl_b, p.dl_ds, row0, R, D, t0, L, rev, p.vec_mask & 2u, tid, 0.f,
-                                   [&](int r, float v) {
-                                       const float xx = v + s_bias[r];
-                                       return sp ? softplus_f(xx) : xx;
-                                   });
-        load_tile<IN_T, T, TL, NT>(s_B, B_b, p.B_ns, 0, Ne, N, t0, L, rev, p.vec_mask & 16u, tid, 0.f,
-                                   [](int, float v) { return v; });
-        if (!AGG) {
-            if (has_z)
-                load_tile<IN_T, T, TL, NT>(s_z, z_b, p.z_ds, row0, R, D, t0, L, rev, p.vec_mask & 4u, tid, 0.f,
-                                           [](int, float v) { return v; });
-            load_tile<IN_T, T, TL, NT>(s_C, C_b, p.C_ns, 0, Ne, N, t0, L, rev, p.vec_mask & 32u, tid, 0.f,
-                                       [](int, float v) { return v; });
+        __syncthreads();   // tiles free (previous epilogue finished), tables initialised
+        if (cur_fast) {
+            tile_commit<IN_T, T, TL, NT, KR>(s_u, q_u, QT, rev, tid, ident);
+            tile_commit<IN_T, T, TL, NT, KR>(s_dl, q_dl, QT, rev, tid, dl_xf);
+            bc_commit<IN_T, TL, NT, K2>(s_B, q_B, NP, rev, tid);
+            if (!AGG) {
+                if (has_z) tile_commit<IN_T, T, TL, NT, KR>(s_z, q_z, QT, rev, tid, ident);
+                bc_commit<IN_T, TL, NT, K2>(s_C, q_C, NP, rev, tid);
+            }
+        } else {
+            load_tile<IN_T, T, TL, NT>(s_u, u_b, p.u_ds, row0, R, D, t0, L, rev, p.vec_mask & 1u, tid, 0.f, ident);
+            load_tile<IN_T, T, TL, NT>(s_dl, dl_b, p.dl_ds, row0, R, D, t0, L, rev, p.vec_mask & 2u, tid, 0.f, dl_xf);
+            bc_load_generic<IN_T, TL, NT>(s_B, B_b, p.B_ns, N, Ne, t0, L, rev, tid);
+            if (!AGG) {
+                if (has_z) load_tile<IN_T, T, TL, NT>(s_z, z_b, p.z_ds, row0, R, D, t0, L, rev, p.vec_mask & 4u, tid, 0.f, ident);
+                bc_load_generic<IN_T, TL, NT>(s_C, C_b, p.C_ns, N, Ne, t0, L, rev, tid);
+            }
         }
         __syncthreads();
+        cur_fast = fast_all && (c + 1) < c_end && (c + 2) * TL <= L;
+        if (cur_fast) prefetch(c + 1);
 
         // ---- per-(token,row) registers: delta and delta*u of my T tokens -------------------------------
         float dl[RD][T], dlu[RD][T];
@@ -127,9 +162,8 @@ __global__ void __launch_bounds__(32 * RQ * NGW) scan_fwd_kernel(const __grid_co
         for (int r = 0; r < RD; ++r) {
 #pragma unroll
             for (int cc = 0; cc < CPT; ++cc) {
-                const int off = lr[r] * TL + 4 * swz_chunk<T>(j * CPT + cc);
-                const float4 d4 = *reinterpret_cast<const float4 *>(s_dl + off);
-                const float4 u4 = *reinterpret_cast<const float4 *>(s_u + off);
+                const float4 d4 = *reinterpret_cast<const float4 *>(s_dl + off_t[r][cc]);
+                const float4 u4 = *reinterpret_cast<const float4 *>(s_u + off_t[r][cc]);
                 dl[r][4 * cc + 0] = d4.x, dl[r][4 * cc + 1] = d4.y, dl[r][4 * cc + 2] = d4.z, dl[r][4 * cc + 3] = d4.w;
                 dlu[r][4 * cc + 0] = d4.x * u4.x, dlu[r][4 * cc + 1] = d4.y * u4.y;
                 dlu[r][4 * cc + 2] = d4.z * u4.z, dlu[r][4 * cc + 3] = d4.w * u4.w;
@@ -145,32 +179,28 @@ __global__ void __launch_bounds__(32 * RQ * NGW) scan_fwd_kernel(const __grid_co
 #pragma unroll
             for (int i = 0; i < T; ++i) y2[r][i] = make_float2(0.f, 0.f);
 
-        for (int pr = pair0; pr < pair1; ++pr) {
+        const float *pB = s_B + pair0 * 2 * TL, *pC = s_C + pair0 * 2 * TL;
+        const float *pA2 = s_A2 + lr0 * Ne + 2 * pair0;
+        float *pcar = s_carry + lr0 * Ne + 2 * pair0;
+        for (int pr = pair0; pr < pair1; ++pr, pB += 2 * TL, pC += 2 * TL, pA2 += 2, pcar += 2) {
             float2 A2[RD], P[RD], hl[RD];
             float2 cp[RD][T];
 #pragma unroll
             for (int r = 0; r < RD; ++r) {
-                A2[r] = *reinterpret_cast<const float2 *>(s_A2 + lr[r] * Ne + 2 * pr);
+                A2[r] = *reinterpret_cast<const float2 *>(pA2 + r * Ne);
                 P[r] = make_float2(1.f, 1.f);
                 hl[r] = make_float2(0.f, 0.f);
             }
-            const float *sB0 = s_B + (2 * pr) * TL, *sB1 = sB0 + TL;
-            const float *sC0 = s_C + (2 * pr) * TL, *sC1 = sC0 + TL;
 #pragma unroll
-            for (int cc = 0; cc < CPT; ++cc) {
-                const int off = 4 * swz_chunk<T>(j * CPT + cc);
-                const float4 b0 = *reinterpret_cast<const float4 *>(sB0 + off);
-                const float4 b1 = *reinterpret_cast<const float4 *>(sB1 + off);
-                float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
-                if (!AGG) {
-                    c0 = *reinterpret_cast<const float4 *>(sC0 + off);
-                    c1 = *reinterpret_cast<const float4 *>(sC1 + off);
-                }
-                const float2 Bv[4] = {{b0.x, b1.x}, {b0.y, b1.y}, {b0.z, b1.z}, {b0.w, b1.w}};
-                const float2 Cv[4] = {{c0.x, c1.x}, {c0.y, c1.y}, {c0.z, c1.z}, {c0.w, c1.w}};
+            for (int cc = 0; cc < T / 2; ++cc) {
+                const float4 b4 = *reinterpret_cast<const float4 *>(pB + off_bc[cc]);    // (B_2p, B_2p+1) of two tokens
+                float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!AGG) c4 = *reinterpret_cast<const float4 *>(pC + off_bc[cc]);
+                const float2 Bv[2] = {make_float2(b4.x, b4.y), make_float2(b4.z, b4.w)};
+                const float2 Cv[2] = {make_float2(c4.x, c4.y), make_float2(c4.z, c4.w)};
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int i = 4 * cc + k;
+                for (int k = 0; k < 2; ++k) {
+                    const int i = 2 * cc + k;
 #pragma unroll
                     for (int r = 0; r < RD; ++r) {
                         const float2 a = ex2(fmul2(splat(dl[r][i]), A2[r]));
@@ -196,23 +226,13 @@ __global__ void __launch_bounds__(32 * RQ * NGW) scan_fwd_kernel(const __grid_co
                         Pi = fmul2(Pi, Pn);
                     }
                 }
-                float *cptr = s_carry + lr[r] * Ne + 2 * pr;
-                const float2 hc = *reinterpret_cast<const float2 *>(cptr);
+                const float2 hc = *reinterpret_cast<const float2 *>(pcar + r * Ne);
                 const float2 send = ffma2(Pi, hc, Hi);   // state after my last token
                 float2 hs = shfl_up2(send, 1, 8);        // state before my first token
                 if (j == 0) hs = hc;
                 __syncwarp();
-                if (j == 7) *reinterpret_cast<float2 *>(cptr) = send;
+                if (j == 7) *reinterpret_cast<float2 *>(pcar + r * Ne) = send;
                 if (!AGG) {
-                    if (p.x != nullptr && (((j + 1) * T) % MMU_STATE_STRIDE) == 0) {
-                        const int kk = (t0 + (j + 1) * T) / MMU_STATE_STRIDE - 1;
-                        const int row = row0 + lr[r];
-                        if (kk < p.nx && row < D) {
-                            float *xp = p.x + (((int64_t)b * D + row) * p.nx + kk) * N + 2 * pr;
-                            xp[0] = send.x;
-                            if (2 * pr + 1 < N) xp[1] = send.y;
-                        }
-                    }
 #pragma unroll
                     for (int i = 0; i < T; ++i) y2[r][i] = ffma2(cp[r][i], hs, y2[r][i]);
                 }
@@ -224,17 +244,15 @@ __global__ void __launch_bounds__(32 * RQ * NGW) scan_fwd_kernel(const __grid_co
 #pragma unroll
         for (int r = 0; r < RD; ++r)
 #pragma unroll
-            for (int cc = 0; cc < CPT; ++cc) {
-                const int off = (g * R + lr[r]) * TL + 4 * swz_chunk<T>(j * CPT + cc);
-                *reinterpret_cast<float4 *>(s_yp + off) =
+            for (int cc = 0; cc < CPT; ++cc)
+                *reinterpret_cast<float4 *>(s_yp + g * R * TL + off_t[r][cc]) =
                     make_float4(y2[r][4 * cc].x + y2[r][4 * cc].y, y2[r][4 * cc + 1].x + y2[r][4 * cc + 1].y,
                                 y2[r][4 * cc + 2].x + y2[r][4 * cc + 2].y, y2[r][4 * cc + 3].x + y2[r][4 * cc + 3].y);
-            }
         __syncthreads();
-        // ---- epilogue: sum groups, D skip, SiLU gate (selective_scan_fwd_kernel.cuh:158,280-298) ---------------
-        for (int idx = tid; idx < R * (TL / 4); idx += NT) {
-            const int r = idx / (TL / 4);
-            const int off = idx * 4;   // raw (swizzled) position: all tiles share the layout
+        // ---- epilogue: sum groups, D skip, SiLU gate (selective_scan_fwd_kernel.cuh:158,280-298), store to global ----
+        for (int idx = tid; idx < QT; idx += NT) {
+            const int r = idx / (TL / 4), cs = idx - r * (TL / 4);
+            const int off = idx * 4;   // raw (swizzled) position: all row tiles share the layout
             float4 y = *reinterpret_cast<const float4 *>(s_yp + off);
 #pragma unroll
             for (int gg = 1; gg < NGW; ++gg) {
@@ -249,10 +267,19 @@ __global__ void __launch_bounds__(32 * RQ * NGW) scan_fwd_kernel(const __grid_co
                 y.x *= z4.x * sigmoid_f(z4.x), y.y *= z4.y * sigmoid_f(z4.y);
                 y.z *= z4.z * sigmoid_f(z4.z), y.w *= z4.w * sigmoid_f(z4.w);
             }
-            *reinterpret_cast<float4 *>(s_z + off) = y;
+            const int row = row0 + r, t = t0 + 4 * swz_chunk<T>(cs);   // the swizzle is an involution
+            if (row < D && t < L) {
+                const float v[4] = {y.x, y.y, y.z, y.w};
+                store_quad<IN_T>(o_b + (int64_t)row * p.o_ds, t, L, rev, p.vec_mask & 8u, v);
+            }
         }
-        __syncthreads();
-        store_tile<IN_T, T, TL, NT>(s_z, o_b, p.o_ds, row0, R, D, t0, L, rev, p.vec_mask & 8u, tid);
+        // ---- the state after this chunk = x[b][row][c][:]  (chunk length == MMU_STATE_STRIDE) --------------------------
+        if (p.x != nullptr && c < p.nx) {
+            for (int i = tid; i < R * Ne; i += NT) {
+                const int r = i / Ne, n = i - r * Ne, row = row0 + r;
+                if (row < D && n < N) p.x[(((int64_t)b * D + row) * p.nx + c) * N + n] = s_carry[i];
+            }
+        }
     }
 
     __syncthreads();
@@ -268,7 +295,7 @@ __global__ void __launch_bounds__(32 * RQ * NGW) scan_fwd_kernel(const __grid_co
                 s += __shfl_xor_sync(0xffffffffu, s, 1);
                 s += __shfl_xor_sync(0xffffffffu, s, 2);
                 s += __shfl_xor_sync(0xffffffffu, s, 4);
-                const int row = row0 + lr[r];
+                const int row = row0 + lr0 + r;
                 if (j == 0 && row < D) p.seg_dsum[((int64_t)b * D + row) * p.nseg + seg] = s;
             }
         }
@@ -306,13 +333,14 @@ struct FwdPlan {
     int nseg, cps, nchunks;
 };
 
-// instantiation table: {T, RD, RQ, NGW}
-constexpr int kNumFwdCfg = 4;
-constexpr int kFwdCfg[kNumFwdCfg][4] = {
-    {16, 1, 2, 4},   // 0: wide default   (8 rows, 8 warps)
-    {16, 1, 4, 2},   // 1: wide, more rows per CTA (16 rows, 8 warps)
-    {16, 1, 1, 4},   // 2: narrow (4 rows, 4 warps)
-    {8, 2, 2, 4},    // 3: two rows per lane (16 rows, 8 warps)
+// instantiation table: {RD, RQ, NGW}
+constexpr int kNumFwdCfg = 5;
+constexpr int kFwdCfg[kNumFwdCfg][3] = {
+    {1, 2, 2},   // 0:  8 rows, 4 warps
+    {1, 1, 4},   // 1:  4 rows, 4 warps (narrow D)
+    {1, 4, 2},   // 2: 16 rows, 8 warps
+    {1, 2, 4},   // 3:  8 rows, 8 warps
+    {2, 2, 2},   // 4: 16 rows, 4 warps, two rows per lane
 };
 
 int env_int(const char *name, int dflt) {
@@ -322,16 +350,16 @@ int env_int(const char *name, int dflt) {
 
 FwdPlan plan_fwd(int B, int D, int L, int /*N*/) {
     FwdPlan pl;
-    pl.cfg = D <= 8 ? 2 : 0;
+    pl.cfg = D <= 4 ? 1 : 0;
     pl.cfg = env_int("MMU_FWD_CFG", pl.cfg);
     if (pl.cfg < 0 || pl.cfg >= kNumFwdCfg) pl.cfg = 0;
     const int *c = kFwdCfg[pl.cfg];
-    pl.R = c[2] * 4 * c[1];
-    pl.TL = 8 * c[0];
+    pl.R = c[1] * 4 * c[0];
+    pl.TL = 64;
     pl.nchunks = (L + pl.TL - 1) / pl.TL;
-    const int warps = B * ((D + pl.R - 1) / pl.R) * c[2] * c[3];
+    const int warps = B * ((D + pl.R - 1) / pl.R) * c[1] * c[2];
     const int target = 148 * 16;
-    int nseg = (target + warps - 1) / warps;
+    int nseg = warps >= 148 * 6 ? 1 : (target + warps - 1) / warps;   // splitting costs a second pass: only when starved
     nseg = std::min(nseg, std::max(1, pl.nchunks / 4));   // at least 4 chunks per segment
     nseg = std::max(1, std::min(nseg, 64));
     nseg = env_int("MMU_FWD_NSEG", nseg);
@@ -341,18 +369,18 @@ FwdPlan plan_fwd(int B, int D, int L, int /*N*/) {
     return pl;
 }
 
-template <typename IN_T, int T, int RD, int RQ, int NGW>
+template <typename IN_T, int RD, int RQ, int NGW>
 int launch_fwd(const FwdArgs &a, bool agg, cudaStream_t st) {
-    using Cfg = FwdCfg<T, RD, RQ, NGW>;
+    using Cfg = FwdCfg<RD, RQ, NGW>;
     const size_t smem = Cfg::smem_bytes(a.Ne);
     if (smem > 227 * 1024) return set_error(MMU_ERR_UNSUPPORTED, "selective_scan_fwd: dstate %d needs %zu B smem", a.N, smem);
     dim3 grid((a.D + Cfg::R - 1) / Cfg::R, a.B, a.nseg), block(Cfg::NT);
     if (agg) {
-        auto k = scan_fwd_kernel<IN_T, T, RD, RQ, NGW, true>;
+        auto k = scan_fwd_kernel<IN_T, RD, RQ, NGW, true>;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k<<<grid, block, smem, st>>>(a);
     } else {
-        auto k = scan_fwd_kernel<IN_T, T, RD, RQ, NGW, false>;
+        auto k = scan_fwd_kernel<IN_T, RD, RQ, NGW, false>;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k<<<grid, block, smem, st>>>(a);
     }
@@ -362,10 +390,11 @@ int launch_fwd(const FwdArgs &a, bool agg, cudaStream_t st) {
 
 template <typename IN_T> int dispatch_fwd(int cfg, const FwdArgs &a, bool agg, cudaStream_t st) {
     switch (cfg) {
-        case 0: return launch_fwd<IN_T, 16, 1, 2, 4>(a, agg, st);
-        case 1: return launch_fwd<IN_T, 16, 1, 4, 2>(a, agg, st);
-        case 2: return launch_fwd<IN_T, 16, 1, 1, 4>(a, agg, st);
-        default: return launch_fwd<IN_T, 8, 2, 2, 4>(a, agg, st);
+        case 0: return launch_fwd<IN_T, 1, 2, 2>(a, agg, st);
+        case 1: return launch_fwd<IN_T, 1, 1, 4>(a, agg, st);
+        case 2: return launch_fwd<IN_T, 1, 4, 2>(a, agg, st);
+        case 3: return launch_fwd<IN_T, 1, 2, 4>(a, agg, st);
+        default: return launch_fwd<IN_T, 2, 2, 2>(a, agg, st);
     }
 }
 
@@ -392,6 +421,8 @@ template <typename IN_T> int run_fwd(const mmu_scan_fwd_params *p, cudaStream_t 
                  (quad_ok<IN_T>(p->out, p->out_bs, p->out_ds, L, rev) ? 8u : 0u) |
                  (quad_ok<IN_T>(p->B, p->B_bs, p->B_ns, L, rev) ? 16u : 0u) |
                  (quad_ok<IN_T>(p->C, p->C_bs, p->C_ns, L, rev) ? 32u : 0u);
+    const unsigned need = 1u | 2u | 16u | 32u | (p->z ? 4u : 0u);
+    if ((a.vec_mask & need) == need && a.Ne <= 16 && env_int("MMU_NO_PREFETCH", 0) == 0) a.vec_mask |= 0x80u;
     if (pl.nseg > 1) {
         const size_t n_state = (size_t)a.B * a.D * pl.nseg * a.Ne;
         const size_t need = 2 * align256(n_state * 4) + align256((size_t)a.B * a.D * pl.nseg * 4);

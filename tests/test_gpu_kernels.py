@@ -142,7 +142,7 @@ def test_scan_sequence_split_matches(nseg, monkeypatch):
     run_scan_case(1, 3, 4096, 16, reverse=True)
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
 def test_scan_fwd_all_tilings(cfg, monkeypatch):
     monkeypatch.setenv("MMU_FWD_CFG", str(cfg))
     run_scan_case(2, 20, 700, 16)
@@ -187,7 +187,7 @@ def test_scan_full_size_properties():
     o2, _, _ = ops.selective_scan_fwd(gpu["u"][1:2, sub].contiguous(), gpu["delta"][1:2, sub].contiguous(), gpu["A"][sub],
                                       gpu["B"][1:2], gpu["C"][1:2], gpu["D"][sub], gpu["z"][1:2, sub].contiguous(),
                                       gpu["delta_bias"][sub], True)
-    assert torch.allclose(out[1:2, sub], o2, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(out[1:2, sub], o2, rtol=1e-4, atol=1e-4)     # different dstate-group split -> different fp32 summation order
     n = lambda t: t[1:2, sub].numpy() if t.dim() == 3 else t
     ro, _ = oracle.selective_scan_fwd(n(cpu["u"]), n(cpu["delta"]), cpu["A"][sub].numpy(), cpu["B"][1:2].numpy(),
                                       cpu["C"][1:2].numpy(), cpu["D"][sub].numpy(), n(cpu["z"]), cpu["delta_bias"][sub].numpy(), True)
