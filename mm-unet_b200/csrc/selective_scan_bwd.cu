@@ -43,12 +43,12 @@ template <int RQ, int NGW> struct BwdCfg {
     static_assert(TL == MMU_STATE_STRIDE, "backward chunk == saved-state stride");
     static size_t smem_floats(int Ne) {
         return (size_t)4 * R * TL + 2 * (size_t)Ne * TL + (size_t)NGW * 3 * R * TL + (size_t)RQ * (Ne / 2) * 4 * TL +
-               (size_t)5 * R * Ne + (size_t)R * Ne * 8 + 4 * R;
+               (size_t)NW * 1024 + (size_t)5 * R * Ne + (size_t)R * Ne * 8 + 4 * R;
     }
 };
 
-template <typename IN_T, int RQ, int NGW, bool AGG>
-__global__ void __launch_bounds__(32 * RQ * NGW, (AGG ? 512 : 384) / (32 * RQ * NGW)) scan_bwd_kernel(const __grid_constant__ BwdArgs p) {
+template <typename IN_T, int RQ, int NGW, bool AGG, int MINB>
+__global__ void __launch_bounds__(32 * RQ * NGW, AGG ? 512 / (32 * RQ * NGW) : MINB) scan_bwd_kernel(const __grid_constant__ BwdArgs p) {
     using Cfg = BwdCfg<RQ, NGW>;
     constexpr int T = Cfg::T, R = Cfg::R, TL = Cfg::TL, NT = Cfg::NT, NW = Cfg::NW;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -65,8 +65,9 @@ __global__ void __launch_bounds__(32 * RQ * NGW, (AGG ? 512 : 384) / (32 * RQ * 
     float *s_B = s_g + R * TL;                           // [NP][TL][2]  pair-interleaved
     float *s_C = s_B + Ne * TL;                          // [NP][TL][2]
     float *s_part = s_C + Ne * TL;                       // [NGW][3][R][TL]  partial S1, S2, y
-    float *s_dbc = s_part + NGW * 3 * R * TL;            // [RQ][NP][4][TL]  row-reduced dB.x dB.y dC.x dC.y
-    float *s_A2 = s_dbc + RQ * NP * 4 * TL;              // [R][Ne]  A*log2e
+    float *s_dbc = s_part + NGW * 3 * R * TL;            // [RQ][NP][8 i][8 j][4]  row-reduced (dB.x dB.y dC.x dC.y), token = 8j+i
+    float *s_stg = s_dbc + RQ * NP * 4 * TL;             // [NW][4 rows][8 i][8 j][4]  per-warp products awaiting the row sum
+    float *s_A2 = s_stg + NW * 1024;                     // [R][Ne]  A*log2e
     float *s_A = s_A2 + R * Ne;                          // [R][Ne]
     float *s_hin = s_A + R * Ne;                         // [R][Ne]  forward state entering the chunk
     float *s_dhc = s_hin + R * Ne;                       // [R][Ne]  dh at the first token of the next chunk
@@ -233,7 +234,8 @@ __global__ void __launch_bounds__(32 * RQ * NGW, (AGG ? 512 : 384) / (32 * RQ * 
 
         const float *pB = s_B + pair0 * 2 * TL, *pC = s_C + pair0 * 2 * TL;
         int tab = lr * Ne + 2 * pair0;          // offset of my (row, pair) in the [R][Ne] tables
-        float *pdbc = s_dbc + ((wq * NP + pair0) * 4 + rg) * TL + j * T;
+        float *pdbc = s_dbc + (wq * NP + pair0) * 4 * TL + lane * 4;   // my two row-summed entries: e = lane, lane + 32
+        float *stg_w = s_stg + warp * 1024 + rg * 256 + j * 4;          // my slot for token i: + i * 32
         float2 *pdA = reinterpret_cast<float2 *>(s_dA) + (lr * NP + pair0) * 8 + j;
         for (int pr = pair0; pr < pair1; ++pr, pB += 2 * TL, pC += 2 * TL, tab += 2, pdbc += 4 * TL, pdA += 8) {
             const float2 A2 = *reinterpret_cast<const float2 *>(s_A2 + tab);
@@ -318,7 +320,6 @@ __global__ void __launch_bounds__(32 * RQ * NGW, (AGG ? 512 : 384) / (32 * RQ * 
             const float2 Av = *reinterpret_cast<const float2 *>(s_A + tab);
             float2 e = fmul2(a_nl, dhn);   // a_{t+1} * dh_{t+1} for my last token
             float2 dAacc = make_float2(0.f, 0.f);
-            float red[T];
 #pragma unroll
             for (int i = T - 1; i >= 0; --i) {
                 const float2 dh = ffma2(Cv[i], splat(dy[i]), e);
@@ -331,16 +332,22 @@ __global__ void __launch_bounds__(32 * RQ * NGW, (AGG ? 512 : 384) / (32 * RQ * 
                 yv[i] = ffma2(Cv[i], h[i], yv[i]);
                 const float2 dBv = fmul2(dh, splat(dlu[i]));
                 const float2 dCv = fmul2(h[i], splat(dy[i]));
-                // butterfly over the 4 rows of the warp: (dB.x dB.y dC.x dC.y) x 4 lanes -> 1 value per lane
-                float2 keep = hi ? dCv : dBv;
-                const float2 snd = hi ? dBv : dCv;
-                keep.x += __shfl_xor_sync(0xffffffffu, snd.x, 16);
-                keep.y += __shfl_xor_sync(0xffffffffu, snd.y, 16);
-                const float k1 = lo ? keep.y : keep.x, s1 = lo ? keep.x : keep.y;
-                red[i] = k1 + __shfl_xor_sync(0xffffffffu, s1, 8);
+                // products of my row; the 4 rows of the warp are summed below through the warp's staging area
+                *reinterpret_cast<float4 *>(stg_w + i * 32) = make_float4(dBv.x, dBv.y, dCv.x, dCv.y);
             }
-            *reinterpret_cast<float4 *>(pdbc) = make_float4(red[0], red[1], red[2], red[3]);
-            *reinterpret_cast<float4 *>(pdbc + 4) = make_float4(red[4], red[5], red[6], red[7]);
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float *src = s_stg + warp * 1024 + (lane + 32 * q) * 4;      // entry e = 8*i + j
+                float4 v0 = *reinterpret_cast<const float4 *>(src);
+                const float4 v1 = *reinterpret_cast<const float4 *>(src + 256);
+                const float4 v2 = *reinterpret_cast<const float4 *>(src + 512);
+                const float4 v3 = *reinterpret_cast<const float4 *>(src + 768);
+                v0.x += v1.x + (v2.x + v3.x), v0.y += v1.y + (v2.y + v3.y);
+                v0.z += v1.z + (v2.z + v3.z), v0.w += v1.w + (v2.w + v3.w);
+                *reinterpret_cast<float4 *>(pdbc + 128 * q) = v0;
+            }
+            __syncwarp();
             *pdA = fadd2(*pdA, dAacc);
         }
         if (AGG) continue;
@@ -413,13 +420,26 @@ __global__ void __launch_bounds__(32 * RQ * NGW, (AGG ? 512 : 384) / (32 * RQ * 
         // ---- epilogue B: dB / dC -> global (sum over the CTA's row-warps, then one atomic per element) ---------------
         if (!p.dbg_no_atomics) {
             float *dB_b = p.dB + (int64_t)b * N * L, *dC_b = p.dC + (int64_t)b * N * L;
-            for (int idx = tid; idx < NP * 4 * TL; idx += NT) {
-                const int tok = idx % TL, kind = (idx / TL) & 3, pr = idx / (4 * TL);
-                float v = s_dbc[idx];
+            for (int idx = tid; idx < NP * TL; idx += NT) {
+                const int tok = idx % TL, pr = idx / TL;
+                const int e = ((tok & 7) << 3) | (tok >> 3);            // staging order: e = 8*i + j for token 8*j + i
+                const float *src = s_dbc + (pr * TL + e) * 4;
+                float4 v = *reinterpret_cast<const float4 *>(src);
 #pragma unroll
-                for (int q = 1; q < RQ; ++q) v += s_dbc[q * NP * 4 * TL + idx];
-                const int n = 2 * pr + (kind & 1), t = t0 + tok;
-                if (n < N && t < L) atomicAdd(((kind & 2) ? dC_b : dB_b) + (int64_t)n * L + (rev ? L - 1 - t : t), v);
+                for (int q = 1; q < RQ; ++q) {
+                    const float4 w = *reinterpret_cast<const float4 *>(src + q * NP * 4 * TL);
+                    v.x += w.x, v.y += w.y, v.z += w.z, v.w += w.w;
+                }
+                const int t = t0 + tok, n0 = 2 * pr;
+                if (t < L) {
+                    const int64_t o = (int64_t)n0 * L + (rev ? L - 1 - t : t);
+                    atomicAdd(dB_b + o, v.x);
+                    atomicAdd(dC_b + o, v.z);
+                    if (n0 + 1 < N) {
+                        atomicAdd(dB_b + o + L, v.y);
+                        atomicAdd(dC_b + o + L, v.w);
+                    }
+                }
             }
         }
     }
@@ -499,8 +519,8 @@ int env_int(const char *name, int dflt) {
 }
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-constexpr int kNumBwdCfg = 3;
-constexpr int kBwdCfg[kNumBwdCfg][2] = {{2, 2}, {1, 4}, {2, 4}};   // {RQ, NGW}
+constexpr int kNumBwdCfg = 5;
+constexpr int kBwdCfg[kNumBwdCfg][2] = {{2, 2}, {1, 4}, {2, 4}, {2, 2}, {2, 2}};   // {RQ, NGW}; 3/4 differ in regs cap
 
 struct BwdPlan {
     int cfg, R, nseg, cps, nchunks;
@@ -508,7 +528,7 @@ struct BwdPlan {
 
 BwdPlan plan_bwd(int B, int D, int L) {
     BwdPlan pl;
-    pl.cfg = D <= 4 ? 1 : 0;
+    pl.cfg = D <= 4 ? 1 : 3;   // 3 = 8 rows x 2 dstate groups, no register cap (no spills): fastest measured on B200
     pl.cfg = env_int("MMU_BWD_CFG", pl.cfg);
     if (pl.cfg < 0 || pl.cfg >= kNumBwdCfg) pl.cfg = 0;
     const int RQ = kBwdCfg[pl.cfg][0], NGW = kBwdCfg[pl.cfg][1];
@@ -526,17 +546,17 @@ BwdPlan plan_bwd(int B, int D, int L) {
     return pl;
 }
 
-template <typename IN_T, int RQ, int NGW> int launch_bwd(const BwdArgs &a, bool agg, cudaStream_t st) {
+template <typename IN_T, int RQ, int NGW, int MINB> int launch_bwd(const BwdArgs &a, bool agg, cudaStream_t st) {
     using Cfg = BwdCfg<RQ, NGW>;
     const size_t smem = Cfg::smem_floats(a.Ne) * sizeof(float);
     if (smem > 227 * 1024) return set_error(MMU_ERR_UNSUPPORTED, "selective_scan_bwd: dstate %d needs %zu B smem", a.N, smem);
     dim3 grid((a.D + Cfg::R - 1) / Cfg::R, a.B, a.nseg), block(Cfg::NT);
     if (agg) {
-        auto k = scan_bwd_kernel<IN_T, RQ, NGW, true>;
+        auto k = scan_bwd_kernel<IN_T, RQ, NGW, true, MINB>;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k<<<grid, block, smem, st>>>(a);
     } else {
-        auto k = scan_bwd_kernel<IN_T, RQ, NGW, false>;
+        auto k = scan_bwd_kernel<IN_T, RQ, NGW, false, MINB>;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k<<<grid, block, smem, st>>>(a);
     }
@@ -546,9 +566,11 @@ template <typename IN_T, int RQ, int NGW> int launch_bwd(const BwdArgs &a, bool 
 
 template <typename IN_T> int dispatch_bwd(int cfg, const BwdArgs &a, bool agg, cudaStream_t st) {
     switch (cfg) {
-        case 0: return launch_bwd<IN_T, 2, 2>(a, agg, st);
-        case 1: return launch_bwd<IN_T, 1, 4>(a, agg, st);
-        default: return launch_bwd<IN_T, 2, 4>(a, agg, st);
+        case 0: return launch_bwd<IN_T, 2, 2, 3>(a, agg, st);
+        case 1: return launch_bwd<IN_T, 1, 4, 3>(a, agg, st);
+        case 2: return launch_bwd<IN_T, 2, 4, 1>(a, agg, st);
+        case 3: return launch_bwd<IN_T, 2, 2, 2>(a, agg, st);
+        default: return launch_bwd<IN_T, 2, 2, 4>(a, agg, st);
     }
 }
 

@@ -59,6 +59,11 @@ if __name__ == "__main__":
             probe(8, 384, 4096, 16, torch.float32, f"f{fc}b{fc % 3}")
         os.environ["MMU_FWD_CFG"] = "0"; os.environ["MMU_BWD_CFG"] = "0"
         probe(8, 384, 4096, 16, torch.bfloat16, "bf16")
+    elif mode == "bcfg":
+        os.environ["MMU_FWD_CFG"] = "0"
+        for bc in (0, 3, 4):
+            os.environ["MMU_BWD_CFG"] = str(bc)
+            probe(8, 384, 4096, 16, torch.float32, f"b{bc}")
     elif mode == "narrow":
         os.environ.pop("MMU_FWD_CFG", None); os.environ.pop("MMU_BWD_CFG", None)
         for L in (1024, 4096, 16384, 65536):

@@ -148,7 +148,7 @@ def test_scan_fwd_all_tilings(cfg, monkeypatch):
     run_scan_case(2, 20, 700, 16)
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
 def test_scan_bwd_all_tilings(cfg, monkeypatch):
     monkeypatch.setenv("MMU_BWD_CFG", str(cfg))
     run_scan_case(2, 20, 700, 16)
