@@ -81,6 +81,11 @@ typedef struct mmu_scan_fwd_params {
     int64_t B_bs, B_ns, C_bs, C_ns;
     void *workspace;
     size_t workspace_bytes;
+    /* pre-gate y = C.h + D*u (dtype `dtype`): written by the forward when non-NULL, read by the backward when non-NULL
+     * (the role of the reference's saved `out`, selective_scan.cpp:311, selective_scan_interface.py:218).  NULL: the
+     * backward recomputes it.  Ignored when z == NULL (then out == y). */
+    void *y;
+    int64_t y_bs, y_ds;
 } mmu_scan_fwd_params;
 
 size_t mmu_selective_scan_fwd_workspace(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate);

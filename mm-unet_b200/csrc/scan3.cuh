@@ -1,0 +1,188 @@
+// Shared pieces of the v3 ("register-resident token lanes") selective-scan kernels for dstate <= 16.
+//
+// Decomposition: a lane owns 8 consecutive tokens of TWO channel rows and walks the states; everything
+// per (row, token) - delta, delta*u, y, the S1/S2 sums of the backward - lives in that lane's registers and never crosses
+// lanes.  The two rows ride in the two halves of packed fp32 instructions (FFMA2/FMUL2): h2 = (h_rowA, h_rowB), so B and C
+// enter as scalar-broadcast operands straight from their natural (state, token) layout - no repacking, the tiles are
+// cp.async copies of global memory.  LPR lanes (16) cover a chunk of 8*LPR tokens of a row pair, a warp covers 32/LPR row
+// pairs; the chunk-level recurrence is closed by one LPR-lane shuffle scan of (prod a, h) per (row pair, state).
+//
+// Budget per SM, from profiles/r1_micro_summary.md: MUFU 2 clk per warp-instr, FMA pipe 0.5 clk per packed op,
+// shared memory 128 B/clk of delivered bytes, SHFL 1 clk.
+#pragma once
+#include "common.cuh"
+
+namespace mmu {
+
+constexpr int kS3T = 8;   // tokens per lane
+
+// ---- 8 consecutive elements -> 8 floats in logical-token order.  e[] is in memory order; REV: logical token i = element 7-i
+// (the lane walks memory backwards: fused flip, mamba_simple.py:230).
+template <bool REV> __device__ __forceinline__ void order8(const float (&e)[8], float (&v)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = e[REV ? 7 - i : i];
+}
+
+template <typename IN_T> struct Raw8;      // 8 elements as they sit in memory / shared memory
+template <> struct Raw8<float> {
+    static constexpr int kQuads = 2;       // 16-byte pieces
+    static __device__ __forceinline__ void unpack(const uint4 (&q)[2], float (&e)[8]) {
+        e[0] = __uint_as_float(q[0].x), e[1] = __uint_as_float(q[0].y), e[2] = __uint_as_float(q[0].z), e[3] = __uint_as_float(q[0].w);
+        e[4] = __uint_as_float(q[1].x), e[5] = __uint_as_float(q[1].y), e[6] = __uint_as_float(q[1].z), e[7] = __uint_as_float(q[1].w);
+    }
+    static __device__ __forceinline__ void pack(const float (&e)[8], uint4 (&q)[2]) {
+        q[0] = make_uint4(__float_as_uint(e[0]), __float_as_uint(e[1]), __float_as_uint(e[2]), __float_as_uint(e[3]));
+        q[1] = make_uint4(__float_as_uint(e[4]), __float_as_uint(e[5]), __float_as_uint(e[6]), __float_as_uint(e[7]));
+    }
+};
+template <> struct Raw8<__nv_bfloat16> {
+    static constexpr int kQuads = 1;
+    static __device__ __forceinline__ void unpack(const uint4 (&q)[1], float (&e)[8]) {
+        const unsigned w[4] = {q[0].x, q[0].y, q[0].z, q[0].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            e[2 * k] = __uint_as_float(w[k] << 16);
+            e[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+        }
+    }
+    static __device__ __forceinline__ void pack(const float (&e)[8], uint4 (&q)[1]) {
+        unsigned w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(e[2 * k], e[2 * k + 1]);
+            w[k] = *reinterpret_cast<const unsigned *>(&h);
+        }
+        q[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+
+// store 8 logical tokens to global (p = lowest address of the 8 elements)
+template <typename IN_T, bool REV> __device__ __forceinline__ void store8(IN_T *p, const float (&v)[8]) {
+    float e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[REV ? 7 - i : i] = v[i];
+    uint4 q[Raw8<IN_T>::kQuads];
+    Raw8<IN_T>::pack(e, q);
+#pragma unroll
+    for (int k = 0; k < Raw8<IN_T>::kQuads; ++k) reinterpret_cast<uint4 *>(p)[k] = q[k];
+}
+template <typename IN_T, bool REV> __device__ __forceinline__ void load8_global(const IN_T *p, float (&v)[8]) {
+    uint4 q[Raw8<IN_T>::kQuads];
+#pragma unroll
+    for (int k = 0; k < Raw8<IN_T>::kQuads; ++k) q[k] = reinterpret_cast<const uint4 *>(p)[k];
+    float e[8];
+    Raw8<IN_T>::unpack(q, e);
+    order8<REV>(e, v);
+}
+
+// ---- cp.async (LDGSTS) ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ float lg2_fast(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// softplus (F.softplus, threshold 20: selective_scan_fwd_kernel.cuh:153-156) and its derivative sigmoid(x), branch free:
+//   e = exp(-|x|);  log1p(e) = lg2(1+e)*ln2, or the alternating series for small e (keeps the RELATIVE error ~1e-7 where
+//   delta is tiny);  softplus = max(x,0) + log1p(e)   (for x > 20 this is x to fp32 precision, as the reference returns).
+__device__ __forceinline__ float softplus3(float x, float &e_out) {
+    const float e = ex2(-fabsf(x) * kLog2e);
+    const float series = e * fmaf(e, fmaf(e, fmaf(e, -0.25f, 0.33333334f), -0.5f), 1.f);
+    const float lg = lg2_fast(1.f + e) * 0.69314718056f;
+    e_out = e;
+    return fmaxf(x, 0.f) + (e < 1.5e-2f ? series : lg);
+}
+__device__ __forceinline__ float softplus3(float x) {
+    float e;
+    return softplus3(x, e);
+}
+// sigmoid(x) from e = exp(-|x|)
+__device__ __forceinline__ float sigmoid_from_e(float x, float e) {
+    const float r = rcp_fast(1.f + e);
+    return x >= 0.f ? r : e * r;
+}
+__device__ __forceinline__ float sigmoid3(float x) { return rcp_fast(1.f + ex2(-x * kLog2e)); }
+
+// ---- B / C tile: natural layout ---------------------------------------------------------------------------------------------
+// fp32 rows of CH tokens in MEMORY order, one row per state, B rows then C rows.  A 16-byte pad after every 128 bytes makes
+// the lanes' 32-byte reads (8 tokens) conflict free: quad q sits at byte 16*q + 16*(q/8).
+template <int LPR> struct BcTile {
+    static constexpr int CH = LPR * kS3T;
+    static constexpr int kRowBytes = CH * 4 + (CH / 32) * 16;
+    static constexpr int kBytes = 2 * 16 * kRowBytes;                     // B[16] | C[16]
+    static __device__ __forceinline__ int quad_off(int q) { return 16 * q + 16 * (q >> 3); }
+};
+
+// Issue the cp.async copies of the tile holding logical tokens [t0, t0 + CH).  Pieces outside the sequence are skipped: the
+// lanes that would read them run with delta = 0, so the stale (finite: the tile is zero-initialised) contents do not matter.
+// ROWB = bytes between rows in shared memory, EPP = elements per 16-byte piece, PPR = pieces per row; `dst_off(q)` maps a
+// piece to its byte offset inside a row.
+template <typename IN_T, int CH, int NT, int ROWB, bool REV, bool WITH_C, typename OFF>
+__device__ __forceinline__ void rows_async(unsigned dst, const IN_T *__restrict__ B_b, const IN_T *__restrict__ C_b, int64_t B_ns,
+                                           int64_t C_ns, int N, int t0, int L, int tid, OFF dst_off) {
+    constexpr int EPP = 16 / (int)sizeof(IN_T), PPR = CH / EPP;
+    constexpr int TPR = NT >= PPR ? PPR : NT, RPP = NT / TPR, QIT = PPR / TPR;
+    const int m0 = REV ? L - t0 - CH : t0;                                // memory index of tile position 0 (may be < 0)
+    const int q0 = tid % TPR, r0 = tid / TPR;
+#pragma unroll
+    for (int qi = 0; qi < QIT; ++qi) {
+        const int q = q0 + qi * TPR, m = m0 + EPP * q;
+        if (m >= 0 && m < L) {
+            const unsigned d = dst + r0 * ROWB + dst_off(q);
+            const IN_T *sb = B_b + (int64_t)r0 * B_ns + m, *sc = C_b + (int64_t)r0 * C_ns + m;
+#pragma unroll
+            for (int k = 0; k < 16 / RPP; ++k) {
+                if (r0 + k * RPP < N) {
+                    cp_async16(d + k * RPP * ROWB, sb + (int64_t)k * RPP * B_ns);
+                    if (WITH_C) cp_async16(d + (16 + k * RPP) * ROWB, sc + (int64_t)k * RPP * C_ns);
+                }
+            }
+        }
+    }
+}
+
+template <int LPR, int NT, bool REV, bool WITH_C>
+__device__ __forceinline__ void tile_async_f32(unsigned tile, const float *__restrict__ B_b, const float *__restrict__ C_b, int64_t B_ns,
+                                               int64_t C_ns, int N, int t0, int L, int tid) {
+    using Tl = BcTile<LPR>;
+    rows_async<float, Tl::CH, NT, Tl::kRowBytes, REV, WITH_C>(tile, B_b, C_b, B_ns, C_ns, N, t0, L, tid,
+                                                               [](int q) { return Tl::quad_off(q); });
+}
+
+// bf16 inputs: cp.async the raw rows (CH*2 bytes each, B rows then C rows) into a staging buffer ...
+template <int LPR, int NT, bool REV, bool WITH_C>
+__device__ __forceinline__ void raw_async_bf16(unsigned raw, const __nv_bfloat16 *__restrict__ B_b, const __nv_bfloat16 *__restrict__ C_b,
+                                               int64_t B_ns, int64_t C_ns, int N, int t0, int L, int tid) {
+    constexpr int CH = LPR * kS3T;
+    rows_async<__nv_bfloat16, CH, NT, CH * 2, REV, WITH_C>(raw, B_b, C_b, B_ns, C_ns, N, t0, L, tid, [](int q) { return 16 * q; });
+}
+// ... and widen them into the fp32 tile the lanes read.
+template <int LPR, int NT, bool WITH_C>
+__device__ __forceinline__ void widen_bf16_tile(unsigned char *tile, const unsigned char *raw, int tid) {
+    using Tl = BcTile<LPR>;
+    constexpr int CH = Tl::CH, PPR = CH / 8;
+    for (int idx = tid; idx < (WITH_C ? 2 : 1) * 16 * PPR; idx += NT) {
+        const int q = idx % PPR, rn = idx / PPR;
+        const uint4 w = *reinterpret_cast<const uint4 *>(raw + (rn * PPR + q) * 16);
+        const uint4 v[1] = {w};
+        float e[8];
+        Raw8<__nv_bfloat16>::unpack(v, e);
+        unsigned char *row = tile + rn * Tl::kRowBytes;
+        *reinterpret_cast<float4 *>(row + Tl::quad_off(2 * q)) = make_float4(e[0], e[1], e[2], e[3]);
+        *reinterpret_cast<float4 *>(row + Tl::quad_off(2 * q + 1)) = make_float4(e[4], e[5], e[6], e[7]);
+    }
+}
+
+}  // namespace mmu

@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include "scan3_fwd.cuh"
 #include "scan_tiles.cuh"
 
 namespace mmu {
@@ -400,7 +401,113 @@ template <typename IN_T> int dispatch_fwd(int cfg, const FwdArgs &a, bool agg, c
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// ---- v3 host side (scan3_fwd.cuh) ------------------------------------------------------------------------------------------
+template <typename IN_T> bool row_aligned16(const void *p, int64_t s0, int64_t s1) {
+    return reinterpret_cast<uintptr_t>(p) % 16 == 0 && (s0 * (int64_t)sizeof(IN_T)) % 16 == 0 && (s1 * (int64_t)sizeof(IN_T)) % 16 == 0;
+}
+
+template <typename IN_T> bool fwd3_eligible(const mmu_scan_fwd_params *p) {
+    if (env_int("MMU_SCAN_V", 3) < 3) return false;
+    if (p->dstate > 16 || p->seqlen % 8 != 0) return false;
+    if (!row_aligned16<IN_T>(p->u, p->u_bs, p->u_ds) || !row_aligned16<IN_T>(p->delta, p->delta_bs, p->delta_ds) ||
+        !row_aligned16<IN_T>(p->out, p->out_bs, p->out_ds) || !row_aligned16<IN_T>(p->B, p->B_bs, p->B_ns) ||
+        !row_aligned16<IN_T>(p->C, p->C_bs, p->C_ns))
+        return false;
+    if (p->z && !row_aligned16<IN_T>(p->z, p->z_bs, p->z_ds)) return false;
+    if (p->y && !row_aligned16<IN_T>(p->y, p->y_bs, p->y_ds)) return false;
+    return true;
+}
+
+struct Fwd3Plan {
+    int LPR, W, nseg, cps, nchunks;
+};
+
+Fwd3Plan plan_fwd3(int B, int D, int L) {
+    Fwd3Plan pl;
+    pl.LPR = env_int("MMU_FWD3_LPR", 32) == 16 ? 16 : 32;
+    if (pl.LPR == 16) {
+        pl.W = 4;
+    } else {
+        pl.W = env_int("MMU_FWD3_W", D <= 2 ? 1 : (D <= 4 ? 2 : 4));
+        if (pl.W != 1 && pl.W != 2) pl.W = 4;
+    }
+    const int RW = 2 * (32 / pl.LPR), R = pl.W * RW, CH = 8 * pl.LPR;
+    pl.nchunks = (L + CH - 1) / CH;
+    const int warps = B * ((D + R - 1) / R) * pl.W;
+    int nseg = warps >= 148 * 4 ? 1 : (148 * 8 + warps - 1) / warps;   // splitting costs a second (aggregate) pass
+    nseg = std::min(nseg, std::max(1, pl.nchunks / 2));
+    nseg = std::max(1, std::min(nseg, 64));
+    nseg = env_int("MMU_FWD_NSEG", nseg);
+    nseg = std::max(1, std::min(nseg, pl.nchunks));
+    pl.cps = (pl.nchunks + nseg - 1) / nseg;
+    pl.nseg = (pl.nchunks + pl.cps - 1) / pl.cps;
+    return pl;
+}
+
+template <typename IN_T, int LPR, int W, bool REV, bool AGG> int launch_fwd3(const Fwd3Args &a, cudaStream_t st) {
+    using Cfg = Fwd3Cfg<IN_T, LPR, W>;
+    dim3 grid((a.D + Cfg::R - 1) / Cfg::R, a.B, a.nseg), block(Cfg::NT);
+    auto k = scan3_fwd_kernel<IN_T, LPR, W, REV, AGG>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
+    k<<<grid, block, Cfg::smem_bytes, st>>>(a);
+    count_launch();
+    return check_launch("selective_scan_fwd(v3)");
+}
+
+template <typename IN_T, bool AGG> int dispatch_fwd3(const Fwd3Args &a, const Fwd3Plan &pl, bool rev, cudaStream_t st) {
+#define MMU_F3(LPR_, W_) (rev ? launch_fwd3<IN_T, LPR_, W_, true, AGG>(a, st) : launch_fwd3<IN_T, LPR_, W_, false, AGG>(a, st))
+    if (pl.LPR == 16) return MMU_F3(16, 4);
+    if (pl.W == 1) return MMU_F3(32, 1);
+    if (pl.W == 2) return MMU_F3(32, 2);
+    return MMU_F3(32, 4);
+#undef MMU_F3
+}
+
+template <typename IN_T> int run_fwd3(const mmu_scan_fwd_params *p, cudaStream_t st) {
+    const Fwd3Plan pl = plan_fwd3(p->batch, p->dim, p->seqlen);
+    Fwd3Args a{};
+    a.u = p->u, a.delta = p->delta, a.z = p->z, a.Bm = p->B, a.Cm = p->C;
+    a.A = p->A, a.Dv = p->D, a.dbias = p->delta_bias;
+    a.out = p->out, a.ysave = p->y, a.x = p->x, a.last_state = p->last_state;
+    a.u_bs = p->u_bs, a.u_ds = p->u_ds, a.dl_bs = p->delta_bs, a.dl_ds = p->delta_ds;
+    a.z_bs = p->z_bs, a.z_ds = p->z_ds, a.o_bs = p->out_bs, a.o_ds = p->out_ds, a.y_bs = p->y_bs, a.y_ds = p->y_ds;
+    a.B_bs = p->B_bs, a.B_ns = p->B_ns, a.C_bs = p->C_bs, a.C_ns = p->C_ns;
+    a.B = p->batch, a.D = p->dim, a.L = p->seqlen, a.N = p->dstate;
+    a.nseg = pl.nseg, a.cps = pl.cps, a.nchunks = pl.nchunks;
+    a.nx = (p->seqlen + MMU_STATE_STRIDE - 1) / MMU_STATE_STRIDE;
+    a.softplus = p->delta_softplus;
+    const bool rev = p->reverse != 0;
+    if (pl.nseg > 1) {
+        const size_t n_state = (size_t)a.B * a.D * pl.nseg * 16;
+        const size_t need = 2 * align256(n_state * 4) + align256((size_t)a.B * a.D * pl.nseg * 4);
+        if (p->workspace == nullptr || p->workspace_bytes < need)
+            return set_error(MMU_ERR_WORKSPACE, "selective_scan_fwd: workspace %zu < %zu", p->workspace_bytes, need);
+        char *w = static_cast<char *>(p->workspace);
+        a.seg_hend = reinterpret_cast<float *>(w);
+        float *hin = reinterpret_cast<float *>(w + align256(n_state * 4));
+        a.seg_dsum = reinterpret_cast<float *>(w + 2 * align256(n_state * 4));
+        a.hin = nullptr;
+        int rc = dispatch_fwd3<IN_T, true>(a, pl, rev, st);
+        if (rc) return rc;
+        const int64_t tot = (int64_t)a.B * a.D * 16;
+        scan_fwd_chain_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(a.A, a.seg_hend, a.seg_dsum, hin, a.B, a.D,
+                                                                             a.N, 16, pl.nseg);
+        count_launch();
+        rc = check_launch("scan_fwd_chain");
+        if (rc) return rc;
+        a.hin = hin;
+    }
+    return dispatch_fwd3<IN_T, false>(a, pl, rev, st);
+}
+
+template <typename IN_T> struct HasV3 { static constexpr bool value = false; };
+template <> struct HasV3<float> { static constexpr bool value = true; };
+template <> struct HasV3<__nv_bfloat16> { static constexpr bool value = true; };
+
 template <typename IN_T> int run_fwd(const mmu_scan_fwd_params *p, cudaStream_t st) {
+    if constexpr (HasV3<IN_T>::value) {
+        if (fwd3_eligible<IN_T>(p)) return run_fwd3<IN_T>(p, st);
+    }
     const FwdPlan pl = plan_fwd(p->batch, p->dim, p->seqlen, p->dstate);
     FwdArgs a{};
     a.u = p->u, a.delta = p->delta, a.z = p->z, a.Bm = p->B, a.Cm = p->C;
@@ -451,7 +558,7 @@ template <typename IN_T> int run_fwd(const mmu_scan_fwd_params *p, cudaStream_t 
 
 extern "C" size_t mmu_selective_scan_fwd_workspace(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate) {
     // upper bound over every plan the dispatcher can pick (nseg <= 64 unless forced by MMU_FWD_NSEG)
-    const int Ne = (dstate + 1) & ~1;
+    const int Ne = dstate <= 16 ? 16 : ((dstate + 1) & ~1);
     const int nchunks = (seqlen + 63) / 64;
     const size_t nseg = (size_t)std::max(1, std::min(nchunks, std::max(64, mmu::env_int("MMU_FWD_NSEG", 1))));
     const size_t n_state = (size_t)batch * dim * nseg * Ne;

@@ -24,7 +24,7 @@ class ScanFwdParams(C.Structure):
         + [(n, _vp) for n in ("u", "delta", "z", "B", "C", "A", "D", "delta_bias", "out", "x", "last_state")]
         + [(n, _i64) for n in ("u_bs", "u_ds", "delta_bs", "delta_ds", "z_bs", "z_ds", "out_bs", "out_ds",
                                "B_bs", "B_ns", "C_bs", "C_ns")]
-        + [("workspace", _vp), ("workspace_bytes", _sz)]
+        + [("workspace", _vp), ("workspace_bytes", _sz), ("y", _vp), ("y_bs", _i64), ("y_ds", _i64)]
     )
 
 
