@@ -1,0 +1,513 @@
+// Selective scan backward, v3 kernel (dstate <= 16, seqlen % 8 == 0, 16-byte aligned rows).  Recompute based: the L x N state is
+// never materialised.  Math: SURVEY.md Appendix A; replaces selective_scan_bwd_kernel (selective_scan_bwd_kernel.cuh:75-489).
+//
+// Geometry as the forward (scan3.cuh): a lane owns 8 tokens of two rows (packed in the halves of FFMA2), 32 lanes = one
+// 256-token chunk of a row pair; chunks are walked last -> first.  Per chunk and state n:
+//   forward recompute   a_i = exp(delta_i A), H = a H + delta_i u_i B_i from zero; the forward kernel saved the true state every
+//                       64 tokens (x), so an 8-lane shuffle scan seeded from x gives each lane its entering state hs, then h_i;
+//   reverse             "e form": e_i = a_i (C_i dy_i + e_{i+1}) with dh_i = C_i dy_i + e_{i+1}; it shares its multipliers with
+//                       the forward, so the lanes' (prod a, e) close with one 32-lane shuffle scan plus a chunk carry;
+//   contributions       dB, dC (summed over the two rows in registers, then red.global.add.v4), S1 = sum_n dh B,
+//                       S2 = sum_n dh a h_prev A (registers, per token), dA (lane-private shared accumulators).
+// The per (row, token) epilogue turns S1, S2 into du, ddelta, and uses the pre-gate y saved by the forward for dz.
+#pragma once
+#include "scan3.cuh"
+
+namespace mmu {
+
+struct Bwd3Args {
+    const void *u, *delta, *z, *dout, *ysave, *Bm, *Cm;
+    const float *A, *Dv, *dbias, *x;
+    void *du, *ddelta, *dz;
+    float *dA, *dB, *dC, *dD, *ddbias;
+    float *seg_E, *seg_dsum;       // AGG pass outputs
+    const float *ein;              // reverse carry entering each segment (main pass, nseg > 1)
+    int64_t u_bs, u_ds, dl_bs, dl_ds, z_bs, z_ds, g_bs, g_ds, y_bs, y_ds, B_bs, B_ns, C_bs, C_ns;
+    int64_t du_bs, du_ds, ddl_bs, ddl_ds, dz_bs, dz_ds;
+    int B, D, L, N;
+    int nseg, cps, nchunks, nx;
+    int softplus;
+};
+
+template <typename IN_T, int W> struct Bwd3Cfg {
+    static constexpr int LPR = 32;
+    static constexpr bool kF32 = sizeof(IN_T) == 4;
+    static constexpr int CH = LPR * kS3T, R = 2 * W, NT = 32 * W, NRP = W;
+    static constexpr int NCK = CH / MMU_STATE_STRIDE;                     // 4 saved states per chunk
+    static constexpr int kRawBytes = kF32 ? 0 : 2 * 16 * CH * 2;
+    static constexpr int NQ = Raw8<IN_T>::kQuads;
+    static constexpr int kLandBytes = 5 * 2 * NQ * NT * 16;               // u | delta | z | dout | y : [tensor][row][quad][thread] x 16 B
+    static constexpr int kZfBytes = 2 * 2 * NT * 16;                      // dz factor, fp32: [row][quad][thread] x 16 B
+    static constexpr int kDABytes = 16 * NT * 8;                          // dA partials [state][thread] float2
+    static constexpr int kSeedBytes = 2 * W * NCK * 16 * 8;               // x seeds [buf][warp][ck][state] float2
+    static constexpr int kTabBytes = 2 * NRP * 16 * 8;                    // A*log2e | e carry
+    static constexpr size_t smem_bytes = (size_t)BcTile<LPR>::kBytes + kRawBytes + kLandBytes + kZfBytes + kDABytes + kSeedBytes + kTabBytes;
+};
+
+__device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <typename IN_T, int W, bool REV, bool AGG>
+__global__ void __launch_bounds__(32 * W, AGG ? 1 : (W >= 4 ? 2 : 4)) scan3_bwd_kernel(const __grid_constant__ Bwd3Args p) {
+    using Cfg = Bwd3Cfg<IN_T, W>;
+    constexpr int LPR = 32;
+    using Tl = BcTile<LPR>;
+    constexpr int CH = Cfg::CH, R = Cfg::R, NT = Cfg::NT, NRP = Cfg::NRP, T = kS3T, NQ = Cfg::NQ, NCK = Cfg::NCK;
+    constexpr int EPQ = 16 / (int)sizeof(IN_T);
+    constexpr bool kF32 = Cfg::kF32;
+    const int tid = threadIdx.x, warp = tid >> 5, j = tid & 31;
+    const int b = blockIdx.y, row0 = blockIdx.x * R, seg = blockIdx.z;
+    const int D = p.D, L = p.L, N = p.N;
+    const bool has_z = p.z != nullptr, sp = p.softplus != 0;
+    const int NS = N;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char *s_tile = smem_raw;
+    unsigned char *s_rawbc = s_tile + Tl::kBytes;
+    unsigned char *s_land = s_rawbc + Cfg::kRawBytes;
+    unsigned char *s_zf = s_land + Cfg::kLandBytes;
+    float2 *s_dA = reinterpret_cast<float2 *>(s_zf + Cfg::kZfBytes);
+    float2 *s_seed = s_dA + 16 * NT;                                       // [2][W][NCK][16]
+    float2 *s_A = s_seed + 2 * W * NCK * 16;                               // [NRP][16]  A*log2e of (row A, row B)
+    float2 *s_ec = s_A + NRP * 16;                                         // [NRP][16]  e entering the chunk from the right
+
+    for (int i = tid; i < (int)((Tl::kBytes + Cfg::kRawBytes + Cfg::kLandBytes + Cfg::kZfBytes + Cfg::kDABytes + Cfg::kSeedBytes) / 16); i += NT)
+        reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < NRP * 16; i += NT) {
+        const int g = i >> 4, n = i & 15;
+        float a[2], e[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int row = row0 + 2 * g + r;
+            const bool ok = row < D && n < N;
+            a[r] = ok ? p.A[(int64_t)row * N + n] * kLog2e : 0.f;
+            e[r] = 0.f;
+            if (!AGG && ok && p.ein != nullptr && seg + 1 < p.nseg) e[r] = p.ein[(((int64_t)b * D + row) * p.nseg + seg) * 16 + n];
+        }
+        s_A[i] = make_float2(a[0], a[1]);
+        s_ec[i] = make_float2(e[0], e[1]);
+    }
+
+    // ---- my two rows; chunks are walked from c_end-1 down to c_begin ------------------------------------------------------
+    const int rowA = row0 + 2 * warp;
+    const int c_begin = seg * p.cps, c_end = min(p.nchunks, c_begin + p.cps);
+    int tl = (c_end - 1) * CH + T * j;                  // first logical token of my 8 in the current chunk
+    const int mo0 = REV ? L - T - tl : tl;
+    constexpr int STEP = REV ? CH : -CH;                // memory step to the next (= previous in time) chunk
+    bool row_ok[2];
+    const IN_T *u_p[2], *d_p[2], *z_p[2], *g_p[2], *y_p[2];     // prefetch pointers
+    IN_T *du_p[2], *dd_p[2], *dz_p[2];                            // output pointers (current chunk)
+    float bias[2], Dsk[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        row_ok[r] = rowA + r < D;
+        const int row = min(rowA + r, D - 1);
+        u_p[r] = reinterpret_cast<const IN_T *>(p.u) + (int64_t)b * p.u_bs + (int64_t)row * p.u_ds + mo0;
+        d_p[r] = reinterpret_cast<const IN_T *>(p.delta) + (int64_t)b * p.dl_bs + (int64_t)row * p.dl_ds + mo0;
+        g_p[r] = reinterpret_cast<const IN_T *>(p.dout) + (int64_t)b * p.g_bs + (int64_t)row * p.g_ds + mo0;
+        z_p[r] = has_z ? reinterpret_cast<const IN_T *>(p.z) + (int64_t)b * p.z_bs + (int64_t)row * p.z_ds + mo0 : nullptr;
+        y_p[r] = has_z ? reinterpret_cast<const IN_T *>(p.ysave) + (int64_t)b * p.y_bs + (int64_t)row * p.y_ds + mo0 : nullptr;
+        du_p[r] = AGG ? nullptr : reinterpret_cast<IN_T *>(p.du) + (int64_t)b * p.du_bs + (int64_t)row * p.du_ds + mo0;
+        dd_p[r] = AGG ? nullptr : reinterpret_cast<IN_T *>(p.ddelta) + (int64_t)b * p.ddl_bs + (int64_t)row * p.ddl_ds + mo0;
+        dz_p[r] = (AGG || !has_z) ? nullptr : reinterpret_cast<IN_T *>(p.dz) + (int64_t)b * p.dz_bs + (int64_t)row * p.dz_ds + mo0;
+        bias[r] = p.dbias != nullptr ? p.dbias[row] : 0.f;
+        Dsk[r] = p.Dv != nullptr ? p.Dv[row] : 0.f;
+    }
+    const IN_T *B_b = reinterpret_cast<const IN_T *>(p.Bm) + (int64_t)b * p.B_bs;
+    const IN_T *C_b = reinterpret_cast<const IN_T *>(p.Cm) + (int64_t)b * p.C_bs;
+    float *dB_b = AGG ? nullptr : p.dB + (int64_t)b * N * L;
+    float *dC_b = AGG ? nullptr : p.dC + (int64_t)b * N * L;
+
+    bool ge_up[3], ge_dn[5];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) ge_up[s] = (j & 7) >= (1 << s);
+#pragma unroll
+    for (int s = 0; s < 5; ++s) ge_dn[s] = j + (1 << s) < 32;
+    const int qa = REV ? 2 * (LPR - 1 - j) : 2 * j;
+    const unsigned char *tile = s_tile + Tl::quad_off(qa);
+    const unsigned s_tile_u32 = smem_u32(s_tile), s_raw_u32 = smem_u32(s_rawbc);
+    const unsigned s_land_u32 = smem_u32(s_land) + tid * 16;
+    const unsigned char *s_land_t = s_land + tid * 16;
+    unsigned char *s_zf_t = s_zf + tid * 16;
+    float2 dDacc = make_float2(0.f, 0.f), dbacc = make_float2(0.f, 0.f);
+    float dsum[2] = {0.f, 0.f};
+
+    auto issue_tile = [&](int c) {
+        if constexpr (kF32) {
+            tile_async_f32<LPR, NT, REV, true>(s_tile_u32, reinterpret_cast<const float *>(B_b), reinterpret_cast<const float *>(C_b), p.B_ns,
+                                               p.C_ns, N, c * CH, L, tid);
+        } else {
+            raw_async_bf16<LPR, NT, REV, true>(s_raw_u32, reinterpret_cast<const __nv_bfloat16 *>(B_b),
+                                               reinterpret_cast<const __nv_bfloat16 *>(C_b), p.B_ns, p.C_ns, N, c * CH, L, tid);
+        }
+    };
+    // landing slots: tensor 0 u, 1 delta, 2 z, 3 dout, 4 y
+    auto issue_in = [&](bool in_seq) {      // u, delta, z, dout of the chunk the prefetch pointers stand on, then move them on
+        if (in_seq) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    cp_async16(s_land_u32 + ((1 * 2 + r) * NQ + q) * NT * 16, d_p[r] + q * EPQ);
+                    cp_async16(s_land_u32 + ((3 * 2 + r) * NQ + q) * NT * 16, g_p[r] + q * EPQ);
+                    if (!AGG) cp_async16(s_land_u32 + ((0 * 2 + r) * NQ + q) * NT * 16, u_p[r] + q * EPQ);
+                    if (has_z) cp_async16(s_land_u32 + ((2 * 2 + r) * NQ + q) * NT * 16, z_p[r] + q * EPQ);
+                }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            u_p[r] += STEP, d_p[r] += STEP, g_p[r] += STEP;
+            if (has_z) z_p[r] += STEP;
+        }
+    };
+    auto issue_y = [&](bool in_seq) {
+        if (!AGG && has_z) {
+            if (in_seq) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) cp_async16(s_land_u32 + ((4 * 2 + r) * NQ + q) * NT * 16, y_p[r] + q * EPQ);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) y_p[r] += STEP;
+        }
+    };
+    auto load_land = [&](int which, int r, float (&v)[T]) {
+        uint4 q[NQ];
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) q[k] = *reinterpret_cast<const uint4 *>(s_land_t + ((which * 2 + r) * NQ + k) * NT * 16);
+        float e[8];
+        Raw8<IN_T>::unpack(q, e);
+        order8<REV>(e, v);
+    };
+    // x seeds of chunk c: state entering the chunk's k-th 64-token block, k = 0..3  ->  s_seed[buf][warp][k][n] (row A, row B)
+    auto load_seeds = [&](int c, int buf) {
+        if (AGG) return;
+#pragma unroll
+        for (int it = 0; it < NCK * 16 / 32; ++it) {
+            const int e = j + 32 * it, ck = e >> 4, n = e & 15;
+            const int kx = c * NCK + ck - 1;
+            float v[2] = {0.f, 0.f};
+            if (kx >= 0 && n < N) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) v[r] = p.x[(((int64_t)b * D + min(rowA + r, D - 1)) * p.nx + kx) * N + n];
+            }
+            s_seed[((buf * W + warp) * NCK + ck) * 16 + n] = make_float2(v[0], v[1]);
+        }
+    };
+
+    __syncthreads();
+    issue_tile(c_end - 1);
+    issue_in(tl < L);
+    issue_y(tl < L);
+    cp_async_commit();
+    load_seeds(c_end - 1, (c_end - 1) & 1);
+
+    for (int c = c_end - 1; c >= c_begin; --c, tl -= CH) {
+        const bool ok = tl < L;
+        cp_async_wait_all();
+        __syncthreads();
+        if constexpr (!kF32) {
+            widen_bf16_tile<LPR, NT, true>(s_tile, s_rawbc, tid);
+            __syncthreads();
+        }
+        // ---- per (row, token) registers (.x = row A, .y = row B) ---------------------------------------------------------------
+        float2 dl[T], dlu[T], dy[T], uu2[T];
+        {
+            float uu[2][T], dd[2][T], gg[2][T], zf[2][T];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                load_land(1, r, dd[r]);
+                load_land(3, r, gg[r]);
+                if (!AGG) load_land(0, r, uu[r]);
+                if (has_z) {
+                    float zz[T];
+                    load_land(2, r, zz);
+#pragma unroll
+                    for (int i = 0; i < T; ++i) {
+                        const float s = sigmoid3(zz[i]);
+                        const float gz = gg[r][i] * s;
+                        zf[r][i] = gz * fmaf(zz[i], 1.f - s, 1.f);          // dz = y * zf      (bwd_kernel.cuh:186-191)
+                        gg[r][i] = gz * zz[i];                              // dy
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < T; ++i) {
+                    const float xx = dd[r][i] + bias[r];
+                    const float v = sp ? softplus3(xx) : xx;
+                    dd[r][i] = (ok && row_ok[r]) ? v : 0.f;        // padding tokens / rows: delta = 0, dy = 0 -> no contribution
+                    gg[r][i] = (ok && row_ok[r]) ? gg[r][i] : 0.f;
+                    if (AGG) dsum[r] += dd[r][i];
+                }
+                if (!AGG && has_z) {
+                    *reinterpret_cast<float4 *>(s_zf_t + (r * 2 + 0) * NT * 16) = make_float4(zf[r][0], zf[r][1], zf[r][2], zf[r][3]);
+                    *reinterpret_cast<float4 *>(s_zf_t + (r * 2 + 1) * NT * 16) = make_float4(zf[r][4], zf[r][5], zf[r][6], zf[r][7]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < T; ++i) {
+                dl[i] = make_float2(dd[0][i], dd[1][i]);
+                dy[i] = make_float2(gg[0][i], gg[1][i]);
+                if (!AGG) {
+                    uu2[i] = make_float2(uu[0][i], uu[1][i]);
+                    dlu[i] = fmul2(dl[i], uu2[i]);
+                    dDacc = ffma2(dy[i], uu2[i], dDacc);
+                }
+            }
+        }
+        // inputs of the next chunk (c-1): the landing slots are private to this thread and were just consumed
+        if (c > c_begin) {
+            issue_in(true);
+            load_seeds(c - 1, (c - 1) & 1);
+        }
+
+        float2 s1[T], s2[T];
+#pragma unroll
+        for (int i = 0; i < T; ++i) s1[i] = s2[i] = make_float2(0.f, 0.f);
+        const float2 *seedp = s_seed + (((c & 1) * W + warp) * NCK + (j >> 3)) * 16;
+
+#pragma unroll 1
+        for (int n = 0; n < NS; ++n) {
+            const float2 A2l = s_A[warp * 16 + n];
+            const float2 ec = s_ec[warp * 16 + n];
+            float Bn[T], Cn[T];
+            {
+                const unsigned char *rowB = tile + n * Tl::kRowBytes, *rowC = rowB + 16 * Tl::kRowBytes;
+                const float4 c0 = *reinterpret_cast<const float4 *>(rowC), c1 = *reinterpret_cast<const float4 *>(rowC + 16);
+                const float ec_[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                order8<REV>(ec_, Cn);
+                if (!AGG) {
+                    const float4 b0 = *reinterpret_cast<const float4 *>(rowB), b1 = *reinterpret_cast<const float4 *>(rowB + 16);
+                    const float eb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    order8<REV>(eb, Bn);
+                }
+            }
+            // ---- a_i, lane aggregates of the forward (H, P) and of the reverse (E) ---------------------------------------------
+            float2 a[T], bu[T], cdy[T];
+            float2 H = make_float2(0.f, 0.f), P, E = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < T; ++i) {
+                a[i] = ex2(fmul2(dl[i], A2l));
+                P = i == 0 ? a[0] : fmul2(P, a[i]);
+                if (!AGG) {
+                    bu[i] = fmul2(dlu[i], splat(Bn[i]));
+                    H = ffma2(a[i], H, bu[i]);
+                }
+                cdy[i] = fmul2(dy[i], splat(Cn[i]));
+            }
+#pragma unroll
+            for (int i = T - 1; i >= 0; --i) E = fmul2(a[i], fadd2(cdy[i], E));
+            // lane 31 absorbs the e entering the chunk from the right
+            {
+                const float2 E31 = ffma2(P, ec, E);
+                if (j == 31) E = E31;
+            }
+            // reverse (suffix) scan over the 32 lanes
+            float2 Pr = P;
+#pragma unroll
+            for (int st = 0; st < 5; ++st) {
+                const float2 En = shfl_down2(E, 1 << st, 32);
+                float2 Pn;
+                if (st < 4) Pn = shfl_down2(Pr, 1 << st, 32);
+                if (ge_dn[st]) {
+                    E = ffma2(Pr, En, E);
+                    if (st < 4) Pr = fmul2(Pr, Pn);
+                }
+            }
+            if (j == 0) s_ec[warp * 16 + n] = E;                            // e at the chunk's first token: carry for chunk c-1
+            if (AGG) continue;
+            float2 e = shfl_down2(E, 1, 32);
+            if (j == 31) e = ec;
+
+            // ---- forward states: 8-lane scan seeded from the saved states ------------------------------------------------------
+            const float2 seed = seedp[n];
+            {
+                const float2 H0 = ffma2(P, seed, H);
+                if ((j & 7) == 0) H = H0;
+            }
+            float2 Pf = P;
+#pragma unroll
+            for (int st = 0; st < 3; ++st) {
+                const float2 Hn = shfl_up2(H, 1 << st, 8);
+                float2 Pn;
+                if (st < 2) Pn = shfl_up2(Pf, 1 << st, 8);
+                if (ge_up[st]) {
+                    H = ffma2(Pf, Hn, H);
+                    if (st < 2) Pf = fmul2(Pf, Pn);
+                }
+            }
+            float2 hprev = shfl_up2(H, 1, 8);
+            if ((j & 7) == 0) hprev = seed;
+            float2 h[T];
+#pragma unroll
+            for (int i = 0; i < T; ++i) {
+                h[i] = ffma2(a[i], i == 0 ? hprev : h[i - 1], bu[i]);
+            }
+            // ---- reverse sweep with the true e, contributions -------------------------------------------------------------------------
+            const float2 A2 = fmul2(A2l, splat(0.69314718056f));
+            float dBn[T], dCn[T];
+            float2 dAacc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = T - 1; i >= 0; --i) {
+                const float2 dh = fadd2(cdy[i], e);
+                e = fmul2(a[i], dh);
+                const float2 hp = i == 0 ? hprev : h[i - 1];
+                const float2 q = fmul2(e, hp);                              // dh * a_i * h_{i-1}
+                const float2 pc = fmul2(dy[i], h[i]);
+                const float2 pb = fmul2(dlu[i], dh);
+                dCn[i] = pc.x + pc.y;
+                dBn[i] = pb.x + pb.y;
+                s1[i] = ffma2(dh, splat(Bn[i]), s1[i]);
+                s2[i] = ffma2(q, A2, s2[i]);
+                dAacc = ffma2(q, dl[i], dAacc);
+            }
+            // dB / dC: my 8 tokens of state n, summed over my two rows
+            if (ok) {
+                const int mo = REV ? L - T - tl : tl;
+                float *pb = dB_b + (int64_t)n * L + mo, *pc = dC_b + (int64_t)n * L + mo;
+                if (REV) {
+                    red_add_v4(pb, dBn[7], dBn[6], dBn[5], dBn[4]);
+                    red_add_v4(pb + 4, dBn[3], dBn[2], dBn[1], dBn[0]);
+                    red_add_v4(pc, dCn[7], dCn[6], dCn[5], dCn[4]);
+                    red_add_v4(pc + 4, dCn[3], dCn[2], dCn[1], dCn[0]);
+                } else {
+                    red_add_v4(pb, dBn[0], dBn[1], dBn[2], dBn[3]);
+                    red_add_v4(pb + 4, dBn[4], dBn[5], dBn[6], dBn[7]);
+                    red_add_v4(pc, dCn[0], dCn[1], dCn[2], dCn[3]);
+                    red_add_v4(pc + 4, dCn[4], dCn[5], dCn[6], dCn[7]);
+                }
+            }
+            s_dA[n * NT + tid] = fadd2(s_dA[n * NT + tid], dAacc);
+        }
+
+        __syncthreads();                // everybody is done with the B/C tile: fetch the next one under the epilogue
+        if (c > c_begin) issue_tile(c - 1);
+        if (!AGG) {
+            // ---- epilogue: du, ddelta, dz ---------------------------------------------------------------------------------------------
+            float yv[2][T], zf[2][T];
+            if (has_z) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    load_land(4, r, yv[r]);
+                    const float4 f0 = *reinterpret_cast<const float4 *>(s_zf_t + (r * 2 + 0) * NT * 16);
+                    const float4 f1 = *reinterpret_cast<const float4 *>(s_zf_t + (r * 2 + 1) * NT * 16);
+                    zf[r][0] = f0.x, zf[r][1] = f0.y, zf[r][2] = f0.z, zf[r][3] = f0.w;
+                    zf[r][4] = f1.x, zf[r][5] = f1.y, zf[r][6] = f1.z, zf[r][7] = f1.w;
+                }
+            }
+            if (c > c_begin) issue_y(true);
+            cp_async_commit();
+            float2 duv[T], ddv[T];
+#pragma unroll
+            for (int i = 0; i < T; ++i) {
+                duv[i] = ffma2(dl[i], s1[i], fmul2(make_float2(Dsk[0], Dsk[1]), dy[i]));      // delta*S1 + D*dy   (bwd_kernel.cuh:211,280-281)
+                float2 t = ffma2(uu2[i], s1[i], s2[i]);                                        // u*S1 + S2         (:282-283)
+                if (sp) {
+                    // softplus'(x) = sigmoid(x) = 1 - exp(-softplus(x)); series where delta is tiny (no cancellation)
+                    const float2 d = dl[i];
+                    const float sx = d.x < 1e-2f ? d.x * fmaf(d.x, fmaf(d.x, 0.16666667f, -0.5f), 1.f) : 1.f - ex2(-d.x * kLog2e);
+                    const float sy = d.y < 1e-2f ? d.y * fmaf(d.y, fmaf(d.y, 0.16666667f, -0.5f), 1.f) : 1.f - ex2(-d.y * kLog2e);
+                    t = fmul2(t, make_float2(sx, sy));
+                }
+                if (!ok) t = make_float2(0.f, 0.f);
+                ddv[i] = t;
+                dbacc = fadd2(dbacc, t);
+            }
+            if (ok) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    if (row_ok[r]) {
+                        float v[T];
+#pragma unroll
+                        for (int i = 0; i < T; ++i) v[i] = r ? duv[i].y : duv[i].x;
+                        store8<IN_T, REV>(du_p[r], v);
+#pragma unroll
+                        for (int i = 0; i < T; ++i) v[i] = r ? ddv[i].y : ddv[i].x;
+                        store8<IN_T, REV>(dd_p[r], v);
+                        if (has_z) {
+#pragma unroll
+                            for (int i = 0; i < T; ++i) v[i] = yv[r][i] * zf[r][i];
+                            store8<IN_T, REV>(dz_p[r], v);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                du_p[r] += STEP, dd_p[r] += STEP;
+                if (has_z) dz_p[r] += STEP;
+            }
+        } else {
+            cp_async_commit();
+        }
+    }
+
+    // ---- end of the segment ---------------------------------------------------------------------------------------------------------
+    __syncthreads();
+    if (AGG) {
+        for (int i = tid; i < NRP * 16; i += NT) {
+            const int g = i >> 4, n = i & 15;
+            const float2 e = s_ec[i];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int row = row0 + 2 * g + r;
+                if (row < D) p.seg_E[(((int64_t)b * D + row) * p.nseg + seg) * 16 + n] = r ? e.y : e.x;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float s = dsum[r];
+#pragma unroll
+            for (int k = 1; k < 32; k <<= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+            if (j == 0 && row_ok[r]) p.seg_dsum[((int64_t)b * D + rowA + r) * p.nseg + seg] = s;
+        }
+    } else {
+        // dA: sum the lane partials of my warp (its row pair), one atomic per (row, state)
+        for (int n = 0; n < N; ++n) {
+            float2 v = s_dA[n * NT + tid];
+#pragma unroll
+            for (int k = 1; k < 32; k <<= 1) {
+                v.x += __shfl_xor_sync(0xffffffffu, v.x, k);
+                v.y += __shfl_xor_sync(0xffffffffu, v.y, k);
+            }
+            if (j == 0) {
+                if (row_ok[0]) atomicAdd(p.dA + (int64_t)rowA * N + n, v.x);
+                if (row_ok[1]) atomicAdd(p.dA + (int64_t)(rowA + 1) * N + n, v.y);
+            }
+        }
+        float2 dd = dDacc, db = dbacc;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            dd.x += __shfl_xor_sync(0xffffffffu, dd.x, k), dd.y += __shfl_xor_sync(0xffffffffu, dd.y, k);
+            db.x += __shfl_xor_sync(0xffffffffu, db.x, k), db.y += __shfl_xor_sync(0xffffffffu, db.y, k);
+        }
+        if (j == 0) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (row_ok[r]) {
+                    if (p.dD != nullptr) atomicAdd(p.dD + rowA + r, r ? dd.y : dd.x);
+                    if (p.ddbias != nullptr) atomicAdd(p.ddbias + rowA + r, r ? db.y : db.x);
+                }
+            }
+        }
+    }
+}
+
+// chain the per-segment reverse aggregates right-to-left: ein[s] = e entering segment s from segment s+1
+__global__ void scan3_bwd_chain_kernel(const float *__restrict__ A, const float *__restrict__ seg_E, const float *__restrict__ seg_dsum,
+                                       float *__restrict__ ein, int B, int D, int N, int nseg) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * D * 16) return;
+    const int n = (int)(i & 15);
+    const int64_t bd = i >> 4;
+    const int row = (int)(bd % D);
+    const float a2 = n < N ? A[(int64_t)row * N + n] * kLog2e : 0.f;
+    float carry = 0.f;
+    for (int s = nseg - 1; s >= 0; --s) {
+        ein[(bd * nseg + s) * 16 + n] = carry;
+        carry = fmaf(ex2(a2 * seg_dsum[bd * nseg + s]), carry, seg_E[(bd * nseg + s) * 16 + n]);
+    }
+}
+
+}  // namespace mmu

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include "scan3_bwd.cuh"
 #include "scan_tiles.cuh"
 
 namespace mmu {
@@ -574,7 +575,116 @@ template <typename IN_T> int dispatch_bwd(int cfg, const BwdArgs &a, bool agg, c
     }
 }
 
+// ---- v3 host side (scan3_bwd.cuh) ------------------------------------------------------------------------------------------
+template <typename IN_T> bool row_aligned16(const void *p, int64_t s0, int64_t s1) {
+    return reinterpret_cast<uintptr_t>(p) % 16 == 0 && (s0 * (int64_t)sizeof(IN_T)) % 16 == 0 && (s1 * (int64_t)sizeof(IN_T)) % 16 == 0;
+}
+
+template <typename IN_T> bool bwd3_eligible(const mmu_scan_bwd_params *p) {
+    const mmu_scan_fwd_params &f = p->f;
+    if (env_int("MMU_SCAN_V", 3) < 3 || env_int("MMU_BWD_V", 3) < 3) return false;
+    if (f.dstate > 16 || f.seqlen % 8 != 0) return false;
+    if (f.z && !f.y) return false;                       // dz needs the pre-gate y the forward saved
+    if (f.seqlen > MMU_STATE_STRIDE && !f.x) return false;
+    if (!row_aligned16<IN_T>(f.u, f.u_bs, f.u_ds) || !row_aligned16<IN_T>(f.delta, f.delta_bs, f.delta_ds) ||
+        !row_aligned16<IN_T>(p->dout, p->dout_bs, p->dout_ds) || !row_aligned16<IN_T>(f.B, f.B_bs, f.B_ns) ||
+        !row_aligned16<IN_T>(f.C, f.C_bs, f.C_ns) || !row_aligned16<IN_T>(p->du, p->du_bs, p->du_ds) ||
+        !row_aligned16<IN_T>(p->ddelta, p->ddelta_bs, p->ddelta_ds))
+        return false;
+    if (f.z && (!row_aligned16<IN_T>(f.z, f.z_bs, f.z_ds) || !row_aligned16<IN_T>(f.y, f.y_bs, f.y_ds) ||
+                !row_aligned16<IN_T>(p->dz, p->dz_bs, p->dz_ds)))
+        return false;
+    if (reinterpret_cast<uintptr_t>(p->dB) % 16 != 0 || reinterpret_cast<uintptr_t>(p->dC) % 16 != 0) return false;
+    return true;
+}
+
+struct Bwd3Plan {
+    int W, nseg, cps, nchunks;
+};
+
+Bwd3Plan plan_bwd3(int B, int D, int L) {
+    Bwd3Plan pl;
+    pl.W = env_int("MMU_BWD3_W", D <= 2 ? 1 : (D <= 4 ? 2 : 4));
+    if (pl.W != 1 && pl.W != 2) pl.W = 4;
+    const int R = 2 * pl.W;
+    pl.nchunks = (L + 255) / 256;
+    const int warps = B * ((D + R - 1) / R) * pl.W;
+    int nseg = warps >= 148 * 4 ? 1 : (148 * 8 + warps - 1) / warps;   // splitting costs a second (aggregate) pass
+    nseg = std::min(nseg, std::max(1, pl.nchunks / 2));
+    nseg = std::max(1, std::min(nseg, 64));
+    nseg = env_int("MMU_BWD_NSEG", nseg);
+    nseg = std::max(1, std::min(nseg, pl.nchunks));
+    pl.cps = (pl.nchunks + nseg - 1) / nseg;
+    pl.nseg = (pl.nchunks + pl.cps - 1) / pl.cps;
+    return pl;
+}
+
+template <typename IN_T, int W, bool REV, bool AGG> int launch_bwd3(const Bwd3Args &a, cudaStream_t st) {
+    using Cfg = Bwd3Cfg<IN_T, W>;
+    dim3 grid((a.D + Cfg::R - 1) / Cfg::R, a.B, a.nseg), block(Cfg::NT);
+    auto k = scan3_bwd_kernel<IN_T, W, REV, AGG>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
+    k<<<grid, block, Cfg::smem_bytes, st>>>(a);
+    count_launch();
+    return check_launch("selective_scan_bwd(v3)");
+}
+
+template <typename IN_T, bool AGG> int dispatch_bwd3(const Bwd3Args &a, int W, bool rev, cudaStream_t st) {
+#define MMU_B3(W_) (rev ? launch_bwd3<IN_T, W_, true, AGG>(a, st) : launch_bwd3<IN_T, W_, false, AGG>(a, st))
+    if (W == 1) return MMU_B3(1);
+    if (W == 2) return MMU_B3(2);
+    return MMU_B3(4);
+#undef MMU_B3
+}
+
+template <typename IN_T> int run_bwd3(const mmu_scan_bwd_params *p, cudaStream_t st) {
+    const mmu_scan_fwd_params &f = p->f;
+    const Bwd3Plan pl = plan_bwd3(f.batch, f.dim, f.seqlen);
+    Bwd3Args a{};
+    a.u = f.u, a.delta = f.delta, a.z = f.z, a.dout = p->dout, a.ysave = f.y, a.Bm = f.B, a.Cm = f.C;
+    a.A = f.A, a.Dv = f.D, a.dbias = f.delta_bias, a.x = f.x;
+    a.du = p->du, a.ddelta = p->ddelta, a.dz = p->dz;
+    a.dA = p->dA, a.dB = p->dB, a.dC = p->dC, a.dD = p->dD, a.ddbias = p->ddelta_bias;
+    a.u_bs = f.u_bs, a.u_ds = f.u_ds, a.dl_bs = f.delta_bs, a.dl_ds = f.delta_ds, a.z_bs = f.z_bs, a.z_ds = f.z_ds;
+    a.g_bs = p->dout_bs, a.g_ds = p->dout_ds, a.y_bs = f.y_bs, a.y_ds = f.y_ds;
+    a.B_bs = f.B_bs, a.B_ns = f.B_ns, a.C_bs = f.C_bs, a.C_ns = f.C_ns;
+    a.du_bs = p->du_bs, a.du_ds = p->du_ds, a.ddl_bs = p->ddelta_bs, a.ddl_ds = p->ddelta_ds;
+    a.dz_bs = p->dz_bs, a.dz_ds = p->dz_ds;
+    a.B = f.batch, a.D = f.dim, a.L = f.seqlen, a.N = f.dstate;
+    a.nseg = pl.nseg, a.cps = pl.cps, a.nchunks = pl.nchunks;
+    a.nx = (f.seqlen + MMU_STATE_STRIDE - 1) / MMU_STATE_STRIDE;
+    a.softplus = f.delta_softplus;
+    const bool rev = f.reverse != 0;
+    if (pl.nseg > 1) {
+        const size_t n_state = (size_t)a.B * a.D * pl.nseg * 16, n_row = (size_t)a.B * a.D * pl.nseg;
+        const size_t need = 2 * align256(n_state * 4) + 2 * align256(n_row * 4);
+        if (f.workspace == nullptr || f.workspace_bytes < need)
+            return set_error(MMU_ERR_WORKSPACE, "selective_scan_bwd: workspace %zu < %zu", f.workspace_bytes, need);
+        char *w = static_cast<char *>(f.workspace);
+        a.seg_E = reinterpret_cast<float *>(w);
+        float *ein = reinterpret_cast<float *>(w + align256(n_state * 4));
+        a.seg_dsum = reinterpret_cast<float *>(w + 2 * align256(n_state * 4));
+        a.ein = nullptr;
+        int rc = dispatch_bwd3<IN_T, true>(a, pl.W, rev, st);
+        if (rc) return rc;
+        const int64_t tot = (int64_t)a.B * a.D * 16;
+        scan3_bwd_chain_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(a.A, a.seg_E, a.seg_dsum, ein, a.B, a.D, a.N, pl.nseg);
+        count_launch();
+        rc = check_launch("scan3_bwd_chain");
+        if (rc) return rc;
+        a.ein = ein;
+    }
+    return dispatch_bwd3<IN_T, false>(a, pl.W, rev, st);
+}
+
+template <typename IN_T> struct HasV3 { static constexpr bool value = false; };
+template <> struct HasV3<float> { static constexpr bool value = true; };
+template <> struct HasV3<__nv_bfloat16> { static constexpr bool value = true; };
+
 template <typename IN_T> int run_bwd(const mmu_scan_bwd_params *p, cudaStream_t st) {
+    if constexpr (HasV3<IN_T>::value) {
+        if (bwd3_eligible<IN_T>(p)) return run_bwd3<IN_T>(p, st);
+    }
     const mmu_scan_fwd_params &f = p->f;
     const BwdPlan pl = plan_bwd(f.batch, f.dim, f.seqlen);
     BwdArgs a{};
@@ -632,7 +742,7 @@ template <typename IN_T> int run_bwd(const mmu_scan_bwd_params *p, cudaStream_t 
 }  // namespace mmu
 
 extern "C" size_t mmu_selective_scan_bwd_workspace(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate) {
-    const int Ne = (dstate + 1) & ~1;
+    const int Ne = dstate <= 16 ? 16 : ((dstate + 1) & ~1);
     const int nchunks = (seqlen + 63) / 64;
     const size_t nseg = (size_t)std::max(1, std::min(nchunks, std::max(64, mmu::env_int("MMU_BWD_NSEG", 1))));
     const size_t n_state = (size_t)batch * dim * nseg * Ne, n_row = (size_t)batch * dim * nseg;

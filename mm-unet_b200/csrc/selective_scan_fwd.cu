@@ -26,15 +26,15 @@ namespace mmu {
 struct FwdArgs {
     const void *u, *delta, *z, *Bm, *Cm;
     const float *A, *Dv, *dbias;
-    void *out;
+    void *out, *ysave;
     float *x, *last_state;
     float *seg_hend, *seg_dsum;
     const float *hin;
-    int64_t u_bs, u_ds, dl_bs, dl_ds, z_bs, z_ds, o_bs, o_ds, B_bs, B_ns, C_bs, C_ns;
+    int64_t u_bs, u_ds, dl_bs, dl_ds, z_bs, z_ds, o_bs, o_ds, y_bs, y_ds, B_bs, B_ns, C_bs, C_ns;
     int B, D, L, N, Ne;
     int nseg, cps, nchunks, nx;
     int softplus, reverse;
-    unsigned vec_mask;   // bit0 u, 1 delta, 2 z, 3 out, 4 B, 5 C
+    unsigned vec_mask;   // bit0 u, 1 delta, 2 z, 3 out, 4 B, 5 C, 6 ysave
 };
 
 template <int RD, int RQ, int NGW> struct FwdCfg {
@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(32 * RQ * NGW, 512 / (32 * RQ * NGW)) scan_fwd
     const IN_T *B_b = reinterpret_cast<const IN_T *>(p.Bm) + (int64_t)b * p.B_bs;
     const IN_T *C_b = reinterpret_cast<const IN_T *>(p.Cm) + (int64_t)b * p.C_bs;
     IN_T *o_b = AGG ? nullptr : reinterpret_cast<IN_T *>(p.out) + (int64_t)b * p.o_bs;
+    IN_T *y_b = (AGG || p.ysave == nullptr) ? nullptr : reinterpret_cast<IN_T *>(p.ysave) + (int64_t)b * p.y_bs;
     const bool rev = p.reverse != 0, sp = p.softplus != 0;
 
     const int npw = (NP + NGW - 1) / NGW;
@@ -263,6 +264,13 @@ __global__ void __launch_bounds__(32 * RQ * NGW, 512 / (32 * RQ * NGW)) scan_fwd
             const float4 u4 = *reinterpret_cast<const float4 *>(s_u + off);
             const float dsk = s_D[r];
             y.x = fmaf(dsk, u4.x, y.x), y.y = fmaf(dsk, u4.y, y.y), y.z = fmaf(dsk, u4.z, y.z), y.w = fmaf(dsk, u4.w, y.w);
+            if (y_b != nullptr) {   // pre-gate y for the backward (the reference's saved `out`)
+                const int row_ = row0 + r, t_ = t0 + 4 * swz_chunk<T>(cs);
+                if (row_ < D && t_ < L) {
+                    const float v_[4] = {y.x, y.y, y.z, y.w};
+                    store_quad<IN_T>(y_b + (int64_t)row_ * p.y_ds, t_, L, rev, p.vec_mask & 64u, v_);
+                }
+            }
             if (has_z) {
                 const float4 z4 = *reinterpret_cast<const float4 *>(s_z + off);
                 y.x *= z4.x * sigmoid_f(z4.x), y.y *= z4.y * sigmoid_f(z4.y);
@@ -468,7 +476,7 @@ template <typename IN_T> int run_fwd3(const mmu_scan_fwd_params *p, cudaStream_t
     Fwd3Args a{};
     a.u = p->u, a.delta = p->delta, a.z = p->z, a.Bm = p->B, a.Cm = p->C;
     a.A = p->A, a.Dv = p->D, a.dbias = p->delta_bias;
-    a.out = p->out, a.ysave = p->y, a.x = p->x, a.last_state = p->last_state;
+    a.out = p->out, a.ysave = p->z ? p->y : nullptr, a.x = p->x, a.last_state = p->last_state;
     a.u_bs = p->u_bs, a.u_ds = p->u_ds, a.dl_bs = p->delta_bs, a.dl_ds = p->delta_ds;
     a.z_bs = p->z_bs, a.z_ds = p->z_ds, a.o_bs = p->out_bs, a.o_ds = p->out_ds, a.y_bs = p->y_bs, a.y_ds = p->y_ds;
     a.B_bs = p->B_bs, a.B_ns = p->B_ns, a.C_bs = p->C_bs, a.C_ns = p->C_ns;
@@ -512,9 +520,9 @@ template <typename IN_T> int run_fwd(const mmu_scan_fwd_params *p, cudaStream_t 
     FwdArgs a{};
     a.u = p->u, a.delta = p->delta, a.z = p->z, a.Bm = p->B, a.Cm = p->C;
     a.A = p->A, a.Dv = p->D, a.dbias = p->delta_bias;
-    a.out = p->out, a.x = p->x, a.last_state = p->last_state;
+    a.out = p->out, a.ysave = p->z ? p->y : nullptr, a.x = p->x, a.last_state = p->last_state;
     a.u_bs = p->u_bs, a.u_ds = p->u_ds, a.dl_bs = p->delta_bs, a.dl_ds = p->delta_ds;
-    a.z_bs = p->z_bs, a.z_ds = p->z_ds, a.o_bs = p->out_bs, a.o_ds = p->out_ds;
+    a.z_bs = p->z_bs, a.z_ds = p->z_ds, a.o_bs = p->out_bs, a.o_ds = p->out_ds, a.y_bs = p->y_bs, a.y_ds = p->y_ds;
     a.B_bs = p->B_bs, a.B_ns = p->B_ns, a.C_bs = p->C_bs, a.C_ns = p->C_ns;
     a.B = p->batch, a.D = p->dim, a.L = p->seqlen, a.N = p->dstate, a.Ne = (p->dstate + 1) & ~1;
     a.nseg = pl.nseg, a.cps = pl.cps, a.nchunks = pl.nchunks;
@@ -527,7 +535,8 @@ template <typename IN_T> int run_fwd(const mmu_scan_fwd_params *p, cudaStream_t 
                  ((p->z && quad_ok<IN_T>(p->z, p->z_bs, p->z_ds, L, rev)) ? 4u : 0u) |
                  (quad_ok<IN_T>(p->out, p->out_bs, p->out_ds, L, rev) ? 8u : 0u) |
                  (quad_ok<IN_T>(p->B, p->B_bs, p->B_ns, L, rev) ? 16u : 0u) |
-                 (quad_ok<IN_T>(p->C, p->C_bs, p->C_ns, L, rev) ? 32u : 0u);
+                 (quad_ok<IN_T>(p->C, p->C_bs, p->C_ns, L, rev) ? 32u : 0u) |
+                 ((p->y && quad_ok<IN_T>(p->y, p->y_bs, p->y_ds, L, rev)) ? 64u : 0u);
     const unsigned need = 1u | 2u | 16u | 32u | (p->z ? 4u : 0u);
     if ((a.vec_mask & need) == need && a.Ne <= 16 && env_int("MMU_NO_PREFETCH", 0) == 0) a.vec_mask |= 0x80u;
     if (pl.nseg > 1) {

@@ -101,9 +101,22 @@ def _fill_fwd(p, u, delta, A, B, C, D, z, delta_bias, softplus, reverse, g, G):
     p.B_bs, p.B_ns, p.C_bs, p.C_ns = B.stride(0), B.stride(2), C.stride(0), C.stride(2)
 
 
+class ScanStates(tuple):
+    """What the forward saves for the backward: x = fp32 states after every 64th token (batch, dim, ceil(L/64), dstate),
+    y = pre-gate output C.h + D*u (input dtype; None without a gate) - the role of the reference's `scan_intermediates`
+    and `out` (selective_scan_interface.py:213-219)."""
+    __slots__ = ()
+
+    def __new__(cls, x, y=None):
+        return super().__new__(cls, (x, y))
+
+    x = property(lambda self: self[0])
+    y = property(lambda self: self[1])
+
+
 def selective_scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, reverse=False,
                        save_states=True, return_last_state=False):
-    """-> (out, x, last_state).  out is y*silu(z) when z is given.  x: (batch, dim, ceil(L/64), dstate) fp32."""
+    """-> (out, states, last_state).  out is y*silu(z) when z is given; states is a ScanStates (or None)."""
     _scan_checks(u, delta, A, B, C, D, z, delta_bias)
     batch, dim, L = u.shape
     N = A.shape[1]
@@ -112,6 +125,7 @@ def selective_scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta
     out = torch.empty_like(u, memory_format=torch.contiguous_format)
     nx = (L + _lib.STATE_STRIDE - 1) // _lib.STATE_STRIDE
     x = torch.empty((batch, dim, nx, N), device=u.device, dtype=torch.float32) if save_states else None
+    y = torch.empty_like(out) if (save_states and z is not None) else None
     last = torch.empty((batch, dim, N), device=u.device, dtype=torch.float32) if return_last_state else None
     H = dim // G
     L_ = _lib.lib()
@@ -124,6 +138,9 @@ def selective_scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta
             p.out = out.data_ptr() + g * H * out.stride(1) * out.element_size()
             p.out_bs, p.out_ds = out.stride(0), out.stride(1)
             p.x = None if x is None else x.data_ptr() + g * H * x.stride(1) * 4
+            if y is not None:
+                p.y = y.data_ptr() + g * H * y.stride(1) * y.element_size()
+                p.y_bs, p.y_ds = y.stride(0), y.stride(1)
             p.last_state = None if last is None else last.data_ptr() + g * H * N * 4
             if G > 1:   # per-group x / last_state slices are not batch-contiguous: run into temporaries
                 xg = torch.empty((batch, H, nx, N), device=u.device, dtype=torch.float32) if save_states else None
@@ -136,7 +153,7 @@ def selective_scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta
                     x[:, g * H:(g + 1) * H] = xg
                 if last is not None:
                     last[:, g * H:(g + 1) * H] = lg
-    return out, x, last
+    return out, (ScanStates(x, y) if save_states else None), last
 
 
 def selective_scan_bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softplus=False, reverse=False,
@@ -144,7 +161,10 @@ def selective_scan_bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softp
     """-> (du, ddelta, dA, dB, dC, dD, dz, ddelta_bias); dA/dB/dC/dD/ddelta_bias fp32.
     du / ddelta / dz may be pre-allocated views (e.g. halves of dxz, as selective_scan_interface.py:244-248)."""
     _scan_checks(u, delta, A, B, C, D, z, delta_bias)
-    _require_cuda(dout, x)
+    y = None
+    if isinstance(x, ScanStates):
+        x, y = x.x, x.y
+    _require_cuda(dout, x, y)
     batch, dim, L = u.shape
     N = A.shape[1]
     G = B.shape[1]
@@ -173,6 +193,9 @@ def selective_scan_bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softp
             _fill_fwd(p.f, u, delta, A, B, C, D, z, delta_bias, delta_softplus, reverse, g, G)
             xg = x if G == 1 else x[:, g * H:(g + 1) * H].contiguous()
             p.f.x = xg.data_ptr()
+            if y is not None and z is not None:
+                p.f.y = y.data_ptr() + g * H * y.stride(1) * es
+                p.f.y_bs, p.f.y_ds = y.stride(0), y.stride(1)
             p.f.workspace, p.f.workspace_bytes = _ptr(ws), ws_bytes
             p.dout = dout.data_ptr() + g * H * dout.stride(1) * es
             p.dout_bs, p.dout_ds = dout.stride(0), dout.stride(1)
@@ -286,14 +309,14 @@ class SelectiveScanFn(torch.autograd.Function):
                                           save_states=True, return_last_state=return_last_state)
         ctx.delta_softplus = delta_softplus
         ctx.has_z = z is not None
-        ctx.save_for_backward(u, delta, A, B, C, D, z, delta_bias, x)
+        ctx.save_for_backward(u, delta, A, B, C, D, z, delta_bias, x.x, x.y)
         return out if not return_last_state else (out, last)
 
     @staticmethod
     def backward(ctx, dout, *args):
-        u, delta, A, B, C, D, z, delta_bias, x = ctx.saved_tensors
+        u, delta, A, B, C, D, z, delta_bias, x, y = ctx.saved_tensors
         du, ddelta, dA, dB, dC, dD, dz, ddelta_bias = selective_scan_bwd(
-            u, delta, A, B, C, D, z, delta_bias, dout, x, ctx.delta_softplus)
+            u, delta, A, B, C, D, z, delta_bias, dout, ScanStates(x, y), ctx.delta_softplus)
         dB = (dB.squeeze(1) if ctx.squeeze_B else dB).to(B.dtype)
         dC = (dC.squeeze(1) if ctx.squeeze_C else dC).to(C.dtype)
         return du, ddelta, dA, dB, dC, dD, dz, ddelta_bias, None, None
@@ -363,13 +386,15 @@ class _InnerCore:
         Cm = x_dbl[:, R + N:].view(batch, L, N).transpose(1, 2).contiguous().unsqueeze(1)
         D = D.contiguous() if D is not None else None
         out_z, xs, _ = selective_scan_fwd(conv_out, delta, A, Bm, Cm, D, z, delta_bias, delta_softplus, reverse=reverse)
-        saved = (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, conv_out, delta, A, Bm, Cm, D, delta_bias, xs)
+        saved = (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, conv_out, delta, A, Bm, Cm, D, delta_bias,
+                 xs.x, xs.y)
         return out_z, saved
 
     @staticmethod
     def backward(saved, dout_y, delta_softplus, reverse=False):
         """dout_y: (b, d, l).  Returns (dxz, dconv_w (d,1,w), dconv_b, dx_proj_w, ddt_proj_w, dA, dD, ddelta_bias)."""
-        (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, conv_out, delta, A, Bm, Cm, D, delta_bias, xs) = saved
+        (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, conv_out, delta, A, Bm, Cm, D, delta_bias, xs_x, xs_y) = saved
+        xs = ScanStates(xs_x, xs_y)
         L = xz.shape[-1]
         R = delta_proj_weight.shape[1]
         N = A.shape[-1]
@@ -478,13 +503,13 @@ class BiMambaInnerFn(torch.autograd.Function):
             x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias)
         out_f, saved = _InnerCore.forward(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C, D,
                                           delta_bias, B_proj_bias, C_proj_bias, delta_softplus)
-        (xz_, conv_w, conv_b, x_dbl, xw, dw, conv_out, delta, A_, Bm, Cm, D_, db_, xs_f) = saved
+        (xz_, conv_w, conv_b, x_dbl, xw, dw, conv_out, delta, A_, Bm, Cm, D_, db_, _xs_fx, _xs_fy) = saved
         z = xz_.chunk(2, dim=1)[1]
         out_b, xs_b, _ = selective_scan_fwd(conv_out, delta, A_b, Bm, Cm, D_, z, db_, delta_softplus, reverse=True)
         out_z = out_f + out_b            # out_b is already stored in un-flipped positions
         ctx.delta_softplus = delta_softplus
         ctx.out_proj_bias_is_None = out_proj_bias is None
-        saved = saved + (out_proj_weight, out_z, A_b, xs_b)
+        saved = saved + (out_proj_weight, out_z, A_b, xs_b.x, xs_b.y)
         ctx.save_for_backward(*[t for t in saved if t is not None])
         ctx.mask = [t is not None for t in saved]
         return F.linear(out_z.transpose(1, 2), out_proj_weight, out_proj_bias)
@@ -494,9 +519,10 @@ class BiMambaInnerFn(torch.autograd.Function):
     def backward(ctx, dout):
         it = iter(ctx.saved_tensors)
         saved = tuple(next(it) if m else None for m in ctx.mask)
-        out_proj_weight, out_z, A_b, xs_b = saved[-4:]
-        core = saved[:-4]
-        (xz, conv_w, conv_b, x_dbl, xw, dw, conv_out, delta, A, Bm, Cm, D, dbias, xs_f) = core
+        out_proj_weight, out_z, A_b, xs_bx, xs_by = saved[-5:]
+        core = saved[:-5]
+        (xz, conv_w, conv_b, x_dbl, xw, dw, conv_out, delta, A, Bm, Cm, D, dbias, xs_fx, xs_fy) = core
+        xs_b, xs_f = ScanStates(xs_bx, xs_by), ScanStates(xs_fx, xs_fy)
         batch, L, e = dout.shape
         d = out_z.shape[1]
         R, N = dw.shape[1], A.shape[-1]

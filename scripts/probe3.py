@@ -20,7 +20,7 @@ def run(B, D, L, N, dtype, bwd=True):
         print(f"v{v} B{B} D{D} L{L} N{N} {str(dtype)[6:]}: fwd {tf:8.1f} us {fb / tf / 1e3:6.0f} GB/s | bwd {tb:8.1f} us {bb / tb / 1e3:6.0f} GB/s", flush=True)
     o1, x1, l1, g1 = res["1"]; o3, x3, l3, g3 = res["3"]
     print(f"   max|out1-out3| {(o1 - o3).abs().max().item():.3e} (|out| max {o1.abs().max().item():.2e})  "
-          f"x {(x1 - x3).abs().max().item():.3e}  last {(l1 - l3).abs().max().item():.3e}", flush=True)
+          f"x {(x1.x - x3.x).abs().max().item():.3e}  last {(l1 - l3).abs().max().item():.3e}", flush=True)
     if bwd:
         names = ["du", "ddelta", "dA", "dB", "dC", "dD", "dz", "dbias"]
         print("   grads:", "  ".join(f"{n} {(a.float() - b.float()).abs().max().item():.2e}/{a.float().abs().max().item():.1e}"
