@@ -27,6 +27,7 @@ struct Bwd3Args {
     int B, D, L, N;
     int nseg, cps, nchunks, nx;
     int softplus;
+    int dbg;                       // timing experiments only (MMU_BWD3_DBG): 1 = skip the dB/dC atomics, 2 = skip the dA accumulation
 };
 
 template <typename IN_T, int W> struct Bwd3Cfg {
@@ -38,10 +39,11 @@ template <typename IN_T, int W> struct Bwd3Cfg {
     static constexpr int NQ = Raw8<IN_T>::kQuads;
     static constexpr int kLandBytes = 5 * 2 * NQ * NT * 16;               // u | delta | z | dout | y : [tensor][row][quad][thread] x 16 B
     static constexpr int kZfBytes = 2 * 2 * NT * 16;                      // dz factor, fp32: [row][quad][thread] x 16 B
-    static constexpr int kDABytes = 16 * NT * 8;                          // dA partials [state][thread] float2
+    static constexpr int kDABytes = 16 * W * 8 * 8;                       // dA partials [state][warp][8 lanes] float2
+    static constexpr int kSlabBytes = 2 * W * 2 * 2 * 32 * 16;            // dB | dC partials of one state: [buf][warp][tensor][quad][lane] float4
     static constexpr int kSeedBytes = 2 * W * NCK * 16 * 8;               // x seeds [buf][warp][ck][state] float2
     static constexpr int kTabBytes = 2 * NRP * 16 * 8;                    // A*log2e | e carry
-    static constexpr size_t smem_bytes = (size_t)BcTile<LPR>::kBytes + kRawBytes + kLandBytes + kZfBytes + kDABytes + kSeedBytes + kTabBytes;
+    static constexpr size_t smem_bytes = (size_t)BcTile<LPR>::kBytes + kRawBytes + kLandBytes + kZfBytes + kDABytes + kSlabBytes + kSeedBytes + kTabBytes;
 };
 
 __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
@@ -60,19 +62,20 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (W >= 4 ? 2 : 4)) scan3_bwd_
     const int b = blockIdx.y, row0 = blockIdx.x * R, seg = blockIdx.z;
     const int D = p.D, L = p.L, N = p.N;
     const bool has_z = p.z != nullptr, sp = p.softplus != 0;
-    const int NS = N;
+    const int NS = (N + 1) & ~1;           // states are walked two at a time (a padding state has A = B = C = 0)
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *s_tile = smem_raw;
     unsigned char *s_rawbc = s_tile + Tl::kBytes;
     unsigned char *s_land = s_rawbc + Cfg::kRawBytes;
     unsigned char *s_zf = s_land + Cfg::kLandBytes;
-    float2 *s_dA = reinterpret_cast<float2 *>(s_zf + Cfg::kZfBytes);
-    float2 *s_seed = s_dA + 16 * NT;                                       // [2][W][NCK][16]
+    float2 *s_dA = reinterpret_cast<float2 *>(s_zf + Cfg::kZfBytes);       // [16][W][8]
+    float4 *s_slab = reinterpret_cast<float4 *>(s_zf + Cfg::kZfBytes + Cfg::kDABytes);   // [2][W][2][2][32]
+    float2 *s_seed = reinterpret_cast<float2 *>(s_zf + Cfg::kZfBytes + Cfg::kDABytes + Cfg::kSlabBytes);   // [2][W][NCK][16]
     float2 *s_A = s_seed + 2 * W * NCK * 16;                               // [NRP][16]  A*log2e of (row A, row B)
     float2 *s_ec = s_A + NRP * 16;                                         // [NRP][16]  e entering the chunk from the right
 
-    for (int i = tid; i < (int)((Tl::kBytes + Cfg::kRawBytes + Cfg::kLandBytes + Cfg::kZfBytes + Cfg::kDABytes + Cfg::kSeedBytes) / 16); i += NT)
+    for (int i = tid; i < (int)((Tl::kBytes + Cfg::kRawBytes + Cfg::kLandBytes + Cfg::kZfBytes + Cfg::kDABytes + Cfg::kSlabBytes + Cfg::kSeedBytes) / 16); i += NT)
         reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = tid; i < NRP * 16; i += NT) {
         const int g = i >> 4, n = i & 15;
@@ -97,6 +100,7 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (W >= 4 ? 2 : 4)) scan3_bwd_
     constexpr int STEP = REV ? CH : -CH;                // memory step to the next (= previous in time) chunk
     bool row_ok[2];
     const IN_T *u_p[2], *d_p[2], *z_p[2], *g_p[2], *y_p[2];     // prefetch pointers
+    const IN_T *uc_p[2];                                           // u of the current chunk (re-read by the epilogue)
     IN_T *du_p[2], *dd_p[2], *dz_p[2];                            // output pointers (current chunk)
     float bias[2], Dsk[2];
 #pragma unroll
@@ -104,6 +108,7 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (W >= 4 ? 2 : 4)) scan3_bwd_
         row_ok[r] = rowA + r < D;
         const int row = min(rowA + r, D - 1);
         u_p[r] = reinterpret_cast<const IN_T *>(p.u) + (int64_t)b * p.u_bs + (int64_t)row * p.u_ds + mo0;
+        uc_p[r] = u_p[r];
         d_p[r] = reinterpret_cast<const IN_T *>(p.delta) + (int64_t)b * p.dl_bs + (int64_t)row * p.dl_ds + mo0;
         g_p[r] = reinterpret_cast<const IN_T *>(p.dout) + (int64_t)b * p.g_bs + (int64_t)row * p.g_ds + mo0;
         z_p[r] = has_z ? reinterpret_cast<const IN_T *>(p.z) + (int64_t)b * p.z_bs + (int64_t)row * p.z_ds + mo0 : nullptr;
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (W >= 4 ? 2 : 4)) scan3_bwd_
             __syncthreads();
         }
         // ---- per (row, token) registers (.x = row A, .y = row B) ---------------------------------------------------------------
-        float2 dl[T], dlu[T], dy[T], uu2[T];
+        float2 dl[T], dlu[T], dy[T];
         {
             float uu[2][T], dd[2][T], gg[2][T], zf[2][T];
 #pragma unroll
@@ -250,9 +255,9 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (W >= 4 ? 2 : 4)) scan3_bwd_
                 dl[i] = make_float2(dd[0][i], dd[1][i]);
                 dy[i] = make_float2(gg[0][i], gg[1][i]);
                 if (!AGG) {
-                    uu2[i] = make_float2(uu[0][i], uu[1][i]);
-                    dlu[i] = fmul2(dl[i], uu2[i]);
-                    dDacc = ffma2(dy[i], uu2[i], dDacc);
+                    const float2 u2 = make_float2(uu[0][i], uu[1][i]);
+                    dlu[i] = fmul2(dl[i], u2);
+                    dDacc = ffma2(dy[i], u2, dDacc);
                 }
             }
         }
@@ -267,93 +272,86 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (W >= 4 ? 2 : 4)) scan3_bwd_
         for (int i = 0; i < T; ++i) s1[i] = s2[i] = make_float2(0.f, 0.f);
         const float2 *seedp = s_seed + (((c & 1) * W + warp) * NCK + (j >> 3)) * 16;
 
-#pragma unroll 1
-        for (int n = 0; n < NS; ++n) {
+        // ---- state loop, software pipelined: phase 1 of state n+1 (a, lane aggregates, both shuffle scans) is independent of
+        //      phase 2 of state n (h, reverse sweep, contributions) and hides the scans' shuffle latency -----------------------
+        auto load_bc = [&](int n, float (&Bn)[T], float (&Cn)[T]) {
+            const unsigned char *rowB = tile + n * Tl::kRowBytes, *rowC = rowB + 16 * Tl::kRowBytes;
+            const float4 c0 = *reinterpret_cast<const float4 *>(rowC), c1 = *reinterpret_cast<const float4 *>(rowC + 16);
+            const float ec_[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+            order8<REV>(ec_, Cn);
+            if (!AGG) {
+                const float4 b0 = *reinterpret_cast<const float4 *>(rowB), b1 = *reinterpret_cast<const float4 *>(rowB + 16);
+                const float eb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                order8<REV>(eb, Bn);
+            }
+        };
+        // phase 1: a_i, the state hs entering my first token, the e entering my last token from the right
+        auto phase1 = [&](int n, float2 (&a)[T], float2 &hs, float2 &ein) {
             const float2 A2l = s_A[warp * 16 + n];
             const float2 ec = s_ec[warp * 16 + n];
             float Bn[T], Cn[T];
-            {
-                const unsigned char *rowB = tile + n * Tl::kRowBytes, *rowC = rowB + 16 * Tl::kRowBytes;
-                const float4 c0 = *reinterpret_cast<const float4 *>(rowC), c1 = *reinterpret_cast<const float4 *>(rowC + 16);
-                const float ec_[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                order8<REV>(ec_, Cn);
-                if (!AGG) {
-                    const float4 b0 = *reinterpret_cast<const float4 *>(rowB), b1 = *reinterpret_cast<const float4 *>(rowB + 16);
-                    const float eb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                    order8<REV>(eb, Bn);
-                }
-            }
-            // ---- a_i, lane aggregates of the forward (H, P) and of the reverse (E) ---------------------------------------------
-            float2 a[T], bu[T], cdy[T];
+            load_bc(n, Bn, Cn);
             float2 H = make_float2(0.f, 0.f), P, E = make_float2(0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < T; ++i) {
                 a[i] = ex2(fmul2(dl[i], A2l));
                 P = i == 0 ? a[0] : fmul2(P, a[i]);
-                if (!AGG) {
-                    bu[i] = fmul2(dlu[i], splat(Bn[i]));
-                    H = ffma2(a[i], H, bu[i]);
-                }
-                cdy[i] = fmul2(dy[i], splat(Cn[i]));
+                if (!AGG) H = ffma2(a[i], H, fmul2(dlu[i], splat(Bn[i])));
             }
 #pragma unroll
-            for (int i = T - 1; i >= 0; --i) E = fmul2(a[i], fadd2(cdy[i], E));
-            // lane 31 absorbs the e entering the chunk from the right
-            {
+            for (int i = T - 1; i >= 0; --i) E = fmul2(a[i], ffma2(dy[i], splat(Cn[i]), E));
+            {   // lane 31 absorbs the e entering the chunk from the right
                 const float2 E31 = ffma2(P, ec, E);
                 if (j == 31) E = E31;
             }
-            // reverse (suffix) scan over the 32 lanes
-            float2 Pr = P;
+            float2 seed = make_float2(0.f, 0.f);
+            if (!AGG) {
+                seed = seedp[n];
+                const float2 H0 = ffma2(P, seed, H);
+                if ((j & 7) == 0) H = H0;
+            }
+            float2 Pr = P, Pf = P;
 #pragma unroll
             for (int st = 0; st < 5; ++st) {
                 const float2 En = shfl_down2(E, 1 << st, 32);
-                float2 Pn;
+                float2 Pn, Hn, Pfn;
                 if (st < 4) Pn = shfl_down2(Pr, 1 << st, 32);
+                if (!AGG && st < 3) {
+                    Hn = shfl_up2(H, 1 << st, 8);
+                    if (st < 2) Pfn = shfl_up2(Pf, 1 << st, 8);
+                }
                 if (ge_dn[st]) {
                     E = ffma2(Pr, En, E);
                     if (st < 4) Pr = fmul2(Pr, Pn);
                 }
-            }
-            if (j == 0) s_ec[warp * 16 + n] = E;                            // e at the chunk's first token: carry for chunk c-1
-            if (AGG) continue;
-            float2 e = shfl_down2(E, 1, 32);
-            if (j == 31) e = ec;
-
-            // ---- forward states: 8-lane scan seeded from the saved states ------------------------------------------------------
-            const float2 seed = seedp[n];
-            {
-                const float2 H0 = ffma2(P, seed, H);
-                if ((j & 7) == 0) H = H0;
-            }
-            float2 Pf = P;
-#pragma unroll
-            for (int st = 0; st < 3; ++st) {
-                const float2 Hn = shfl_up2(H, 1 << st, 8);
-                float2 Pn;
-                if (st < 2) Pn = shfl_up2(Pf, 1 << st, 8);
-                if (ge_up[st]) {
+                if (!AGG && st < 3 && ge_up[st]) {
                     H = ffma2(Pf, Hn, H);
-                    if (st < 2) Pf = fmul2(Pf, Pn);
+                    if (st < 2) Pf = fmul2(Pf, Pfn);
                 }
             }
-            float2 hprev = shfl_up2(H, 1, 8);
-            if ((j & 7) == 0) hprev = seed;
+            if (j == 0) s_ec[warp * 16 + n] = E;                            // e at the chunk's first token: carry for chunk c-1
+            ein = shfl_down2(E, 1, 32);
+            if (j == 31) ein = ec;
+            if (!AGG) {
+                hs = shfl_up2(H, 1, 8);
+                if ((j & 7) == 0) hs = seed;
+            }
+        };
+        // phase 2: forward states, reverse sweep, contributions
+        auto phase2 = [&](int n, const float2 (&a)[T], float2 hs, float2 e) {
+            float Bn[T], Cn[T];
+            load_bc(n, Bn, Cn);
             float2 h[T];
 #pragma unroll
-            for (int i = 0; i < T; ++i) {
-                h[i] = ffma2(a[i], i == 0 ? hprev : h[i - 1], bu[i]);
-            }
-            // ---- reverse sweep with the true e, contributions -------------------------------------------------------------------------
-            const float2 A2 = fmul2(A2l, splat(0.69314718056f));
+            for (int i = 0; i < T; ++i) h[i] = ffma2(a[i], i == 0 ? hs : h[i - 1], fmul2(dlu[i], splat(Bn[i])));
+            const float2 A2 = fmul2(s_A[warp * 16 + n], splat(0.69314718056f));
             float dBn[T], dCn[T];
             float2 dAacc = make_float2(0.f, 0.f);
 #pragma unroll
             for (int i = T - 1; i >= 0; --i) {
-                const float2 dh = fadd2(cdy[i], e);
+                const float2 dh = ffma2(dy[i], splat(Cn[i]), e);
                 e = fmul2(a[i], dh);
-                const float2 hp = i == 0 ? hprev : h[i - 1];
-                const float2 q = fmul2(e, hp);                              // dh * a_i * h_{i-1}
+                const float2 q = fmul2(e, i == 0 ? hs : h[i - 1]);          // dh * a_i * h_{i-1}
                 const float2 pc = fmul2(dy[i], h[i]);
                 const float2 pb = fmul2(dlu[i], dh);
                 dCn[i] = pc.x + pc.y;
@@ -362,30 +360,70 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (W >= 4 ? 2 : 4)) scan3_bwd_
                 s2[i] = ffma2(q, A2, s2[i]);
                 dAacc = ffma2(q, dl[i], dAacc);
             }
-            // dB / dC: my 8 tokens of state n, summed over my two rows
-            if (ok) {
-                const int mo = REV ? L - T - tl : tl;
-                float *pb = dB_b + (int64_t)n * L + mo, *pc = dC_b + (int64_t)n * L + mo;
-                if (REV) {
-                    red_add_v4(pb, dBn[7], dBn[6], dBn[5], dBn[4]);
-                    red_add_v4(pb + 4, dBn[3], dBn[2], dBn[1], dBn[0]);
-                    red_add_v4(pc, dCn[7], dCn[6], dCn[5], dCn[4]);
-                    red_add_v4(pc + 4, dCn[3], dCn[2], dCn[1], dCn[0]);
-                } else {
-                    red_add_v4(pb, dBn[0], dBn[1], dBn[2], dBn[3]);
-                    red_add_v4(pb + 4, dBn[4], dBn[5], dBn[6], dBn[7]);
-                    red_add_v4(pc, dCn[0], dCn[1], dCn[2], dCn[3]);
-                    red_add_v4(pc + 4, dCn[4], dCn[5], dCn[6], dCn[7]);
+            // dB / dC: my 8 tokens of state n, summed over my two rows -> CTA slab -> summed over the CTA's warps -> one
+            // red.global.add.v4 per 4 tokens (8x fewer L2 atomics than one per row pair)
+            {
+                float4 *sl = s_slab + (((n & 1) * W + warp) * 4) * 32 + j;
+                sl[0 * 32] = make_float4(dBn[0], dBn[1], dBn[2], dBn[3]);
+                sl[1 * 32] = make_float4(dBn[4], dBn[5], dBn[6], dBn[7]);
+                sl[2 * 32] = make_float4(dCn[0], dCn[1], dCn[2], dCn[3]);
+                sl[3 * 32] = make_float4(dCn[4], dCn[5], dCn[6], dCn[7]);
+            }
+            // dA: fold the 32 lane partials to 8, accumulate those in shared memory
+            dAacc.x += __shfl_xor_sync(0xffffffffu, dAacc.x, 16), dAacc.y += __shfl_xor_sync(0xffffffffu, dAacc.y, 16);
+            dAacc.x += __shfl_xor_sync(0xffffffffu, dAacc.x, 8), dAacc.y += __shfl_xor_sync(0xffffffffu, dAacc.y, 8);
+            if (j < 8) s_dA[(n * W + warp) * 8 + j] = fadd2(s_dA[(n * W + warp) * 8 + j], dAacc);
+            __syncthreads();
+            if (n < N && !(p.dbg & 1)) {
+                const int t0c = tl - T * j;                                 // first token of the chunk
+                for (int idx = tid; idx < 128; idx += NT) {
+                    const int which = idx >> 6, q = (idx >> 5) & 1, l = idx & 31;
+                    const float4 *src = s_slab + (((n & 1) * W) * 4 + which * 2 + q) * 32 + l;
+                    float4 v = src[0];
+#pragma unroll
+                    for (int w = 1; w < W; ++w) {
+                        const float4 t = src[w * 4 * 32];
+                        v.x += t.x, v.y += t.y, v.z += t.z, v.w += t.w;
+                    }
+                    const int tq = t0c + 8 * l + 4 * q;
+                    if (tq < L) {
+                        float *dst = (which ? dC_b : dB_b) + (int64_t)n * L + (REV ? L - 4 - tq : tq);
+                        if (REV) red_add_v4(dst, v.w, v.z, v.y, v.x);
+                        else red_add_v4(dst, v.x, v.y, v.z, v.w);
+                    }
                 }
             }
-            s_dA[n * NT + tid] = fadd2(s_dA[n * NT + tid], dAacc);
+        };
+
+        if (AGG) {
+#pragma unroll 1
+            for (int n = 0; n < NS; ++n) {
+                float2 a0[T], hs0, e0;
+                phase1(n, a0, hs0, e0);
+            }
+        } else {
+            float2 a0[T], a1[T], hs0, hs1, e0, e1;
+            phase1(0, a0, hs0, e0);
+#pragma unroll 1
+            for (int n = 0; n < NS; n += 2) {
+                phase1(n + 1, a1, hs1, e1);
+                phase2(n, a0, hs0, e0);
+                if (n + 2 < NS) phase1(n + 2, a0, hs0, e0);
+                phase2(n + 1, a1, hs1, e1);
+            }
         }
 
         __syncthreads();                // everybody is done with the B/C tile: fetch the next one under the epilogue
         if (c > c_begin) issue_tile(c - 1);
         if (!AGG) {
             // ---- epilogue: du, ddelta, dz ---------------------------------------------------------------------------------------------
-            float yv[2][T], zf[2][T];
+            float yv[2][T], zf[2][T], uu[2][T];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {       // u of this chunk again (an L2 hit)
+#pragma unroll
+                for (int i = 0; i < T; ++i) uu[r][i] = 0.f;
+                if (ok) load8_global<IN_T, REV>(uc_p[r], uu[r]);
+            }
             if (has_z) {
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
@@ -402,7 +440,7 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (W >= 4 ? 2 : 4)) scan3_bwd_
 #pragma unroll
             for (int i = 0; i < T; ++i) {
                 duv[i] = ffma2(dl[i], s1[i], fmul2(make_float2(Dsk[0], Dsk[1]), dy[i]));      // delta*S1 + D*dy   (bwd_kernel.cuh:211,280-281)
-                float2 t = ffma2(uu2[i], s1[i], s2[i]);                                        // u*S1 + S2         (:282-283)
+                float2 t = ffma2(make_float2(uu[0][i], uu[1][i]), s1[i], s2[i]);                  // u*S1 + S2         (:282-283)
                 if (sp) {
                     // softplus'(x) = sigmoid(x) = 1 - exp(-softplus(x)); series where delta is tiny (no cancellation)
                     const float2 d = dl[i];
@@ -435,7 +473,7 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (W >= 4 ? 2 : 4)) scan3_bwd_
             }
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                du_p[r] += STEP, dd_p[r] += STEP;
+                du_p[r] += STEP, dd_p[r] += STEP, uc_p[r] += STEP;
                 if (has_z) dz_p[r] += STEP;
             }
         } else {
@@ -463,15 +501,15 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (W >= 4 ? 2 : 4)) scan3_bwd_
             if (j == 0 && row_ok[r]) p.seg_dsum[((int64_t)b * D + rowA + r) * p.nseg + seg] = s;
         }
     } else {
-        // dA: sum the lane partials of my warp (its row pair), one atomic per (row, state)
+        // dA: sum the 8 lane partials of my warp (its row pair), one atomic per (row, state)
         for (int n = 0; n < N; ++n) {
-            float2 v = s_dA[n * NT + tid];
+            float2 v = j < 8 ? s_dA[(n * W + warp) * 8 + j] : make_float2(0.f, 0.f);
 #pragma unroll
-            for (int k = 1; k < 32; k <<= 1) {
+            for (int k = 1; k < 8; k <<= 1) {
                 v.x += __shfl_xor_sync(0xffffffffu, v.x, k);
                 v.y += __shfl_xor_sync(0xffffffffu, v.y, k);
             }
-            if (j == 0) {
+            if (j == 0 && !(p.dbg & 2)) {
                 if (row_ok[0]) atomicAdd(p.dA + (int64_t)rowA * N + n, v.x);
                 if (row_ok[1]) atomicAdd(p.dA + (int64_t)(rowA + 1) * N + n, v.y);
             }

@@ -623,8 +623,9 @@ template <typename IN_T, int W, bool REV, bool AGG> int launch_bwd3(const Bwd3Ar
     using Cfg = Bwd3Cfg<IN_T, W>;
     dim3 grid((a.D + Cfg::R - 1) / Cfg::R, a.B, a.nseg), block(Cfg::NT);
     auto k = scan3_bwd_kernel<IN_T, W, REV, AGG>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
-    k<<<grid, block, Cfg::smem_bytes, st>>>(a);
+    const size_t smem = Cfg::smem_bytes + (size_t)env_int("MMU_BWD3_SMEM_PAD", 0);   // occupancy experiments
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<grid, block, smem, st>>>(a);
     count_launch();
     return check_launch("selective_scan_bwd(v3)");
 }
@@ -654,6 +655,7 @@ template <typename IN_T> int run_bwd3(const mmu_scan_bwd_params *p, cudaStream_t
     a.nseg = pl.nseg, a.cps = pl.cps, a.nchunks = pl.nchunks;
     a.nx = (f.seqlen + MMU_STATE_STRIDE - 1) / MMU_STATE_STRIDE;
     a.softplus = f.delta_softplus;
+    a.dbg = env_int("MMU_BWD3_DBG", 0);
     const bool rev = f.reverse != 0;
     if (pl.nseg > 1) {
         const size_t n_state = (size_t)a.B * a.D * pl.nseg * 16, n_row = (size_t)a.B * a.D * pl.nseg;
