@@ -144,14 +144,77 @@ def test_scan_sequence_split_matches(nseg, monkeypatch):
 
 @pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
 def test_scan_fwd_all_tilings(cfg, monkeypatch):
+    monkeypatch.setenv("MMU_SCAN_V", "1")
     monkeypatch.setenv("MMU_FWD_CFG", str(cfg))
     run_scan_case(2, 20, 700, 16)
+    run_scan_case(2, 20, 704, 16)
 
 
 @pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
 def test_scan_bwd_all_tilings(cfg, monkeypatch):
+    monkeypatch.setenv("MMU_SCAN_V", "1")
     monkeypatch.setenv("MMU_BWD_CFG", str(cfg))
     run_scan_case(2, 20, 700, 16)
+    run_scan_case(2, 20, 704, 16)
+
+
+# ---- both kernel generations: v3 (register-resident token lanes; dstate <= 16, L % 8 == 0, 16-byte aligned rows) and the
+# generic v1 kernels must agree with the oracle on the same cases; MMU_SCAN_V=1 forces v1.
+V3_SHAPES = [(2, 6, 1024, 16), (1, 2, 256, 16), (3, 5, 264, 5), (2, 16, 2048, 8), (1, 9, 8, 16), (2, 7, 1000, 4),
+             (1, 20, 4104, 16), (2, 3, 64, 1)]
+
+
+@pytest.mark.parametrize("ver", ["1", "3"])
+@pytest.mark.parametrize("shape", V3_SHAPES)
+def test_scan_kernel_generations(ver, shape, monkeypatch):
+    monkeypatch.setenv("MMU_SCAN_V", ver)
+    run_scan_case(*shape)
+    run_scan_case(*shape, reverse=True)
+
+
+@pytest.mark.parametrize("flags", [dict(has_z=False), dict(has_D=False), dict(has_bias=False),
+                                   dict(has_z=False, has_D=False, has_bias=False)])
+@pytest.mark.parametrize("softplus", [False, True])
+def test_scan_v3_optional_inputs(flags, softplus):
+    run_scan_case(2, 6, 520, 16, softplus=softplus, **flags)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16])
+@pytest.mark.parametrize("reverse", [False, True])
+def test_scan_v3_bf16(dtype, reverse):
+    run_scan_case(2, 8, 1024, 16, dtype=dtype, reverse=reverse)
+    run_scan_case(1, 6, 776, 16, dtype=dtype, reverse=reverse)          # ragged last chunk
+    run_scan_case(3, 8, 512, 16, dtype=dtype, reverse=reverse, xz_layout=True)
+
+
+@pytest.mark.parametrize("nseg", [2, 3, 7])
+def test_scan_v3_sequence_split(nseg, monkeypatch):
+    monkeypatch.setenv("MMU_FWD_NSEG", str(nseg))
+    monkeypatch.setenv("MMU_BWD_NSEG", str(nseg))
+    run_scan_case(2, 6, 2048, 16)
+    run_scan_case(1, 3, 4096, 16, reverse=True)
+    run_scan_case(2, 2, 1800, 16, dtype=torch.bfloat16)
+
+
+def test_scan_v3_narrow_long():
+    """MM-UNet's MMConv regime: D = 6 rows, long L -> the sequence is split over CTAs by the planner."""
+    run_scan_case(2, 6, 16384, 16)
+    run_scan_case(1, 2, 8192, 16, reverse=True)
+
+
+@pytest.mark.parametrize("fwd_v,bwd_v", [("1", "3"), ("3", "1")])
+def test_scan_generations_interoperate(fwd_v, bwd_v, monkeypatch):
+    """The saved states (x every 64 tokens, pre-gate y) have one format: a v1 forward feeds a v3 backward and vice versa."""
+    cpu, gpu = make_scan_inputs(2, 6, 1024, 16)
+    n = lambda t: t.numpy()
+    rg = oracle.selective_scan_bwd(*(n(cpu[k]) for k in ("u", "delta", "A", "B", "C", "D", "z", "delta_bias", "dout")), True)
+    monkeypatch.setenv("MMU_SCAN_V", fwd_v)
+    out, st, _ = ops.selective_scan_fwd(*(gpu[k] for k in ("u", "delta", "A", "B", "C", "D", "z", "delta_bias")), True)
+    monkeypatch.setenv("MMU_SCAN_V", bwd_v)
+    g = ops.selective_scan_bwd(*(gpu[k] for k in ("u", "delta", "A", "B", "C", "D", "z", "delta_bias", "dout")), st, True)
+    check("du", g[0], rg["du"], 1e-3, 4e-3)
+    check("dz", g[6], rg["dz"], 1e-3, 2e-3)
+    check("dB", g[3], rg["dB"][:, None] if rg["dB"].ndim == 3 else rg["dB"], 1e-3, 2e-3)
 
 
 def test_scan_golden_fixtures():
