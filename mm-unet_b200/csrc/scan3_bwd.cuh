@@ -21,7 +21,8 @@ struct Bwd3Args {
     void *du, *ddelta, *dz;
     float *dA, *dB, *dC, *dD, *ddbias;
     float *seg_E, *seg_dsum;       // AGG pass outputs
-    const float *ein;              // reverse carry entering each segment (main pass, nseg > 1)
+    float *ein;                    // reverse carry entering each segment (main pass, nseg > 1); written by the chained kernel
+    int *chain_flags, *chain_ticket;   // chained segments (no aggregate pass): carry-ready flags [group][seg], work ticket
     int64_t u_bs, u_ds, dl_bs, dl_ds, z_bs, z_ds, g_bs, g_ds, y_bs, y_ds, B_bs, B_ns, C_bs, C_ns;
     int64_t du_bs, du_ds, ddl_bs, ddl_ds, dz_bs, dz_ds;
     int B, D, L, N;
@@ -59,9 +60,25 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (W >= 4 ? 2 : 4)) scan3_bwd_
     constexpr int EPQ = 16 / (int)sizeof(IN_T);
     constexpr bool kF32 = Cfg::kF32;
     const int tid = threadIdx.x, warp = tid >> 5, j = tid & 31;
-    const int b = blockIdx.y, row0 = blockIdx.x * R, seg = blockIdx.z;
     const int D = p.D, L = p.L, N = p.N;
     const bool has_z = p.z != nullptr, sp = p.softplus != 0;
+    // Work item.  Plain launch: (row group, batch, segment) = blockIdx.  Chained launch (wide problems whose CTAs do not fill
+    // whole waves): segments of one row group are separate CTAs, LAST segment first; a CTA takes its item from a ticket
+    // counter, so the CTA that owns the segment to its right always started earlier and a spin-wait on its carry cannot
+    // deadlock.  No aggregate pass is needed: the forward states come from x, only e flows between segments.
+    __shared__ int s_item;
+    const bool chained = !AGG && p.chain_ticket != nullptr;
+    int bx = blockIdx.x, b = blockIdx.y, seg = blockIdx.z;
+    int gidx = 0;
+    if (chained) {
+        if (tid == 0) s_item = atomicAdd(p.chain_ticket, 1);
+        __syncthreads();
+        const int G = gridDim.x * gridDim.y;
+        gidx = s_item % G;
+        seg = p.nseg - 1 - s_item / G;
+        bx = gidx % gridDim.x, b = gidx / gridDim.x;
+    }
+    const int row0 = bx * R;
     const int NS = (N + 1) & ~1;           // states are walked two at a time (a padding state has A = B = C = 0)
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -77,6 +94,14 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (W >= 4 ? 2 : 4)) scan3_bwd_
 
     for (int i = tid; i < (int)((Tl::kBytes + Cfg::kRawBytes + Cfg::kLandBytes + Cfg::kZfBytes + Cfg::kDABytes + Cfg::kSlabBytes + Cfg::kSeedBytes) / 16); i += NT)
         reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (chained && seg + 1 < p.nseg) {
+        if (tid == 0) {
+            volatile int *f = p.chain_flags + gidx * p.nseg + seg;
+            while (*f == 0) __nanosleep(200);
+            __threadfence();
+        }
+        __syncthreads();
+    }
     for (int i = tid; i < NRP * 16; i += NT) {
         const int g = i >> 4, n = i & 15;
         float a[2], e[2];
@@ -86,7 +111,7 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (W >= 4 ? 2 : 4)) scan3_bwd_
             const bool ok = row < D && n < N;
             a[r] = ok ? p.A[(int64_t)row * N + n] * kLog2e : 0.f;
             e[r] = 0.f;
-            if (!AGG && ok && p.ein != nullptr && seg + 1 < p.nseg) e[r] = p.ein[(((int64_t)b * D + row) * p.nseg + seg) * 16 + n];
+            if (!AGG && ok && p.ein != nullptr && seg + 1 < p.nseg) e[r] = __ldcg(p.ein + (((int64_t)b * D + row) * p.nseg + seg) * 16 + n);
         }
         s_A[i] = make_float2(a[0], a[1]);
         s_ec[i] = make_float2(e[0], e[1]);
@@ -501,6 +526,20 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (W >= 4 ? 2 : 4)) scan3_bwd_
             if (j == 0 && row_ok[r]) p.seg_dsum[((int64_t)b * D + rowA + r) * p.nseg + seg] = s;
         }
     } else {
+        if (chained && seg > 0) {   // publish e at my first token: the carry entering the segment to my left
+            for (int i = tid; i < NRP * 16; i += NT) {
+                const int g = i >> 4, n = i & 15;
+                const float2 e = s_ec[i];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int row = row0 + 2 * g + r;
+                    if (row < D) __stcg(p.ein + (((int64_t)b * D + row) * p.nseg + seg - 1) * 16 + n, r ? e.y : e.x);
+                }
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicExch(p.chain_flags + gidx * p.nseg + seg - 1, 1);
+        }
         // dA: sum the 8 lane partials of my warp (its row pair), one atomic per (row, state)
         for (int n = 0; n < N; ++n) {
             float2 v = j < 8 ? s_dA[(n * W + warp) * 8 + j] : make_float2(0.f, 0.f);

@@ -600,6 +600,7 @@ template <typename IN_T> bool bwd3_eligible(const mmu_scan_bwd_params *p) {
 
 struct Bwd3Plan {
     int W, nseg, cps, nchunks;
+    bool chain;     // segments are chained CTAs (no aggregate pass)
 };
 
 Bwd3Plan plan_bwd3(int B, int D, int L) {
@@ -613,9 +614,20 @@ Bwd3Plan plan_bwd3(int B, int D, int L) {
     nseg = std::min(nseg, std::max(1, pl.nchunks / 2));
     nseg = std::max(1, std::min(nseg, 64));
     nseg = env_int("MMU_BWD_NSEG", nseg);
+    pl.chain = false;
+    {
+        // Wide problem: one CTA per row group walks the whole sequence.  When those CTAs do not fill whole waves (2 CTAs of
+        // 4 warps per SM), cut the sequence into chained segments so the tail wave shrinks (measured at config 2: 578 ->
+        // 482 us with 3 segments).  MMU_BWD_CHAIN=k forces k chained segments (tests), 1 disables.
+        const int slots = 148 * 2, ctas = warps / pl.W, rem = ctas % slots;
+        int want = (nseg == 1 && warps >= 148 * 4 && ctas > slots && rem != 0 && rem < slots * 3 / 4 && pl.nchunks >= 6) ? 3 : 1;
+        want = env_int("MMU_BWD_CHAIN", want);
+        if (want > 1 && pl.nchunks >= want) nseg = want, pl.chain = true;
+    }
     nseg = std::max(1, std::min(nseg, pl.nchunks));
     pl.cps = (pl.nchunks + nseg - 1) / nseg;
     pl.nseg = (pl.nchunks + pl.cps - 1) / pl.cps;
+    if (pl.nseg == 1) pl.chain = false;
     return pl;
 }
 
@@ -657,6 +669,19 @@ template <typename IN_T> int run_bwd3(const mmu_scan_bwd_params *p, cudaStream_t
     a.softplus = f.delta_softplus;
     a.dbg = env_int("MMU_BWD3_DBG", 0);
     const bool rev = f.reverse != 0;
+    if (pl.nseg > 1 && pl.chain) {
+        const size_t n_state = (size_t)a.B * a.D * pl.nseg * 16;
+        const size_t n_flags = (size_t)a.B * ((a.D + 2 * pl.W - 1) / (2 * pl.W)) * pl.nseg + 1;
+        const size_t need = align256(n_state * 4) + align256(n_flags * 4);
+        if (f.workspace == nullptr || f.workspace_bytes < need)
+            return set_error(MMU_ERR_WORKSPACE, "selective_scan_bwd: workspace %zu < %zu", f.workspace_bytes, need);
+        char *w = static_cast<char *>(f.workspace);
+        a.ein = reinterpret_cast<float *>(w);
+        a.chain_flags = reinterpret_cast<int *>(w + align256(n_state * 4));
+        a.chain_ticket = a.chain_flags + (n_flags - 1);
+        cudaMemsetAsync(a.chain_flags, 0, n_flags * 4, st);
+        return dispatch_bwd3<IN_T, false>(a, pl.W, rev, st);
+    }
     if (pl.nseg > 1) {
         const size_t n_state = (size_t)a.B * a.D * pl.nseg * 16, n_row = (size_t)a.B * a.D * pl.nseg;
         const size_t need = 2 * align256(n_state * 4) + 2 * align256(n_row * 4);

@@ -196,6 +196,15 @@ def test_scan_v3_sequence_split(nseg, monkeypatch):
     run_scan_case(2, 2, 1800, 16, dtype=torch.bfloat16)
 
 
+@pytest.mark.parametrize("k", [2, 3, 5])
+def test_scan_v3_chained_segments(k, monkeypatch):
+    """Chained backward segments (ticketed CTAs passing the reverse carry through global memory, no aggregate pass)."""
+    monkeypatch.setenv("MMU_BWD_CHAIN", str(k))
+    run_scan_case(2, 6, 2048, 16)
+    run_scan_case(1, 20, 1536, 16, reverse=True)
+    run_scan_case(3, 8, 1288, 8, dtype=torch.bfloat16)
+
+
 def test_scan_v3_narrow_long():
     """MM-UNet's MMConv regime: D = 6 rows, long L -> the sequence is split over CTAs by the planner."""
     run_scan_case(2, 6, 16384, 16)
