@@ -136,6 +136,7 @@ __device__ __forceinline__ void rows_async(unsigned dst, const IN_T *__restrict_
     constexpr int TPR = NT >= PPR ? PPR : NT, RPP = NT / TPR, QIT = PPR / TPR;
     const int m0 = REV ? L - t0 - CH : t0;                                // memory index of tile position 0 (may be < 0)
     const int q0 = tid % TPR, r0 = tid / TPR;
+    if (r0 >= RPP) return;                                                // NT not a multiple of the row width: idle tail threads
 #pragma unroll
     for (int qi = 0; qi < QIT; ++qi) {
         const int q = q0 + qi * TPR, m = m0 + EPP * q;
@@ -143,8 +144,8 @@ __device__ __forceinline__ void rows_async(unsigned dst, const IN_T *__restrict_
             const unsigned d = dst + r0 * ROWB + dst_off(q);
             const IN_T *sb = B_b + (int64_t)r0 * B_ns + m, *sc = C_b + (int64_t)r0 * C_ns + m;
 #pragma unroll
-            for (int k = 0; k < 16 / RPP; ++k) {
-                if (r0 + k * RPP < N) {
+            for (int k = 0; k < (16 + RPP - 1) / RPP; ++k) {
+                if (r0 + k * RPP < min(N, 16)) {
                     cp_async16(d + k * RPP * ROWB, sb + (int64_t)k * RPP * B_ns);
                     if (WITH_C) cp_async16(d + (16 + k * RPP) * ROWB, sc + (int64_t)k * RPP * C_ns);
                 }

@@ -52,7 +52,7 @@ __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, 
 }
 
 template <typename IN_T, int W, bool REV, bool AGG>
-__global__ void __launch_bounds__(32 * W, AGG ? 1 : (W >= 4 ? 2 : 4)) scan3_bwd_kernel(const __grid_constant__ Bwd3Args p) {
+__global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(const __grid_constant__ Bwd3Args p) {
     using Cfg = Bwd3Cfg<IN_T, W>;
     constexpr int LPR = 32;
     using Tl = BcTile<LPR>;

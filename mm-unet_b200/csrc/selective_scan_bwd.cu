@@ -605,8 +605,8 @@ struct Bwd3Plan {
 
 Bwd3Plan plan_bwd3(int B, int D, int L) {
     Bwd3Plan pl;
-    pl.W = env_int("MMU_BWD3_W", D <= 2 ? 1 : (D <= 4 ? 2 : 4));
-    if (pl.W != 1 && pl.W != 2) pl.W = 4;
+    pl.W = env_int("MMU_BWD3_W", D <= 2 ? 1 : (D <= 4 ? 2 : 4));   // W = 3 (6 rows) measured slower than 4 with idle lanes
+    if (pl.W < 1 || pl.W > 4) pl.W = 4;
     const int R = 2 * pl.W;
     pl.nchunks = (L + 255) / 256;
     const int warps = B * ((D + R - 1) / R) * pl.W;
@@ -646,6 +646,7 @@ template <typename IN_T, bool AGG> int dispatch_bwd3(const Bwd3Args &a, int W, b
 #define MMU_B3(W_) (rev ? launch_bwd3<IN_T, W_, true, AGG>(a, st) : launch_bwd3<IN_T, W_, false, AGG>(a, st))
     if (W == 1) return MMU_B3(1);
     if (W == 2) return MMU_B3(2);
+    if (W == 3) return MMU_B3(3);
     return MMU_B3(4);
 #undef MMU_B3
 }

@@ -436,8 +436,8 @@ Fwd3Plan plan_fwd3(int B, int D, int L) {
     if (pl.LPR == 16) {
         pl.W = 4;
     } else {
-        pl.W = env_int("MMU_FWD3_W", D <= 2 ? 1 : (D <= 4 ? 2 : 4));
-        if (pl.W != 1 && pl.W != 2) pl.W = 4;
+        pl.W = env_int("MMU_FWD3_W", D <= 2 ? 1 : (D <= 4 ? 2 : (D % 8 != 0 && D % 6 == 0 ? 3 : 4)));
+        if (pl.W < 1 || pl.W > 4) pl.W = 4;
     }
     const int RW = 2 * (32 / pl.LPR), R = pl.W * RW, CH = 8 * pl.LPR;
     pl.nchunks = (L + CH - 1) / CH;
@@ -467,6 +467,7 @@ template <typename IN_T, bool AGG> int dispatch_fwd3(const Fwd3Args &a, const Fw
     if (pl.LPR == 16) return MMU_F3(16, 4);
     if (pl.W == 1) return MMU_F3(32, 1);
     if (pl.W == 2) return MMU_F3(32, 2);
+    if (pl.W == 3) return MMU_F3(32, 3);
     return MMU_F3(32, 4);
 #undef MMU_F3
 }
