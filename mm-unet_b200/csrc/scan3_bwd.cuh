@@ -212,18 +212,20 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
         order8<REV>(e, v);
     };
     // x seeds of chunk c: state entering the chunk's k-th 64-token block, k = 0..3  ->  s_seed[buf][warp][k][n] (row A, row B)
-    auto load_seeds = [&](int c, int buf) {
+    const unsigned s_seed_u32 = smem_u32(s_seed);
+    auto load_seeds = [&](int c, int buf) {       // asynchronous: part of the chunk's cp.async group
         if (AGG) return;
 #pragma unroll
         for (int it = 0; it < NCK * 16 / 32; ++it) {
             const int e = j + 32 * it, ck = e >> 4, n = e & 15;
             const int kx = c * NCK + ck - 1;
-            float v[2] = {0.f, 0.f};
+            const unsigned dst = s_seed_u32 + (((buf * W + warp) * NCK + ck) * 16 + n) * 8;
             if (kx >= 0 && n < N) {
 #pragma unroll
-                for (int r = 0; r < 2; ++r) v[r] = p.x[(((int64_t)b * D + min(rowA + r, D - 1)) * p.nx + kx) * N + n];
+                for (int r = 0; r < 2; ++r) cp_async4(dst + 4 * r, p.x + (((int64_t)b * D + min(rowA + r, D - 1)) * p.nx + kx) * N + n);
+            } else {
+                s_seed[((buf * W + warp) * NCK + ck) * 16 + n] = make_float2(0.f, 0.f);
             }
-            s_seed[((buf * W + warp) * NCK + ck) * 16 + n] = make_float2(v[0], v[1]);
         }
     };
 
@@ -231,8 +233,8 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
     issue_tile(c_end - 1);
     issue_in(tl < L);
     issue_y(tl < L);
-    cp_async_commit();
     load_seeds(c_end - 1, (c_end - 1) & 1);
+    cp_async_commit();
 
     for (int c = c_end - 1; c >= c_begin; --c, tl -= CH) {
         const bool ok = tl < L;
