@@ -99,6 +99,20 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def reduce_max_ms(ms, dist, device=None):
+    """Timing rule of the bench contract: a multi-rank number is the MAX over ranks (backend-agnostic: NCCL or gloo)."""
+    if dist is None or not dist.is_initialized():
+        return float(ms)
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def whole_job_gbps(world, bytes_per_rank, ms):
+    """Weak scaling: every rank processes its own batch; value = all ranks' algorithmic bytes / max-over-ranks time."""
+    return world * bytes_per_rank / (ms * 1e-3) / 1e9
+
+
 def ncu_traffic():
     """dram bytes per launch of the dominant kernel from the committed ncu summary (profiles/), or None."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
@@ -233,9 +247,7 @@ def main():
     wall = time.perf_counter() - t0
     launches = _lib.launch_count() - n0
     dev_ms = start.elapsed_time(stop)
-    tm = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
-    if dist: dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    dev_ms = float(tm.item())
+    dev_ms = reduce_max_ms(dev_ms, dist, dev)
     per_kernel = {n: sum(ev[i][k].elapsed_time(ev[i][k + 1]) for i in range(args.steps)) / args.steps for k, n in enumerate(names)}
 
     # ---------------- end-to-end arm: public autograd API, pinned host buffers, H2D + D2H inside the timed region ---
@@ -269,9 +281,7 @@ def main():
         e2e_step()
     e2.record()
     torch.cuda.synchronize()
-    tm2 = torch.tensor([s2.elapsed_time(e2)], device=dev, dtype=torch.float64)
-    if dist: dist.all_reduce(tm2, op=dist.ReduceOp.MAX)
-    e2e_ms = float(tm2.item()) / e2e_steps
+    e2e_ms = reduce_max_ms(s2.elapsed_time(e2), dist, dev) / e2e_steps
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join(timeout=3)
@@ -282,7 +292,7 @@ def main():
         return
     peak, peak_src = peaks()
     ms = dev_ms / args.steps
-    value = world * nbytes["step"] / (ms * 1e-3) / 1e9
+    value = whole_job_gbps(world, nbytes["step"], ms)
     dom = max(("scan_bwd", "scan_fwd"), key=lambda n: per_kernel[n])
     ach = nbytes[dom] / (per_kernel[dom] * 1e-3) / 1e9
     traffic = ncu_traffic().get(f"{dom}_{args.dtype}")
@@ -293,7 +303,7 @@ def main():
         "config": {"workload": f"isolated Mamba block: causal_conv1d(w={W},silu) fwd -> selective_scan fwd -> bwd -> conv1d bwd; "
                                f"B={B} D={D} L={L} d_state={N}, z+D+delta_bias+softplus; per-GPU batch fixed (weak scaling)",
                    "l2": "inputs (818 MB fp32 / 409 MB bf16 per step) larger than the 126 MB L2", "io_dtype": args.dtype},
-        "e2e": {"value": world * nbytes["step"] / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
+        "e2e": {"value": whole_job_gbps(world, nbytes["step"], e2e_ms), "unit": "GB/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
                 "api": "causal_conv1d_fn + selective_scan_fn (autograd), pinned host inputs, loss read back"},
         "gpu_launches": int(launches),

@@ -1,0 +1,75 @@
+"""N > 1 on CPU (gloo, world_size 2): the hot path shards by batch with NO data-path collective - every rank
+runs its own batch shard, and the only cross-rank traffic is the max-over-ranks timing reduce of bench.py."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+import oracle
+
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _inputs(batch, seed):
+    g = np.random.default_rng(seed)
+    D, L, N = 6, 96, 16
+    f = lambda *s: g.standard_normal(s).astype(np.float32)
+    return dict(u=f(batch, D, L), delta=(0.5 * g.random((batch, D, L))).astype(np.float32), B=f(batch, 1, N, L), C=f(batch, 1, N, L),
+                z=f(batch, D, L), dout=f(batch, D, L))
+
+
+def _weights():
+    g = np.random.default_rng(123)
+    D, N = 6, 16
+    return dict(A=(-0.5 * g.random((D, N))).astype(np.float32), D=g.standard_normal(D).astype(np.float32),
+                bias=(0.5 * g.random(D)).astype(np.float32))
+
+
+def _worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+    w = _weights()
+    t = _inputs(2, seed=rank)                                   # per-rank batch shard, as bench.py seeds by rank
+    out, last = oracle.selective_scan_fwd(t["u"], t["delta"], w["A"], t["B"], t["C"], w["D"], t["z"], w["bias"], True)
+    g = oracle.selective_scan_bwd(t["u"], t["delta"], w["A"], t["B"], t["C"], w["D"], t["z"], w["bias"], t["dout"], True)
+    # weight gradients are the only quantities a data-parallel trainer would all-reduce (outside the hot path)
+    dA = torch.from_numpy(np.ascontiguousarray(g["dA"]).astype(np.float64))
+    dist.all_reduce(dA)
+    gathered = [torch.zeros(out.shape, dtype=torch.float32) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(np.ascontiguousarray(out).astype(np.float32)))
+    ms = bench.reduce_max_ms(10.0 + 5.0 * rank, dist)            # max over ranks
+    if rank == 0:
+        np.savez(os.path.join(tmp, "r0.npz"), out=torch.cat(gathered).numpy(), dA=dA.numpy(), ms=ms,
+                 value=bench.whole_job_gbps(world, 1e9, ms))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_shard_by_batch(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r = np.load(tmp_path / "r0.npz")
+    w = _weights()
+    shards = [_inputs(2, seed=k) for k in range(world)]
+    full = {k: np.concatenate([s[k] for s in shards]) for k in shards[0]}
+    out, _ = oracle.selective_scan_fwd(full["u"], full["delta"], w["A"], full["B"], full["C"], w["D"], full["z"], w["bias"], True)
+    g = oracle.selective_scan_bwd(full["u"], full["delta"], w["A"], full["B"], full["C"], w["D"], full["z"], w["bias"], full["dout"], True)
+    assert np.array_equal(r["out"], out.astype(np.float32))       # bit-exact: a batch element never sees another rank's data
+    np.testing.assert_allclose(r["dA"], g["dA"], rtol=1e-5, atol=1e-5)    # sum of per-rank weight grads == full-batch grad
+    assert float(r["ms"]) == 15.0                                 # max over ranks
+    assert abs(float(r["value"]) - 2 * 1e9 / 15e-3 / 1e9) < 1e-9  # whole-job value = all ranks' bytes / max time
