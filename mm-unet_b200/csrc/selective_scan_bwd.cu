@@ -606,7 +606,7 @@ struct Bwd3Plan {
 Bwd3Plan plan_bwd3(int B, int D, int L) {
     Bwd3Plan pl;
     pl.W = env_int("MMU_BWD3_W", D <= 2 ? 1 : (D <= 4 ? 2 : 4));   // W = 3 (6 rows) measured slower than 4 with idle lanes
-    if (pl.W < 1 || pl.W > 4) pl.W = 4;
+    if (pl.W != 8 && (pl.W < 1 || pl.W > 4)) pl.W = 4;
     const int R = 2 * pl.W;
     pl.nchunks = (L + 255) / 256;
     const int warps = B * ((D + R - 1) / R) * pl.W;
@@ -619,7 +619,7 @@ Bwd3Plan plan_bwd3(int B, int D, int L) {
         // Wide problem: one CTA per row group walks the whole sequence.  When those CTAs do not fill whole waves (2 CTAs of
         // 4 warps per SM), cut the sequence into chained segments so the tail wave shrinks (measured at config 2: 578 ->
         // 482 us with 3 segments).  MMU_BWD_CHAIN=k forces k chained segments (tests), 1 disables.
-        const int slots = 148 * 2, ctas = warps / pl.W, rem = ctas % slots;
+        const int slots = 148 * (pl.W == 8 ? 1 : 2), ctas = warps / pl.W, rem = ctas % slots;
         int want = (nseg == 1 && warps >= 148 * 4 && ctas > slots && rem != 0 && rem < slots * 3 / 4 && pl.nchunks >= 6) ? 3 : 1;
         want = env_int("MMU_BWD_CHAIN", want);
         if (want > 1 && pl.nchunks >= want) nseg = want, pl.chain = true;
@@ -647,6 +647,7 @@ template <typename IN_T, bool AGG> int dispatch_bwd3(const Bwd3Args &a, int W, b
     if (W == 1) return MMU_B3(1);
     if (W == 2) return MMU_B3(2);
     if (W == 3) return MMU_B3(3);
+    if (W == 8) return MMU_B3(8);
     return MMU_B3(4);
 #undef MMU_B3
 }
