@@ -400,7 +400,12 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
             dAacc.x += __shfl_xor_sync(0xffffffffu, dAacc.x, 16), dAacc.y += __shfl_xor_sync(0xffffffffu, dAacc.y, 16);
             dAacc.x += __shfl_xor_sync(0xffffffffu, dAacc.x, 8), dAacc.y += __shfl_xor_sync(0xffffffffu, dAacc.y, 8);
             if (j < 8) s_dA[(n * W + warp) * 8 + j] = fadd2(s_dA[(n * W + warp) * 8 + j], dAacc);
-            __syncthreads();
+            // publish: named barrier 1 + (n & 1); the matching sync sits in reduce_state(n), one phase of work later
+            asm volatile("bar.arrive %0, %1;" ::"r"(1 + (n & 1)), "r"(2 * NT) : "memory");
+        };
+        // sum the CTA's slabs of state n and add them to global memory
+        auto reduce_state = [&](int n) {
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + (n & 1)), "r"(2 * NT) : "memory");
             if (n < N && !(p.dbg & 1)) {
                 const int t0c = tl - T * j;                                 // first token of the chunk
                 for (int idx = tid; idx < 128; idx += NT) {
@@ -434,10 +439,13 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
 #pragma unroll 1
             for (int n = 0; n < NS; n += 2) {
                 phase1(n + 1, a1, hs1, e1);
+                if (n > 0) reduce_state(n - 1);
                 phase2(n, a0, hs0, e0);
                 if (n + 2 < NS) phase1(n + 2, a0, hs0, e0);
+                reduce_state(n);
                 phase2(n + 1, a1, hs1, e1);
             }
+            reduce_state(NS - 1);
         }
 
         __syncthreads();                // everybody is done with the B/C tile: fetch the next one under the epilogue

@@ -178,11 +178,15 @@ def selective_scan_bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softp
     ddelta = torch.empty_like(delta, memory_format=torch.contiguous_format) if ddelta is None else ddelta
     if z is not None and dz is None:
         dz = torch.empty_like(z, memory_format=torch.contiguous_format)
-    dA = torch.zeros_like(A)
-    dB = torch.zeros((batch, G, N, L), device=u.device, dtype=torch.float32)
-    dC = torch.zeros((batch, G, N, L), device=u.device, dtype=torch.float32)
-    dD = torch.zeros(dim, device=u.device, dtype=torch.float32) if D is not None else None
-    dbias = torch.zeros(dim, device=u.device, dtype=torch.float32) if delta_bias is not None else None
+    # one zero fill for every accumulated-into output (they are atomically added to, selective_scan.cpp:458-466)
+    nBC = batch * G * N * L
+    nA = (dim * N + 3) // 4 * 4           # keeps dB / dC 16-byte aligned
+    acc = torch.zeros(2 * nBC + nA + 2 * dim, device=u.device, dtype=torch.float32)
+    dB = acc[:nBC].view(batch, G, N, L)
+    dC = acc[nBC:2 * nBC].view(batch, G, N, L)
+    dA = acc[2 * nBC:2 * nBC + dim * N].view(dim, N)
+    dD = acc[2 * nBC + nA:2 * nBC + nA + dim] if D is not None else None
+    dbias = acc[2 * nBC + nA + dim:] if delta_bias is not None else None
     L_ = _lib.lib()
     ws_bytes = L_.mmu_selective_scan_bwd_workspace(batch, H, L, N)
     ws = torch.empty(ws_bytes, device=u.device, dtype=torch.uint8) if ws_bytes else None
