@@ -8,6 +8,7 @@ What is executed (all from /root/reference, loaded by path, nothing copied):
   * causal_conv1d_ref                            requirements/Mamba/causal-conv1d/causal_conv1d/causal_conv1d_interface.py
   * TFM Mamba (v3 forward+backward)              requirements/mamba_simple.py
   * MMConv.two_row_columnwise_flatten_grad_safe / inverse   src/UM_Net/MMUNet.py
+  * MM_Net forward + backward (64x64, batch 2)    src/UM_Net/MMUNet.py
 Harness-side patches only: stub modules `causal_conv1d_cuda` / `selective_scan_cuda`,
 a stub `timm`, and a `mamba_ssm` namespace whose fused-op names are bound to the reference's own
 *_ref functions (the reference has no CPU implementation of the fused ops other than those refs).
@@ -215,6 +216,61 @@ def gen_orders(mm):
     np.savez_compressed(os.path.join(OUT, "scan_orders.npz"), **cases)
 
 
+def gen_mm_net(ms, mm):
+    """The reference MM_Net (src/UM_Net/MMUNet.py:474-585), unmodified, forward + backward on CPU at 64x64.
+    Harness-side patches only: `Mamba` is the reference class behind the v1 shim (constructs as
+    "v3" - the shipped constructor asserts it - then runs lines :190-209 + :304-318 for "v1"); MMConv's device default
+    -> "cpu"; Dropout2d p -> 0 so that train-mode outputs are deterministic."""
+    class ShimMamba(ms.Mamba):
+        def __init__(self, *a, bimamba_type="none", **kw):
+            super().__init__(*a, bimamba_type="v3", **kw)
+            self.bimamba_type = bimamba_type
+
+        def forward(self, hidden_states, inference_params=None):
+            if self.bimamba_type in ("v2", "v3"):
+                return super().forward(hidden_states, inference_params)
+            from einops import rearrange
+            L = hidden_states.shape[1]
+            xz = rearrange(self.in_proj.weight @ rearrange(hidden_states, "b l d -> d (b l)"), "d (b l) -> b d l", l=L)
+            A = -torch.exp(self.A_log.float())
+            iface = sys.modules["mamba_ssm.ops.selective_scan_interface"]
+            out = iface.mamba_inner_fn(xz, self.conv1d.weight, self.conv1d.bias, self.x_proj.weight, self.dt_proj.weight,
+                                       self.out_proj.weight, self.out_proj.bias, A, None, None, self.D.float(),
+                                       delta_bias=self.dt_proj.bias.float(), delta_softplus=True)
+            return out, None, None, None
+
+    mm.Mamba = ShimMamba
+    d = list(mm.MMConv.__init__.__defaults__)
+    d[6] = "cpu"
+    mm.MMConv.__init__.__defaults__ = tuple(d)
+    torch.manual_seed(50)                                    # train.py:160
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = mm.MM_Net(num_classes=1)
+    for m in net.modules():
+        if isinstance(m, torch.nn.Dropout2d):
+            m.p = 0.0
+    net.train()
+    torch.manual_seed(1)
+    x = torch.randn(2, 3, 64, 64, requires_grad=True)
+    g = torch.randn(2, 1, 64, 64)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}      # before the BatchNorm running stats move
+    out = net(x)
+    out.backward(g)
+    cases = {"x": npy(x), "dout": npy(g), "out": npy(out), "dx": npy(x.grad)}
+    cases["param_names"] = np.array(list(sd.keys()))
+    cases["param_sums"] = np.array([float(v.double().sum()) for v in sd.values()])
+    cases["param_abs_sums"] = np.array([float(v.double().abs().sum()) for v in sd.values()])
+    grads = {k: p.grad for k, p in net.named_parameters()}
+    cases["nograd_names"] = np.array([k for k, v in grads.items() if v is None])
+    for k in ("encoder1.0.weight", "encoder2.0.block1.0.mamba.A_log", "encoder2.0.block1.0.mamba.x_proj.weight",
+              "encoder2.0.block1.0.altho", "encoder2.0.block1.0.offset_conv.weight", "encoder2.2.block1.3.dsc_conv_x.weight",
+              "down5.0.mamba.in_proj.weight", "rcg2.mamba.A_s_log", "rcg2.mamba.conv1d_b.weight", "rcg4.mamba.out_proj.weight",
+              "rcg3.mamba.dt_proj_s.bias", "side2.conv2.weight", "decoder2.conv1.0.mamba.dt_proj.weight", "line_predict.weight"):
+        cases["grad." + k] = npy(grads[k])
+    np.savez_compressed(os.path.join(OUT, "mm_net.npz"), **cases)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     cci, ssi, ms, mm = load_reference()
@@ -223,5 +279,6 @@ if __name__ == "__main__":
     gen_inner(ssi)
     gen_module(ms)
     gen_orders(mm)
+    gen_mm_net(ms, mm)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
