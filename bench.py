@@ -181,6 +181,45 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def train_leg(args, rank, world, dev, dist):
+    """MM-UNet (MM_Net) training img/s on synthetic DRIVE-shaped batches: forward, DiceFocal loss, backward, AdamW step;
+    bf16 autocast; one rank per GPU with torch DDP (NCCL gradient all-reduce overlapped with backward).  Every step starts
+    from PINNED HOST tensors (H2D inside the timed region) and ends with the loss copied back to the host."""
+    from mmunet_b200 import _lib
+    from mmunet_b200.train import Trainer
+    tr = Trainer(image_size=args.train_size, batch_per_rank=args.train_batch, dtype="bf16", device=dev)
+    batches = [tr.synthetic_batch() for _ in range(2)]
+    host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+    for i in range(3):
+        tr.step(*batches[i % 2])
+    torch.cuda.synchronize()
+    if dist: dist.barrier()
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    s.record()
+    for i in range(args.train_steps):
+        loss = tr.step(*batches[i % 2])
+        host_loss.copy_(loss.reshape(1), non_blocking=True)
+    e.record()
+    torch.cuda.synchronize()
+    if dist: dist.barrier()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = reduce_max_ms(s.elapsed_time(e), dist, dev) / args.train_steps
+    xb, yb = batches[0]
+    return {"metric": "MM-UNet train img/s", "value": world * args.train_batch / (ms * 1e-3), "unit": "img/s",
+            "ms_per_step": ms, "steps": args.train_steps, "warmup": 3, "n_gpus": world, "scaling": "weak",
+            "config": {"model": "MM_Net (mmunet_b200/mm_net.py, 50 Mamba blocks)", "image": f"{args.train_size}x{args.train_size} RGB",
+                       "per_gpu_batch": args.train_batch, "global_batch": world * args.train_batch, "dtype": "bf16 autocast",
+                       "optimizer": "AdamW lr 1e-3 wd 0.05 betas (0.9,0.95)", "loss": "DiceFocal",
+                       "parallelism": f"dp{world}" + (" (DDP, NCCL all-reduce overlapped with backward)" if world > 1 else "")},
+            "h2d_bytes_per_step": xb.numel() * xb.element_size() + yb.numel() * yb.element_size(), "d2h_bytes_per_step": 4,
+            "hot_path_launches_per_step": (int(_lib.launch_count()) - int(n0)) // args.train_steps,
+            "loss": float(host_loss.item()), "wall_s": wall, "data": "synthetic", "peak_mem_gib": torch.cuda.max_memory_allocated() / 2**30}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -189,6 +228,10 @@ def main():
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the MM_Net training leg (the `train` object)")
+    ap.add_argument("--train-steps", type=int, default=6)
+    ap.add_argument("--train-batch", type=int, default=16, help="per-GPU batch of the training leg")
+    ap.add_argument("--train-size", type=int, default=512)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -287,6 +330,16 @@ def main():
         sampler.join(timeout=3)
     h2d = sum(v.numel() * v.element_size() for v in ht.values())
 
+    # ---------------- MM-UNet training leg (BASELINE configs[2]): the caller of the path, img/s ---------------------
+    train = None
+    if not args.no_train:
+        del ht, dbuf, t, du, dd, dz, dx
+        torch.cuda.empty_cache()
+        try:
+            train = train_leg(args, rank, world, dev, dist)
+        except Exception as exc:      # the training leg must not hide the hot-path numbers
+            train = {"error": repr(exc)}
+
     if rank != 0:
         if dist: dist.destroy_process_group()
         return
@@ -317,6 +370,8 @@ def main():
                          "GBps": (nbytes["scan_fwd"] + nbytes["scan_bwd"]) / ((per_kernel["scan_fwd"] + per_kernel["scan_bwd"]) * 1e-3) / 1e9},
         "clocks": sampler.summary(), "wall_s": wall,
     }
+    if train is not None:
+        line["train"] = train
     line["scan_fwd_bwd"]["frac_of_peak"] = line["scan_fwd_bwd"]["GBps"] / peak
     if world == 1 and not args.no_cpu_baseline:
         try:

@@ -243,6 +243,39 @@ def gen_mm_net(ms, mm):
     d = list(mm.MMConv.__init__.__defaults__)
     d[6] = "cpu"
     mm.MMConv.__init__.__defaults__ = tuple(d)
+    # ---- single blocks (well conditioned: errors are not amplified through 50 layers) ---------------------------------
+    blocks = {}
+    for name, (cin, cout, K, H, W) in {"k3_even": (8, 8, 3, 12, 10), "k3_oddH": (8, 12, 3, 7, 9), "k1": (16, 8, 1, 6, 8),
+                                        "k9": (4, 4, 9, 10, 16)}.items():
+        torch.manual_seed(7)
+        conv = mm.MMConv(cin, cout, kernel_size=K, num_slices=4)
+        x = torch.randn(2, cin, H, W, requires_grad=True)
+        out = conv(x)
+        g = torch.randn_like(out)
+        out.backward(g)
+        rec = {"x": x, "dout": g, "out": out, "dx": x.grad, "shape": torch.tensor([cin, cout, K])}
+        for k, p in conv.named_parameters():
+            if p.grad is not None:
+                rec["grad:" + k] = p.grad
+        for k, v in rec.items():
+            blocks[f"mmconv_{name}.{k}"] = npy(v)
+    torch.manual_seed(7)
+    rcg = mm.RCG(num_slices=4)
+    rcg.train()
+    pre = torch.randn(2, 1, 8, 8, requires_grad=True)
+    edge = torch.randn(2, 64, 16, 16, requires_grad=True)
+    f = torch.randn(2, 64, 8, 8, requires_grad=True)
+    out = rcg(pre, edge, f)
+    g = torch.randn_like(out)
+    out.backward(g)
+    rec = {"pre": pre, "edge": edge, "f": f, "dout": g, "out": out, "dpre": pre.grad, "dedge": edge.grad, "df": f.grad}
+    for k in ("mamba.A_log", "mamba.A_b_log", "mamba.A_s_log", "mamba.x_proj_s.weight", "mamba.conv1d_b.weight",
+              "mamba.dt_proj.bias", "mamba.D_s", "conv1.0.altho", "conv1.0.mamba.in_proj.weight", "mlp.0.weight"):
+        rec["grad:" + k] = dict(rcg.named_parameters())[k].grad
+    for k, v in rec.items():
+        blocks[f"rcg.{k}"] = npy(v)
+    np.savez_compressed(os.path.join(OUT, "mm_blocks.npz"), **blocks)
+
     torch.manual_seed(50)                                    # train.py:160
     import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
