@@ -188,9 +188,11 @@ def train_leg(args, rank, world, dev, dist):
     from mmunet_b200 import _lib
     from mmunet_b200.train import Trainer
     tr = Trainer(image_size=args.train_size, batch_per_rank=args.train_batch, dtype="bf16", device=dev)
+    tr.set_epoch(tr.warmup_epochs)        # full learning rate (epoch 0 of the reference's schedule trains with lr = 0)
     batches = [tr.synthetic_batch() for _ in range(2)]
     host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
-    for i in range(3):
+    warm = tr.graph_warmup + 3 if tr.use_graph else 3     # eager warm-up, CUDA-graph capture, then replayed warm-up steps
+    for i in range(warm):
         tr.step(*batches[i % 2])
     torch.cuda.synchronize()
     if dist: dist.barrier()
@@ -210,7 +212,8 @@ def train_leg(args, rank, world, dev, dist):
     ms = reduce_max_ms(s.elapsed_time(e), dist, dev) / args.train_steps
     xb, yb = batches[0]
     return {"metric": "MM-UNet train img/s", "value": world * args.train_batch / (ms * 1e-3), "unit": "img/s",
-            "ms_per_step": ms, "steps": args.train_steps, "warmup": 3, "n_gpus": world, "scaling": "weak",
+            "ms_per_step": ms, "steps": args.train_steps, "warmup": warm, "n_gpus": world, "scaling": "weak",
+            "cuda_graph": tr.graph is not None,
             "config": {"model": "MM_Net (mmunet_b200/mm_net.py, 50 Mamba blocks)", "image": f"{args.train_size}x{args.train_size} RGB",
                        "per_gpu_batch": args.train_batch, "global_batch": world * args.train_batch, "dtype": "bf16 autocast",
                        "optimizer": "AdamW lr 1e-3 wd 0.05 betas (0.9,0.95)", "loss": "DiceFocal",

@@ -130,7 +130,8 @@ class CBAM(nn.Module):
         self.sigmoid = nn.Sigmoid()
 
     def forward(self, x):
-        y = self.sigmoid(self.mlp(self.avg_pool(x)) + self.mlp(self.max_pool(x))) * x
+        # amax == AdaptiveMaxPool2d(1) (one reduction kernel instead of the 3.4 ms adaptive-pool kernel at 256x256)
+        y = self.sigmoid(self.mlp(self.avg_pool(x)) + self.mlp(x.amax(dim=(2, 3), keepdim=True))) * x
         s = torch.cat((y.amax(dim=1, keepdim=True), y.mean(dim=1, keepdim=True)), 1)
         return self.sigmoid(self.conv(s)) * y
 

@@ -51,7 +51,7 @@ def warmup_cosine_lr(epoch: int, base_lr: float, warmup_epochs: int, max_epochs:
     return eta_min + 0.5 * (base_lr - eta_min) * (1 + math.cos(math.pi * (epoch - warmup_epochs) / (max_epochs - warmup_epochs)))
 
 
-def make_optimizer(model, lr=1e-3, weight_decay=0.05, betas=(0.9, 0.95)):
+def make_optimizer(model, lr=1e-3, weight_decay=0.05, betas=(0.9, 0.95), capturable=False):
     decay, no_decay = [], []
     for name, p in model.named_parameters():
         if not p.requires_grad:
@@ -59,19 +59,27 @@ def make_optimizer(model, lr=1e-3, weight_decay=0.05, betas=(0.9, 0.95)):
         (no_decay if (p.ndim <= 1 or name.endswith(".bias")) else decay).append(p)
     groups = [{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": weight_decay}]
     fused = all(p.is_cuda for g in groups for p in g["params"])
-    return torch.optim.AdamW(groups, lr=lr, betas=betas, fused=fused)
+    if capturable:      # CUDA-graph capture: the step counter and the learning rate live on the device
+        lr = torch.tensor(float(lr), device=groups[1]["params"][0].device)
+    return torch.optim.AdamW(groups, lr=lr, betas=betas, fused=fused, capturable=capturable)
 
 
 class Trainer:
-    """One rank of a (possibly data-parallel) synthetic-data MM_Net training job."""
+    """One rank of a (possibly data-parallel) synthetic-data MM_Net training job.
+
+    graph=True (default): after `graph_warmup` eager steps the whole step - forward, loss, backward (with DDP's bucketed
+    NCCL all-reduces), AdamW - is captured once into a CUDA graph and replayed; the ~10 k kernel launches of a step then
+    cost one host call instead of ~200 ms of Python / dispatcher time (the eager step is CPU-bound on a B200)."""
 
     def __init__(self, image_size=512, batch_per_rank=16, dtype="bf16", device=None, seed=50, lr=1e-3, weight_decay=0.05,
-                 warmup_epochs=2, max_epochs=3000, ddp=None, channels_last=False):
+                 warmup_epochs=2, max_epochs=3000, ddp=None, channels_last=False, graph=True, graph_warmup=None):
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.device = torch.device(device if device is not None else f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}")
         self.autocast_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": None, "f32": None}[dtype]
         self.image_size, self.batch = image_size, batch_per_rank
+        self.channels_last = channels_last
+        self.stream = torch.cuda.Stream(self.device)                      # all training work runs on this side stream
         torch.manual_seed(seed)                                           # same initial weights on every rank (train.py:160)
         net = MM_Net(num_classes=1).to(self.device)
         frozen = set(net.unused_parameters())
@@ -82,18 +90,32 @@ class Trainer:
             net = net.to(memory_format=torch.channels_last)
         self.net = net.train()
         use_ddp = (self.world > 1) if ddp is None else ddp
-        self.model = (torch.nn.parallel.DistributedDataParallel(net, device_ids=[self.device.index], bucket_cap_mb=25,
-                                                                gradient_as_bucket_view=True, broadcast_buffers=False)
-                      if use_ddp else net)
-        self.opt = make_optimizer(net, lr, weight_decay)
+        self.use_graph = bool(int(os.environ.get("MMU_TRAIN_GRAPH", "1" if graph else "0")))
+        with torch.cuda.stream(self.stream):                              # DDP must be built on the stream it is captured on
+            self.model = (torch.nn.parallel.DistributedDataParallel(net, device_ids=[self.device.index], bucket_cap_mb=25,
+                                                                    gradient_as_bucket_view=True, broadcast_buffers=False)
+                          if use_ddp else net)
+        self.opt = make_optimizer(net, lr, weight_decay, capturable=self.use_graph)
         self.base_lr, self.warmup_epochs, self.max_epochs = lr, warmup_epochs, max_epochs
         self.set_epoch(0)
         self.gen = torch.Generator(device="cpu").manual_seed(1234 + self.rank)
+        self.graph = None
+        self.graph_warmup = graph_warmup if graph_warmup is not None else (11 if use_ddp else 3)
+        self.steps_done = 0
+        S, B = image_size, batch_per_rank
+        self.x_dev = torch.empty(B, 3, S, S, device=self.device)
+        if channels_last:
+            self.x_dev = self.x_dev.contiguous(memory_format=torch.channels_last)
+        self.y_dev = torch.empty(B, 1, S, S, device=self.device, dtype=torch.uint8)
+        self.loss_dev = torch.zeros((), device=self.device)
 
     def set_epoch(self, epoch: int):
         lr = warmup_cosine_lr(epoch, self.base_lr, self.warmup_epochs, self.max_epochs)
         for g in self.opt.param_groups:
-            g["lr"] = lr
+            if torch.is_tensor(g["lr"]):
+                g["lr"].fill_(lr)
+            else:
+                g["lr"] = lr
 
     def synthetic_batch(self, pinned=True):
         """Host-side batch (pinned): image fp32 (B,3,S,S), vessel mask uint8 (B,1,S,S)."""
@@ -102,17 +124,37 @@ class Trainer:
         y = (torch.rand(B, 1, S, S, generator=self.gen) < 0.1).to(torch.uint8)
         return (x.pin_memory(), y.pin_memory()) if pinned else (x, y)
 
-    def step(self, x_host, y_host):
-        """One optimisation step from HOST tensors; returns the loss as a device scalar (no sync)."""
-        x = x_host.to(self.device, non_blocking=True)
-        y = y_host.to(self.device, non_blocking=True)
+    def _fwd_bwd_opt(self):
         if self.autocast_dtype is not None:
             with torch.autocast("cuda", dtype=self.autocast_dtype):
-                logits = self.model(x)
+                logits = self.model(self.x_dev)
         else:
-            logits = self.model(x)
-        loss = dice_focal_loss(logits, y)
+            logits = self.model(self.x_dev)
+        loss = dice_focal_loss(logits, self.y_dev)
         loss.backward()
         self.opt.step()
-        self.opt.zero_grad(set_to_none=True)
-        return loss.detach()
+        self.loss_dev.copy_(loss.detach())
+
+    def step(self, x_host, y_host):
+        """One optimisation step from HOST tensors; returns the loss as a device scalar (no host sync)."""
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            self.x_dev.copy_(x_host, non_blocking=True)
+            self.y_dev.copy_(y_host, non_blocking=True)
+            if self.graph is not None:
+                self.graph.replay()
+            elif self.use_graph and self.steps_done >= self.graph_warmup:
+                self.opt.zero_grad(set_to_none=True)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.stream):
+                    self._fwd_bwd_opt()
+                    self.opt.zero_grad(set_to_none=True)      # gradients live in the graph's private pool
+                self.graph = g
+                g.replay()                                    # capture does not execute: run the step once
+            else:
+                self._fwd_bwd_opt()
+                self.opt.zero_grad(set_to_none=True)
+        cur.wait_stream(self.stream)
+        self.steps_done += 1
+        return self.loss_dev

@@ -6,10 +6,12 @@ from mmunet_b200.train import Trainer
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 dtype = sys.argv[3] if len(sys.argv) > 3 else "bf16"
-prof = len(sys.argv) > 4
-tr = Trainer(image_size=size, batch_per_rank=batch, dtype=dtype, device="cuda:0", ddp=False)
+prof = len(sys.argv) > 4 and sys.argv[4] == "prof"
+cl = "cl" in sys.argv[4:]
+tr = Trainer(image_size=size, batch_per_rank=batch, dtype=dtype, device="cuda:0", ddp=False, channels_last=cl)
+tr.set_epoch(2)
 x, y = tr.synthetic_batch()
-for _ in range(3):
+for _ in range(tr.graph_warmup + 3 if tr.use_graph else 3):
     tr.step(x, y)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -18,7 +20,7 @@ t0 = time.perf_counter(); e0.record()
 for _ in range(n):
     loss = tr.step(x, y)
 e1.record(); torch.cuda.synchronize(); t1 = time.perf_counter()
-print(f"size {size} batch {batch} {dtype}: {e0.elapsed_time(e1)/n:.1f} ms/step (wall {(t1-t0)/n*1e3:.1f} ms), {batch*n/(e0.elapsed_time(e1)/1e3):.2f} img/s, "
+print(f"graph={tr.graph is not None} channels_last={cl} size {size} batch {batch} {dtype}: {e0.elapsed_time(e1)/n:.1f} ms/step (wall {(t1-t0)/n*1e3:.1f} ms), {batch*n/(e0.elapsed_time(e1)/1e3):.2f} img/s, "
       f"loss {float(loss):.4f}, peak mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB", flush=True)
 if prof:
     from torch.profiler import profile, ProfilerActivity
