@@ -185,7 +185,6 @@ def train_leg(args, rank, world, dev, dist):
     """MM-UNet (MM_Net) training img/s on synthetic DRIVE-shaped batches: forward, DiceFocal loss, backward, AdamW step;
     bf16 autocast; one rank per GPU with torch DDP (NCCL gradient all-reduce overlapped with backward).  Every step starts
     from PINNED HOST tensors (H2D inside the timed region) and ends with the loss copied back to the host."""
-    from mmunet_b200 import _lib
     from mmunet_b200.train import Trainer
     tr = Trainer(image_size=args.train_size, batch_per_rank=args.train_batch, dtype="bf16", device=dev)
     tr.set_epoch(tr.warmup_epochs)        # full learning rate (epoch 0 of the reference's schedule trains with lr = 0)
@@ -197,7 +196,6 @@ def train_leg(args, rank, world, dev, dist):
     torch.cuda.synchronize()
     if dist: dist.barrier()
     torch.cuda.synchronize()
-    n0 = _lib.launch_count()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     s.record()
@@ -219,7 +217,7 @@ def train_leg(args, rank, world, dev, dist):
                        "optimizer": "AdamW lr 1e-3 wd 0.05 betas (0.9,0.95)", "loss": "DiceFocal",
                        "parallelism": f"dp{world}" + (" (DDP, NCCL all-reduce overlapped with backward)" if world > 1 else "")},
             "h2d_bytes_per_step": xb.numel() * xb.element_size() + yb.numel() * yb.element_size(), "d2h_bytes_per_step": 4,
-            "hot_path_launches_per_step": (int(_lib.launch_count()) - int(n0)) // args.train_steps,
+            "hot_path_launches_per_step": int(tr.hot_path_launches),
             "loss": float(host_loss.item()), "wall_s": wall, "data": "synthetic", "peak_mem_gib": torch.cuda.max_memory_allocated() / 2**30}
 
 

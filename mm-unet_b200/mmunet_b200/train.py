@@ -15,6 +15,7 @@ Synthetic DRIVE-shaped batches: x ~ N(0,1) (B,3,S,S), target ~ Bernoulli(0.1) (B
 """
 from __future__ import annotations
 
+import contextlib
 import math
 import os
 
@@ -22,6 +23,7 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
+from . import _lib
 from .mm_net import MM_Net
 
 
@@ -79,7 +81,8 @@ class Trainer:
         self.autocast_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": None, "f32": None}[dtype]
         self.image_size, self.batch = image_size, batch_per_rank
         self.channels_last = channels_last
-        self.stream = torch.cuda.Stream(self.device)                      # all training work runs on this side stream
+        self.is_cuda = self.device.type == "cuda"       # "cpu" only works with the tests' oracle stand-ins for the Mamba ops
+        self.stream = torch.cuda.Stream(self.device) if self.is_cuda else None    # all training work runs on this side stream
         torch.manual_seed(seed)                                           # same initial weights on every rank (train.py:160)
         net = MM_Net(num_classes=1).to(self.device)
         frozen = set(net.unused_parameters())
@@ -90,10 +93,11 @@ class Trainer:
             net = net.to(memory_format=torch.channels_last)
         self.net = net.train()
         use_ddp = (self.world > 1) if ddp is None else ddp
-        self.use_graph = bool(int(os.environ.get("MMU_TRAIN_GRAPH", "1" if graph else "0")))
-        with torch.cuda.stream(self.stream):                              # DDP must be built on the stream it is captured on
-            self.model = (torch.nn.parallel.DistributedDataParallel(net, device_ids=[self.device.index], bucket_cap_mb=25,
-                                                                    gradient_as_bucket_view=True, broadcast_buffers=False)
+        self.use_graph = self.is_cuda and bool(int(os.environ.get("MMU_TRAIN_GRAPH", "1" if graph else "0")))
+        with (torch.cuda.stream(self.stream) if self.is_cuda else contextlib.nullcontext()):   # DDP is built on the stream it is captured on
+            self.model = (torch.nn.parallel.DistributedDataParallel(net, device_ids=[self.device.index] if self.is_cuda else None,
+                                                                    bucket_cap_mb=25, gradient_as_bucket_view=True,
+                                                                    broadcast_buffers=False)
                           if use_ddp else net)
         self.opt = make_optimizer(net, lr, weight_decay, capturable=self.use_graph)
         self.base_lr, self.warmup_epochs, self.max_epochs = lr, warmup_epochs, max_epochs
@@ -102,6 +106,7 @@ class Trainer:
         self.graph = None
         self.graph_warmup = graph_warmup if graph_warmup is not None else (11 if use_ddp else 3)
         self.steps_done = 0
+        self.hot_path_launches = 0
         S, B = image_size, batch_per_rank
         self.x_dev = torch.empty(B, 3, S, S, device=self.device)
         if channels_last:
@@ -122,11 +127,11 @@ class Trainer:
         S, B = self.image_size, self.batch
         x = torch.randn(B, 3, S, S, generator=self.gen)
         y = (torch.rand(B, 1, S, S, generator=self.gen) < 0.1).to(torch.uint8)
-        return (x.pin_memory(), y.pin_memory()) if pinned else (x, y)
+        return (x.pin_memory(), y.pin_memory()) if (pinned and self.is_cuda) else (x, y)
 
     def _fwd_bwd_opt(self):
         if self.autocast_dtype is not None:
-            with torch.autocast("cuda", dtype=self.autocast_dtype):
+            with torch.autocast(self.device.type, dtype=self.autocast_dtype):
                 logits = self.model(self.x_dev)
         else:
             logits = self.model(self.x_dev)
@@ -137,6 +142,13 @@ class Trainer:
 
     def step(self, x_host, y_host):
         """One optimisation step from HOST tensors; returns the loss as a device scalar (no host sync)."""
+        if not self.is_cuda:
+            self.x_dev.copy_(x_host)
+            self.y_dev.copy_(y_host)
+            self._fwd_bwd_opt()
+            self.opt.zero_grad(set_to_none=True)
+            self.steps_done += 1
+            return self.loss_dev
         cur = torch.cuda.current_stream(self.device)
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
@@ -153,8 +165,10 @@ class Trainer:
                 self.graph = g
                 g.replay()                                    # capture does not execute: run the step once
             else:
+                n0 = _lib.launch_count()
                 self._fwd_bwd_opt()
                 self.opt.zero_grad(set_to_none=True)
+                self.hot_path_launches = _lib.launch_count() - n0      # C-ABI kernel launches of one step (what a graph replays)
         cur.wait_stream(self.stream)
         self.steps_done += 1
         return self.loss_dev

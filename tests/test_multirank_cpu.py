@@ -73,3 +73,58 @@ def test_two_ranks_shard_by_batch(tmp_path):
     np.testing.assert_allclose(r["dA"], g["dA"], rtol=1e-5, atol=1e-5)    # sum of per-rank weight grads == full-batch grad
     assert float(r["ms"]) == 15.0                                 # max over ranks
     assert abs(float(r["value"]) - 2 * 1e9 / 15e-3 / 1e9) < 1e-9  # whole-job value = all ranks' bytes / max time
+
+
+# ---- the caller of the path: data-parallel MM_Net training, gloo, world_size 2 ---------------------------
+def _ddp_train_worker(rank, world, port, q):
+    try:
+        _ddp_train_body(rank, world, port, q)
+    except Exception as exc:   # report instead of leaving the parent waiting on the queue
+        q.put((rank, repr(exc)))
+        raise
+
+
+def _ddp_train_body(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, os.path.join(ROOT, "mm-unet_b200"))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import torch_ref
+    from mmunet_b200 import mamba as mamba_mod, mm_net, train
+
+    class OracleMamba(mamba_mod.Mamba):          # CPU stand-in for the CUDA Mamba block (tests only)
+        def forward(self, hidden_states, inference_params=None):
+            return torch_ref.mamba_forward(self, hidden_states)
+
+    mm_net.Mamba, mm_net._flatten_two_row, mm_net._unflatten_two_row = OracleMamba, torch_ref.two_row_flatten, torch_ref.two_row_unflatten
+    tr = train.Trainer(image_size=64, batch_per_rank=2, dtype="fp32", device="cpu")
+    tr.set_epoch(2)
+    x, y = tr.synthetic_batch()
+    w0 = tr.net.encoder1[0].weight.detach().clone()
+    losses = [float(tr.step(x, y)) for _ in range(2)]
+    # after the all-reduced update every rank must hold the same weights although the ranks saw different batches
+    w = tr.net.encoder1[0].weight.detach().clone()
+    gathered = [torch.empty_like(w) for _ in range(world)]
+    dist.all_gather(gathered, w)
+    frozen = [n for n, p in tr.net.named_parameters() if not p.requires_grad]
+    q.put((rank, losses, bool(torch.equal(gathered[0], gathered[1])), float((w - w0).abs().max()), len(frozen),
+           float(x.sum())))
+    dist.destroy_process_group()
+
+
+def test_ddp_trainer_two_ranks_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(len(r) > 2 for r in res), res
+    (r0, l0, same0, moved0, nfrozen0, xs0), (r1, l1, same1, moved1, nfrozen1, xs1) = res
+    assert same0 and same1, "ranks diverged: the gradient all-reduce did not average the update"
+    assert moved0 > 0 and np.isfinite(l0 + l1).all()
+    assert xs0 != xs1, "ranks must train on different shards"
+    assert nfrozen0 == nfrozen1 == 47 * (2 + 14), "dsc_conv_y (2) + the _b/_s Mamba sets (2 x 7 tensors) of the 47 MMConvs are frozen"
