@@ -295,14 +295,27 @@ def main():
     per_kernel = {n: sum(ev[i][k].elapsed_time(ev[i][k + 1]) for i in range(args.steps)) / args.steps for k, n in enumerate(names)}
 
     # ---------------- end-to-end arm: public autograd API, pinned host buffers, H2D + D2H inside the timed region ---
+    # Every step copies ITS inputs from pinned host memory and reads its loss back.  The copies run on a second stream into
+    # one of two device buffer sets, so the H2D of step i+1 overlaps the kernels of step i (PCIe is the e2e bound here:
+    # 205 MB fp32 per step); events order copy -> compute -> buffer reuse.
     ht, _ = make_inputs(B, dtype, dev, seed=rank, pin=True)
-    dbuf = {k: torch.empty_like(v, device=dev) for k, v in ht.items()}
+    dbufs = [{k: torch.empty_like(v, device=dev) for k, v in ht.items()} for _ in range(2)]
     host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
     params = {k: w[k].clone().requires_grad_() for k in ("A", "Dp", "dbias", "cw", "cb")}
+    copy_stream = torch.cuda.Stream(dev)
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_step():
-        for k in ht:
-            dbuf[k].copy_(ht[k], non_blocking=True)
+    def e2e_copy(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i % 2])                 # the compute that last read this buffer set is done
+            for k in ht:
+                dbufs[i % 2][k].copy_(ht[k], non_blocking=True)
+            copied[i % 2].record(copy_stream)
+
+    def e2e_compute(i):
+        dbuf = dbufs[i % 2]
+        torch.cuda.current_stream().wait_event(copied[i % 2])
         x = dbuf["x"].requires_grad_()
         u = ops.causal_conv1d_fn(x, params["cw"], params["cb"], "silu")
         out = ops.selective_scan_fn(u, dbuf["delta"], params["A"], dbuf["Bm"], dbuf["Cm"], params["Dp"], dbuf["z"],
@@ -310,19 +323,28 @@ def main():
         loss = (out.float() * dbuf["dout"].float()).sum()
         loss.backward()
         host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+        consumed[i % 2].record()
         dbuf["x"] = dbuf["x"].detach()
         for p_ in params.values():
             p_.grad = None
 
+    def e2e_run(n):
+        e2e_copy(0)
+        for i in range(n):
+            if i + 1 < n:
+                e2e_copy(i + 1)
+            e2e_compute(i)
+
     e2e_steps = max(3, args.steps // 3)
-    for _ in range(3):
-        e2e_step()
+    for ev_ in consumed:
+        ev_.record()
+    e2e_run(3)
     torch.cuda.synchronize()
     if dist: dist.barrier()
     s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s2.record()
-    for _ in range(e2e_steps):
-        e2e_step()
+    copy_stream.wait_event(s2)                                      # no copy starts before the timed region does
+    e2e_run(e2e_steps)
     e2.record()
     torch.cuda.synchronize()
     e2e_ms = reduce_max_ms(s2.elapsed_time(e2), dist, dev) / e2e_steps
@@ -334,7 +356,7 @@ def main():
     # ---------------- MM-UNet training leg (BASELINE configs[2]): the caller of the path, img/s ---------------------
     train = None
     if not args.no_train:
-        del ht, dbuf, t, du, dd, dz, dx
+        del ht, dbufs, t, du, dd, dz, dx
         torch.cuda.empty_cache()
         try:
             train = train_leg(args, rank, world, dev, dist)
@@ -359,7 +381,8 @@ def main():
                    "l2": "inputs (818 MB fp32 / 409 MB bf16 per step) larger than the 126 MB L2", "io_dtype": args.dtype},
         "e2e": {"value": whole_job_gbps(world, nbytes["step"], e2e_ms), "unit": "GB/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
-                "api": "causal_conv1d_fn + selective_scan_fn (autograd), pinned host inputs, loss read back"},
+                "api": "causal_conv1d_fn + selective_scan_fn (autograd), pinned host inputs (H2D of step i+1 on a copy stream overlaps "
+                       "step i), loss read back"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": traffic, "peak_source": peak_src,
