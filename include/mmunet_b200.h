@@ -158,6 +158,22 @@ int mmu_scan_order_scatter(const void *src, void *dst, int32_t dtype, int64_t ro
 int mmu_scan_order_index(int64_t *idx_dev, int32_t order, int32_t H, int32_t W, int32_t nslices, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * snake row sampler of MMConv (the caller of the Mamba block).  replaces the
+ * coordinate rescale + F.grid_sample(bilinear, zeros, align_corners=True) of src/UM_Net/MMUNet.py:190-224
+ * (get_coordinate_map_2D's rearrange, _coordinate_map_scaling, get_interpolated_feature), morph 0:
+ *   feat (B, C, H, W) contiguous, dtype in_dtype;  y (B, K, H, W) fp32 row coordinates in pixels (unclamped)
+ *   out  (B, C, H*K, W) contiguous, dtype out_dtype:
+ *        out[b,c,h*K+k,w] = lerp over rows of feat[b,c,:,clamp(w+k-K/2, 0, W-1)] at clamp(y[b,k,h,w], 0, H-1)
+ *   bwd: dout (B, C, H*K, W) dtype out_dtype;  dfeat (B, C, H, W) fp32 and dy (B, K, H, W) fp32 are ACCUMULATED INTO
+ *        (caller zero-fills); dy may be NULL.
+ *   dtypes: MMU_F32 / MMU_BF16 in any combination.
+ * --------------------------------------------------------------------------------------------- */
+int mmu_snake_sample_fwd(const void *feat, const float *y, void *out, int32_t in_dtype, int32_t out_dtype, int32_t B,
+                         int32_t C, int32_t H, int32_t W, int32_t K, void *stream);
+int mmu_snake_sample_bwd(const void *feat, const float *y, const void *dout, float *dfeat, float *dy, int32_t in_dtype,
+                         int32_t out_dtype, int32_t B, int32_t C, int32_t H, int32_t W, int32_t K, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * misc
  * --------------------------------------------------------------------------------------------- */
 int mmu_version(void);

@@ -1,0 +1,158 @@
+// Snake (dynamic-snake-conv) row sampler for MMConv, sm_100a: the bilinear gather that follows the Mamba-refined row
+// coordinates (the caller of the hot path).
+//
+// Reference: src/UM_Net/MMUNet.py:190-224 builds, per tap k of a K-tap vertical snake kernel, a coordinate map
+//   y[b,k,h,w] (learned, fractional) and x = w + (k - K/2) (integer), clamps both to the image, rescales them to [-1,1]
+//   (:229-242) and calls F.grid_sample(bilinear, zeros, align_corners=True) on a (B, H*K, W, 2) grid -> (B, C, H*K, W).
+// With integer x the bilinear stencil degenerates to a 2-tap interpolation along rows:
+//   yc = clamp(y, 0, H-1), r0 = floor(yc), f = yc - r0, xk = clamp(w + k - K/2, 0, W-1)
+//   out[b,c,h*K+k,w] = (1-f) * feat[b,c,r0,xk] + f * feat[b,c,r0+1,xk]          (row r0+1 == H contributes 0: then f == 0)
+// One thread owns one (b, h, k, w) sample - r0, f, xk are computed once - and walks a block of channels; consecutive
+// threads are consecutive w, so loads and stores are coalesced rows.  No (B,H*K,W,2) grid, no fp32 up-cast of the feature
+// map, output written directly in the consumer's dtype.
+// Backward: d_feat (fp32, caller zero-fills) receives the two taps by red.global.add.f32; d_y[b,k,h,w] = sum_c dout * (v1 - v0)
+// inside the clamp range (torch.clamp passes the gradient on the closed interval), accumulated across channel blocks.
+#include "common.cuh"
+
+namespace mmu {
+
+template <typename T> __device__ __forceinline__ float ldf(const T *p) { return Elem<T>::to_f(*p); }
+
+struct SnakeGeom {
+    int B, C, H, W, K, cpb;   // cpb = channels per thread
+};
+
+__device__ __forceinline__ bool snake_coord(const SnakeGeom &g, const float *__restrict__ y, int64_t s, int &b, int &h, int &k, int &w,
+                                            int &r0, int &r1ok, float &f, int &xk, bool &inside) {
+    const int64_t total = (int64_t)g.B * g.H * g.K * g.W;
+    if (s >= total) return false;
+    w = (int)(s % g.W);
+    int64_t t = s / g.W;
+    k = (int)(t % g.K);
+    t /= g.K;
+    h = (int)(t % g.H);
+    b = (int)(t / g.H);
+    const float yv = y[(((int64_t)b * g.K + k) * g.H + h) * g.W + w];
+    const float hi = (float)(g.H - 1);
+    inside = yv >= 0.f && yv <= hi;
+    const float yc = fminf(fmaxf(yv, 0.f), hi);
+    const float fl = floorf(yc);
+    r0 = (int)fl;
+    f = yc - fl;
+    r1ok = r0 + 1 < g.H;
+    xk = min(max(w + k - g.K / 2, 0), g.W - 1);
+    return true;
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) snake_fwd_kernel(const TI *__restrict__ feat, const float *__restrict__ y, TO *__restrict__ out,
+                                                        SnakeGeom g) {
+    int b, h, k, w, r0, r1ok, xk;
+    float f;
+    bool inside;
+    if (!snake_coord(g, y, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, b, h, k, w, r0, r1ok, f, xk, inside)) return;
+    const int c0 = blockIdx.y * g.cpb, c1 = min(g.C, c0 + g.cpb);
+    const int64_t plane = (int64_t)g.H * g.W;
+    const TI *p0 = feat + ((int64_t)b * g.C + c0) * plane + (int64_t)r0 * g.W + xk;
+    TO *o = out + (((int64_t)b * g.C + c0) * g.H + h) * g.K * g.W + (int64_t)k * g.W + w;
+    const int64_t oplane = plane * g.K;
+    const float f0 = 1.f - f;
+    const int d1 = r1ok ? g.W : 0;           // row r0+1 outside the map: weight f is 0, re-read row r0
+#pragma unroll 4
+    for (int c = c0; c < c1; ++c, p0 += plane, o += oplane) {
+        const float v0 = ldf(p0), v1 = ldf(p0 + d1);
+        *o = Elem<TO>::from_f(fmaf(f, v1, f0 * v0));
+    }
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) snake_bwd_kernel(const TI *__restrict__ feat, const float *__restrict__ y, const TO *__restrict__ dout,
+                                                        float *__restrict__ dfeat, float *__restrict__ dy, SnakeGeom g) {
+    int b, h, k, w, r0, r1ok, xk;
+    float f;
+    bool inside;
+    if (!snake_coord(g, y, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, b, h, k, w, r0, r1ok, f, xk, inside)) return;
+    const int c0 = blockIdx.y * g.cpb, c1 = min(g.C, c0 + g.cpb);
+    const int64_t plane = (int64_t)g.H * g.W, oplane = plane * g.K;
+    const int64_t fo = ((int64_t)b * g.C + c0) * plane + (int64_t)r0 * g.W + xk;
+    const TI *p0 = feat + fo;
+    float *d0 = dfeat + fo;
+    const TO *go = dout + (((int64_t)b * g.C + c0) * g.H + h) * g.K * g.W + (int64_t)k * g.W + w;
+    const float f0 = 1.f - f;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int c = c0; c < c1; ++c, p0 += plane, d0 += plane, go += oplane) {
+        const float gv = ldf(go);
+        const float v0 = ldf(p0);
+        atomicAdd(d0, f0 * gv);
+        if (r1ok) {
+            const float v1 = ldf(p0 + g.W);
+            atomicAdd(d0 + g.W, f * gv);
+            acc = fmaf(gv, v1 - v0, acc);
+        } else {
+            acc = fmaf(gv, -v0, acc);       // zero padding below the last row
+        }
+    }
+    if (dy != nullptr && inside) atomicAdd(dy + (((int64_t)b * g.K + k) * g.H + h) * g.W + w, acc);
+}
+
+namespace {
+int geom(SnakeGeom &g, int B, int C, int H, int W, int K, dim3 &grid) {
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0) return set_error(MMU_ERR_INVALID, "snake_sample: bad shape B%d C%d H%d W%d K%d", B, C, H, W, K);
+    const int64_t samples = (int64_t)B * H * K * W;
+    if (samples * C > (int64_t)1 << 40) return set_error(MMU_ERR_UNSUPPORTED, "snake_sample: problem too large");
+    const int64_t blocks = (samples + 255) / 256;
+    if (blocks > INT32_MAX) return set_error(MMU_ERR_UNSUPPORTED, "snake_sample: too many samples");
+    // channel blocks: enough CTAs to fill the GPU a few times over, at least 8 channels per thread to amortise the coordinates
+    int cblocks = 1;
+    while (blocks * cblocks < 148 * 16 && C / (cblocks * 2) >= 8) cblocks *= 2;
+    g = {B, C, H, W, K, (C + cblocks - 1) / cblocks};
+    grid = dim3((unsigned)blocks, (unsigned)((C + g.cpb - 1) / g.cpb));
+    return MMU_OK;
+}
+}  // namespace
+}  // namespace mmu
+
+extern "C" int mmu_snake_sample_fwd(const void *feat, const float *y, void *out, int32_t in_dtype, int32_t out_dtype, int32_t B,
+                                    int32_t C, int32_t H, int32_t W, int32_t K, void *stream) {
+    using namespace mmu;
+    SnakeGeom g;
+    dim3 grid;
+    if (int rc = geom(g, B, C, H, W, K, grid)) return rc;
+    if (!feat || !y || !out) return set_error(MMU_ERR_INVALID, "snake_sample_fwd: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (in_dtype == MMU_F32 && out_dtype == MMU_F32)
+        snake_fwd_kernel<float, float><<<grid, 256, 0, st>>>((const float *)feat, y, (float *)out, g);
+    else if (in_dtype == MMU_F32 && out_dtype == MMU_BF16)
+        snake_fwd_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float *)feat, y, (__nv_bfloat16 *)out, g);
+    else if (in_dtype == MMU_BF16 && out_dtype == MMU_BF16)
+        snake_fwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)feat, y, (__nv_bfloat16 *)out, g);
+    else if (in_dtype == MMU_BF16 && out_dtype == MMU_F32)
+        snake_fwd_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)feat, y, (float *)out, g);
+    else
+        return set_error(MMU_ERR_UNSUPPORTED, "snake_sample_fwd: dtypes %d -> %d", in_dtype, out_dtype);
+    count_launch();
+    return check_launch("snake_sample_fwd");
+}
+
+extern "C" int mmu_snake_sample_bwd(const void *feat, const float *y, const void *dout, float *dfeat, float *dy, int32_t in_dtype,
+                                    int32_t out_dtype, int32_t B, int32_t C, int32_t H, int32_t W, int32_t K, void *stream) {
+    using namespace mmu;
+    SnakeGeom g;
+    dim3 grid;
+    if (int rc = geom(g, B, C, H, W, K, grid)) return rc;
+    if (!feat || !y || !dout || !dfeat) return set_error(MMU_ERR_INVALID, "snake_sample_bwd: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (in_dtype == MMU_F32 && out_dtype == MMU_F32)
+        snake_bwd_kernel<float, float><<<grid, 256, 0, st>>>((const float *)feat, y, (const float *)dout, dfeat, dy, g);
+    else if (in_dtype == MMU_F32 && out_dtype == MMU_BF16)
+        snake_bwd_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float *)feat, y, (const __nv_bfloat16 *)dout, dfeat, dy, g);
+    else if (in_dtype == MMU_BF16 && out_dtype == MMU_BF16)
+        snake_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)feat, y, (const __nv_bfloat16 *)dout, dfeat, dy, g);
+    else if (in_dtype == MMU_BF16 && out_dtype == MMU_F32)
+        snake_bwd_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)feat, y, (const float *)dout, dfeat, dy, g);
+    else
+        return set_error(MMU_ERR_UNSUPPORTED, "snake_sample_bwd: dtypes %d -> %d", in_dtype, out_dtype);
+    count_launch();
+    return check_launch("snake_sample_bwd");
+}

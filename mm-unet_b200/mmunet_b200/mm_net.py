@@ -36,6 +36,7 @@ from .mamba import Mamba
 # Tests swap these three for CPU oracle stand-ins (the product path has no CPU implementation).
 _flatten_two_row = ops.two_row_flatten
 _unflatten_two_row = ops.two_row_unflatten
+_snake_sample = ops.snake_sample          # None -> the reference's torch formulation (grid rescale + F.grid_sample)
 
 
 class MMConv(nn.Module):
@@ -102,17 +103,27 @@ class MMConv(nn.Module):
         gain = torch.clamp(F.softplus(self.altho), min=0.01)                   #                      (:186-187)
         return gain * refined.float() + (rows + self._snake_offsets(dy).float() * self.extend_scope)
 
+    def _grid_sample(self, input, y):
+        """The reference formulation: rescale both coordinate maps to [-1, 1] and bilinear grid_sample."""
+        B, K, H, W = y.shape
+        _, xmap = self._base_grids(H, W, y.device)
+        ymap = y.permute(0, 2, 1, 3).reshape(B, H * K, W)                      # "b k h w -> b (h k) w"   (:190)
+        ymap = -1.0 + (2.0 / (H - 1)) * ymap.clamp(0, H - 1)                   # (:205-209, 229-242)
+        grid = torch.stack([xmap.expand(B, -1, -1), ymap], dim=-1)             # (B, H*K, W, 2) = (x, y)  (:211-216)
+        src = input if input.dtype == grid.dtype or torch.is_autocast_enabled(input.device.type) else input.to(grid.dtype)
+        return F.grid_sample(src, grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+
     def forward(self, input):
         offset = self.tanh(self.gn_offset(self.offset_conv(input)))            # (:247-250)
         B, _, H, W = offset.shape
         K = self.kernel_size
         y = self.row_coordinates(offset)                                       # (B, K, H, W)
-        _, xmap = self._base_grids(H, W, offset.device)
-        ymap = y.permute(0, 2, 1, 3).reshape(B, H * K, W)                      # "b k h w -> b (h k) w"   (:190)
-        ymap = -1.0 + (2.0 / (H - 1)) * ymap.clamp(0, H - 1)                   # (:205-209, 229-242)
-        grid = torch.stack([xmap.expand(B, -1, -1), ymap], dim=-1)             # (B, H*K, W, 2) = (x, y)  (:211-216)
-        src = input if input.dtype == grid.dtype or torch.is_autocast_enabled(input.device.type) else input.to(grid.dtype)
-        feat = F.grid_sample(src, grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+        if _snake_sample is not None and self.morph == 0:
+            # fused clamp + row interpolation, written in the dtype the strided conv consumes (MMUNet.py:190-224)
+            dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else input.dtype
+            feat = _snake_sample(input, y, dt if dt in (torch.float32, torch.bfloat16) else torch.float32)
+        else:
+            feat = self._grid_sample(input, y)
         out = self.dsc_conv_x(feat) if self.morph == 0 else self.dsc_conv_y(feat)
         return self.gn(out)
 

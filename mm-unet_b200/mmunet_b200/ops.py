@@ -660,3 +660,50 @@ def two_row_unflatten(x_flat, H, W):
     """inverse (MMUNet.py:95-121): (B,C,L) -> (B,C,H,W)."""
     B, C_, L = x_flat.shape
     return scan_order_scatter(x_flat, _lib.ORDER_TWOROW, H, W).view(B, C_, H, W)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# MMConv's snake row sampler (the caller of the Mamba block; replaces coordinate rescale + F.grid_sample, MMUNet.py:190-224)
+# ----------------------------------------------------------------------------------------------------------
+
+class _SnakeSampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, y, out_dtype):
+        _require_cuda(feat, y)
+        if feat.dtype not in (torch.float32, torch.bfloat16) or out_dtype not in (torch.float32, torch.bfloat16):
+            raise RuntimeError("snake_sample: feature / output dtype must be float32 or bfloat16")
+        if feat.dim() != 4 or y.dim() != 4 or y.shape[0] != feat.shape[0] or y.shape[2:] != feat.shape[2:]:
+            raise RuntimeError(f"snake_sample: feat (B,C,H,W) / y (B,K,H,W) mismatch: {tuple(feat.shape)} vs {tuple(y.shape)}")
+        feat = feat.contiguous()
+        y = y.float().contiguous()
+        B, C_, H, W = feat.shape
+        K = y.shape[1]
+        out = torch.empty((B, C_, H * K, W), device=feat.device, dtype=out_dtype)
+        with torch.cuda.device(feat.device):
+            _lib.check(_lib.lib().mmu_snake_sample_fwd(feat.data_ptr(), y.data_ptr(), out.data_ptr(), _DT[feat.dtype], _DT[out_dtype],
+                                                       B, C_, H, W, K, _stream()), "snake_sample_fwd")
+        ctx.save_for_backward(feat, y)
+        ctx.out_dtype = out_dtype
+        ctx.need_dy = y.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        feat, y = ctx.saved_tensors
+        B, C_, H, W = feat.shape
+        K = y.shape[1]
+        dout = dout.to(ctx.out_dtype).contiguous()
+        nf = feat.numel()
+        acc = torch.zeros(nf + y.numel(), device=feat.device, dtype=torch.float32)     # one zero fill for both accumulators
+        dfeat, dy = acc[:nf].view_as(feat), acc[nf:].view_as(y)
+        with torch.cuda.device(feat.device):
+            _lib.check(_lib.lib().mmu_snake_sample_bwd(feat.data_ptr(), y.data_ptr(), dout.data_ptr(), dfeat.data_ptr(), dy.data_ptr(),
+                                                       _DT[feat.dtype], _DT[ctx.out_dtype], B, C_, H, W, K, _stream()),
+                       "snake_sample_bwd")
+        return dfeat.to(feat.dtype), dy, None
+
+
+def snake_sample(feat, y, out_dtype=None):
+    """feat (B,C,H,W), y (B,K,H,W) fp32 row coordinates in pixels -> (B,C,H*K,W): row-interpolated samples at
+    (clamp(y,0,H-1), clamp(w+k-K//2,0,W-1)) - MMConv's deformed feature map (MMUNet.py:190-224)."""
+    return _SnakeSampleFn.apply(feat, y, feat.dtype if out_dtype is None else out_dtype)

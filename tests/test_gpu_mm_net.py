@@ -73,3 +73,32 @@ def test_trainer_steps_reduce_loss(dtype):
     losses = [float(tr.step(x, y)) for _ in range(8)]
     assert all(np.isfinite(losses)), losses
     assert losses[-1] < losses[0], losses
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 12, 10, 3), (1, 5, 7, 9, 3), (2, 16, 6, 8, 1), (1, 4, 10, 16, 9), (3, 32, 33, 17, 3)])
+@pytest.mark.parametrize("dtypes", [("fp32", "fp32"), ("fp32", "bf16"), ("bf16", "bf16")])
+def test_snake_sample_matches_grid_sample(no_tf32, shape, dtypes):
+    """The fused sampler vs the reference formulation (coordinate rescale + F.grid_sample, MMUNet.py:190-224) on the same
+    inputs, forward and both gradients; y reaches well outside [0, H-1] so that the clamp and its gradient mask are hit."""
+    from mmunet_b200 import mm_net, ops
+    B, C, H, W, K = shape
+    tin, tout = (torch.float32 if d == "fp32" else torch.bfloat16 for d in dtypes)
+    torch.manual_seed(3)
+    conv = mm_net.MMConv(C, 4, kernel_size=K).cuda()
+    feat = torch.randn(B, C, H, W, device="cuda").to(tin)
+    y = (torch.arange(H, device="cuda").view(1, 1, H, 1) + 1.7 * torch.randn(B, K, H, W, device="cuda")).float()
+    f1, y1 = feat.clone().requires_grad_(), y.clone().requires_grad_()
+    f2, y2 = feat.float().clone().requires_grad_(), y.clone().requires_grad_()
+    got = ops.snake_sample(f1, y1, tout)
+    ref = conv._grid_sample(f2, y2)
+    assert got.dtype == tout and got.shape == ref.shape
+    tol = 1e-5 if tout == torch.float32 else 1e-2
+    torch.testing.assert_close(got.float(), ref, rtol=tol, atol=tol)
+    g = torch.randn_like(ref)
+    got.backward(g.to(tout))
+    ref.backward(g.to(tout).float())
+    gt = 1e-4 if tin == torch.float32 and tout == torch.float32 else 2e-2
+    torch.testing.assert_close(f1.grad.float(), f2.grad, rtol=gt, atol=gt * float(f2.grad.abs().max()))
+    # d/dy: piecewise constant in y, so a sample within rounding distance of an integer row may take the neighbouring slope
+    bad = ((y1.grad - y2.grad).abs() > gt * (float(y2.grad.abs().max()) + y2.grad.abs())).float().mean()
+    assert bad <= 2e-3, f"{bad:.4f} of d_y elements differ"

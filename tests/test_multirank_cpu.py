@@ -97,6 +97,7 @@ def _ddp_train_body(rank, world, port, q):
             return torch_ref.mamba_forward(self, hidden_states)
 
     mm_net.Mamba, mm_net._flatten_two_row, mm_net._unflatten_two_row = OracleMamba, torch_ref.two_row_flatten, torch_ref.two_row_unflatten
+    mm_net._snake_sample = None
     tr = train.Trainer(image_size=64, batch_per_rank=2, dtype="fp32", device="cpu")
     tr.set_epoch(2)
     x, y = tr.synthetic_batch()
