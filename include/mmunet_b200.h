@@ -167,11 +167,14 @@ int mmu_scan_order_index(int64_t *idx_dev, int32_t order, int32_t H, int32_t W, 
  *   bwd: dout (B, C, H*K, W) dtype out_dtype;  dfeat (B, C, H, W) fp32 and dy (B, K, H, W) fp32 are ACCUMULATED INTO
  *        (caller zero-fills); dy may be NULL.
  *   dtypes: MMU_F32 / MMU_BF16 in any combination.
+ *   channels_last != 0: feat, out, dout, dfeat are NHWC in memory (feat[b][h][w][c], out[b][h*K+k][w][c]); C must be
+ *        4 * a power of two.  y / dy stay (B, K, H, W).
  * --------------------------------------------------------------------------------------------- */
 int mmu_snake_sample_fwd(const void *feat, const float *y, void *out, int32_t in_dtype, int32_t out_dtype, int32_t B,
-                         int32_t C, int32_t H, int32_t W, int32_t K, void *stream);
+                         int32_t C, int32_t H, int32_t W, int32_t K, int32_t channels_last, void *stream);
 int mmu_snake_sample_bwd(const void *feat, const float *y, const void *dout, float *dfeat, float *dy, int32_t in_dtype,
-                         int32_t out_dtype, int32_t B, int32_t C, int32_t H, int32_t W, int32_t K, void *stream);
+                         int32_t out_dtype, int32_t B, int32_t C, int32_t H, int32_t W, int32_t K, int32_t channels_last,
+                         void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * misc

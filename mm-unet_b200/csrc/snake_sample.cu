@@ -96,7 +96,97 @@ __global__ void __launch_bounds__(256) snake_bwd_kernel(const TI *__restrict__ f
     if (dy != nullptr && inside) atomicAdd(dy + (((int64_t)b * g.K + k) * g.H + h) * g.W + w, acc);
 }
 
+// ---- channels-last (NHWC) variants: feat[b][r][x][c], out[b][h*K+k][w][c].  A thread owns 4 consecutive channels of one sample,
+// consecutive threads walk the channel axis: every access is a coalesced 8/16-byte vector; the backward uses
+// red.global.add.v4.f32 for the two taps and a shuffle reduction over the sample's channel threads for d_y.
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+    static __device__ __forceinline__ void ld(const float *p, float (&v)[4]) {
+        const float4 q = *reinterpret_cast<const float4 *>(p);
+        v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+    }
+    static __device__ __forceinline__ void st(float *p, const float (&v)[4]) { *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Vec4<__nv_bfloat16> {
+    static __device__ __forceinline__ void ld(const __nv_bfloat16 *p, float (&v)[4]) {
+        const uint2 q = *reinterpret_cast<const uint2 *>(p);
+        v[0] = __uint_as_float(q.x << 16), v[1] = __uint_as_float(q.x & 0xffff0000u);
+        v[2] = __uint_as_float(q.y << 16), v[3] = __uint_as_float(q.y & 0xffff0000u);
+    }
+    static __device__ __forceinline__ void st(__nv_bfloat16 *p, const float (&v)[4]) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+        *reinterpret_cast<uint2 *>(p) = make_uint2(*reinterpret_cast<const unsigned *>(&a), *reinterpret_cast<const unsigned *>(&b));
+    }
+};
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) snake_fwd_nhwc_kernel(const TI *__restrict__ feat, const float *__restrict__ y, TO *__restrict__ out,
+                                                             SnakeGeom g) {
+    const int cv = g.C >> 2;                                    // channel vectors per sample
+    const int64_t tix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int b, h, k, w, r0, r1ok, xk;
+    float f;
+    bool inside;
+    if (!snake_coord(g, y, tix / cv, b, h, k, w, r0, r1ok, f, xk, inside)) return;
+    const int c = (int)(tix % cv) << 2;
+    const TI *p0 = feat + (((int64_t)b * g.H + r0) * g.W + xk) * g.C + c;
+    float v0[4], v1[4], o[4];
+    Vec4<TI>::ld(p0, v0);
+    Vec4<TI>::ld(p0 + (r1ok ? (int64_t)g.W * g.C : 0), v1);
+    const float f0 = 1.f - f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = fmaf(f, v1[i], f0 * v0[i]);
+    Vec4<TO>::st(out + ((((int64_t)b * g.H + h) * g.K + k) * g.W + w) * g.C + c, o);
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) snake_bwd_nhwc_kernel(const TI *__restrict__ feat, const float *__restrict__ y, const TO *__restrict__ dout,
+                                                             float *__restrict__ dfeat, float *__restrict__ dy, SnakeGeom g) {
+    const int cv = g.C >> 2;
+    const int64_t tix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int b, h, k, w, r0, r1ok, xk;
+    float f;
+    bool inside;
+    const bool live = snake_coord(g, y, tix / cv, b, h, k, w, r0, r1ok, f, xk, inside);
+    float acc = 0.f;
+    if (live) {
+        const int c = (int)(tix % cv) << 2;
+        const int64_t fo = (((int64_t)b * g.H + r0) * g.W + xk) * g.C + c;
+        float gv[4], v0[4], v1[4] = {0.f, 0.f, 0.f, 0.f};
+        Vec4<TO>::ld(dout + ((((int64_t)b * g.H + h) * g.K + k) * g.W + w) * g.C + c, gv);
+        Vec4<TI>::ld(feat + fo, v0);
+        const float f0 = 1.f - f;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dfeat + fo), "f"(f0 * gv[0]), "f"(f0 * gv[1]), "f"(f0 * gv[2]),
+                     "f"(f0 * gv[3]) : "memory");
+        if (r1ok) {
+            const int64_t f1 = fo + (int64_t)g.W * g.C;
+            Vec4<TI>::ld(feat + f1, v1);
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dfeat + f1), "f"(f * gv[0]), "f"(f * gv[1]), "f"(f * gv[2]),
+                         "f"(f * gv[3]) : "memory");
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc = fmaf(gv[i], v1[i] - v0[i], acc);
+        if (!inside) acc = 0.f;
+    }
+    // d_y: sum over the sample's channel threads.  cv is a power of two (checked by the host): groups of min(cv, 32) lanes
+    const int grp = cv < 32 ? cv : 32;
+    for (int o = grp >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (live && dy != nullptr && (threadIdx.x & (grp - 1)) == 0 && acc != 0.f)
+        atomicAdd(dy + (((int64_t)b * g.K + k) * g.H + h) * g.W + w, acc);
+}
+
 namespace {
+int geom_nhwc(SnakeGeom &g, int B, int C, int H, int W, int K, dim3 &grid) {
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0) return set_error(MMU_ERR_INVALID, "snake_sample: bad shape B%d C%d H%d W%d K%d", B, C, H, W, K);
+    if (C % 4 != 0 || ((C / 4) & (C / 4 - 1)) != 0)
+        return set_error(MMU_ERR_UNSUPPORTED, "snake_sample (channels-last): C=%d must be 4 * a power of two", C);
+    const int64_t threads = (int64_t)B * H * K * W * (C / 4);
+    if ((threads + 255) / 256 > INT32_MAX) return set_error(MMU_ERR_UNSUPPORTED, "snake_sample: problem too large");
+    g = {B, C, H, W, K, 4};
+    grid = dim3((unsigned)((threads + 255) / 256));
+    return MMU_OK;
+}
+
 int geom(SnakeGeom &g, int B, int C, int H, int W, int K, dim3 &grid) {
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0) return set_error(MMU_ERR_INVALID, "snake_sample: bad shape B%d C%d H%d W%d K%d", B, C, H, W, K);
     const int64_t samples = (int64_t)B * H * K * W;
@@ -114,13 +204,27 @@ int geom(SnakeGeom &g, int B, int C, int H, int W, int K, dim3 &grid) {
 }  // namespace mmu
 
 extern "C" int mmu_snake_sample_fwd(const void *feat, const float *y, void *out, int32_t in_dtype, int32_t out_dtype, int32_t B,
-                                    int32_t C, int32_t H, int32_t W, int32_t K, void *stream) {
+                                    int32_t C, int32_t H, int32_t W, int32_t K, int32_t channels_last, void *stream) {
     using namespace mmu;
     SnakeGeom g;
     dim3 grid;
-    if (int rc = geom(g, B, C, H, W, K, grid)) return rc;
+    if (int rc = channels_last ? geom_nhwc(g, B, C, H, W, K, grid) : geom(g, B, C, H, W, K, grid)) return rc;
     if (!feat || !y || !out) return set_error(MMU_ERR_INVALID, "snake_sample_fwd: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (channels_last) {
+        if (in_dtype == MMU_F32 && out_dtype == MMU_F32)
+            snake_fwd_nhwc_kernel<float, float><<<grid, 256, 0, st>>>((const float *)feat, y, (float *)out, g);
+        else if (in_dtype == MMU_F32 && out_dtype == MMU_BF16)
+            snake_fwd_nhwc_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float *)feat, y, (__nv_bfloat16 *)out, g);
+        else if (in_dtype == MMU_BF16 && out_dtype == MMU_BF16)
+            snake_fwd_nhwc_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)feat, y, (__nv_bfloat16 *)out, g);
+        else if (in_dtype == MMU_BF16 && out_dtype == MMU_F32)
+            snake_fwd_nhwc_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)feat, y, (float *)out, g);
+        else
+            return set_error(MMU_ERR_UNSUPPORTED, "snake_sample_fwd: dtypes %d -> %d", in_dtype, out_dtype);
+        count_launch();
+        return check_launch("snake_sample_fwd (channels-last)");
+    }
     if (in_dtype == MMU_F32 && out_dtype == MMU_F32)
         snake_fwd_kernel<float, float><<<grid, 256, 0, st>>>((const float *)feat, y, (float *)out, g);
     else if (in_dtype == MMU_F32 && out_dtype == MMU_BF16)
@@ -136,13 +240,28 @@ extern "C" int mmu_snake_sample_fwd(const void *feat, const float *y, void *out,
 }
 
 extern "C" int mmu_snake_sample_bwd(const void *feat, const float *y, const void *dout, float *dfeat, float *dy, int32_t in_dtype,
-                                    int32_t out_dtype, int32_t B, int32_t C, int32_t H, int32_t W, int32_t K, void *stream) {
+                                    int32_t out_dtype, int32_t B, int32_t C, int32_t H, int32_t W, int32_t K, int32_t channels_last,
+                                    void *stream) {
     using namespace mmu;
     SnakeGeom g;
     dim3 grid;
-    if (int rc = geom(g, B, C, H, W, K, grid)) return rc;
+    if (int rc = channels_last ? geom_nhwc(g, B, C, H, W, K, grid) : geom(g, B, C, H, W, K, grid)) return rc;
     if (!feat || !y || !dout || !dfeat) return set_error(MMU_ERR_INVALID, "snake_sample_bwd: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (channels_last) {
+        if (in_dtype == MMU_F32 && out_dtype == MMU_F32)
+            snake_bwd_nhwc_kernel<float, float><<<grid, 256, 0, st>>>((const float *)feat, y, (const float *)dout, dfeat, dy, g);
+        else if (in_dtype == MMU_F32 && out_dtype == MMU_BF16)
+            snake_bwd_nhwc_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float *)feat, y, (const __nv_bfloat16 *)dout, dfeat, dy, g);
+        else if (in_dtype == MMU_BF16 && out_dtype == MMU_BF16)
+            snake_bwd_nhwc_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)feat, y, (const __nv_bfloat16 *)dout, dfeat, dy, g);
+        else if (in_dtype == MMU_BF16 && out_dtype == MMU_F32)
+            snake_bwd_nhwc_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)feat, y, (const float *)dout, dfeat, dy, g);
+        else
+            return set_error(MMU_ERR_UNSUPPORTED, "snake_sample_bwd: dtypes %d -> %d", in_dtype, out_dtype);
+        count_launch();
+        return check_launch("snake_sample_bwd (channels-last)");
+    }
     if (in_dtype == MMU_F32 && out_dtype == MMU_F32)
         snake_bwd_kernel<float, float><<<grid, 256, 0, st>>>((const float *)feat, y, (const float *)dout, dfeat, dy, g);
     else if (in_dtype == MMU_F32 && out_dtype == MMU_BF16)

@@ -82,8 +82,8 @@ def lib() -> C.CDLL:
     for n in ("mmu_scan_order_gather", "mmu_scan_order_scatter"):
         getattr(L, n).argtypes = [_vp, _vp, _i32, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp]
     L.mmu_scan_order_index.argtypes = [_vp, _i32, _i32, _i32, _i32, _vp]
-    L.mmu_snake_sample_fwd.argtypes = [_vp, _vp, _vp] + [_i32] * 7 + [_vp]
-    L.mmu_snake_sample_bwd.argtypes = [_vp, _vp, _vp, _vp, _vp] + [_i32] * 7 + [_vp]
+    L.mmu_snake_sample_fwd.argtypes = [_vp, _vp, _vp] + [_i32] * 8 + [_vp]
+    L.mmu_snake_sample_bwd.argtypes = [_vp, _vp, _vp, _vp, _vp] + [_i32] * 8 + [_vp]
     for n in EXPORTS:      # fail loudly on a stale library
         getattr(L, n)
     _lib = L

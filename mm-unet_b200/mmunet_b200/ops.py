@@ -666,6 +666,12 @@ def two_row_unflatten(x_flat, H, W):
 # MMConv's snake row sampler (the caller of the Mamba block; replaces coordinate rescale + F.grid_sample, MMUNet.py:190-224)
 # ----------------------------------------------------------------------------------------------------------
 
+def _nhwc_ok(t):
+    C_ = t.shape[1]
+    return (t.dim() == 4 and C_ % 4 == 0 and ((C_ // 4) & (C_ // 4 - 1)) == 0 and not t.is_contiguous()
+            and t.is_contiguous(memory_format=torch.channels_last))
+
+
 class _SnakeSampleFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, y, out_dtype):
@@ -674,17 +680,18 @@ class _SnakeSampleFn(torch.autograd.Function):
             raise RuntimeError("snake_sample: feature / output dtype must be float32 or bfloat16")
         if feat.dim() != 4 or y.dim() != 4 or y.shape[0] != feat.shape[0] or y.shape[2:] != feat.shape[2:]:
             raise RuntimeError(f"snake_sample: feat (B,C,H,W) / y (B,K,H,W) mismatch: {tuple(feat.shape)} vs {tuple(y.shape)}")
-        feat = feat.contiguous()
+        cl = _nhwc_ok(feat)                       # channels-last feature maps are consumed and produced in place (NHWC kernels)
+        fmt = torch.channels_last if cl else torch.contiguous_format
+        feat = feat.contiguous(memory_format=fmt)
         y = y.float().contiguous()
         B, C_, H, W = feat.shape
         K = y.shape[1]
-        out = torch.empty((B, C_, H * K, W), device=feat.device, dtype=out_dtype)
+        out = torch.empty((B, C_, H * K, W), device=feat.device, dtype=out_dtype, memory_format=fmt)
         with torch.cuda.device(feat.device):
             _lib.check(_lib.lib().mmu_snake_sample_fwd(feat.data_ptr(), y.data_ptr(), out.data_ptr(), _DT[feat.dtype], _DT[out_dtype],
-                                                       B, C_, H, W, K, _stream()), "snake_sample_fwd")
+                                                       B, C_, H, W, K, int(cl), _stream()), "snake_sample_fwd")
         ctx.save_for_backward(feat, y)
-        ctx.out_dtype = out_dtype
-        ctx.need_dy = y.requires_grad
+        ctx.out_dtype, ctx.cl = out_dtype, cl
         return out
 
     @staticmethod
@@ -692,13 +699,15 @@ class _SnakeSampleFn(torch.autograd.Function):
         feat, y = ctx.saved_tensors
         B, C_, H, W = feat.shape
         K = y.shape[1]
-        dout = dout.to(ctx.out_dtype).contiguous()
+        fmt = torch.channels_last if ctx.cl else torch.contiguous_format
+        dout = dout.to(ctx.out_dtype).contiguous(memory_format=fmt)
         nf = feat.numel()
         acc = torch.zeros(nf + y.numel(), device=feat.device, dtype=torch.float32)     # one zero fill for both accumulators
-        dfeat, dy = acc[:nf].view_as(feat), acc[nf:].view_as(y)
+        dfeat = acc[:nf].view(B, H, W, C_).permute(0, 3, 1, 2) if ctx.cl else acc[:nf].view(B, C_, H, W)
+        dy = acc[nf:].view_as(y)
         with torch.cuda.device(feat.device):
             _lib.check(_lib.lib().mmu_snake_sample_bwd(feat.data_ptr(), y.data_ptr(), dout.data_ptr(), dfeat.data_ptr(), dy.data_ptr(),
-                                                       _DT[feat.dtype], _DT[ctx.out_dtype], B, C_, H, W, K, _stream()),
+                                                       _DT[feat.dtype], _DT[ctx.out_dtype], B, C_, H, W, K, int(ctx.cl), _stream()),
                        "snake_sample_bwd")
         return dfeat.to(feat.dtype), dy, None
 

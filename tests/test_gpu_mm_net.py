@@ -77,7 +77,8 @@ def test_trainer_steps_reduce_loss(dtype):
 
 @pytest.mark.parametrize("shape", [(2, 8, 12, 10, 3), (1, 5, 7, 9, 3), (2, 16, 6, 8, 1), (1, 4, 10, 16, 9), (3, 32, 33, 17, 3)])
 @pytest.mark.parametrize("dtypes", [("fp32", "fp32"), ("fp32", "bf16"), ("bf16", "bf16")])
-def test_snake_sample_matches_grid_sample(no_tf32, shape, dtypes):
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_snake_sample_matches_grid_sample(no_tf32, shape, dtypes, channels_last):
     """The fused sampler vs the reference formulation (coordinate rescale + F.grid_sample, MMUNet.py:190-224) on the same
     inputs, forward and both gradients; y reaches well outside [0, H-1] so that the clamp and its gradient mask are hit."""
     from mmunet_b200 import mm_net, ops
@@ -86,12 +87,16 @@ def test_snake_sample_matches_grid_sample(no_tf32, shape, dtypes):
     torch.manual_seed(3)
     conv = mm_net.MMConv(C, 4, kernel_size=K).cuda()
     feat = torch.randn(B, C, H, W, device="cuda").to(tin)
+    if channels_last:      # NHWC kernels when C = 4 * 2^k, else the op falls back to the NCHW kernels on a contiguous copy
+        feat = feat.contiguous(memory_format=torch.channels_last)
     y = (torch.arange(H, device="cuda").view(1, 1, H, 1) + 1.7 * torch.randn(B, K, H, W, device="cuda")).float()
     f1, y1 = feat.clone().requires_grad_(), y.clone().requires_grad_()
     f2, y2 = feat.float().clone().requires_grad_(), y.clone().requires_grad_()
     got = ops.snake_sample(f1, y1, tout)
     ref = conv._grid_sample(f2, y2)
     assert got.dtype == tout and got.shape == ref.shape
+    if channels_last and C in (4, 8, 16, 32):
+        assert got.is_contiguous(memory_format=torch.channels_last)
     tol = 1e-5 if tout == torch.float32 else 1e-2
     torch.testing.assert_close(got.float(), ref, rtol=tol, atol=tol)
     g = torch.randn_like(ref)
