@@ -186,7 +186,7 @@ def train_leg(args, rank, world, dev, dist):
     bf16 autocast; one rank per GPU with torch DDP (NCCL gradient all-reduce overlapped with backward).  Every step starts
     from PINNED HOST tensors (H2D inside the timed region) and ends with the loss copied back to the host."""
     from mmunet_b200.train import Trainer
-    tr = Trainer(image_size=args.train_size, batch_per_rank=args.train_batch, dtype="bf16", device=dev)
+    tr = Trainer(image_size=args.train_size, batch_per_rank=args.train_batch, dtype="bf16", device=dev, channels_last=True)
     tr.set_epoch(tr.warmup_epochs)        # full learning rate (epoch 0 of the reference's schedule trains with lr = 0)
     batches = [tr.synthetic_batch() for _ in range(2)]
     host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
@@ -213,7 +213,7 @@ def train_leg(args, rank, world, dev, dist):
             "ms_per_step": ms, "steps": args.train_steps, "warmup": warm, "n_gpus": world, "scaling": "weak",
             "cuda_graph": tr.graph is not None,
             "config": {"model": "MM_Net (mmunet_b200/mm_net.py, 50 Mamba blocks)", "image": f"{args.train_size}x{args.train_size} RGB",
-                       "per_gpu_batch": args.train_batch, "global_batch": world * args.train_batch, "dtype": "bf16 autocast",
+                       "per_gpu_batch": args.train_batch, "global_batch": world * args.train_batch, "dtype": "bf16 autocast", "memory_format": "channels_last",
                        "optimizer": "AdamW lr 1e-3 wd 0.05 betas (0.9,0.95)", "loss": "DiceFocal",
                        "parallelism": f"dp{world}" + (" (DDP, NCCL all-reduce overlapped with backward)" if world > 1 else "")},
             "h2d_bytes_per_step": xb.numel() * xb.element_size() + yb.numel() * yb.element_size(), "d2h_bytes_per_step": 4,
