@@ -178,7 +178,7 @@ def run_reference(args):
                              "sample": f"batch {sample_batch} of {B} per step; pure-PyTorch selective_scan_ref/causal_conv1d_ref "
                                        "algorithm (oracle/torch_ref.py), autograd backward"},
             "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def train_leg(args, rank, world, dev, dist):
@@ -221,6 +221,23 @@ def train_leg(args, rank, world, dev, dist):
             "loss": float(host_loss.item()), "wall_s": wall, "data": "synthetic", "peak_mem_gib": torch.cuda.max_memory_allocated() / 2**30}
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Only the JSON line may reach stdout: libraries (NCCL prints its version banner there) get stderr instead."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -234,6 +251,7 @@ def main():
     ap.add_argument("--train-batch", type=int, default=16, help="per-GPU batch of the training leg")
     ap.add_argument("--train-size", type=int, default=512)
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -402,7 +420,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline_port()
         except Exception as exc:  # the oracle is a checker; its absence must not hide the GPU number
             line["cpu_baseline"] = {"error": repr(exc)}
-    print(json.dumps(line))
+    emit(line)
     if dist: dist.destroy_process_group()
 
 
