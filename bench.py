@@ -148,9 +148,12 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import torch_ref
-    sample_batch = 1
+    sample_batch, sample_dim = 1, 128           # bounded sample: batch 1 of 8, channels 0..127 of 384 (B/C are per batch)
     t, w = make_inputs(sample_batch, torch.float32, "cpu")
+    t = {k: (v[:, :sample_dim].contiguous() if k in ("x", "delta", "z", "dout") else v) for k, v in t.items()}
+    w = {k: v[:sample_dim].contiguous() for k, v in w.items()}
     torch.set_num_threads(os.cpu_count() or 1)
+    s_bytes = ((11 * sample_dim + 6 * N) + 5 * sample_dim) * sample_batch * L * 4     # scan fwd+bwd + conv fwd+bwd, fp32
 
     def step():
         x = t["x"].clone().requires_grad_()
@@ -169,13 +172,13 @@ def run_reference(args):
     for _ in range(args.steps):
         step()
     dt = (time.perf_counter() - t0) / args.steps
-    val = algo_bytes(sample_batch, 4)["step"] / dt / 1e9
+    val = s_bytes / dt / 1e9
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"isolated Mamba block B={B} D={D} L={L} N={N} conv_width={W}; CPU sample = batch {sample_batch}"},
+            "config": {"workload": f"isolated Mamba block B={B} D={D} L={L} N={N} conv_width={W}; CPU sample = batch {sample_batch}, channels 0..{sample_dim - 1}"},
             "cpu_baseline": {"value": val, "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"batch {sample_batch} of {B} per step; pure-PyTorch selective_scan_ref/causal_conv1d_ref "
+                             "sample": f"batch {sample_batch} of {B}, {sample_dim} of {D} channels per step; pure-PyTorch selective_scan_ref/causal_conv1d_ref "
                                        "algorithm (oracle/torch_ref.py), autograd backward"},
             "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
