@@ -106,6 +106,9 @@ typedef struct mmu_scan_bwd_params {
     void *du, *ddelta, *dz;
     int64_t du_bs, du_ds, ddelta_bs, ddelta_ds, dz_bs, dz_ds;
     float *dA, *dB, *dC, *dD, *ddelta_bias;
+    /* batch strides (elements) of dB / dC; 0 = contiguous (dstate*seqlen).  Lets both accumulate into row slices of one
+     * (batch, R + 2*dstate, seqlen) gradient buffer of the x_proj output (selective_scan_interface.py:256-262). */
+    int64_t dB_bs, dC_bs;
 } mmu_scan_bwd_params;
 
 size_t mmu_selective_scan_bwd_workspace(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate);

@@ -25,6 +25,7 @@ struct Bwd3Args {
     int *chain_flags, *chain_ticket;   // chained segments (no aggregate pass): carry-ready flags [group][seg], work ticket
     int64_t u_bs, u_ds, dl_bs, dl_ds, z_bs, z_ds, g_bs, g_ds, y_bs, y_ds, B_bs, B_ns, C_bs, C_ns;
     int64_t du_bs, du_ds, ddl_bs, ddl_ds, dz_bs, dz_ds;
+    int64_t dB_bs, dC_bs;          // batch strides of dB / dC (elements)
     int B, D, L, N;
     int nseg, cps, nchunks, nx;
     int softplus;
@@ -146,8 +147,8 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
     }
     const IN_T *B_b = reinterpret_cast<const IN_T *>(p.Bm) + (int64_t)b * p.B_bs;
     const IN_T *C_b = reinterpret_cast<const IN_T *>(p.Cm) + (int64_t)b * p.C_bs;
-    float *dB_b = AGG ? nullptr : p.dB + (int64_t)b * N * L;
-    float *dC_b = AGG ? nullptr : p.dC + (int64_t)b * N * L;
+    float *dB_b = AGG ? nullptr : p.dB + (int64_t)b * p.dB_bs;
+    float *dC_b = AGG ? nullptr : p.dC + (int64_t)b * p.dC_bs;
 
     bool ge_up[3], ge_dn[5];
 #pragma unroll

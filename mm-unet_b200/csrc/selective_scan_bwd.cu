@@ -31,6 +31,7 @@ struct BwdArgs {
     const float *dhin;
     int64_t u_bs, u_ds, dl_bs, dl_ds, z_bs, z_ds, g_bs, g_ds, B_bs, B_ns, C_bs, C_ns;
     int64_t du_bs, du_ds, ddl_bs, ddl_ds, dz_bs, dz_ds;
+    int64_t dB_bs, dC_bs;
     int B, D, L, N, Ne;
     int nseg, cps, nchunks, nx;
     int softplus, reverse;
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(32 * RQ * NGW, AGG ? 512 / (32 * RQ * NGW) : M
         }
         // ---- epilogue B: dB / dC -> global (sum over the CTA's row-warps, then one atomic per element) ---------------
         if (!p.dbg_no_atomics) {
-            float *dB_b = p.dB + (int64_t)b * N * L, *dC_b = p.dC + (int64_t)b * N * L;
+            float *dB_b = p.dB + (int64_t)b * p.dB_bs, *dC_b = p.dC + (int64_t)b * p.dC_bs;
             for (int idx = tid; idx < NP * TL; idx += NT) {
                 const int tok = idx % TL, pr = idx / TL;
                 const int e = ((tok & 7) << 3) | (tok >> 3);            // staging order: e = 8*i + j for token 8*j + i
@@ -595,6 +596,7 @@ template <typename IN_T> bool bwd3_eligible(const mmu_scan_bwd_params *p) {
                 !row_aligned16<IN_T>(p->dz, p->dz_bs, p->dz_ds)))
         return false;
     if (reinterpret_cast<uintptr_t>(p->dB) % 16 != 0 || reinterpret_cast<uintptr_t>(p->dC) % 16 != 0) return false;
+    if ((p->dB_bs * 4) % 16 != 0 || (p->dC_bs * 4) % 16 != 0) return false;
     return true;
 }
 
@@ -665,6 +667,7 @@ template <typename IN_T> int run_bwd3(const mmu_scan_bwd_params *p, cudaStream_t
     a.B_bs = f.B_bs, a.B_ns = f.B_ns, a.C_bs = f.C_bs, a.C_ns = f.C_ns;
     a.du_bs = p->du_bs, a.du_ds = p->du_ds, a.ddl_bs = p->ddelta_bs, a.ddl_ds = p->ddelta_ds;
     a.dz_bs = p->dz_bs, a.dz_ds = p->dz_ds;
+    a.dB_bs = p->dB_bs ? p->dB_bs : (int64_t)f.dstate * f.seqlen, a.dC_bs = p->dC_bs ? p->dC_bs : (int64_t)f.dstate * f.seqlen;
     a.B = f.batch, a.D = f.dim, a.L = f.seqlen, a.N = f.dstate;
     a.nseg = pl.nseg, a.cps = pl.cps, a.nchunks = pl.nchunks;
     a.nx = (f.seqlen + MMU_STATE_STRIDE - 1) / MMU_STATE_STRIDE;
@@ -725,6 +728,7 @@ template <typename IN_T> int run_bwd(const mmu_scan_bwd_params *p, cudaStream_t 
     a.g_bs = p->dout_bs, a.g_ds = p->dout_ds, a.B_bs = f.B_bs, a.B_ns = f.B_ns, a.C_bs = f.C_bs, a.C_ns = f.C_ns;
     a.du_bs = p->du_bs, a.du_ds = p->du_ds, a.ddl_bs = p->ddelta_bs, a.ddl_ds = p->ddelta_ds;
     a.dz_bs = p->dz_bs, a.dz_ds = p->dz_ds;
+    a.dB_bs = p->dB_bs ? p->dB_bs : (int64_t)f.dstate * f.seqlen, a.dC_bs = p->dC_bs ? p->dC_bs : (int64_t)f.dstate * f.seqlen;
     a.B = f.batch, a.D = f.dim, a.L = f.seqlen, a.N = f.dstate, a.Ne = (f.dstate + 1) & ~1;
     a.nseg = pl.nseg, a.cps = pl.cps, a.nchunks = pl.nchunks;
     a.nx = (f.seqlen + MMU_STATE_STRIDE - 1) / MMU_STATE_STRIDE;

@@ -103,9 +103,15 @@ class Mamba(nn.Module):
         if inference_params is not None:
             raise NotImplementedError("mmunet_b200.Mamba: decode / inference_params is outside the training hot path")
         batch, seqlen, dim = hidden_states.shape
-        # matmul and BLD -> BDL transpose in one go (mamba_simple.py:201-205): xz is a (b, 2d, l) view, strides (l, b*l, 1)
-        xz = (self.in_proj.weight @ hidden_states.permute(2, 0, 1).reshape(dim, batch * seqlen))
-        xz = xz.view(-1, batch, seqlen).transpose(0, 1)
+        # in_proj and BLD -> BDL in one go (mamba_simple.py:201-205).  MM-UNet's token tensors are transposed views of
+        # channel-major (b, d_model, l) maps (MMUNet.py:180, 405): then xz = W @ X[b] is a contiguous (b, 2d, l) batched
+        # matmul with no copy; otherwise the reference's "d (b l)" form, a (b, 2d, l) view with strides (l, b*l, 1).
+        tokens_cm = hidden_states.transpose(1, 2)
+        if tokens_cm.stride(-1) == 1 or seqlen == 1:
+            xz = torch.matmul(self.in_proj.weight, tokens_cm)
+        else:
+            xz = (self.in_proj.weight @ hidden_states.permute(2, 0, 1).reshape(dim, batch * seqlen))
+            xz = xz.view(-1, batch, seqlen).transpose(0, 1)
         if self.in_proj.bias is not None:
             xz = xz + self.in_proj.bias.to(dtype=xz.dtype)[:, None]
         o_1 = o_2 = o_3 = None
@@ -125,7 +131,7 @@ class Mamba(nn.Module):
                 total = total + out_s
                 if self.return_directional:
                     o_1, o_2, o_3 = out_f, out_b.flip([-1]), out_s
-            out = F.linear(total.transpose(1, 2), self.out_proj.weight, self.out_proj.bias)
+            out = ops._out_proj_autograd(total, self.out_proj.weight, self.out_proj.bias)
         else:
             A = -torch.exp(self.A_log.float())
             out = ops.mamba_inner_fn(xz, self.conv1d.weight, self.conv1d.bias, self.x_proj.weight, self.dt_proj.weight,

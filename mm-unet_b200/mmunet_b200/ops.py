@@ -157,9 +157,11 @@ def selective_scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta
 
 
 def selective_scan_bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softplus=False, reverse=False,
-                       du=None, ddelta=None, dz=None):
+                       du=None, ddelta=None, dz=None, dBC=None):
     """-> (du, ddelta, dA, dB, dC, dD, dz, ddelta_bias); dA/dB/dC/dD/ddelta_bias fp32.
-    du / ddelta / dz may be pre-allocated views (e.g. halves of dxz, as selective_scan_interface.py:244-248)."""
+    du / ddelta / dz may be pre-allocated views (e.g. halves of dxz, as selective_scan_interface.py:244-248).
+    dBC: optional ZERO-FILLED fp32 (batch, 2*dstate, L) buffer (or a row slice of a larger (batch, rows, L) one) that
+    receives dB in rows [0, dstate) and dC in rows [dstate, 2*dstate) (n_groups == 1 only)."""
     _scan_checks(u, delta, A, B, C, D, z, delta_bias)
     y = None
     if isinstance(x, ScanStates):
@@ -179,11 +181,16 @@ def selective_scan_bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softp
     if z is not None and dz is None:
         dz = torch.empty_like(z, memory_format=torch.contiguous_format)
     # one zero fill for every accumulated-into output (they are atomically added to, selective_scan.cpp:458-466)
-    nBC = batch * G * N * L
+    nBC = batch * G * N * L if dBC is None else 0
     nA = (dim * N + 3) // 4 * 4           # keeps dB / dC 16-byte aligned
     acc = torch.zeros(2 * nBC + nA + 2 * dim, device=u.device, dtype=torch.float32)
-    dB = acc[:nBC].view(batch, G, N, L)
-    dC = acc[nBC:2 * nBC].view(batch, G, N, L)
+    if dBC is None:
+        dB = acc[:nBC].view(batch, G, N, L)
+        dC = acc[nBC:2 * nBC].view(batch, G, N, L)
+    else:
+        if G != 1 or dBC.dtype != torch.float32 or dBC.shape != (batch, 2 * N, L) or dBC.stride(2) != 1 or dBC.stride(1) != L:
+            raise RuntimeError("selective_scan_bwd: dBC must be fp32 (batch, 2*dstate, L) with contiguous rows and n_groups == 1")
+        dB, dC = dBC[:, :N].unsqueeze(1), dBC[:, N:].unsqueeze(1)
     dA = acc[2 * nBC:2 * nBC + dim * N].view(dim, N)
     dD = acc[2 * nBC + nA:2 * nBC + nA + dim] if D is not None else None
     dbias = acc[2 * nBC + nA + dim:] if delta_bias is not None else None
@@ -213,6 +220,7 @@ def selective_scan_bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softp
             p.dA = dA.data_ptr() + g * H * N * 4
             if G == 1:
                 p.dB, p.dC = dB.data_ptr(), dC.data_ptr()
+                p.dB_bs, p.dC_bs = dB.stride(0), dC.stride(0)
             else:
                 dBg = torch.zeros((batch, 1, N, L), device=u.device, dtype=torch.float32)
                 dCg = torch.zeros_like(dBg)
@@ -364,7 +372,13 @@ def _autocast_dtype():
 
 
 class _InnerCore:
-    """Shared forward/backward of the fused inner functions (conv -> x_proj -> dt_proj -> scan)."""
+    """Shared forward/backward of the fused inner functions (conv -> x_proj -> dt_proj -> scan).
+
+    Layout: everything stays channel-major, (batch, channels, L) with L contiguous.  The reference flattens to
+    "(b l) d" rows for F.linear (selective_scan_interface.py:181-207), which costs a transpose copy of conv_out, two
+    transpose copies for B and C and their mirror images in the backward; here the skinny projections are batched
+    matmuls W @ X[b], so x_dbl is (batch, R + 2N, L) and B / C / the dt rows are row slices of it that the scan kernels
+    read (and, in the backward, accumulate into) in place through their batch / state strides."""
 
     @staticmethod
     def forward(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C, D, delta_bias,
@@ -374,7 +388,6 @@ class _InnerCore:
                                       "(the only form MM-UNet's Mamba uses)")
         if A.is_complex():
             raise NotImplementedError("mmunet_b200: complex A is not supported")
-        L = xz.shape[-1]
         R = delta_proj_weight.shape[1]
         N = A.shape[-1]
         if xz.stride(-1) != 1:
@@ -383,48 +396,77 @@ class _InnerCore:
         x, z = xz.chunk(2, dim=1)
         conv_b = conv1d_bias.contiguous() if conv1d_bias is not None else None
         conv_out = causal_conv1d_fwd(x, conv_w, conv_b, True, reverse=reverse)      # (b, d, l) contiguous
-        batch, d = conv_out.shape[0], conv_out.shape[1]
-        x_dbl = F.linear(conv_out.transpose(1, 2).reshape(batch * L, d), x_proj_weight)      # (b l, R+2N)
-        delta = (delta_proj_weight @ x_dbl[:, :R].t()).view(d, batch, L).transpose(0, 1)      # (b, d, l) view
-        Bm = x_dbl[:, R:R + N].view(batch, L, N).transpose(1, 2).contiguous().unsqueeze(1)    # (b, 1, n, l)
-        Cm = x_dbl[:, R + N:].view(batch, L, N).transpose(1, 2).contiguous().unsqueeze(1)
+        x_dbl = torch.matmul(x_proj_weight, conv_out)                               # (b, R+2N, l)   (:181)
+        delta = torch.matmul(delta_proj_weight, x_dbl[:, :R])                       # (b, d, l)      (:182)
+        Bm = x_dbl[:, R:R + N].unsqueeze(1)                                         # (b, 1, n, l) views of x_dbl
+        Cm = x_dbl[:, R + N:].unsqueeze(1)
         D = D.contiguous() if D is not None else None
         out_z, xs, _ = selective_scan_fwd(conv_out, delta, A, Bm, Cm, D, z, delta_bias, delta_softplus, reverse=reverse)
-        saved = (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, conv_out, delta, A, Bm, Cm, D, delta_bias,
+        saved = (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, conv_out, delta, A, None, None, D, delta_bias,
                  xs.x, xs.y)
         return out_z, saved
 
     @staticmethod
+    def project_grads(x_dbl, x_proj_weight, delta_proj_weight, conv_out, ddelta, dBC, dconv_out):
+        """Backward of the two skinny projections in the channel-major layout (selective_scan_interface.py:256-277).
+        ddelta (b,d,l), dBC fp32 (b,2N,l), dconv_out (b,d,l) = the scan's du.  -> (dconv_out total, dx_proj_w, ddt_proj_w)."""
+        R = delta_proj_weight.shape[1]
+        dx_dbl = torch.empty_like(x_dbl)
+        dx_dbl[:, R:] = dBC                                                          # one cast copy for dB and dC
+        dx_dbl[:, :R] = torch.matmul(delta_proj_weight.t(), ddelta)                  # (b, R, l)
+        ddt_proj_w = torch.bmm(ddelta, x_dbl[:, :R].transpose(1, 2)).sum(0)          # (d, R)
+        dx_proj_w = torch.bmm(dx_dbl, conv_out.transpose(1, 2)).sum(0)               # (R+2N, d)
+        dconv_out = torch.baddbmm(dconv_out, x_proj_weight.t().unsqueeze(0).expand(x_dbl.shape[0], -1, -1), dx_dbl)
+        return dconv_out, dx_proj_w, ddt_proj_w
+
+    @staticmethod
     def backward(saved, dout_y, delta_softplus, reverse=False):
         """dout_y: (b, d, l).  Returns (dxz, dconv_w (d,1,w), dconv_b, dx_proj_w, ddt_proj_w, dA, dD, ddelta_bias)."""
-        (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, conv_out, delta, A, Bm, Cm, D, delta_bias, xs_x, xs_y) = saved
+        (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, conv_out, delta, A, _, _, D, delta_bias, xs_x, xs_y) = saved
         xs = ScanStates(xs_x, xs_y)
         L = xz.shape[-1]
         R = delta_proj_weight.shape[1]
         N = A.shape[-1]
         x, z = xz.chunk(2, dim=1)
-        batch, d = x.shape[0], x.shape[1]
+        batch = x.shape[0]
+        Bm, Cm = x_dbl[:, R:R + N].unsqueeze(1), x_dbl[:, R + N:].unsqueeze(1)
         dxz = torch.empty_like(xz)
         dx, dz = dxz.chunk(2, dim=1)
-        # (d, b, l)-major gradients: their "d (b l)" views feed the projection GEMMs without a transpose copy
-        du_buf = torch.empty((d, batch, L), device=xz.device, dtype=xz.dtype).transpose(0, 1)
-        ddl_buf = torch.empty((d, batch, L), device=xz.device, dtype=xz.dtype).transpose(0, 1)
-        dconv_out, ddelta, dA, dB, dC, dD, dz, ddelta_bias = selective_scan_bwd(
-            conv_out, delta, A, Bm, Cm, D, z, delta_bias, dout_y, xs, delta_softplus, reverse=reverse, dz=dz,
-            du=du_buf, ddelta=ddl_buf)
-        dx_dbl = torch.empty_like(x_dbl)
-        dx_dbl[:, R:R + N] = dB.view(batch, N, L).transpose(1, 2).reshape(batch * L, N)
-        dx_dbl[:, R + N:] = dC.view(batch, N, L).transpose(1, 2).reshape(batch * L, N)
-        ddelta2 = ddelta.transpose(0, 1).reshape(d, batch * L)                      # (d, b l)
-        ddt_proj_w = ddelta2 @ x_dbl[:, :R]                                         # (d, R)
-        dx_dbl[:, :R] = ddelta2.t() @ delta_proj_weight                             # (b l, R)
-        conv_flat = conv_out.transpose(1, 2).reshape(batch * L, d)
-        dx_proj_w = dx_dbl.t() @ conv_flat                                          # (R+2N, d)
-        dconv2 = dconv_out.transpose(0, 1).reshape(d, batch * L)
-        dconv2 = torch.addmm(dconv2, x_proj_weight.t(), dx_dbl.t())                 # (d, b l)
-        dconv_out = dconv2.view(d, batch, L).transpose(0, 1)                        # (b, d, l) view, stride(-1)==1
+        dBC = torch.zeros((batch, 2 * N, L), device=xz.device, dtype=torch.float32)
+        dconv_out, ddelta, dA, _, _, dD, dz, ddelta_bias = selective_scan_bwd(
+            conv_out, delta, A, Bm, Cm, D, z, delta_bias, dout_y, xs, delta_softplus, reverse=reverse, dz=dz, dBC=dBC)
+        dconv_out, dx_proj_w, ddt_proj_w = _InnerCore.project_grads(x_dbl, x_proj_weight, delta_proj_weight, conv_out, ddelta,
+                                                                    dBC, dconv_out)
         _, dconv_w, dconv_b = causal_conv1d_bwd(x, conv_w, conv_b, dconv_out, True, dx=dx, reverse=reverse)
         return dxz, dconv_w.unsqueeze(1), dconv_b, dx_proj_w, ddt_proj_w, dA, dD, ddelta_bias
+
+
+def _out_proj(out_z, weight, bias):
+    """(b, d, l) -> (b, l, e) = F.linear(out_z^T, W, bias) (selective_scan_interface.py:365) computed channel-major:
+    the result is a transposed VIEW of a contiguous (b, e, l) tensor, which is what MM-UNet's callers transpose back to."""
+    out = torch.matmul(weight, out_z)
+    if bias is not None:
+        out = out + bias.to(out.dtype)[:, None]
+    return out.transpose(1, 2)
+
+
+def _out_proj_autograd(total, weight, bias):
+    """Plain-autograd flavour of _out_proj for the v2/v3 branch (requirements/mamba_simple.py:270): (b, d, l) -> (b, l, e)."""
+    out = torch.matmul(weight, total)
+    if bias is not None:
+        out = out + bias.to(out.dtype)[:, None]
+    return out.transpose(1, 2)
+
+
+def _out_proj_bwd(dout, out_z, weight, has_bias):
+    """dout (b, l, e) -> (dout_y (b, d, l) contiguous, dweight (e, d), dbias)."""
+    dout_t = dout.transpose(1, 2)                                                    # (b, e, l)
+    if dout_t.stride(-1) != 1:
+        dout_t = dout_t.contiguous()
+    dout_t = dout_t.to(weight.dtype)
+    dout_y = torch.matmul(weight.t(), dout_t)                                        # (b, d, l)
+    dweight = torch.bmm(dout_t, out_z.transpose(1, 2)).sum(0)                        # (e, d)
+    return dout_y, dweight, (dout_t.sum((0, 2)) if has_bias else None)
 
 
 def _cast_proj(*ws):
@@ -475,7 +517,7 @@ class MambaInnerFn(torch.autograd.Function):
         saved = saved + (out_proj_weight, out_z)
         ctx.save_for_backward(*[t for t in saved if t is not None])
         ctx.mask = [t is not None for t in saved]
-        return F.linear(out_z.transpose(1, 2), out_proj_weight, out_proj_bias)
+        return _out_proj(out_z, out_proj_weight, out_proj_bias)
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
@@ -483,14 +525,8 @@ class MambaInnerFn(torch.autograd.Function):
         it = iter(ctx.saved_tensors)
         saved = tuple(next(it) if m else None for m in ctx.mask)
         out_proj_weight, out_z = saved[-2], saved[-1]
-        batch, L, e = dout.shape
-        dout2 = dout.reshape(batch * L, e)                                          # (b l, e)
-        d = out_z.shape[1]
-        dout_y = (dout2 @ out_proj_weight).view(batch, L, d).transpose(1, 2)        # (b, d, l), stride(-1) != 1
-        dout_y = dout_y.contiguous()
+        dout_y, dout_proj_w, dout_proj_b = _out_proj_bwd(dout, out_z, out_proj_weight, not ctx.out_proj_bias_is_None)
         dxz, dcw, dcb, dxw, ddw, dA, dD, ddb = _InnerCore.backward(saved[:-2], dout_y, ctx.delta_softplus)
-        dout_proj_w = dout2.t() @ out_z.transpose(1, 2).reshape(batch * L, d)       # (e, d)
-        dout_proj_b = dout2.sum(0) if not ctx.out_proj_bias_is_None else None
         return (dxz, dcw, dcb, dxw, ddw, dout_proj_w, dout_proj_b, dA, None, None, dD, ddb, None, None, None, None)
 
 
@@ -507,7 +543,9 @@ class BiMambaInnerFn(torch.autograd.Function):
             x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias)
         out_f, saved = _InnerCore.forward(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C, D,
                                           delta_bias, B_proj_bias, C_proj_bias, delta_softplus)
-        (xz_, conv_w, conv_b, x_dbl, xw, dw, conv_out, delta, A_, Bm, Cm, D_, db_, _xs_fx, _xs_fy) = saved
+        (xz_, conv_w, conv_b, x_dbl, xw, dw, conv_out, delta, A_, _, _, D_, db_, _xs_fx, _xs_fy) = saved
+        R, N = dw.shape[1], A.shape[-1]
+        Bm, Cm = x_dbl[:, R:R + N].unsqueeze(1), x_dbl[:, R + N:].unsqueeze(1)
         z = xz_.chunk(2, dim=1)[1]
         out_b, xs_b, _ = selective_scan_fwd(conv_out, delta, A_b, Bm, Cm, D_, z, db_, delta_softplus, reverse=True)
         out_z = out_f + out_b            # out_b is already stored in un-flipped positions
@@ -516,7 +554,7 @@ class BiMambaInnerFn(torch.autograd.Function):
         saved = saved + (out_proj_weight, out_z, A_b, xs_b.x, xs_b.y)
         ctx.save_for_backward(*[t for t in saved if t is not None])
         ctx.mask = [t is not None for t in saved]
-        return F.linear(out_z.transpose(1, 2), out_proj_weight, out_proj_bias)
+        return _out_proj(out_z, out_proj_weight, out_proj_bias)
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
@@ -525,39 +563,26 @@ class BiMambaInnerFn(torch.autograd.Function):
         saved = tuple(next(it) if m else None for m in ctx.mask)
         out_proj_weight, out_z, A_b, xs_bx, xs_by = saved[-5:]
         core = saved[:-5]
-        (xz, conv_w, conv_b, x_dbl, xw, dw, conv_out, delta, A, Bm, Cm, D, dbias, xs_fx, xs_fy) = core
+        (xz, conv_w, conv_b, x_dbl, xw, dw, conv_out, delta, A, _, _, D, dbias, xs_fx, xs_fy) = core
         xs_b, xs_f = ScanStates(xs_bx, xs_by), ScanStates(xs_fx, xs_fy)
-        batch, L, e = dout.shape
-        d = out_z.shape[1]
+        batch, L = xz.shape[0], xz.shape[-1]
         R, N = dw.shape[1], A.shape[-1]
-        dout2 = dout.reshape(batch * L, e)
-        dout_y = (dout2 @ out_proj_weight).view(batch, L, d).transpose(1, 2).contiguous()
-        z = xz.chunk(2, dim=1)[1]
-        # reverse-direction scan gradients first (plain tensors), then fold them into the shared backward
-        du_b, ddl_b, dA_b, dB_b, dC_b, dD_b, dz_b, ddb_b = selective_scan_bwd(
-            conv_out, delta, A_b, Bm, Cm, D, z, dbias, dout_y, xs_b, ctx.delta_softplus, reverse=True)
-        x = xz.chunk(2, dim=1)[0]
+        Bm, Cm = x_dbl[:, R:R + N].unsqueeze(1), x_dbl[:, R + N:].unsqueeze(1)
+        dout_y, dout_proj_w, dout_proj_b = _out_proj_bwd(dout, out_z, out_proj_weight, not ctx.out_proj_bias_is_None)
+        x, z = xz.chunk(2, dim=1)
+        # both directions accumulate dB / dC into the same buffer; the other gradients are summed afterwards
+        dBC = torch.zeros((batch, 2 * N, L), device=xz.device, dtype=torch.float32)
+        du_b, ddl_b, dA_b, _, _, dD_b, dz_b, ddb_b = selective_scan_bwd(
+            conv_out, delta, A_b, Bm, Cm, D, z, dbias, dout_y, xs_b, ctx.delta_softplus, reverse=True, dBC=dBC)
         dxz = torch.empty_like(xz)
         dx, dz = dxz.chunk(2, dim=1)
-        du_f, ddl_f, dA, dB_f, dC_f, dD_f, dz, ddb_f = selective_scan_bwd(
-            conv_out, delta, A, Bm, Cm, D, z, dbias, dout_y, xs_f, ctx.delta_softplus, dz=dz)
+        du_f, ddl_f, dA, _, _, dD_f, dz, ddb_f = selective_scan_bwd(
+            conv_out, delta, A, Bm, Cm, D, z, dbias, dout_y, xs_f, ctx.delta_softplus, dz=dz, dBC=dBC)
         dz += dz_b
-        dconv_out, ddelta = du_f + du_b, ddl_f + ddl_b
-        dB, dC = dB_f + dB_b, dC_f + dC_b
         dD = None if D is None else dD_f + dD_b
         ddb = None if dbias is None else ddb_f + ddb_b
-        dx_dbl = torch.empty_like(x_dbl)
-        dx_dbl[:, R:R + N] = dB.view(batch, N, L).transpose(1, 2).reshape(batch * L, N)
-        dx_dbl[:, R + N:] = dC.view(batch, N, L).transpose(1, 2).reshape(batch * L, N)
-        ddelta2 = ddelta.transpose(0, 1).reshape(d, batch * L)
-        ddw = ddelta2 @ x_dbl[:, :R]
-        dx_dbl[:, :R] = ddelta2.t() @ dw
-        dxw = dx_dbl.t() @ conv_out.transpose(1, 2).reshape(batch * L, d)
-        dconv2 = torch.addmm(dconv_out.transpose(0, 1).reshape(d, batch * L), xw.t(), dx_dbl.t())
-        dconv_out = dconv2.view(d, batch, L).transpose(0, 1)
+        dconv_out, dxw, ddw = _InnerCore.project_grads(x_dbl, xw, dw, conv_out, ddl_f + ddl_b, dBC, du_f + du_b)
         _, dcw, dcb = causal_conv1d_bwd(x, conv_w, conv_b, dconv_out, True, dx=dx)
-        dout_proj_w = dout2.t() @ out_z.transpose(1, 2).reshape(batch * L, d)
-        dout_proj_b = dout2.sum(0) if not ctx.out_proj_bias_is_None else None
         return (dxz, dcw.unsqueeze(1), dcb, dxw, ddw, dout_proj_w, dout_proj_b, dA, dA_b, None, None, dD, ddb,
                 None, None, None, None)
 
