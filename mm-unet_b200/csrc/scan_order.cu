@@ -44,6 +44,44 @@ __global__ void __launch_bounds__(256) scan_order_kernel(const T *__restrict__ s
     }
 }
 
+// NSLICES through shared memory: per row the map is the transpose of an (ns x Ls) matrix (gather: dst[j*ns+s] = src[s*Ls+j];
+// scatter: the inverse).  A CTA moves TJ = 64 consecutive j of every slice: global reads and writes are both contiguous
+// runs (TJ elements per slice on the sliced side, TJ*ns elements on the interleaved side) instead of one element per sector.
+template <typename T, bool SCATTER>
+__global__ void __launch_bounds__(256) nslices_tiled_kernel(const T *__restrict__ src, T *__restrict__ dst, int64_t rows, int64_t src_rs,
+                                                            int64_t dst_rs, int ns, int Ls) {
+    constexpr int TJ = 64;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *tile = reinterpret_cast<T *>(smem_raw);                  // [ns][TJ + 1]
+    const int j0 = blockIdx.x * TJ, nj = min(TJ, Ls - j0), tid = threadIdx.x;
+    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+        const T *s = src + r * src_rs;
+        T *d = dst + r * dst_rs;
+        if (!SCATTER) {
+            for (int e = tid; e < ns * TJ; e += 256) {          // sliced side: TJ-element runs
+                const int sl = e / TJ, j = e - sl * TJ;
+                if (j < nj) tile[sl * (TJ + 1) + j] = s[(int64_t)sl * Ls + j0 + j];
+            }
+            __syncthreads();
+            for (int e = tid; e < nj * ns; e += 256) {          // interleaved side: one contiguous run of nj*ns elements
+                const int j = e / ns, sl = e - j * ns;
+                d[(int64_t)j0 * ns + e] = tile[sl * (TJ + 1) + j];
+            }
+        } else {
+            for (int e = tid; e < nj * ns; e += 256) {
+                const int j = e / ns, sl = e - j * ns;
+                tile[sl * (TJ + 1) + j] = s[(int64_t)j0 * ns + e];
+            }
+            __syncthreads();
+            for (int e = tid; e < ns * TJ; e += 256) {
+                const int sl = e / TJ, j = e - sl * TJ;
+                if (j < nj) d[(int64_t)sl * Ls + j0 + j] = tile[sl * (TJ + 1) + j];
+            }
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void scan_order_index_kernel(int64_t *idx, OrderMap m) {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l < m.L) idx[l] = m(l);
@@ -70,6 +108,20 @@ int run_order(const void *src, void *dst, int dtype, int64_t rows, int64_t src_r
     if (rows <= 0) return set_error(MMU_ERR_INVALID, "scan_order: rows=%lld", (long long)rows);
     if (!src || !dst) return set_error(MMU_ERR_INVALID, "scan_order: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (order == MMU_ORDER_NSLICES && m.ns >= 2 && m.ns <= 256 && m.Ls >= 16 && (dtype == MMU_F32 || dtype == MMU_BF16 || dtype == MMU_F16)) {
+        dim3 tg((m.Ls + 63) / 64, (unsigned)std::min<int64_t>(rows, 65535));
+        const size_t es = dtype == MMU_F32 ? 4 : 2, smem = (size_t)m.ns * 65 * es;
+        if (dtype == MMU_F32) {
+            auto k = nslices_tiled_kernel<float, SCATTER>;
+            if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k<<<tg, 256, smem, st>>>((const float *)src, (float *)dst, rows, src_rs, dst_rs, m.ns, m.Ls);
+        } else {
+            auto k = nslices_tiled_kernel<uint16_t, SCATTER>;
+            k<<<tg, 256, smem, st>>>((const uint16_t *)src, (uint16_t *)dst, rows, src_rs, dst_rs, m.ns, m.Ls);
+        }
+        count_launch();
+        return check_launch("scan_order (nslices, tiled)");
+    }
     dim3 grid((m.L + 255) / 256, (unsigned)std::min<int64_t>(rows, 65535));
     if (dtype == MMU_F32)
         scan_order_kernel<float, SCATTER><<<grid, 256, 0, st>>>((const float *)src, (float *)dst, rows, src_rs, dst_rs, m);

@@ -363,7 +363,9 @@ def test_conv_determinism():
 # scan orders: bit-exact
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("order,H,W,ns", [(3, 4, 6, 1), (3, 5, 3, 1), (3, 1, 7, 1), (3, 64, 64, 1), (3, 37, 19, 1),
-                                          (2, 1, 64, 16), (2, 1, 36, 6), (2, 16, 16, 32), (1, 1, 17, 1), (0, 3, 3, 1)])
+                                          (2, 1, 64, 16), (2, 1, 36, 6), (2, 16, 16, 32), (1, 1, 17, 1), (0, 3, 3, 1),
+                                          # shared-memory tiled nslices kernel (L/ns >= 16), ragged last tile, wide ns
+                                          (2, 64, 64, 16), (2, 128, 128, 64), (2, 30, 40, 6), (2, 32, 64, 128), (2, 1, 65 * 8, 8)])
 def test_scan_order_bit_exact(order, H, W, ns):
     ref = oracle.scan_order_index(order, H, W, ns)
     idx = ops.scan_order_index(order, H, W, ns)
