@@ -95,7 +95,8 @@ int mmu_selective_scan_fwd(const mmu_scan_fwd_params *p, void *stream);
  * selective scan backward.  replaces selective_scan_cuda.bwd  (selective_scan.cpp:338-492)
  *   inputs as forward + dout (batch, dim, seqlen) and x from the forward.
  *   du, ddelta, dz : (batch, dim, seqlen) dtype `dtype` (dz NULL iff z NULL)
- *   dA (dim,dstate), dD (dim), ddelta_bias (dim), dB, dC (batch,1,dstate,seqlen contiguous): fp32,
+ *   dA (dim,dstate), dD (dim), ddelta_bias (dim), dB, dC (batch,1,dstate,seqlen; rows contiguous, batch strides
+ *   dB_bs / dC_bs, 0 = dstate*seqlen): fp32,
  *   ACCUMULATED INTO (atomics) — the caller zero-fills them, as the reference does
  *   (selective_scan.cpp:458-466).  dD / ddelta_bias may be NULL when D / delta_bias are NULL.
  * --------------------------------------------------------------------------------------------- */
