@@ -181,6 +181,20 @@ int mmu_snake_sample_bwd(const void *feat, const float *y, const void *dout, flo
                          void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * GroupNorm that closes every MMConv (`nn.GroupNorm(out_channels // 4, out_channels)`, src/UM_Net/MMUNet.py:46, 271) for
+ * channels-last maps: x, y, dy, dx are (B, HW, C) in memory with C = 4 * G (4 channels per group); gamma, beta (C) fp32.
+ *   fwd: sums (B*G*2 fp32, caller zero-fills) is scratch; mean, rstd (B*G fp32) are written for the backward.
+ *   bwd: dy has dtype out_dtype, dx has in_dtype; sums2 (B*G*2) and dgamma_dbeta (2*C: dgamma | dbeta) are fp32 accumulators
+ *        the caller zero-fills.
+ * Replaces at::native_group_norm(+backward), which is NCHW-only.
+ * --------------------------------------------------------------------------------------------- */
+int mmu_group_norm_nhwc_fwd(const void *x, const float *gamma, const float *beta, void *y, float *sums, float *mean, float *rstd,
+                            int32_t in_dtype, int32_t out_dtype, int32_t B, int32_t C, int32_t HW, int32_t G, float eps, void *stream);
+int mmu_group_norm_nhwc_bwd(const void *x, const float *gamma, const void *dy, const float *mean, const float *rstd, void *dx,
+                            float *sums2, float *dgamma_dbeta, int32_t in_dtype, int32_t out_dtype, int32_t B, int32_t C, int32_t HW,
+                            int32_t G, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * misc
  * --------------------------------------------------------------------------------------------- */
 int mmu_version(void);

@@ -55,6 +55,7 @@ EXPORTS = (
     "mmu_causal_conv1d_fwd", "mmu_causal_conv1d_bwd",
     "mmu_scan_order_gather", "mmu_scan_order_scatter", "mmu_scan_order_index",
     "mmu_snake_sample_fwd", "mmu_snake_sample_bwd",
+    "mmu_group_norm_nhwc_fwd", "mmu_group_norm_nhwc_bwd",
 )
 
 _lib = None
@@ -85,6 +86,8 @@ def lib() -> C.CDLL:
     L.mmu_scan_order_index.argtypes = [_vp, _i32, _i32, _i32, _i32, _vp]
     L.mmu_snake_sample_fwd.argtypes = [_vp, _vp, _vp] + [_i32] * 8 + [_vp]
     L.mmu_snake_sample_bwd.argtypes = [_vp, _vp, _vp, _vp, _vp] + [_i32] * 8 + [_vp]
+    L.mmu_group_norm_nhwc_fwd.argtypes = [_vp] * 7 + [_i32] * 6 + [C.c_float, _vp]
+    L.mmu_group_norm_nhwc_bwd.argtypes = [_vp] * 8 + [_i32] * 6 + [_vp]
     for n in EXPORTS:      # fail loudly on a stale library
         getattr(L, n)
     _lib = L

@@ -37,6 +37,7 @@ from .mamba import Mamba
 _flatten_two_row = ops.two_row_flatten
 _unflatten_two_row = ops.two_row_unflatten
 _snake_sample = ops.snake_sample          # None -> the reference's torch formulation (grid rescale + F.grid_sample)
+_group_norm_nhwc = ops.group_norm_nhwc    # None -> always nn.GroupNorm
 
 
 class MMConv(nn.Module):
@@ -125,6 +126,10 @@ class MMConv(nn.Module):
         else:
             feat = self._grid_sample(input, y)
         out = self.dsc_conv_x(feat) if self.morph == 0 else self.dsc_conv_y(feat)
+        if _group_norm_nhwc is not None and out.is_cuda and ops.group_norm_nhwc_supported(out, self.gn.num_groups):
+            # channels-last model: normalise in place of layout (ATen's GroupNorm would copy to NCHW, return NCHW and, under
+            # autocast, fp32); the output keeps the conv's dtype, statistics are fp32
+            return _group_norm_nhwc(out, self.gn.num_groups, self.gn.weight, self.gn.bias, self.gn.eps)
         return self.gn(out)
 
 

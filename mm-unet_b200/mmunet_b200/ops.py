@@ -741,3 +741,55 @@ def snake_sample(feat, y, out_dtype=None):
     """feat (B,C,H,W), y (B,K,H,W) fp32 row coordinates in pixels -> (B,C,H*K,W): row-interpolated samples at
     (clamp(y,0,H-1), clamp(w+k-K//2,0,W-1)) - MMConv's deformed feature map (MMUNet.py:190-224)."""
     return _SnakeSampleFn.apply(feat, y, feat.dtype if out_dtype is None else out_dtype)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# channels-last GroupNorm with 4 channels per group (MMConv's closing norm, MMUNet.py:46, 271)
+# ----------------------------------------------------------------------------------------------------------
+
+def group_norm_nhwc_supported(x, num_groups):
+    C_ = x.shape[1] if x.dim() == 4 else 0
+    G = num_groups
+    return (x.is_cuda and x.dim() == 4 and C_ == 4 * G and (G >= 256 or 256 % G == 0) and x.dtype in (torch.float32, torch.bfloat16)
+            and x.is_contiguous(memory_format=torch.channels_last) and not (x.is_contiguous() and C_ > 1 and x.shape[2] * x.shape[3] > 1))
+
+
+class _GroupNormNhwcFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, num_groups, eps, out_dtype):
+        B, C_, H, W = x.shape
+        G = num_groups
+        w32, b32 = weight.float().contiguous(), bias.float().contiguous()
+        y = torch.empty((B, C_, H, W), device=x.device, dtype=out_dtype, memory_format=torch.channels_last)
+        stats = torch.zeros(4 * B * G, device=x.device, dtype=torch.float32)          # sums (2BG) | mean (BG) | rstd (BG)
+        sums, mean, rstd = stats[:2 * B * G], stats[2 * B * G:3 * B * G], stats[3 * B * G:]
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().mmu_group_norm_nhwc_fwd(x.data_ptr(), w32.data_ptr(), b32.data_ptr(), y.data_ptr(), sums.data_ptr(),
+                                                          mean.data_ptr(), rstd.data_ptr(), _DT[x.dtype], _DT[out_dtype], B, C_, H * W, G,
+                                                          float(eps), _stream()), "group_norm_nhwc_fwd")
+        ctx.save_for_backward(x, w32, mean, rstd)
+        ctx.G, ctx.out_dtype, ctx.wdtype = G, out_dtype, weight.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w32, mean, rstd = ctx.saved_tensors
+        B, C_, H, W = x.shape
+        G = ctx.G
+        dy = dy.to(ctx.out_dtype).contiguous(memory_format=torch.channels_last)
+        dx = torch.empty_like(x, memory_format=torch.channels_last)
+        acc = torch.zeros(2 * B * G + 2 * C_, device=x.device, dtype=torch.float32)    # S1,S2 per (b, group) | dgamma | dbeta
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().mmu_group_norm_nhwc_bwd(x.data_ptr(), w32.data_ptr(), dy.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                                          dx.data_ptr(), acc.data_ptr(), acc[2 * B * G:].data_ptr(), _DT[x.dtype],
+                                                          _DT[ctx.out_dtype], B, C_, H * W, G, _stream()), "group_norm_nhwc_bwd")
+        dgamma, dbeta = acc[2 * B * G:2 * B * G + C_], acc[2 * B * G + C_:]
+        return dx, dgamma.to(ctx.wdtype), dbeta.to(ctx.wdtype), None, None, None
+
+
+def group_norm_nhwc(x, num_groups, weight, bias, eps=1e-5, out_dtype=None):
+    """F.group_norm for a channels-last (B, C, H, W) tensor with C == 4 * num_groups; statistics in fp32, output channels-last in
+    `out_dtype` (default: x.dtype).  Raises if the layout / shape is not supported - check group_norm_nhwc_supported first."""
+    if not group_norm_nhwc_supported(x, num_groups):
+        raise RuntimeError("group_norm_nhwc: needs a CUDA channels-last (B, 4*G, H, W) fp32/bf16 tensor with G | 256 or G >= 256")
+    return _GroupNormNhwcFn.apply(x, weight, bias, num_groups, eps, x.dtype if out_dtype is None else out_dtype)

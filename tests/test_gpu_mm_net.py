@@ -107,3 +107,35 @@ def test_snake_sample_matches_grid_sample(no_tf32, shape, dtypes, channels_last)
     # d/dy: piecewise constant in y, so a sample within rounding distance of an integer row may take the neighbouring slope
     bad = ((y1.grad - y2.grad).abs() > gt * (float(y2.grad.abs().max()) + y2.grad.abs())).float().mean()
     assert bad <= 2e-3, f"{bad:.4f} of d_y elements differ"
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 12, 10), (3, 16, 7, 9), (1, 512, 4, 4), (2, 128, 33, 17), (2, 8, 5, 5)])
+@pytest.mark.parametrize("dtypes", [("fp32", "fp32"), ("bf16", "bf16"), ("fp32", "bf16")])
+def test_group_norm_nhwc_matches_torch(shape, dtypes):
+    """Channels-last GroupNorm (4 channels per group) vs F.group_norm evaluated in fp32 on the same (rounded) inputs."""
+    import torch.nn.functional as F
+    from mmunet_b200 import ops
+    B, C, H, W = shape
+    G = C // 4
+    tin, tout = (torch.float32 if d == "fp32" else torch.bfloat16 for d in dtypes)
+    torch.manual_seed(5)
+    x = (1.5 * torch.randn(B, C, H, W, device="cuda") + 0.7).to(tin).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(C, device="cuda")
+    b = torch.randn(C, device="cuda")
+    assert ops.group_norm_nhwc_supported(x, G)
+    x1, w1, b1 = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    x2, w2, b2 = x.float().clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    y = ops.group_norm_nhwc(x1, G, w1, b1, 1e-5, tout)
+    ref = F.group_norm(x2, G, w2, b2, 1e-5)
+    assert y.dtype == tout and y.is_contiguous(memory_format=torch.channels_last)
+    tol = 2e-5 if tout == torch.float32 else 2e-2
+    torch.testing.assert_close(y.float(), ref, rtol=tol, atol=tol)
+    g = torch.randn_like(ref)
+    y.backward(g.to(tout))
+    ref.backward(g.to(tout).float())
+    gt = 2e-4 if (tin, tout) == (torch.float32, torch.float32) else 3e-2
+    for got, want, name in ((x1.grad, x2.grad, "dx"), (w1.grad, w2.grad, "dgamma"), (b1.grad, b2.grad, "dbeta")):
+        torch.testing.assert_close(got.float(), want, rtol=gt, atol=gt * float(want.abs().max()), msg=lambda m: f"{name}: {m}")
+    # unsupported layouts are refused (the model then falls back to nn.GroupNorm)
+    assert not ops.group_norm_nhwc_supported(x.contiguous(), G) or H * W == 1
+    assert not ops.group_norm_nhwc_supported(x, G * 2)
