@@ -118,7 +118,6 @@ __global__ void __launch_bounds__(32 * RQ * NGW, AGG ? 512 / (32 * RQ * NGW) : M
     const int npw = (NP + NGW - 1) / NGW;
     const int pair0 = g * npw, pair1 = min(NP, pair0 + npw);
     const int lr = wq * 4 + rg;
-    const bool hi = (rg & 2) != 0, lo = (rg & 1) != 0;
     float dsum = 0.f, dfirst = 0.f;
 
     // per-thread constant shared-memory offsets (hoisted out of every loop)

@@ -64,15 +64,41 @@ def test_mm_net_matches_reference_fp32(no_tf32):
     assert sorted(k for k, v in grads.items() if v is None) == sorted(str(k) for k in g["nograd_names"])
 
 
-@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
-def test_trainer_steps_reduce_loss(dtype):
+@pytest.mark.parametrize("dtype,channels_last,graph", [("fp32", False, False), ("bf16", False, False), ("bf16", True, False),
+                                                       ("bf16", True, True)])
+def test_trainer_steps_reduce_loss(dtype, channels_last, graph):
+    """Eager and whole-step CUDA-graph training, NCHW and channels-last (the latter runs the NHWC sampler / GroupNorm kernels)."""
     from mmunet_b200.train import Trainer
-    tr = Trainer(image_size=64, batch_per_rank=2, dtype=dtype, device="cuda:0", ddp=False)
+    tr = Trainer(image_size=64, batch_per_rank=2, dtype=dtype, device="cuda:0", ddp=False, channels_last=channels_last, graph=graph)
     tr.set_epoch(2)                       # past the warm-up: lr = 1e-3
     x, y = tr.synthetic_batch()
     losses = [float(tr.step(x, y)) for _ in range(8)]
     assert all(np.isfinite(losses)), losses
     assert losses[-1] < losses[0], losses
+    assert (tr.graph is not None) == graph
+
+
+def test_mm_net_ragged_sizes_channels_last(no_tf32):
+    """96x96 input (the model needs a multiple of 32, like the reference): feature maps 48, 24, 12, 6, 3 - an odd map (two-row
+    flatten with a tail row) and L = 9 / 36 on the generic scan kernels next to L = 144 / 576 / 2304 on the v3 kernels - in
+    channels-last bf16; and the channels-last model must agree with the NCHW model on the same weights (different kernels:
+    NHWC sampler / GroupNorm vs NCHW sampler / ATen GroupNorm; TF32 off, it alone moves the logits by 3 %)."""
+    from mmunet_b200.mm_net import MM_Net
+    torch.manual_seed(50)
+    net = MM_Net(num_classes=1).cuda().eval()          # eval: BatchNorm uses running stats -> well conditioned comparison
+    x = torch.randn(2, 3, 64, 64, device="cuda")
+    with torch.no_grad():
+        ref = net(x)
+        got = net.to(memory_format=torch.channels_last)(x.contiguous(memory_format=torch.channels_last))
+    torch.testing.assert_close(got, ref, rtol=2e-3, atol=2e-3 * float(ref.abs().max()))
+    net.train()
+    xr = torch.randn(2, 3, 96, 96, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = net(xr)
+    assert out.shape == (2, 1, 96, 96) and torch.isfinite(out).all()
+    out.float().sum().backward()
+    assert torch.isfinite(xr.grad).all()
+    assert all(torch.isfinite(p.grad).all() for p in net.parameters() if p.grad is not None)
 
 
 @pytest.mark.parametrize("shape", [(2, 8, 12, 10, 3), (1, 5, 7, 9, 3), (2, 16, 6, 8, 1), (1, 4, 10, 16, 9), (3, 32, 33, 17, 3)])
