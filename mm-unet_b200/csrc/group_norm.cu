@@ -81,14 +81,14 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const TI *__restrict__ x, const float *__restrict__ sums, const float *__restrict__ gamma,
                                                        const float *__restrict__ beta, TO *__restrict__ y, float *__restrict__ mean_out,
                                                        float *__restrict__ rstd_out, GnGeom g) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // (b, p, group)
-    if (i >= (int64_t)g.B * g.HW * g.G) return;
-    const int gi = (int)(i % g.G);
-    const int64_t bp = i / g.G;
-    const int b = (int)(bp / g.HW);
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;                  // (pixel, group) of batch element blockIdx.y
+    if (i >= (unsigned)g.HW * (unsigned)g.G) return;
+    const unsigned pix = i / (unsigned)g.G;                                    // 32-bit only: 64-bit div/mod would dominate
+    const int gi = (int)(i - pix * (unsigned)g.G), b = blockIdx.y;
+    const int64_t bp = (int64_t)b * g.HW + pix;
     float mean, rstd;
     gn_moments(sums, (int64_t)b * g.G + gi, 4.f * g.HW, g.eps, mean, rstd);
-    if (bp % g.HW == 0) mean_out[(int64_t)b * g.G + gi] = mean, rstd_out[(int64_t)b * g.G + gi] = rstd;
+    if (pix == 0) mean_out[(int64_t)b * g.G + gi] = mean, rstd_out[(int64_t)b * g.G + gi] = rstd;
     float v[4], o[4];
     V4<TI>::ld(x + bp * g.C + 4 * gi, v);
     const float4 ga = *reinterpret_cast<const float4 *>(gamma + 4 * gi), be = *reinterpret_cast<const float4 *>(beta + 4 * gi);
@@ -148,10 +148,11 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const TI *__restrict__ x, const TO *__restrict__ dy, const float *__restrict__ mean,
                                                            const float *__restrict__ rstd, const float *__restrict__ gamma,
                                                            const float *__restrict__ sums2, TI *__restrict__ dx, GnGeom g) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)g.B * g.HW * g.G) return;
-    const int gi = (int)(i % g.G);
-    const int64_t bp = i / g.G, bg = (bp / g.HW) * g.G + gi;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (unsigned)g.HW * (unsigned)g.G) return;
+    const unsigned pix = i / (unsigned)g.G;
+    const int gi = (int)(i - pix * (unsigned)g.G), b = blockIdx.y;
+    const int64_t bp = (int64_t)b * g.HW + pix, bg = (int64_t)b * g.G + gi;
     const float mu = mean[bg], rs = rstd[bg], inv_n = 1.f / (4.f * g.HW);
     const float s1 = sums2[bg * 2] * inv_n, s2 = sums2[bg * 2 + 1] * inv_n;
     float v[4], d[4], o[4];
@@ -172,14 +173,14 @@ int gn_geom(GnGeom &g, int B, int C, int HW, int G, float eps, dim3 &rgrid, dim3
     if (B <= 0 || C <= 0 || HW <= 0 || G <= 0) return set_error(MMU_ERR_INVALID, "group_norm: bad shape B%d C%d HW%d G%d", B, C, HW, G);
     if (C != 4 * G) return set_error(MMU_ERR_UNSUPPORTED, "group_norm (channels-last): only 4 channels per group (C=%d, G=%d)", C, G);
     if (G < kGnThreads && kGnThreads % G != 0) return set_error(MMU_ERR_UNSUPPORTED, "group_norm: G=%d must divide %d or be >= it", G, kGnThreads);
-    const int64_t items = (int64_t)B * HW * G;
-    if ((items + 255) / 256 > INT32_MAX) return set_error(MMU_ERR_UNSUPPORTED, "group_norm: problem too large");
+    const int64_t items = (int64_t)HW * G;                      // per batch element
+    if (items > 0x7fffffffLL || B > 65535) return set_error(MMU_ERR_UNSUPPORTED, "group_norm: problem too large");
     // reduction grid: enough blocks to fill the GPU (~8 per SM), at least one pixel per lane
     const int lanes = G >= kGnThreads ? 1 : kGnThreads / G;
     int pblocks = (int)std::min<int64_t>((HW + lanes - 1) / lanes, std::max<int64_t>(1, (148 * 8 + B - 1) / B));
     g = {B, C, HW, G, (HW + pblocks - 1) / pblocks, eps};
     rgrid = dim3((unsigned)((HW + g.ppb - 1) / g.ppb), (unsigned)B);
-    agrid = dim3((unsigned)((items + 255) / 256));
+    agrid = dim3((unsigned)((items + 255) / 256), (unsigned)B);
     return MMU_OK;
 }
 }  // namespace

@@ -22,16 +22,14 @@ struct SnakeGeom {
     int B, C, H, W, K, cpb;   // cpb = channels per thread
 };
 
-__device__ __forceinline__ bool snake_coord(const SnakeGeom &g, const float *__restrict__ y, int64_t s, int &b, int &h, int &k, int &w,
+// Sample coordinates.  `row` = (b*H + h)*K + k (one output row of W samples), decomposed with 32-bit arithmetic only (64-bit
+// div/mod by runtime values costs hundreds of instructions per thread and dominated the first version of these kernels).
+__device__ __forceinline__ void snake_coord(const SnakeGeom &g, const float *__restrict__ y, unsigned row, int w, int &b, int &h, int &k,
                                             int &r0, int &r1ok, float &f, int &xk, bool &inside) {
-    const int64_t total = (int64_t)g.B * g.H * g.K * g.W;
-    if (s >= total) return false;
-    w = (int)(s % g.W);
-    int64_t t = s / g.W;
-    k = (int)(t % g.K);
-    t /= g.K;
-    h = (int)(t % g.H);
-    b = (int)(t / g.H);
+    const unsigned bh = row / (unsigned)g.K;
+    k = (int)(row - bh * (unsigned)g.K);
+    b = (int)(bh / (unsigned)g.H);
+    h = (int)(bh - (unsigned)b * (unsigned)g.H);
     const float yv = y[(((int64_t)b * g.K + k) * g.H + h) * g.W + w];
     const float hi = (float)(g.H - 1);
     inside = yv >= 0.f && yv <= hi;
@@ -41,17 +39,18 @@ __device__ __forceinline__ bool snake_coord(const SnakeGeom &g, const float *__r
     f = yc - fl;
     r1ok = r0 + 1 < g.H;
     xk = min(max(w + k - g.K / 2, 0), g.W - 1);
-    return true;
 }
 
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) snake_fwd_kernel(const TI *__restrict__ feat, const float *__restrict__ y, TO *__restrict__ out,
                                                         SnakeGeom g) {
-    int b, h, k, w, r0, r1ok, xk;
+    int b, h, k, r0, r1ok, xk;
     float f;
     bool inside;
-    if (!snake_coord(g, y, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, b, h, k, w, r0, r1ok, f, xk, inside)) return;
-    const int c0 = blockIdx.y * g.cpb, c1 = min(g.C, c0 + g.cpb);
+    const int w = blockIdx.y * blockDim.x + threadIdx.x;          // grid: (output row, w block, channel block)
+    if (w >= g.W) return;
+    snake_coord(g, y, blockIdx.x, w, b, h, k, r0, r1ok, f, xk, inside);
+    const int c0 = blockIdx.z * g.cpb, c1 = min(g.C, c0 + g.cpb);
     const int64_t plane = (int64_t)g.H * g.W;
     const TI *p0 = feat + ((int64_t)b * g.C + c0) * plane + (int64_t)r0 * g.W + xk;
     TO *o = out + (((int64_t)b * g.C + c0) * g.H + h) * g.K * g.W + (int64_t)k * g.W + w;
@@ -68,11 +67,13 @@ __global__ void __launch_bounds__(256) snake_fwd_kernel(const TI *__restrict__ f
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) snake_bwd_kernel(const TI *__restrict__ feat, const float *__restrict__ y, const TO *__restrict__ dout,
                                                         float *__restrict__ dfeat, float *__restrict__ dy, SnakeGeom g) {
-    int b, h, k, w, r0, r1ok, xk;
+    int b, h, k, r0, r1ok, xk;
     float f;
     bool inside;
-    if (!snake_coord(g, y, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, b, h, k, w, r0, r1ok, f, xk, inside)) return;
-    const int c0 = blockIdx.y * g.cpb, c1 = min(g.C, c0 + g.cpb);
+    const int w = blockIdx.y * blockDim.x + threadIdx.x;          // grid: (output row, w block, channel block)
+    if (w >= g.W) return;
+    snake_coord(g, y, blockIdx.x, w, b, h, k, r0, r1ok, f, xk, inside);
+    const int c0 = blockIdx.z * g.cpb, c1 = min(g.C, c0 + g.cpb);
     const int64_t plane = (int64_t)g.H * g.W, oplane = plane * g.K;
     const int64_t fo = ((int64_t)b * g.C + c0) * plane + (int64_t)r0 * g.W + xk;
     const TI *p0 = feat + fo;
@@ -122,13 +123,15 @@ template <> struct Vec4<__nv_bfloat16> {
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) snake_fwd_nhwc_kernel(const TI *__restrict__ feat, const float *__restrict__ y, TO *__restrict__ out,
                                                              SnakeGeom g) {
-    const int cv = g.C >> 2;                                    // channel vectors per sample
-    const int64_t tix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int b, h, k, w, r0, r1ok, xk;
+    const unsigned cv = (unsigned)g.C >> 2;                     // channel vectors per sample (a power of two)
+    const unsigned tix = blockIdx.y * blockDim.x + threadIdx.x;  // (w, channel vector) inside output row blockIdx.x
+    const int w = (int)(tix >> g.cpb);                          // cpb holds log2(cv) for the channels-last kernels
+    if (w >= g.W) return;
+    int b, h, k, r0, r1ok, xk;
     float f;
     bool inside;
-    if (!snake_coord(g, y, tix / cv, b, h, k, w, r0, r1ok, f, xk, inside)) return;
-    const int c = (int)(tix % cv) << 2;
+    snake_coord(g, y, blockIdx.x, w, b, h, k, r0, r1ok, f, xk, inside);
+    const int c = (int)(tix & (cv - 1)) << 2;
     const TI *p0 = feat + (((int64_t)b * g.H + r0) * g.W + xk) * g.C + c;
     float v0[4], v1[4], o[4];
     Vec4<TI>::ld(p0, v0);
@@ -142,15 +145,17 @@ __global__ void __launch_bounds__(256) snake_fwd_nhwc_kernel(const TI *__restric
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) snake_bwd_nhwc_kernel(const TI *__restrict__ feat, const float *__restrict__ y, const TO *__restrict__ dout,
                                                              float *__restrict__ dfeat, float *__restrict__ dy, SnakeGeom g) {
-    const int cv = g.C >> 2;
-    const int64_t tix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int b, h, k, w, r0, r1ok, xk;
-    float f;
-    bool inside;
-    const bool live = snake_coord(g, y, tix / cv, b, h, k, w, r0, r1ok, f, xk, inside);
+    const unsigned cv = (unsigned)g.C >> 2;
+    const unsigned tix = blockIdx.y * blockDim.x + threadIdx.x;
+    const int w = (int)(tix >> g.cpb);
+    int b = 0, h = 0, k = 0, r0 = 0, r1ok = 0, xk = 0;
+    float f = 0.f;
+    bool inside = false;
+    const bool live = w < g.W;
     float acc = 0.f;
     if (live) {
-        const int c = (int)(tix % cv) << 2;
+        snake_coord(g, y, blockIdx.x, w, b, h, k, r0, r1ok, f, xk, inside);
+        const int c = (int)(tix & (cv - 1)) << 2;
         const int64_t fo = (((int64_t)b * g.H + r0) * g.W + xk) * g.C + c;
         float gv[4], v0[4], v1[4] = {0.f, 0.f, 0.f, 0.f};
         Vec4<TO>::ld(dout + ((((int64_t)b * g.H + h) * g.K + k) * g.W + w) * g.C + c, gv);
@@ -169,35 +174,40 @@ __global__ void __launch_bounds__(256) snake_bwd_nhwc_kernel(const TI *__restric
         if (!inside) acc = 0.f;
     }
     // d_y: sum over the sample's channel threads.  cv is a power of two (checked by the host): groups of min(cv, 32) lanes
-    const int grp = cv < 32 ? cv : 32;
+    const int grp = cv < 32 ? (int)cv : 32;
     for (int o = grp >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (live && dy != nullptr && (threadIdx.x & (grp - 1)) == 0 && acc != 0.f)
         atomicAdd(dy + (((int64_t)b * g.K + k) * g.H + h) * g.W + w, acc);
 }
 
 namespace {
-int geom_nhwc(SnakeGeom &g, int B, int C, int H, int W, int K, dim3 &grid) {
+int geom_nhwc(SnakeGeom &g, int B, int C, int H, int W, int K, dim3 &grid, int &threads) {
+    threads = 256;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0) return set_error(MMU_ERR_INVALID, "snake_sample: bad shape B%d C%d H%d W%d K%d", B, C, H, W, K);
     if (C % 4 != 0 || ((C / 4) & (C / 4 - 1)) != 0)
         return set_error(MMU_ERR_UNSUPPORTED, "snake_sample (channels-last): C=%d must be 4 * a power of two", C);
-    const int64_t threads = (int64_t)B * H * K * W * (C / 4);
-    if ((threads + 255) / 256 > INT32_MAX) return set_error(MMU_ERR_UNSUPPORTED, "snake_sample: problem too large");
-    g = {B, C, H, W, K, 4};
-    grid = dim3((unsigned)((threads + 255) / 256));
+    const int64_t rows = (int64_t)B * H * K, per_row = (int64_t)W * (C / 4);
+    if (rows > 0x7fffffffLL || (per_row + 255) / 256 > 65535) return set_error(MMU_ERR_UNSUPPORTED, "snake_sample: problem too large");
+    int lg = 0;
+    while ((1 << lg) < C / 4) ++lg;
+    g = {B, C, H, W, K, lg};                       // cpb = log2(channel vectors per sample)
+    grid = dim3((unsigned)rows, (unsigned)((per_row + 255) / 256));
     return MMU_OK;
 }
 
-int geom(SnakeGeom &g, int B, int C, int H, int W, int K, dim3 &grid) {
+int geom(SnakeGeom &g, int B, int C, int H, int W, int K, dim3 &grid, int &threads) {
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0) return set_error(MMU_ERR_INVALID, "snake_sample: bad shape B%d C%d H%d W%d K%d", B, C, H, W, K);
-    const int64_t samples = (int64_t)B * H * K * W;
-    if (samples * C > (int64_t)1 << 40) return set_error(MMU_ERR_UNSUPPORTED, "snake_sample: problem too large");
-    const int64_t blocks = (samples + 255) / 256;
-    if (blocks > INT32_MAX) return set_error(MMU_ERR_UNSUPPORTED, "snake_sample: too many samples");
+    const int64_t rows = (int64_t)B * H * K;
+    if (rows > 0x7fffffffLL) return set_error(MMU_ERR_UNSUPPORTED, "snake_sample: too many rows");
     // channel blocks: enough CTAs to fill the GPU a few times over, at least 8 channels per thread to amortise the coordinates
+    threads = W >= 128 ? 128 : ((W + 31) / 32) * 32;           // one output row per block row; narrow maps use narrow blocks
+    const int wblocks = (W + threads - 1) / threads;
+    const int64_t blocks = rows * wblocks;
     int cblocks = 1;
-    while (blocks * cblocks < 148 * 16 && C / (cblocks * 2) >= 8) cblocks *= 2;
+    while (blocks * cblocks < 148 * 16 && C / (cblocks * 2) >= 8 && cblocks < 32768) cblocks *= 2;
     g = {B, C, H, W, K, (C + cblocks - 1) / cblocks};
-    grid = dim3((unsigned)blocks, (unsigned)((C + g.cpb - 1) / g.cpb));
+    if (wblocks > 65535) return set_error(MMU_ERR_UNSUPPORTED, "snake_sample: W too large");
+    grid = dim3((unsigned)rows, (unsigned)wblocks, (unsigned)((C + g.cpb - 1) / g.cpb));
     return MMU_OK;
 }
 }  // namespace
@@ -208,7 +218,8 @@ extern "C" int mmu_snake_sample_fwd(const void *feat, const float *y, void *out,
     using namespace mmu;
     SnakeGeom g;
     dim3 grid;
-    if (int rc = channels_last ? geom_nhwc(g, B, C, H, W, K, grid) : geom(g, B, C, H, W, K, grid)) return rc;
+    int nthr = 0;
+    if (int rc = channels_last ? geom_nhwc(g, B, C, H, W, K, grid, nthr) : geom(g, B, C, H, W, K, grid, nthr)) return rc;
     if (!feat || !y || !out) return set_error(MMU_ERR_INVALID, "snake_sample_fwd: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (channels_last) {
@@ -226,13 +237,13 @@ extern "C" int mmu_snake_sample_fwd(const void *feat, const float *y, void *out,
         return check_launch("snake_sample_fwd (channels-last)");
     }
     if (in_dtype == MMU_F32 && out_dtype == MMU_F32)
-        snake_fwd_kernel<float, float><<<grid, 256, 0, st>>>((const float *)feat, y, (float *)out, g);
+        snake_fwd_kernel<float, float><<<grid, nthr, 0, st>>>((const float *)feat, y, (float *)out, g);
     else if (in_dtype == MMU_F32 && out_dtype == MMU_BF16)
-        snake_fwd_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float *)feat, y, (__nv_bfloat16 *)out, g);
+        snake_fwd_kernel<float, __nv_bfloat16><<<grid, nthr, 0, st>>>((const float *)feat, y, (__nv_bfloat16 *)out, g);
     else if (in_dtype == MMU_BF16 && out_dtype == MMU_BF16)
-        snake_fwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)feat, y, (__nv_bfloat16 *)out, g);
+        snake_fwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, nthr, 0, st>>>((const __nv_bfloat16 *)feat, y, (__nv_bfloat16 *)out, g);
     else if (in_dtype == MMU_BF16 && out_dtype == MMU_F32)
-        snake_fwd_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)feat, y, (float *)out, g);
+        snake_fwd_kernel<__nv_bfloat16, float><<<grid, nthr, 0, st>>>((const __nv_bfloat16 *)feat, y, (float *)out, g);
     else
         return set_error(MMU_ERR_UNSUPPORTED, "snake_sample_fwd: dtypes %d -> %d", in_dtype, out_dtype);
     count_launch();
@@ -245,7 +256,8 @@ extern "C" int mmu_snake_sample_bwd(const void *feat, const float *y, const void
     using namespace mmu;
     SnakeGeom g;
     dim3 grid;
-    if (int rc = channels_last ? geom_nhwc(g, B, C, H, W, K, grid) : geom(g, B, C, H, W, K, grid)) return rc;
+    int nthr = 0;
+    if (int rc = channels_last ? geom_nhwc(g, B, C, H, W, K, grid, nthr) : geom(g, B, C, H, W, K, grid, nthr)) return rc;
     if (!feat || !y || !dout || !dfeat) return set_error(MMU_ERR_INVALID, "snake_sample_bwd: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (channels_last) {
@@ -263,13 +275,13 @@ extern "C" int mmu_snake_sample_bwd(const void *feat, const float *y, const void
         return check_launch("snake_sample_bwd (channels-last)");
     }
     if (in_dtype == MMU_F32 && out_dtype == MMU_F32)
-        snake_bwd_kernel<float, float><<<grid, 256, 0, st>>>((const float *)feat, y, (const float *)dout, dfeat, dy, g);
+        snake_bwd_kernel<float, float><<<grid, nthr, 0, st>>>((const float *)feat, y, (const float *)dout, dfeat, dy, g);
     else if (in_dtype == MMU_F32 && out_dtype == MMU_BF16)
-        snake_bwd_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float *)feat, y, (const __nv_bfloat16 *)dout, dfeat, dy, g);
+        snake_bwd_kernel<float, __nv_bfloat16><<<grid, nthr, 0, st>>>((const float *)feat, y, (const __nv_bfloat16 *)dout, dfeat, dy, g);
     else if (in_dtype == MMU_BF16 && out_dtype == MMU_BF16)
-        snake_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)feat, y, (const __nv_bfloat16 *)dout, dfeat, dy, g);
+        snake_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, nthr, 0, st>>>((const __nv_bfloat16 *)feat, y, (const __nv_bfloat16 *)dout, dfeat, dy, g);
     else if (in_dtype == MMU_BF16 && out_dtype == MMU_F32)
-        snake_bwd_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)feat, y, (const float *)dout, dfeat, dy, g);
+        snake_bwd_kernel<__nv_bfloat16, float><<<grid, nthr, 0, st>>>((const __nv_bfloat16 *)feat, y, (const float *)dout, dfeat, dy, g);
     else
         return set_error(MMU_ERR_UNSUPPORTED, "snake_sample_bwd: dtypes %d -> %d", in_dtype, out_dtype);
     count_launch();
