@@ -40,6 +40,8 @@ class Mamba(nn.Module):
         self.use_fast_path, self.layer_idx = use_fast_path, layer_idx
         self.bimamba_type, self.nslices = bimamba_type, nslices
         self.return_directional = True
+        self.concurrent_directions = True      # v2 / v3: run the independent scan directions on side streams
+        self._side_streams = {}
         self.activation = "silu"
         self.act = nn.SiLU()
         di, R, N = self.d_inner, self.dt_rank, d_state
@@ -89,6 +91,12 @@ class Mamba(nn.Module):
         self.D_s = d_skip()
         self.out_proj = nn.Linear(di, d_model, bias=bias, **fk)
 
+    def _streams(self, device):
+        key = (device.type, device.index)
+        if key not in self._side_streams:
+            self._side_streams[key] = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+        return self._side_streams[key]
+
     def _inner(self, xz, sfx, reverse=False):
         conv = getattr(self, "conv1d" + sfx)
         dtp = getattr(self, "dt_proj" + sfx)
@@ -118,16 +126,41 @@ class Mamba(nn.Module):
         if not self.use_fast_path:
             out = self._slow_path(xz, seqlen)
         elif self.bimamba_type in ("v2", "v3"):
-            out_f = self._inner(xz, "")
-            out_b = self._inner(xz, "_b", reverse=True)               # already in un-flipped token order
-            total = out_f + out_b
-            if self.bimamba_type == "v3":
-                ns = self.nslices
-                if seqlen % ns != 0:
-                    raise RuntimeError(f"Mamba v3: sequence length {seqlen} is not divisible by nslices {ns} "
-                                       "(torch.stack fails in the reference, mamba_simple.py:245-246)")
+            v3 = self.bimamba_type == "v3"
+            ns = self.nslices
+            if v3 and seqlen % ns != 0:
+                raise RuntimeError(f"Mamba v3: sequence length {seqlen} is not divisible by nslices {ns} "
+                                   "(torch.stack fails in the reference, mamba_simple.py:245-246)")
+
+            def slice_direction():
                 xz_s = ops.scan_order_gather(xz, _lib.ORDER_NSLICES, 1, seqlen, ns)
-                out_s = ops.scan_order_scatter(self._inner(xz_s, "_s"), _lib.ORDER_NSLICES, 1, seqlen, ns)
+                return ops.scan_order_scatter(self._inner(xz_s, "_s"), _lib.ORDER_NSLICES, 1, seqlen, ns)
+
+            if self.concurrent_directions and xz.is_cuda:
+                # The directions are independent until the sum: run them on side streams so that their kernels share the GPU
+                # (one direction's scan is 256 CTAs at MM-UNet's RCG shapes, about half of the resident-CTA slots).  Autograd
+                # replays each direction's backward on the stream its forward ran on; a captured CUDA graph keeps the fork.
+                cur = torch.cuda.current_stream(xz.device)
+                side = self._streams(xz.device)
+                for st in side:
+                    st.wait_stream(cur)
+                out_f = self._inner(xz, "")
+                with torch.cuda.stream(side[0]):
+                    out_b = self._inner(xz, "_b", reverse=True)       # already in un-flipped token order
+                    out_b.record_stream(cur)
+                out_s = None
+                if v3:
+                    with torch.cuda.stream(side[1]):
+                        out_s = slice_direction()
+                        out_s.record_stream(cur)
+                for st in side:
+                    cur.wait_stream(st)
+            else:
+                out_f = self._inner(xz, "")
+                out_b = self._inner(xz, "_b", reverse=True)
+                out_s = slice_direction() if v3 else None
+            total = out_f + out_b
+            if v3:
                 total = total + out_s
                 if self.return_directional:
                     o_1, o_2, o_3 = out_f, out_b.flip([-1]), out_s
