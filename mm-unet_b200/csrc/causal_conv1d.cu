@@ -4,7 +4,8 @@
 // (requirements/Mamba/causal-conv1d/csrc/causal_conv1d_fwd.cu:39-130, causal_conv1d_bwd.cu:46-240).
 // The reference walks one (batch, channel) row per CTA, chunk after chunk; a conv has no long-range dependency, so
 // here the grid is (token-blocks, channel, batch): MM-UNet's D=6 / L=65536 rows spread over all SMs.
-// Each thread owns VT = 8 consecutive tokens (one or two 16-byte vectors) plus a 3-token halo that hits L1.
+// Each thread owns VT consecutive tokens - 8 for fp32, 16 for the 2-byte types, i.e. 32 bytes per tensor in flight either way -
+// plus a 3-token halo that hits L1.
 //   fwd : out[l]  = act(bias + sum_k w[k] x[l-(W-1-k)])
 //   bwd : dpre[l] = dout[l] * silu'(pre[l]) (pre recomputed, causal_conv1d_bwd.cu:153-164)
 //         dx[l]   = sum_k w[k] dpre[l+(W-1-k)]        dw[k] = sum_{b,l} x[l-(W-1-k)] dpre[l]       db = sum dpre
@@ -24,31 +25,32 @@ struct ConvArgs {
     unsigned vec_mask;   // bit0 x, bit1 out/dx, bit2 dout
 };
 
-constexpr int kConvVT = 8, kConvNT = 128;
+constexpr int kConvNT = 128;
+template <typename IN_T> struct ConvVT { static constexpr int value = sizeof(IN_T) == 4 ? 8 : 16; };
 
 // logical token t lives at memory position t (forward) or L-1-t (reverse)
 __device__ __forceinline__ int mpos(int t, int L, bool rev) { return rev ? L - 1 - t : t; }
 
-template <typename IN_T>
-__device__ __forceinline__ void load8(const IN_T *rp, int t, int L, bool vec, bool rev, float v[kConvVT]) {
-    if (vec && t + kConvVT <= L) {
+template <typename IN_T, int VT>
+__device__ __forceinline__ void loadv(const IN_T *rp, int t, int L, bool vec, bool rev, float *v) {
+    if (vec && t + VT <= L) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < VT / 4; ++h) {
             const Quad<IN_T> q = *reinterpret_cast<const Quad<IN_T> *>(rp + (rev ? L - 4 - (t + 4 * h) : t + 4 * h));
 #pragma unroll
             for (int k = 0; k < 4; ++k) v[4 * h + k] = Elem<IN_T>::to_f(q.v[rev ? 3 - k : k]);
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < kConvVT; ++k) v[k] = (t + k < L) ? Elem<IN_T>::to_f(rp[mpos(t + k, L, rev)]) : 0.f;
+        for (int k = 0; k < VT; ++k) v[k] = (t + k < L) ? Elem<IN_T>::to_f(rp[mpos(t + k, L, rev)]) : 0.f;
     }
 }
 
-template <typename OUT_T>
-__device__ __forceinline__ void store8(OUT_T *rp, int t, int L, bool vec, bool rev, const float v[kConvVT]) {
-    if (vec && t + kConvVT <= L) {
+template <typename OUT_T, int VT>
+__device__ __forceinline__ void storev(OUT_T *rp, int t, int L, bool vec, bool rev, const float *v) {
+    if (vec && t + VT <= L) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < VT / 4; ++h) {
             Quad<OUT_T> q;
 #pragma unroll
             for (int k = 0; k < 4; ++k) q.v[rev ? 3 - k : k] = Elem<OUT_T>::from_f(v[4 * h + k]);
@@ -56,7 +58,7 @@ __device__ __forceinline__ void store8(OUT_T *rp, int t, int L, bool vec, bool r
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < kConvVT; ++k)
+        for (int k = 0; k < VT; ++k)
             if (t + k < L) rp[mpos(t + k, L, rev)] = Elem<OUT_T>::from_f(v[k]);
     }
 }
@@ -71,6 +73,7 @@ __device__ __forceinline__ void load_taps(const ConvArgs &p, int d, float w4[4],
 }
 
 template <typename IN_T> __global__ void __launch_bounds__(kConvNT) conv1d_fwd_kernel(const __grid_constant__ ConvArgs p) {
+    constexpr int kConvVT = ConvVT<IN_T>::value;
     const int d = blockIdx.y, b = blockIdx.z;
     const int t = (blockIdx.x * kConvNT + threadIdx.x) * kConvVT;
     if (t >= p.L) return;
@@ -81,7 +84,7 @@ template <typename IN_T> __global__ void __launch_bounds__(kConvNT) conv1d_fwd_k
     const bool rev = p.reverse != 0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) xv[k] = (t - 3 + k >= 0) ? Elem<IN_T>::to_f(xr[mpos(t - 3 + k, p.L, rev)]) : 0.f;
-    load8<IN_T>(xr, t, p.L, p.vec_mask & 1u, rev, xv + 3);
+    loadv<IN_T, kConvVT>(xr, t, p.L, p.vec_mask & 1u, rev, xv + 3);
     float o[kConvVT];
 #pragma unroll
     for (int i = 0; i < kConvVT; ++i) {
@@ -90,11 +93,12 @@ template <typename IN_T> __global__ void __launch_bounds__(kConvNT) conv1d_fwd_k
         for (int k = 0; k < 4; ++k) acc = fmaf(w4[k], xv[i + k], acc);
         o[i] = p.silu ? acc * sigmoid_f(acc) : acc;
     }
-    store8<IN_T>(reinterpret_cast<IN_T *>(p.out) + (int64_t)b * p.o_bs + (int64_t)d * p.o_ds, t, p.L, p.vec_mask & 2u,
+    storev<IN_T, kConvVT>(reinterpret_cast<IN_T *>(p.out) + (int64_t)b * p.o_bs + (int64_t)d * p.o_ds, t, p.L, p.vec_mask & 2u,
                  rev, o);
 }
 
 template <typename IN_T> __global__ void __launch_bounds__(kConvNT) conv1d_bwd_kernel(const __grid_constant__ ConvArgs p) {
+    constexpr int kConvVT = ConvVT<IN_T>::value;
     const int d = blockIdx.y, b = blockIdx.z;
     const int t = (blockIdx.x * kConvNT + threadIdx.x) * kConvVT;
     float w4[4], bias;
@@ -107,8 +111,8 @@ template <typename IN_T> __global__ void __launch_bounds__(kConvNT) conv1d_bwd_k
         float xv[kConvVT + 6], gv[kConvVT + 3];   // x[t-3 .. t+10], dout[t .. t+10]
 #pragma unroll
         for (int k = 0; k < 3; ++k) xv[k] = (t - 3 + k >= 0) ? Elem<IN_T>::to_f(xr[mpos(t - 3 + k, p.L, rev)]) : 0.f;
-        load8<IN_T>(xr, t, p.L, p.vec_mask & 1u, rev, xv + 3);
-        load8<IN_T>(gr, t, p.L, p.vec_mask & 4u, rev, gv);
+        loadv<IN_T, kConvVT>(xr, t, p.L, p.vec_mask & 1u, rev, xv + 3);
+        loadv<IN_T, kConvVT>(gr, t, p.L, p.vec_mask & 4u, rev, gv);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const int tt = t + kConvVT + k;
@@ -139,7 +143,7 @@ template <typename IN_T> __global__ void __launch_bounds__(kConvNT) conv1d_bwd_k
 #pragma unroll
             for (int k = 0; k < 4; ++k) part[k] = fmaf(xv[i + k], dpre[i], part[k]);
         }
-        store8<IN_T>(reinterpret_cast<IN_T *>(p.dx) + (int64_t)b * p.dx_bs + (int64_t)d * p.dx_ds, t, p.L, p.vec_mask & 2u,
+        storev<IN_T, kConvVT>(reinterpret_cast<IN_T *>(p.dx) + (int64_t)b * p.dx_bs + (int64_t)d * p.dx_ds, t, p.L, p.vec_mask & 2u,
                      rev, dxv);
     }
     // block reduce -> one atomic per (channel, tap) per CTA
@@ -182,7 +186,7 @@ template <typename IN_T> int run_conv(const mmu_conv_params *p, bool bwd, cudaSt
         a.vec_mask |= quad_ok<IN_T>(p->dx, p->dx_bs, p->dx_ds, L, rv) ? 2u : 0u;
         a.vec_mask |= quad_ok<IN_T>(p->dout, p->dout_bs, p->dout_ds, L, rv) ? 4u : 0u;
     }
-    const int per_block = kConvNT * kConvVT;
+    const int per_block = kConvNT * ConvVT<IN_T>::value;
     dim3 grid((L + per_block - 1) / per_block, p->dim, p->batch);
     if (grid.y > 65535 || grid.z > 65535) return set_error(MMU_ERR_UNSUPPORTED, "causal_conv1d: dim/batch > 65535");
     if (bwd) conv1d_bwd_kernel<IN_T><<<grid, kConvNT, 0, st>>>(a);
