@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const TI *__restri
         float s = 0.f, ss = 0.f;
         if (gi < G && lp < lanes) {
             const TI *xp = x + ((int64_t)b * g.HW) * g.C + 4 * gi;
+#pragma unroll 4
             for (int p = p0 + lp; p < p1; p += lanes) {
                 float v[4];
                 V4<TI>::ld(xp + (int64_t)p * g.C, v);
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_bwd_reduce_kernel(const TI *__r
             const float4 ga = *reinterpret_cast<const float4 *>(gamma + 4 * gi);
             const float gam[4] = {ga.x, ga.y, ga.z, ga.w};
             const int64_t base = ((int64_t)b * g.HW) * g.C + 4 * gi;
+#pragma unroll 4
             for (int p = p0 + lp; p < p1; p += lanes) {
                 float v[4], d[4];
                 V4<TI>::ld(x + base + (int64_t)p * g.C, v);
