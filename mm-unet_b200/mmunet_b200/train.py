@@ -113,6 +113,13 @@ class Trainer:
             self.x_dev = self.x_dev.contiguous(memory_format=torch.channels_last)
         self.y_dev = torch.empty(B, 1, S, S, device=self.device, dtype=torch.uint8)
         self.loss_dev = torch.zeros((), device=self.device)
+        if self.is_cuda:
+            self.copy_stream = torch.cuda.Stream(self.device)
+            self.stage = [(torch.empty_like(self.x_dev), torch.empty_like(self.y_dev)) for _ in range(2)]
+            self.stage_ready = [torch.cuda.Event() for _ in range(2)]
+            self.stage_free = [torch.cuda.Event() for _ in range(2)]
+            for e in self.stage_free:
+                e.record(self.stream)
 
     def set_epoch(self, epoch: int):
         lr = warmup_cosine_lr(epoch, self.base_lr, self.warmup_epochs, self.max_epochs)
@@ -151,9 +158,19 @@ class Trainer:
             return self.loss_dev
         cur = torch.cuda.current_stream(self.device)
         self.stream.wait_stream(cur)
+        # host -> device on a copy stream into one of two staging sets: the copy of step i overlaps the kernels of step i-1
+        # (the host runs ahead of the GPU); the training stream then moves the batch into the graph's static inputs (D2D).
+        k = self.steps_done % 2
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.stage_free[k])
+            self.stage[k][0].copy_(x_host, non_blocking=True)
+            self.stage[k][1].copy_(y_host, non_blocking=True)
+            self.stage_ready[k].record(self.copy_stream)
         with torch.cuda.stream(self.stream):
-            self.x_dev.copy_(x_host, non_blocking=True)
-            self.y_dev.copy_(y_host, non_blocking=True)
+            self.stream.wait_event(self.stage_ready[k])
+            self.x_dev.copy_(self.stage[k][0], non_blocking=True)
+            self.y_dev.copy_(self.stage[k][1], non_blocking=True)
+            self.stage_free[k].record(self.stream)
             if self.graph is not None:
                 self.graph.replay()
             elif self.use_graph and self.steps_done >= self.graph_warmup:
