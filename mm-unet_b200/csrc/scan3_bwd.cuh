@@ -126,7 +126,6 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
     constexpr int STEP = REV ? CH : -CH;                // memory step to the next (= previous in time) chunk
     bool row_ok[2];
     const IN_T *u_p[2], *d_p[2], *z_p[2], *g_p[2], *y_p[2];     // prefetch pointers
-    const IN_T *uc_p[2];                                           // u of the current chunk (re-read by the epilogue)
     IN_T *du_p[2], *dd_p[2], *dz_p[2];                            // output pointers (current chunk)
     float bias[2], Dsk[2];
 #pragma unroll
@@ -134,7 +133,6 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
         row_ok[r] = rowA + r < D;
         const int row = min(rowA + r, D - 1);
         u_p[r] = reinterpret_cast<const IN_T *>(p.u) + (int64_t)b * p.u_bs + (int64_t)row * p.u_ds + mo0;
-        uc_p[r] = u_p[r];
         d_p[r] = reinterpret_cast<const IN_T *>(p.delta) + (int64_t)b * p.dl_bs + (int64_t)row * p.dl_ds + mo0;
         g_p[r] = reinterpret_cast<const IN_T *>(p.dout) + (int64_t)b * p.g_bs + (int64_t)row * p.g_ds + mo0;
         z_p[r] = has_z ? reinterpret_cast<const IN_T *>(p.z) + (int64_t)b * p.z_bs + (int64_t)row * p.z_ds + mo0 : nullptr;
@@ -184,24 +182,14 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
                     cp_async16(s_land_u32 + ((3 * 2 + r) * NQ + q) * NT * 16, g_p[r] + q * EPQ);
                     if (!AGG) cp_async16(s_land_u32 + ((0 * 2 + r) * NQ + q) * NT * 16, u_p[r] + q * EPQ);
                     if (has_z) cp_async16(s_land_u32 + ((2 * 2 + r) * NQ + q) * NT * 16, z_p[r] + q * EPQ);
+                    if (!AGG && has_z) cp_async16(s_land_u32 + ((4 * 2 + r) * NQ + q) * NT * 16, y_p[r] + q * EPQ);
                 }
         }
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             u_p[r] += STEP, d_p[r] += STEP, g_p[r] += STEP;
             if (has_z) z_p[r] += STEP;
-        }
-    };
-    auto issue_y = [&](bool in_seq) {
-        if (!AGG && has_z) {
-            if (in_seq) {
-#pragma unroll
-                for (int r = 0; r < 2; ++r)
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q) cp_async16(s_land_u32 + ((4 * 2 + r) * NQ + q) * NT * 16, y_p[r] + q * EPQ);
-            }
-#pragma unroll
-            for (int r = 0; r < 2; ++r) y_p[r] += STEP;
+            if (!AGG && has_z) y_p[r] += STEP;
         }
     };
     auto load_land = [&](int which, int r, float (&v)[T]) {
@@ -233,7 +221,6 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
     __syncthreads();
     issue_tile(c_end - 1);
     issue_in(tl < L);
-    issue_y(tl < L);
     load_seeds(c_end - 1, (c_end - 1) & 1);
     cp_async_commit();
 
@@ -255,15 +242,18 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
                 load_land(3, r, gg[r]);
                 if (!AGG) load_land(0, r, uu[r]);
                 if (has_z) {
-                    float zz[T];
+                    float zz[T], yv[T];
                     load_land(2, r, zz);
+                    if (!AGG) load_land(4, r, yv);
 #pragma unroll
                     for (int i = 0; i < T; ++i) {
                         const float s = sigmoid3(zz[i]);
                         const float gz = gg[r][i] * s;
-                        zf[r][i] = gz * fmaf(zz[i], 1.f - s, 1.f);          // dz = y * zf      (bwd_kernel.cuh:186-191)
+                        zf[r][i] = AGG ? 0.f : yv[i] * (gz * fmaf(zz[i], 1.f - s, 1.f));   // dz = y * g * d silu(z)/dz  (bwd_kernel.cuh:186-191)
                         gg[r][i] = gz * zz[i];                              // dy
                     }
+                    // dz needs nothing from the state loop: store it now, so that neither y nor the gate factor has to be kept
+                    if (!AGG && ok && row_ok[r]) store8<IN_T, REV>(dz_p[r], zf[r]);
                 }
 #pragma unroll
                 for (int i = 0; i < T; ++i) {
@@ -273,9 +263,9 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
                     gg[r][i] = (ok && row_ok[r]) ? gg[r][i] : 0.f;
                     if (AGG) dsum[r] += dd[r][i];
                 }
-                if (!AGG && has_z) {
-                    *reinterpret_cast<float4 *>(s_zf_t + (r * 2 + 0) * NT * 16) = make_float4(zf[r][0], zf[r][1], zf[r][2], zf[r][3]);
-                    *reinterpret_cast<float4 *>(s_zf_t + (r * 2 + 1) * NT * 16) = make_float4(zf[r][4], zf[r][5], zf[r][6], zf[r][7]);
+                if (!AGG) {      // u is needed again by the epilogue (ddelta = u*S1 + S2): keep it in shared memory, not in registers
+                    *reinterpret_cast<float4 *>(s_zf_t + (r * 2 + 0) * NT * 16) = make_float4(uu[r][0], uu[r][1], uu[r][2], uu[r][3]);
+                    *reinterpret_cast<float4 *>(s_zf_t + (r * 2 + 1) * NT * 16) = make_float4(uu[r][4], uu[r][5], uu[r][6], uu[r][7]);
                 }
             }
 #pragma unroll
@@ -453,24 +443,14 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
         if (c > c_begin) issue_tile(c - 1);
         if (!AGG) {
             // ---- epilogue: du, ddelta, dz ---------------------------------------------------------------------------------------------
-            float yv[2][T], zf[2][T], uu[2][T];
+            float uu[2][T];
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {       // u of this chunk again (an L2 hit)
-#pragma unroll
-                for (int i = 0; i < T; ++i) uu[r][i] = 0.f;
-                if (ok) load8_global<IN_T, REV>(uc_p[r], uu[r]);
+            for (int r = 0; r < 2; ++r) {
+                const float4 f0 = *reinterpret_cast<const float4 *>(s_zf_t + (r * 2 + 0) * NT * 16);
+                const float4 f1 = *reinterpret_cast<const float4 *>(s_zf_t + (r * 2 + 1) * NT * 16);
+                uu[r][0] = f0.x, uu[r][1] = f0.y, uu[r][2] = f0.z, uu[r][3] = f0.w;
+                uu[r][4] = f1.x, uu[r][5] = f1.y, uu[r][6] = f1.z, uu[r][7] = f1.w;
             }
-            if (has_z) {
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    load_land(4, r, yv[r]);
-                    const float4 f0 = *reinterpret_cast<const float4 *>(s_zf_t + (r * 2 + 0) * NT * 16);
-                    const float4 f1 = *reinterpret_cast<const float4 *>(s_zf_t + (r * 2 + 1) * NT * 16);
-                    zf[r][0] = f0.x, zf[r][1] = f0.y, zf[r][2] = f0.z, zf[r][3] = f0.w;
-                    zf[r][4] = f1.x, zf[r][5] = f1.y, zf[r][6] = f1.z, zf[r][7] = f1.w;
-                }
-            }
-            if (c > c_begin) issue_y(true);
             cp_async_commit();
             float2 duv[T], ddv[T];
 #pragma unroll
@@ -499,17 +479,12 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
 #pragma unroll
                         for (int i = 0; i < T; ++i) v[i] = r ? ddv[i].y : ddv[i].x;
                         store8<IN_T, REV>(dd_p[r], v);
-                        if (has_z) {
-#pragma unroll
-                            for (int i = 0; i < T; ++i) v[i] = yv[r][i] * zf[r][i];
-                            store8<IN_T, REV>(dz_p[r], v);
-                        }
                     }
                 }
             }
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                du_p[r] += STEP, dd_p[r] += STEP, uc_p[r] += STEP;
+                du_p[r] += STEP, dd_p[r] += STEP;
                 if (has_z) dz_p[r] += STEP;
             }
         } else {
