@@ -85,6 +85,7 @@ __device__ __forceinline__ void cp_async4(unsigned dst, const void *src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_last() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }   // all but the newest group
 
 __device__ __forceinline__ float lg2_fast(float x) {
     float y;

@@ -218,20 +218,19 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
         }
     };
 
+    // Two cp.async groups per chunk: (A) this thread's u / delta / z / dout / y slots and the x seeds, issued a whole chunk ahead;
+    // (B) the B/C tile, which can only be refilled after the state loop.  The prologue needs A only, so the tile's latency
+    // hides under the per-(row, token) prologue instead of stalling the top of the chunk.
     __syncthreads();
-    issue_tile(c_end - 1);
     issue_in(tl < L);
     load_seeds(c_end - 1, (c_end - 1) & 1);
+    cp_async_commit();
+    issue_tile(c_end - 1);
     cp_async_commit();
 
     for (int c = c_end - 1; c >= c_begin; --c, tl -= CH) {
         const bool ok = tl < L;
-        cp_async_wait_all();
-        __syncthreads();
-        if constexpr (!kF32) {
-            widen_bf16_tile<LPR, NT, true>(s_tile, s_rawbc, tid);
-            __syncthreads();
-        }
+        cp_async_wait_but_last();       // group A of this chunk (my own landing slots: no barrier needed to read them)
         // ---- per (row, token) registers (.x = row A, .y = row B) ---------------------------------------------------------------
         float2 dl[T], dlu[T], dy[T];
         {
@@ -280,10 +279,17 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
             }
         }
         // inputs of the next chunk (c-1): the landing slots are private to this thread and were just consumed
+        cp_async_wait_all();            // group B: the B/C tile (and everybody's seeds) of this chunk
+        __syncthreads();
+        if constexpr (!kF32) {
+            widen_bf16_tile<LPR, NT, true>(s_tile, s_rawbc, tid);
+            __syncthreads();
+        }
         if (c > c_begin) {
             issue_in(true);
             load_seeds(c - 1, (c - 1) & 1);
         }
+        cp_async_commit();              // group A of chunk c-1
 
         float2 s1[T], s2[T];
 #pragma unroll
@@ -387,12 +393,13 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
                 sl[2 * 32] = make_float4(dCn[0], dCn[1], dCn[2], dCn[3]);
                 sl[3 * 32] = make_float4(dCn[4], dCn[5], dCn[6], dCn[7]);
             }
-            // dA: fold the 32 lane partials to 8, accumulate those in shared memory
+            // publish the slab: named barrier 1 + (n & 1); the matching sync sits in reduce_state(n), one phase of work later
+            asm volatile("bar.arrive %0, %1;" ::"r"(1 + (n & 1)), "r"(2 * NT) : "memory");
+            // dA: fold the 32 lane partials to 8, accumulate those in (warp-private) shared memory.  After the arrive, so that the
+            // shuffle latency overlaps the next phase instead of delaying the barrier.
             dAacc.x += __shfl_xor_sync(0xffffffffu, dAacc.x, 16), dAacc.y += __shfl_xor_sync(0xffffffffu, dAacc.y, 16);
             dAacc.x += __shfl_xor_sync(0xffffffffu, dAacc.x, 8), dAacc.y += __shfl_xor_sync(0xffffffffu, dAacc.y, 8);
             if (j < 8) s_dA[(n * W + warp) * 8 + j] = fadd2(s_dA[(n * W + warp) * 8 + j], dAacc);
-            // publish: named barrier 1 + (n & 1); the matching sync sits in reduce_state(n), one phase of work later
-            asm volatile("bar.arrive %0, %1;" ::"r"(1 + (n & 1)), "r"(2 * NT) : "memory");
         };
         // sum the CTA's slabs of state n and add them to global memory
         auto reduce_state = [&](int n) {

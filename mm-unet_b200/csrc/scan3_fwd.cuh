@@ -157,20 +157,19 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
         order8<REV>(e, v);
     };
 
+    // Two cp.async groups per chunk: (A) this thread's u / delta slots, issued a whole chunk ahead; (B) the B/C tile and z, which
+    // are refilled after the state loop.  The per-(row, token) prologue (softplus, delta*u, D*u) needs A only, so the tile's latency
+    // hides under it instead of stalling the top of the chunk.
     __syncthreads();                    // zero fill and tables visible before the first copies land
-    issue_tile(c_begin);
     issue_ud(tl < L);
+    cp_async_commit();
+    issue_tile(c_begin);
     issue_z(tl < L);
     cp_async_commit();
 
     for (int c = c_begin; c < c_end; ++c, tl += CH) {
         const bool ok = tl < L;
-        cp_async_wait_all();
-        __syncthreads();                // chunk c has landed
-        if constexpr (!kF32) {
-            widen_bf16_tile<LPR, NT, !AGG>(s_tile, s_rawbc, tid);
-            __syncthreads();
-        }
+        cp_async_wait_but_last();       // group A: my own u / delta slots (thread-private: no barrier needed)
         // ---- per (row, token) registers, the two rows packed: .x = row A, .y = row B ------------------------------------
         float2 dl[T], dlu[T], ya[T];
         {
@@ -194,8 +193,15 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
                 ya[i] = make_float2(Dsk[0] * uu[0][i], Dsk[1] * uu[1][i]);
             }
         }
+        cp_async_wait_all();            // group B: the B/C tile and z of this chunk
+        __syncthreads();
+        if constexpr (!kF32) {
+            widen_bf16_tile<LPR, NT, !AGG>(s_tile, s_rawbc, tid);
+            __syncthreads();
+        }
         // u / delta of the next chunk (the staging slots are private to this thread and were just consumed)
         if (c + 1 < c_end) issue_ud(tl + CH < L);
+        cp_async_commit();              // group A of chunk c+1
 
 #pragma unroll 2
         for (int n0 = 0; n0 < NS; n0 += 2) {
