@@ -122,8 +122,11 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
     const int rowA = row0 + 2 * warp;
     const int c_begin = seg * p.cps, c_end = min(p.nchunks, c_begin + p.cps);
     int tl = (c_end - 1) * CH + T * j;                  // first logical token of my 8 in the current chunk
-    const int mo0 = REV ? L - T - tl : tl;
     constexpr int STEP = REV ? CH : -CH;                // memory step to the next (= previous in time) chunk
+    // Every pointer starts ONE STEP BEHIND and is advanced just before it is used: a cp.async / store keeps its address
+    // registers busy until it has been accepted by the memory pipe, and advancing them right AFTER the access (the natural
+    // form) stalled on that release at the top of every chunk (long-scoreboard samples on the pointer updates in ncu).
+    const int mo0 = (REV ? L - T - tl : tl) - STEP;
     bool row_ok[2];
     const IN_T *u_p[2], *d_p[2], *z_p[2], *g_p[2], *y_p[2];     // prefetch pointers
     IN_T *du_p[2], *dd_p[2], *dz_p[2];                            // output pointers (current chunk)
@@ -172,7 +175,13 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
         }
     };
     // landing slots: tensor 0 u, 1 delta, 2 z, 3 dout, 4 y
-    auto issue_in = [&](bool in_seq) {      // u, delta, z, dout of the chunk the prefetch pointers stand on, then move them on
+    auto issue_in = [&](bool in_seq) {      // move the prefetch pointers on to the next chunk, then fetch its u, delta, z, dout, y
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            u_p[r] += STEP, d_p[r] += STEP, g_p[r] += STEP;
+            if (has_z) z_p[r] += STEP;
+            if (!AGG && has_z) y_p[r] += STEP;
+        }
         if (in_seq) {
 #pragma unroll
             for (int r = 0; r < 2; ++r)
@@ -184,12 +193,6 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
                     if (has_z) cp_async16(s_land_u32 + ((2 * 2 + r) * NQ + q) * NT * 16, z_p[r] + q * EPQ);
                     if (!AGG && has_z) cp_async16(s_land_u32 + ((4 * 2 + r) * NQ + q) * NT * 16, y_p[r] + q * EPQ);
                 }
-        }
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            u_p[r] += STEP, d_p[r] += STEP, g_p[r] += STEP;
-            if (has_z) z_p[r] += STEP;
-            if (!AGG && has_z) y_p[r] += STEP;
         }
     };
     auto load_land = [&](int which, int r, float (&v)[T]) {
@@ -252,7 +255,10 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
                         gg[r][i] = gz * zz[i];                              // dy
                     }
                     // dz needs nothing from the state loop: store it now, so that neither y nor the gate factor has to be kept
-                    if (!AGG && ok && row_ok[r]) store8<IN_T, REV>(dz_p[r], zf[r]);
+                    if (!AGG) {
+                        dz_p[r] += STEP;
+                        if (ok && row_ok[r]) store8<IN_T, REV>(dz_p[r], zf[r]);
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < T; ++i) {
@@ -453,6 +459,7 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
             float uu[2][T];
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
+                du_p[r] += STEP, dd_p[r] += STEP;
                 const float4 f0 = *reinterpret_cast<const float4 *>(s_zf_t + (r * 2 + 0) * NT * 16);
                 const float4 f1 = *reinterpret_cast<const float4 *>(s_zf_t + (r * 2 + 1) * NT * 16);
                 uu[r][0] = f0.x, uu[r][1] = f0.y, uu[r][2] = f0.z, uu[r][3] = f0.w;
@@ -488,11 +495,6 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
                         store8<IN_T, REV>(dd_p[r], v);
                     }
                 }
-            }
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                du_p[r] += STEP, dd_p[r] += STEP;
-                if (has_z) dz_p[r] += STEP;
             }
         } else {
             cp_async_commit();

@@ -81,7 +81,10 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
     const int c_begin = seg * p.cps, c_end = min(p.nchunks, c_begin + p.cps);
     // memory index of my 8 tokens in chunk c_begin (advances by +-CH per chunk)
     int tl = c_begin * CH + T * j;
-    const int mo0 = REV ? L - T - tl : tl;
+    constexpr int STEP = REV ? -CH : CH;
+    // pointers start one step behind and are advanced just before use (see scan3_bwd.cuh: no write-after-read stall on the
+    // address registers of a cp.async / store that is still in the memory pipe's queue)
+    const int mo0 = (REV ? L - T - tl : tl) - STEP;
     bool row_ok[2];
     const IN_T *u_p[2], *d_p[2], *z_p[2];               // point at my 8 tokens of the chunk being PREFETCHED
     IN_T *o_p[2], *y_p[2];                               // point at my 8 tokens of the chunk being COMPUTED
@@ -99,7 +102,6 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
         bias[r] = p.dbias != nullptr ? p.dbias[row] : 0.f;
         Dsk[r] = p.Dv != nullptr ? p.Dv[row] : 0.f;
     }
-    constexpr int STEP = REV ? -CH : CH;
     const IN_T *B_b = reinterpret_cast<const IN_T *>(p.Bm) + (int64_t)b * p.B_bs;
     const IN_T *C_b = reinterpret_cast<const IN_T *>(p.Cm) + (int64_t)b * p.C_bs;
 
@@ -123,7 +125,9 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
                                                reinterpret_cast<const __nv_bfloat16 *>(C_b), p.B_ns, p.C_ns, N, c * CH, L, tid);
         }
     };
-    auto issue_ud = [&](bool in_seq) {      // u and delta of the chunk the prefetch pointers stand on, then advance them
+    auto issue_ud = [&](bool in_seq) {      // advance the prefetch pointers to the next chunk, then fetch its u and delta
+#pragma unroll
+        for (int r = 0; r < 2; ++r) u_p[r] += STEP, d_p[r] += STEP;
         if (in_seq) {
 #pragma unroll
             for (int r = 0; r < 2; ++r)
@@ -133,19 +137,17 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
                     cp_async16(s_elem_u32 + ((1 * 2 + r) * NQ + q) * NT * 16, d_p[r] + q * EPQ);
                 }
         }
-#pragma unroll
-        for (int r = 0; r < 2; ++r) u_p[r] += STEP, d_p[r] += STEP;
     };
     auto issue_z = [&](bool in_seq) {
         if (!AGG && has_z) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) z_p[r] += STEP;
             if (in_seq) {
 #pragma unroll
                 for (int r = 0; r < 2; ++r)
 #pragma unroll
                     for (int q = 0; q < NQ; ++q) cp_async16(s_elem_u32 + ((2 * 2 + r) * NQ + q) * NT * 16, z_p[r] + q * EPQ);
             }
-#pragma unroll
-            for (int r = 0; r < 2; ++r) z_p[r] += STEP;
         }
     };
     auto load_elem = [&](int which, int r, float (&v)[T]) {      // my 8 tokens of tensor `which`, row r, from the staging area
@@ -282,6 +284,11 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
             }
             if (c + 1 < c_end) issue_z(tl + CH < L);
             cp_async_commit();
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                o_p[r] += STEP;
+                if (y_p[r] != nullptr) y_p[r] += STEP;
+            }
             if (ok) {
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
@@ -297,11 +304,6 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
                         store8<IN_T, REV>(o_p[r], yv);
                     }
                 }
-            }
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                o_p[r] += STEP;
-                if (y_p[r] != nullptr) y_p[r] += STEP;
             }
             // ---- saved states x[b][row][k][n] = h after token 64(k+1)-1 (the __syncthreads above ordered the s_ck writes) -------
             if (p.x != nullptr) {
