@@ -87,6 +87,34 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_but_last() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }   // all but the newest group
 
+// ---- TMA 1-D bulk copies (cp.async.bulk, UBLKCP) with mbarrier completion: the B/C tile --------------------------------------
+// One warp issues the whole tile - a handful of bulk copies instead of ~1 100 16-byte LDGSTS spread over the CTA - and every
+// thread waits on the mbarrier's phase.  (The per-thread input slots stay on cp.async: they are thread-private 16-byte pieces.)
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "MBAR_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MBAR_DONE_%=;\n\t"
+        "bra MBAR_WAIT_%=;\n"
+        "MBAR_DONE_%=:\n\t}" ::"r"(mbar),
+        "r"(parity)
+        : "memory");
+}
+
 __device__ __forceinline__ float lg2_fast(float x) {
     float y;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -128,6 +156,43 @@ template <int LPR> struct BcTile {
     static constexpr int kBytes = 2 * 16 * kRowBytes;                     // B[16] | C[16]
     static __device__ __forceinline__ int quad_off(int q) { return 16 * q + 16 * (q >> 3); }
 };
+
+// Tile of logical tokens [t0, t0 + CH): lane `lane` of the issuing warp owns row `lane` (rows 0..15 = B states, 16..31 = C states).
+// fp32: the row is copied in 128-byte pieces into the padded layout (quad_off); 2-byte types: one copy of the raw row (widened
+// later).  Pieces outside [0, L) are skipped (those lanes run with delta = 0).  The mbarrier must have been initialised with a
+// count of 32: every lane arrives with its own byte count.
+template <typename IN_T, int LPR, bool REV, bool WITH_C>
+__device__ __forceinline__ void tile_bulk_issue(unsigned tile_or_raw, unsigned mbar, const IN_T *__restrict__ B_b, const IN_T *__restrict__ C_b,
+                                                int64_t B_ns, int64_t C_ns, int N, int t0, int L, int lane) {
+    using Tl = BcTile<LPR>;
+    constexpr int CH = Tl::CH;
+    constexpr bool kF32 = sizeof(IN_T) == 4;
+    constexpr int PT = kF32 ? 32 : CH;                       // tokens per piece
+    constexpr int ROWB = kF32 ? Tl::kRowBytes : CH * 2;
+    const int m0 = REV ? L - t0 - CH : t0;                   // memory index of tile position 0 (may be < 0)
+    const int st = lane & 15;
+    const bool isC = lane >= 16, live = st < min(N, 16) && (WITH_C || !isC);
+    const IN_T *src = (isC ? C_b + (int64_t)st * C_ns : B_b + (int64_t)st * B_ns);
+    const unsigned dst = tile_or_raw + lane * ROWB;
+    unsigned bytes = 0;
+    int lo[CH / PT], n[CH / PT];
+#pragma unroll
+    for (int pc = 0; pc < CH / PT; ++pc) {
+        const int a = max(m0 + pc * PT, 0), b = min(m0 + (pc + 1) * PT, L);
+        lo[pc] = a, n[pc] = live && b > a ? b - a : 0;
+        bytes += (unsigned)n[pc] * (unsigned)sizeof(IN_T);
+    }
+    fence_proxy_async();                                     // the tile was read through the generic proxy until the barrier before this call
+    mbar_arrive_expect_tx(mbar, bytes);
+#pragma unroll
+    for (int pc = 0; pc < CH / PT; ++pc) {
+        if (n[pc] > 0) {
+            const int off = lo[pc] - m0;                     // token offset inside the tile row (multiple of 8)
+            const unsigned d = dst + (kF32 ? (unsigned)Tl::quad_off(off >> 2) : (unsigned)off * 2u);
+            bulk_g2s(d, src + lo[pc], (unsigned)n[pc] * (unsigned)sizeof(IN_T), mbar);
+        }
+    }
+}
 
 // Issue the cp.async copies of the tile holding logical tokens [t0, t0 + CH).  Pieces outside the sequence are skipped: the
 // lanes that would read them run with delta = 0, so the stale (finite: the tile is zero-initialised) contents do not matter.

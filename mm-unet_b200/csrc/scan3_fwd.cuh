@@ -9,6 +9,15 @@
 #pragma once
 #include "scan3.cuh"
 
+// MMU_BULK_TILE=1 loads the B/C tile with TMA 1-D bulk copies (cp.async.bulk + mbarrier, scan3.cuh:tile_bulk_issue) issued by
+// one warp instead of per-thread cp.async.  Measured on B200 at config 2 (forward, us): fp32 265 vs 175, bf16 156 vs 150; RCG
+// L = 65 536 bf16 1 966 vs 1 799 - the padded (bank-conflict-free) row layout forces 128-byte pieces (256 bulk copies per fp32 tile),
+// too small for the bulk path, so the default stays cp.async.  A tensor-map copy (cp.async.bulk.tensor, 128B swizzle) is the
+// version that can win: one instruction per tile and no padding.
+#ifndef MMU_BULK_TILE
+#define MMU_BULK_TILE 0
+#endif
+
 namespace mmu {
 
 struct Fwd3Args {
@@ -42,6 +51,7 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
     constexpr int CH = Cfg::CH, RPW = Cfg::RPW, R = Cfg::R, NT = Cfg::NT, NRP = Cfg::NRP, T = kS3T, NQ = Cfg::NQ, NCK = Cfg::NCK;
     constexpr int EPQ = 16 / (int)sizeof(IN_T);          // elements per 16-byte piece
     constexpr bool kF32 = Cfg::kF32;
+    constexpr bool kBulkTile = MMU_BULK_TILE != 0;       // B/C tile by cp.async.bulk (TMA) instead of per-thread cp.async
     constexpr int NSTEP = LPR == 32 ? 5 : (LPR == 16 ? 4 : 3);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rp = lane / LPR, j = lane % LPR;
@@ -116,7 +126,19 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
     const unsigned s_elem_u32 = smem_u32(s_elem) + tid * 16;
     const unsigned char *s_elem_t = s_elem + tid * 16;
 
+    __shared__ __align__(8) unsigned long long s_mbar;
+    const unsigned mbar = smem_u32(&s_mbar);
+    unsigned tile_phase = 0;
+    if (tid == 0) {
+        mbar_init(mbar, 32);
+        fence_mbar_init();
+    }
     auto issue_tile = [&](int c) {
+        if (kBulkTile) {            // TMA bulk copies issued by warp 0, completion on the mbarrier
+            if (warp == 0)
+                tile_bulk_issue<IN_T, LPR, REV, !AGG>(kF32 ? s_tile_u32 : s_raw_u32, mbar, B_b, C_b, p.B_ns, p.C_ns, N, c * CH, L, lane);
+            return;
+        }
         if constexpr (kF32) {
             tile_async_f32<LPR, NT, REV, !AGG>(s_tile_u32, reinterpret_cast<const float *>(B_b), reinterpret_cast<const float *>(C_b),
                                                p.B_ns, p.C_ns, N, c * CH, L, tid);
@@ -196,6 +218,7 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
             }
         }
         cp_async_wait_all();            // group B: the B/C tile and z of this chunk
+        if (kBulkTile) mbar_wait(mbar, tile_phase++ & 1u);
         __syncthreads();
         if constexpr (!kF32) {
             widen_bf16_tile<LPR, NT, !AGG>(s_tile, s_rawbc, tid);
