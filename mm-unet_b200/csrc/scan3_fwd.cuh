@@ -14,6 +14,8 @@
 // L = 65 536 bf16 1 966 vs 1 799 - the padded (bank-conflict-free) row layout forces 128-byte pieces (256 bulk copies per fp32 tile),
 // too small for the bulk path, so the default stays cp.async.  A tensor-map copy (cp.async.bulk.tensor, 128B swizzle) is the
 // version that can win: one instruction per tile and no padding.
+// (Also measured and NOT kept in this kernel, unlike the backward: two cp.async groups per chunk and pointers advanced before
+// use - together 173 -> 180 us here.)
 #ifndef MMU_BULK_TILE
 #define MMU_BULK_TILE 0
 #endif
@@ -91,10 +93,7 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
     const int c_begin = seg * p.cps, c_end = min(p.nchunks, c_begin + p.cps);
     // memory index of my 8 tokens in chunk c_begin (advances by +-CH per chunk)
     int tl = c_begin * CH + T * j;
-    constexpr int STEP = REV ? -CH : CH;
-    // pointers start one step behind and are advanced just before use (see scan3_bwd.cuh: no write-after-read stall on the
-    // address registers of a cp.async / store that is still in the memory pipe's queue)
-    const int mo0 = (REV ? L - T - tl : tl) - STEP;
+    const int mo0 = REV ? L - T - tl : tl;
     bool row_ok[2];
     const IN_T *u_p[2], *d_p[2], *z_p[2];               // point at my 8 tokens of the chunk being PREFETCHED
     IN_T *o_p[2], *y_p[2];                               // point at my 8 tokens of the chunk being COMPUTED
@@ -112,6 +111,7 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
         bias[r] = p.dbias != nullptr ? p.dbias[row] : 0.f;
         Dsk[r] = p.Dv != nullptr ? p.Dv[row] : 0.f;
     }
+    constexpr int STEP = REV ? -CH : CH;
     const IN_T *B_b = reinterpret_cast<const IN_T *>(p.Bm) + (int64_t)b * p.B_bs;
     const IN_T *C_b = reinterpret_cast<const IN_T *>(p.Cm) + (int64_t)b * p.C_bs;
 
@@ -126,15 +126,17 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
     const unsigned s_elem_u32 = smem_u32(s_elem) + tid * 16;
     const unsigned char *s_elem_t = s_elem + tid * 16;
 
-    __shared__ __align__(8) unsigned long long s_mbar;
+    __shared__ __align__(8) unsigned long long s_mbar;       // used by the bulk-copy variant only
     const unsigned mbar = smem_u32(&s_mbar);
-    unsigned tile_phase = 0;
-    if (tid == 0) {
-        mbar_init(mbar, 32);
-        fence_mbar_init();
+    [[maybe_unused]] unsigned tile_phase = 0;
+    if constexpr (kBulkTile) {
+        if (tid == 0) {
+            mbar_init(mbar, 32);
+            fence_mbar_init();
+        }
     }
     auto issue_tile = [&](int c) {
-        if (kBulkTile) {            // TMA bulk copies issued by warp 0, completion on the mbarrier
+        if constexpr (kBulkTile) {      // TMA bulk copies issued by warp 0, completion on the mbarrier
             if (warp == 0)
                 tile_bulk_issue<IN_T, LPR, REV, !AGG>(kF32 ? s_tile_u32 : s_raw_u32, mbar, B_b, C_b, p.B_ns, p.C_ns, N, c * CH, L, lane);
             return;
@@ -147,9 +149,7 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
                                                reinterpret_cast<const __nv_bfloat16 *>(C_b), p.B_ns, p.C_ns, N, c * CH, L, tid);
         }
     };
-    auto issue_ud = [&](bool in_seq) {      // advance the prefetch pointers to the next chunk, then fetch its u and delta
-#pragma unroll
-        for (int r = 0; r < 2; ++r) u_p[r] += STEP, d_p[r] += STEP;
+    auto issue_ud = [&](bool in_seq) {      // u and delta of the chunk the prefetch pointers stand on, then advance them
         if (in_seq) {
 #pragma unroll
             for (int r = 0; r < 2; ++r)
@@ -159,17 +159,19 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
                     cp_async16(s_elem_u32 + ((1 * 2 + r) * NQ + q) * NT * 16, d_p[r] + q * EPQ);
                 }
         }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) u_p[r] += STEP, d_p[r] += STEP;
     };
     auto issue_z = [&](bool in_seq) {
         if (!AGG && has_z) {
-#pragma unroll
-            for (int r = 0; r < 2; ++r) z_p[r] += STEP;
             if (in_seq) {
 #pragma unroll
                 for (int r = 0; r < 2; ++r)
 #pragma unroll
                     for (int q = 0; q < NQ; ++q) cp_async16(s_elem_u32 + ((2 * 2 + r) * NQ + q) * NT * 16, z_p[r] + q * EPQ);
             }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) z_p[r] += STEP;
         }
     };
     auto load_elem = [&](int which, int r, float (&v)[T]) {      // my 8 tokens of tensor `which`, row r, from the staging area
@@ -181,19 +183,21 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
         order8<REV>(e, v);
     };
 
-    // Two cp.async groups per chunk: (A) this thread's u / delta slots, issued a whole chunk ahead; (B) the B/C tile and z, which
-    // are refilled after the state loop.  The per-(row, token) prologue (softplus, delta*u, D*u) needs A only, so the tile's latency
-    // hides under it instead of stalling the top of the chunk.
     __syncthreads();                    // zero fill and tables visible before the first copies land
-    issue_ud(tl < L);
-    cp_async_commit();
     issue_tile(c_begin);
+    issue_ud(tl < L);
     issue_z(tl < L);
     cp_async_commit();
 
     for (int c = c_begin; c < c_end; ++c, tl += CH) {
         const bool ok = tl < L;
-        cp_async_wait_but_last();       // group A: my own u / delta slots (thread-private: no barrier needed)
+        cp_async_wait_all();
+        if constexpr (kBulkTile) mbar_wait(mbar, tile_phase++ & 1u);
+        __syncthreads();                // chunk c has landed
+        if constexpr (!kF32) {
+            widen_bf16_tile<LPR, NT, !AGG>(s_tile, s_rawbc, tid);
+            __syncthreads();
+        }
         // ---- per (row, token) registers, the two rows packed: .x = row A, .y = row B ------------------------------------
         float2 dl[T], dlu[T], ya[T];
         {
@@ -217,16 +221,8 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
                 ya[i] = make_float2(Dsk[0] * uu[0][i], Dsk[1] * uu[1][i]);
             }
         }
-        cp_async_wait_all();            // group B: the B/C tile and z of this chunk
-        if (kBulkTile) mbar_wait(mbar, tile_phase++ & 1u);
-        __syncthreads();
-        if constexpr (!kF32) {
-            widen_bf16_tile<LPR, NT, !AGG>(s_tile, s_rawbc, tid);
-            __syncthreads();
-        }
         // u / delta of the next chunk (the staging slots are private to this thread and were just consumed)
         if (c + 1 < c_end) issue_ud(tl + CH < L);
-        cp_async_commit();              // group A of chunk c+1
 
 #pragma unroll 2
         for (int n0 = 0; n0 < NS; n0 += 2) {
@@ -307,11 +303,6 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
             }
             if (c + 1 < c_end) issue_z(tl + CH < L);
             cp_async_commit();
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                o_p[r] += STEP;
-                if (y_p[r] != nullptr) y_p[r] += STEP;
-            }
             if (ok) {
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
@@ -327,6 +318,11 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
                         store8<IN_T, REV>(o_p[r], yv);
                     }
                 }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                o_p[r] += STEP;
+                if (y_p[r] != nullptr) y_p[r] += STEP;
             }
             // ---- saved states x[b][row][k][n] = h after token 64(k+1)-1 (the __syncthreads above ordered the s_ck writes) -------
             if (p.x != nullptr) {
