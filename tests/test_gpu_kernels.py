@@ -332,6 +332,14 @@ def test_conv_reverse_is_flipped_conv(L):
     run_conv_case(2, 6, L, 4, True, True, reverse=True)
 
 
+@pytest.mark.parametrize("L", [1, 7, 16, 24, 40, 151, 1000, 2056])
+@pytest.mark.parametrize("reverse", [False, True])
+def test_conv_two_byte_ragged_lengths(L, reverse):
+    """bf16 / fp16 threads own 16 tokens (two 16-byte vectors): lengths around and off that granularity, both directions."""
+    run_conv_case(2, 6, L, 4, True, True, torch.bfloat16, reverse=reverse)
+    run_conv_case(1, 3, L, 3, False, True, torch.float16, reverse=reverse)
+
+
 def test_conv_golden_and_autograd():
     for name, c in load_golden("causal_conv1d.npz").items():
         x = torch.tensor(c["x"], device=DEV, requires_grad=True)
