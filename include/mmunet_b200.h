@@ -96,7 +96,7 @@ int mmu_selective_scan_fwd(const mmu_scan_fwd_params *p, void *stream);
  *   inputs as forward + dout (batch, dim, seqlen) and x from the forward.
  *   du, ddelta, dz : (batch, dim, seqlen) dtype `dtype` (dz NULL iff z NULL)
  *   dA (dim,dstate), dD (dim), ddelta_bias (dim), dB, dC (batch,1,dstate,seqlen; rows contiguous, batch strides
- *   dB_bs / dC_bs, 0 = dstate*seqlen): fp32,
+ *   dB_bs / dC_bs and state strides dB_ns / dC_ns, 0 = contiguous): fp32,
  *   ACCUMULATED INTO (atomics) — the caller zero-fills them, as the reference does
  *   (selective_scan.cpp:458-466).  dD / ddelta_bias may be NULL when D / delta_bias are NULL.
  * --------------------------------------------------------------------------------------------- */
@@ -107,9 +107,10 @@ typedef struct mmu_scan_bwd_params {
     void *du, *ddelta, *dz;
     int64_t du_bs, du_ds, ddelta_bs, ddelta_ds, dz_bs, dz_ds;
     float *dA, *dB, *dC, *dD, *ddelta_bias;
-    /* batch strides (elements) of dB / dC; 0 = contiguous (dstate*seqlen).  Lets both accumulate into row slices of one
-     * (batch, R + 2*dstate, seqlen) gradient buffer of the x_proj output (selective_scan_interface.py:256-262). */
-    int64_t dB_bs, dC_bs;
+    /* batch and state strides (elements) of dB / dC; 0 = contiguous (dstate*seqlen, seqlen).  Lets both accumulate into row
+     * slices of the gradient buffer of the x_proj output in whatever layout the caller keeps it - (batch, R + 2*dstate, seqlen)
+     * or the GEMM-friendly (R + 2*dstate, batch, seqlen) (selective_scan_interface.py:256-262). */
+    int64_t dB_bs, dC_bs, dB_ns, dC_ns;
 } mmu_scan_bwd_params;
 
 size_t mmu_selective_scan_bwd_workspace(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate);

@@ -25,7 +25,7 @@ struct Bwd3Args {
     int *chain_flags, *chain_ticket;   // chained segments (no aggregate pass): carry-ready flags [group][seg], work ticket
     int64_t u_bs, u_ds, dl_bs, dl_ds, z_bs, z_ds, g_bs, g_ds, y_bs, y_ds, B_bs, B_ns, C_bs, C_ns;
     int64_t du_bs, du_ds, ddl_bs, ddl_ds, dz_bs, dz_ds;
-    int64_t dB_bs, dC_bs;          // batch strides of dB / dC (elements)
+    int64_t dB_bs, dC_bs, dB_ns, dC_ns;   // batch / state strides of dB / dC (elements)
     int B, D, L, N;
     int nseg, cps, nchunks, nx;
     int softplus;
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
                     }
                     const int tq = t0c + 8 * l + 4 * q;
                     if (tq < L) {
-                        float *dst = (which ? dC_b : dB_b) + (int64_t)n * L + (REV ? L - 4 - tq : tq);
+                        float *dst = (which ? dC_b + (int64_t)n * p.dC_ns : dB_b + (int64_t)n * p.dB_ns) + (REV ? L - 4 - tq : tq);
                         if (REV) red_add_v4(dst, v.w, v.z, v.y, v.x);
                         else red_add_v4(dst, v.x, v.y, v.z, v.w);
                     }

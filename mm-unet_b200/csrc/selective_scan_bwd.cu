@@ -31,7 +31,7 @@ struct BwdArgs {
     const float *dhin;
     int64_t u_bs, u_ds, dl_bs, dl_ds, z_bs, z_ds, g_bs, g_ds, B_bs, B_ns, C_bs, C_ns;
     int64_t du_bs, du_ds, ddl_bs, ddl_ds, dz_bs, dz_ds;
-    int64_t dB_bs, dC_bs;
+    int64_t dB_bs, dC_bs, dB_ns, dC_ns;
     int B, D, L, N, Ne;
     int nseg, cps, nchunks, nx;
     int softplus, reverse;
@@ -433,12 +433,12 @@ __global__ void __launch_bounds__(32 * RQ * NGW, AGG ? 512 / (32 * RQ * NGW) : M
                 }
                 const int t = t0 + tok, n0 = 2 * pr;
                 if (t < L) {
-                    const int64_t o = (int64_t)n0 * L + (rev ? L - 1 - t : t);
-                    atomicAdd(dB_b + o, v.x);
-                    atomicAdd(dC_b + o, v.z);
+                    const int64_t m = rev ? L - 1 - t : t;
+                    atomicAdd(dB_b + (int64_t)n0 * p.dB_ns + m, v.x);
+                    atomicAdd(dC_b + (int64_t)n0 * p.dC_ns + m, v.z);
                     if (n0 + 1 < N) {
-                        atomicAdd(dB_b + o + L, v.y);
-                        atomicAdd(dC_b + o + L, v.w);
+                        atomicAdd(dB_b + (int64_t)(n0 + 1) * p.dB_ns + m, v.y);
+                        atomicAdd(dC_b + (int64_t)(n0 + 1) * p.dC_ns + m, v.w);
                     }
                 }
             }
@@ -595,7 +595,7 @@ template <typename IN_T> bool bwd3_eligible(const mmu_scan_bwd_params *p) {
                 !row_aligned16<IN_T>(p->dz, p->dz_bs, p->dz_ds)))
         return false;
     if (reinterpret_cast<uintptr_t>(p->dB) % 16 != 0 || reinterpret_cast<uintptr_t>(p->dC) % 16 != 0) return false;
-    if ((p->dB_bs * 4) % 16 != 0 || (p->dC_bs * 4) % 16 != 0) return false;
+    if ((p->dB_bs * 4) % 16 != 0 || (p->dC_bs * 4) % 16 != 0 || (p->dB_ns * 4) % 16 != 0 || (p->dC_ns * 4) % 16 != 0) return false;
     return true;
 }
 
@@ -667,6 +667,7 @@ template <typename IN_T> int run_bwd3(const mmu_scan_bwd_params *p, cudaStream_t
     a.du_bs = p->du_bs, a.du_ds = p->du_ds, a.ddl_bs = p->ddelta_bs, a.ddl_ds = p->ddelta_ds;
     a.dz_bs = p->dz_bs, a.dz_ds = p->dz_ds;
     a.dB_bs = p->dB_bs ? p->dB_bs : (int64_t)f.dstate * f.seqlen, a.dC_bs = p->dC_bs ? p->dC_bs : (int64_t)f.dstate * f.seqlen;
+    a.dB_ns = p->dB_ns ? p->dB_ns : f.seqlen, a.dC_ns = p->dC_ns ? p->dC_ns : f.seqlen;
     a.B = f.batch, a.D = f.dim, a.L = f.seqlen, a.N = f.dstate;
     a.nseg = pl.nseg, a.cps = pl.cps, a.nchunks = pl.nchunks;
     a.nx = (f.seqlen + MMU_STATE_STRIDE - 1) / MMU_STATE_STRIDE;
@@ -728,6 +729,7 @@ template <typename IN_T> int run_bwd(const mmu_scan_bwd_params *p, cudaStream_t 
     a.du_bs = p->du_bs, a.du_ds = p->du_ds, a.ddl_bs = p->ddelta_bs, a.ddl_ds = p->ddelta_ds;
     a.dz_bs = p->dz_bs, a.dz_ds = p->dz_ds;
     a.dB_bs = p->dB_bs ? p->dB_bs : (int64_t)f.dstate * f.seqlen, a.dC_bs = p->dC_bs ? p->dC_bs : (int64_t)f.dstate * f.seqlen;
+    a.dB_ns = p->dB_ns ? p->dB_ns : f.seqlen, a.dC_ns = p->dC_ns ? p->dC_ns : f.seqlen;
     a.B = f.batch, a.D = f.dim, a.L = f.seqlen, a.N = f.dstate, a.Ne = (f.dstate + 1) & ~1;
     a.nseg = pl.nseg, a.cps = pl.cps, a.nchunks = pl.nchunks;
     a.nx = (f.seqlen + MMU_STATE_STRIDE - 1) / MMU_STATE_STRIDE;

@@ -34,7 +34,7 @@ class ScanBwdParams(C.Structure):
         + [(n, _vp) for n in ("du", "ddelta", "dz")]
         + [(n, _i64) for n in ("du_bs", "du_ds", "ddelta_bs", "ddelta_ds", "dz_bs", "dz_ds")]
         + [(n, _vp) for n in ("dA", "dB", "dC", "dD", "ddelta_bias")]
-        + [("dB_bs", _i64), ("dC_bs", _i64)]
+        + [("dB_bs", _i64), ("dC_bs", _i64), ("dB_ns", _i64), ("dC_ns", _i64)]
     )
 
 

@@ -160,8 +160,8 @@ def selective_scan_bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softp
                        du=None, ddelta=None, dz=None, dBC=None):
     """-> (du, ddelta, dA, dB, dC, dD, dz, ddelta_bias); dA/dB/dC/dD/ddelta_bias fp32.
     du / ddelta / dz may be pre-allocated views (e.g. halves of dxz, as selective_scan_interface.py:244-248).
-    dBC: optional ZERO-FILLED fp32 (batch, 2*dstate, L) buffer (or a row slice of a larger (batch, rows, L) one) that
-    receives dB in rows [0, dstate) and dC in rows [dstate, 2*dstate) (n_groups == 1 only)."""
+    dBC: optional pair (dB, dC) of ZERO-FILLED fp32 (batch, dstate, L) views with unit sequence stride and free batch / state
+    strides that receive the gradients in place (n_groups == 1 only), e.g. row slices of the x_proj gradient buffer."""
     _scan_checks(u, delta, A, B, C, D, z, delta_bias)
     y = None
     if isinstance(x, ScanStates):
@@ -188,9 +188,11 @@ def selective_scan_bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softp
         dB = acc[:nBC].view(batch, G, N, L)
         dC = acc[nBC:2 * nBC].view(batch, G, N, L)
     else:
-        if G != 1 or dBC.dtype != torch.float32 or dBC.shape != (batch, 2 * N, L) or dBC.stride(2) != 1 or dBC.stride(1) != L:
-            raise RuntimeError("selective_scan_bwd: dBC must be fp32 (batch, 2*dstate, L) with contiguous rows and n_groups == 1")
-        dB, dC = dBC[:, :N].unsqueeze(1), dBC[:, N:].unsqueeze(1)
+        dB, dC = dBC
+        for t in (dB, dC):
+            if G != 1 or t.dtype != torch.float32 or t.shape != (batch, N, L) or (t.stride(2) != 1 and L > 1):
+                raise RuntimeError("selective_scan_bwd: dBC must be two fp32 (batch, dstate, L) views with stride(-1) == 1, n_groups == 1")
+        dB, dC = dB.unsqueeze(1), dC.unsqueeze(1)
     dA = acc[2 * nBC:2 * nBC + dim * N].view(dim, N)
     dD = acc[2 * nBC + nA:2 * nBC + nA + dim] if D is not None else None
     dbias = acc[2 * nBC + nA + dim:] if delta_bias is not None else None
@@ -220,7 +222,7 @@ def selective_scan_bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softp
             p.dA = dA.data_ptr() + g * H * N * 4
             if G == 1:
                 p.dB, p.dC = dB.data_ptr(), dC.data_ptr()
-                p.dB_bs, p.dC_bs = dB.stride(0), dC.stride(0)
+                p.dB_bs, p.dC_bs, p.dB_ns, p.dC_ns = dB.stride(0), dC.stride(0), dB.stride(2), dC.stride(2)
             else:
                 dBg = torch.zeros((batch, 1, N, L), device=u.device, dtype=torch.float32)
                 dCg = torch.zeros_like(dBg)
@@ -252,14 +254,18 @@ def _conv_params(x, weight, bias, silu, reverse=False):
     return p
 
 
-def causal_conv1d_fwd(x, weight, bias=None, silu=False, reverse=False):
-    """x (B,D,L) with stride(-1)==1; weight (D,W) / bias (D) are used in fp32."""
+def causal_conv1d_fwd(x, weight, bias=None, silu=False, reverse=False, out=None):
+    """x (B,D,L) with stride(-1)==1; weight (D,W) / bias (D) are used in fp32.  `out`: optional pre-allocated (B,D,L) result
+    with unit sequence stride and free batch / channel strides."""
     if x.stride(-1) != 1 and x.shape[-1] > 1:
         x = x.contiguous()
     weight = weight.float()
     bias = None if bias is None else bias.float().contiguous()
     p = _conv_params(x, weight, bias, silu, reverse)
-    out = torch.empty_like(x, memory_format=torch.contiguous_format)
+    if out is None:
+        out = torch.empty_like(x, memory_format=torch.contiguous_format)
+    elif out.shape != x.shape or out.dtype != x.dtype or (out.stride(-1) != 1 and out.shape[-1] > 1):
+        raise RuntimeError("causal_conv1d_fwd: out must match x in shape / dtype with stride(-1) == 1")
     p.out, p.out_bs, p.out_ds = out.data_ptr(), out.stride(0), out.stride(1)
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().mmu_causal_conv1d_fwd(ct.byref(p), _stream()), "causal_conv1d_fwd")
@@ -374,11 +380,19 @@ def _autocast_dtype():
 class _InnerCore:
     """Shared forward/backward of the fused inner functions (conv -> x_proj -> dt_proj -> scan).
 
-    Layout: everything stays channel-major, (batch, channels, L) with L contiguous.  The reference flattens to
-    "(b l) d" rows for F.linear (selective_scan_interface.py:181-207), which costs a transpose copy of conv_out, two
-    transpose copies for B and C and their mirror images in the backward; here the skinny projections are batched
-    matmuls W @ X[b], so x_dbl is (batch, R + 2N, L) and B / C / the dt rows are row slices of it that the scan kernels
-    read (and, in the backward, accumulate into) in place through their batch / state strides."""
+    Layout: the tensors the skinny projections touch live channel-major ACROSS the batch, storage (channels, batch, L), so
+    that every projection and every weight gradient is ONE 2-D GEMM on a (channels, batch*L) matrix (K = batch*L for the
+    weight gradients: cuBLAS split-K instead of `batch` small K = L products), while the scan / conv kernels see the same
+    storage as (batch, channels, L) views with strides (L, batch*L, 1).  x_dbl is (R + 2N, batch, L): B, C and the dt rows are
+    row slices of it that the kernels read - and, in the backward, accumulate into - in place.  None of the reference's
+    "(b l) d" flattening (selective_scan_interface.py:181-207), i.e. no transpose copies of conv_out, B, C or their gradients."""
+
+    @staticmethod
+    def _cbl(channels, batch, L, like, dtype=None, zero=False):
+        """(channels, batch, L) storage and its (batch, channels, L) view."""
+        mk = torch.zeros if zero else torch.empty
+        st = mk((channels, batch, L), device=like.device, dtype=like.dtype if dtype is None else dtype)
+        return st, st.permute(1, 0, 2)
 
     @staticmethod
     def forward(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C, D, delta_bias,
@@ -392,51 +406,62 @@ class _InnerCore:
         N = A.shape[-1]
         if xz.stride(-1) != 1:
             xz = xz.contiguous()
+        batch, L = xz.shape[0], xz.shape[-1]
         conv_w = conv1d_weight.reshape(conv1d_weight.shape[0], -1)
+        d = conv_w.shape[0]
         x, z = xz.chunk(2, dim=1)
         conv_b = conv1d_bias.contiguous() if conv1d_bias is not None else None
-        conv_out = causal_conv1d_fwd(x, conv_w, conv_b, True, reverse=reverse)      # (b, d, l) contiguous
-        x_dbl = torch.matmul(x_proj_weight, conv_out)                               # (b, R+2N, l)   (:181)
-        delta = torch.matmul(delta_proj_weight, x_dbl[:, :R])                       # (b, d, l)      (:182)
-        Bm = x_dbl[:, R:R + N].unsqueeze(1)                                         # (b, 1, n, l) views of x_dbl
-        Cm = x_dbl[:, R + N:].unsqueeze(1)
+        conv_st, conv_out = _InnerCore._cbl(d, batch, L, xz)
+        causal_conv1d_fwd(x, conv_w, conv_b, True, reverse=reverse, out=conv_out)
+        x_dbl = torch.mm(x_proj_weight, conv_st.view(d, batch * L))                 # (R+2N, b*l)     (:181)
+        delta = torch.mm(delta_proj_weight, x_dbl[:R]).view(d, batch, L).permute(1, 0, 2)      # (b, d, l) view    (:182)
+        x3 = x_dbl.view(-1, batch, L)
+        Bm = x3[R:R + N].permute(1, 0, 2).unsqueeze(1)                              # (b, 1, n, l) views of x_dbl
+        Cm = x3[R + N:].permute(1, 0, 2).unsqueeze(1)
         D = D.contiguous() if D is not None else None
         out_z, xs, _ = selective_scan_fwd(conv_out, delta, A, Bm, Cm, D, z, delta_bias, delta_softplus, reverse=reverse)
-        saved = (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, conv_out, delta, A, None, None, D, delta_bias,
+        saved = (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, conv_st, delta, A, None, None, D, delta_bias,
                  xs.x, xs.y)
         return out_z, saved
 
     @staticmethod
-    def project_grads(x_dbl, x_proj_weight, delta_proj_weight, conv_out, ddelta, dBC, dconv_out):
-        """Backward of the two skinny projections in the channel-major layout (selective_scan_interface.py:256-277).
-        ddelta (b,d,l), dBC fp32 (b,2N,l), dconv_out (b,d,l) = the scan's du.  -> (dconv_out total, dx_proj_w, ddt_proj_w)."""
+    def project_grads(x_dbl, x_proj_weight, delta_proj_weight, conv_st, ddelta_st, dBC_st, dconv_st):
+        """Backward of the two skinny projections (selective_scan_interface.py:256-277) on (channels, batch*L) matrices.
+        ddelta_st (d,b,l), dBC_st fp32 (2N,b,l), dconv_st (d,b,l) = the scan's du.  -> (dconv_out (b,d,l) view, dx_proj_w, ddt_proj_w)."""
         R = delta_proj_weight.shape[1]
+        d, batch, L = conv_st.shape
+        ddelta2 = ddelta_st.view(d, batch * L)
         dx_dbl = torch.empty_like(x_dbl)
-        dx_dbl[:, R:] = dBC                                                          # one cast copy for dB and dC
-        dx_dbl[:, :R] = torch.matmul(delta_proj_weight.t(), ddelta)                  # (b, R, l)
-        ddt_proj_w = torch.bmm(ddelta, x_dbl[:, :R].transpose(1, 2)).sum(0)          # (d, R)
-        dx_proj_w = torch.bmm(dx_dbl, conv_out.transpose(1, 2)).sum(0)               # (R+2N, d)
-        dconv_out = torch.baddbmm(dconv_out, x_proj_weight.t().unsqueeze(0).expand(x_dbl.shape[0], -1, -1), dx_dbl)
-        return dconv_out, dx_proj_w, ddt_proj_w
+        dx_dbl[R:] = dBC_st.view(-1, batch * L)                                      # one cast copy for dB and dC
+        torch.mm(delta_proj_weight.t(), ddelta2, out=dx_dbl[:R])                     # (R, b*l)
+        ddt_proj_w = torch.mm(ddelta2, x_dbl[:R].t())                                # (d, R), K = b*l
+        dx_proj_w = torch.mm(dx_dbl, conv_st.view(d, batch * L).t())                 # (R+2N, d), K = b*l
+        dconv = torch.addmm(dconv_st.view(d, batch * L), x_proj_weight.t(), dx_dbl)  # (d, b*l)
+        return dconv.view(d, batch, L).permute(1, 0, 2), dx_proj_w, ddt_proj_w
 
     @staticmethod
     def backward(saved, dout_y, delta_softplus, reverse=False):
         """dout_y: (b, d, l).  Returns (dxz, dconv_w (d,1,w), dconv_b, dx_proj_w, ddt_proj_w, dA, dD, ddelta_bias)."""
-        (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, conv_out, delta, A, _, _, D, delta_bias, xs_x, xs_y) = saved
+        (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, conv_st, delta, A, _, _, D, delta_bias, xs_x, xs_y) = saved
         xs = ScanStates(xs_x, xs_y)
-        L = xz.shape[-1]
         R = delta_proj_weight.shape[1]
         N = A.shape[-1]
+        d, batch, L = conv_st.shape
         x, z = xz.chunk(2, dim=1)
-        batch = x.shape[0]
-        Bm, Cm = x_dbl[:, R:R + N].unsqueeze(1), x_dbl[:, R + N:].unsqueeze(1)
+        conv_out = conv_st.permute(1, 0, 2)
+        x3 = x_dbl.view(-1, batch, L)
+        Bm, Cm = x3[R:R + N].permute(1, 0, 2).unsqueeze(1), x3[R + N:].permute(1, 0, 2).unsqueeze(1)
         dxz = torch.empty_like(xz)
         dx, dz = dxz.chunk(2, dim=1)
-        dBC = torch.zeros((batch, 2 * N, L), device=xz.device, dtype=torch.float32)
-        dconv_out, ddelta, dA, _, _, dD, dz, ddelta_bias = selective_scan_bwd(
-            conv_out, delta, A, Bm, Cm, D, z, delta_bias, dout_y, xs, delta_softplus, reverse=reverse, dz=dz, dBC=dBC)
-        dconv_out, dx_proj_w, ddt_proj_w = _InnerCore.project_grads(x_dbl, x_proj_weight, delta_proj_weight, conv_out, ddelta,
-                                                                    dBC, dconv_out)
+        du_st, du = _InnerCore._cbl(d, batch, L, xz)
+        ddl_st, ddl = _InnerCore._cbl(d, batch, L, xz)
+        dBC_st, _ = _InnerCore._cbl(2 * N, batch, L, xz, dtype=torch.float32, zero=True)
+        dBC = (dBC_st[:N].permute(1, 0, 2), dBC_st[N:].permute(1, 0, 2))
+        _, _, dA, _, _, dD, dz, ddelta_bias = selective_scan_bwd(
+            conv_out, delta, A, Bm, Cm, D, z, delta_bias, dout_y, xs, delta_softplus, reverse=reverse, dz=dz, dBC=dBC,
+            du=du, ddelta=ddl)
+        dconv_out, dx_proj_w, ddt_proj_w = _InnerCore.project_grads(x_dbl, x_proj_weight, delta_proj_weight, conv_st, ddl_st,
+                                                                    dBC_st, du_st)
         _, dconv_w, dconv_b = causal_conv1d_bwd(x, conv_w, conv_b, dconv_out, True, dx=dx, reverse=reverse)
         return dxz, dconv_w.unsqueeze(1), dconv_b, dx_proj_w, ddt_proj_w, dA, dD, ddelta_bias
 
@@ -543,11 +568,13 @@ class BiMambaInnerFn(torch.autograd.Function):
             x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias)
         out_f, saved = _InnerCore.forward(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C, D,
                                           delta_bias, B_proj_bias, C_proj_bias, delta_softplus)
-        (xz_, conv_w, conv_b, x_dbl, xw, dw, conv_out, delta, A_, _, _, D_, db_, _xs_fx, _xs_fy) = saved
+        (xz_, conv_w, conv_b, x_dbl, xw, dw, conv_st, delta, A_, _, _, D_, db_, _xs_fx, _xs_fy) = saved
         R, N = dw.shape[1], A.shape[-1]
-        Bm, Cm = x_dbl[:, R:R + N].unsqueeze(1), x_dbl[:, R + N:].unsqueeze(1)
+        d, batch, L = conv_st.shape
+        x3 = x_dbl.view(-1, batch, L)
+        Bm, Cm = x3[R:R + N].permute(1, 0, 2).unsqueeze(1), x3[R + N:].permute(1, 0, 2).unsqueeze(1)
         z = xz_.chunk(2, dim=1)[1]
-        out_b, xs_b, _ = selective_scan_fwd(conv_out, delta, A_b, Bm, Cm, D_, z, db_, delta_softplus, reverse=True)
+        out_b, xs_b, _ = selective_scan_fwd(conv_st.permute(1, 0, 2), delta, A_b, Bm, Cm, D_, z, db_, delta_softplus, reverse=True)
         out_z = out_f + out_b            # out_b is already stored in un-flipped positions
         ctx.delta_softplus = delta_softplus
         ctx.out_proj_bias_is_None = out_proj_bias is None
@@ -563,25 +590,32 @@ class BiMambaInnerFn(torch.autograd.Function):
         saved = tuple(next(it) if m else None for m in ctx.mask)
         out_proj_weight, out_z, A_b, xs_bx, xs_by = saved[-5:]
         core = saved[:-5]
-        (xz, conv_w, conv_b, x_dbl, xw, dw, conv_out, delta, A, _, _, D, dbias, xs_fx, xs_fy) = core
+        (xz, conv_w, conv_b, x_dbl, xw, dw, conv_st, delta, A, _, _, D, dbias, xs_fx, xs_fy) = core
         xs_b, xs_f = ScanStates(xs_bx, xs_by), ScanStates(xs_fx, xs_fy)
-        batch, L = xz.shape[0], xz.shape[-1]
         R, N = dw.shape[1], A.shape[-1]
-        Bm, Cm = x_dbl[:, R:R + N].unsqueeze(1), x_dbl[:, R + N:].unsqueeze(1)
+        d, batch, L = conv_st.shape
+        conv_out = conv_st.permute(1, 0, 2)
+        x3 = x_dbl.view(-1, batch, L)
+        Bm, Cm = x3[R:R + N].permute(1, 0, 2).unsqueeze(1), x3[R + N:].permute(1, 0, 2).unsqueeze(1)
         dout_y, dout_proj_w, dout_proj_b = _out_proj_bwd(dout, out_z, out_proj_weight, not ctx.out_proj_bias_is_None)
         x, z = xz.chunk(2, dim=1)
         # both directions accumulate dB / dC into the same buffer; the other gradients are summed afterwards
-        dBC = torch.zeros((batch, 2 * N, L), device=xz.device, dtype=torch.float32)
-        du_b, ddl_b, dA_b, _, _, dD_b, dz_b, ddb_b = selective_scan_bwd(
-            conv_out, delta, A_b, Bm, Cm, D, z, dbias, dout_y, xs_b, ctx.delta_softplus, reverse=True, dBC=dBC)
+        dBC_st, _ = _InnerCore._cbl(2 * N, batch, L, xz, dtype=torch.float32, zero=True)
+        dBC = (dBC_st[:N].permute(1, 0, 2), dBC_st[N:].permute(1, 0, 2))
+        dub_st, dub = _InnerCore._cbl(d, batch, L, xz)
+        ddb_st, ddb_ = _InnerCore._cbl(d, batch, L, xz)
+        _, _, dA_b, _, _, dD_b, dz_b, ddb_b = selective_scan_bwd(
+            conv_out, delta, A_b, Bm, Cm, D, z, dbias, dout_y, xs_b, ctx.delta_softplus, reverse=True, dBC=dBC, du=dub, ddelta=ddb_)
         dxz = torch.empty_like(xz)
         dx, dz = dxz.chunk(2, dim=1)
-        du_f, ddl_f, dA, _, _, dD_f, dz, ddb_f = selective_scan_bwd(
-            conv_out, delta, A, Bm, Cm, D, z, dbias, dout_y, xs_f, ctx.delta_softplus, dz=dz, dBC=dBC)
+        duf_st, duf = _InnerCore._cbl(d, batch, L, xz)
+        ddf_st, ddf = _InnerCore._cbl(d, batch, L, xz)
+        _, _, dA, _, _, dD_f, dz, ddb_f = selective_scan_bwd(
+            conv_out, delta, A, Bm, Cm, D, z, dbias, dout_y, xs_f, ctx.delta_softplus, dz=dz, dBC=dBC, du=duf, ddelta=ddf)
         dz += dz_b
         dD = None if D is None else dD_f + dD_b
         ddb = None if dbias is None else ddb_f + ddb_b
-        dconv_out, dxw, ddw = _InnerCore.project_grads(x_dbl, xw, dw, conv_out, ddl_f + ddl_b, dBC, du_f + du_b)
+        dconv_out, dxw, ddw = _InnerCore.project_grads(x_dbl, xw, dw, conv_st, ddf_st + ddb_st, dBC_st, duf_st + dub_st)
         _, dcw, dcb = causal_conv1d_bwd(x, conv_w, conv_b, dconv_out, True, dx=dx)
         return (dxz, dcw.unsqueeze(1), dcb, dxw, ddw, dout_proj_w, dout_proj_b, dA, dA_b, None, None, dD, ddb,
                 None, None, None, None)
