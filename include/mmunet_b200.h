@@ -49,8 +49,8 @@ enum mmu_error {
     MMU_ERR_WORKSPACE = -3     /* workspace too small */
 };
 
-/* x[b][d][k][n] holds the scan state h after token (k+1)*MMU_STATE_STRIDE-1 (fp32).  It plays the role of
- * the reference's `x` / scan_intermediates tensor (selective_scan.cpp:313) at a finer grain. */
+/* x[b][d][k][n] holds the scan state h after token (k+1)*stride-1 (fp32), stride = x_stride (default MMU_STATE_STRIDE).
+ * It plays the role of the reference's `x` / scan_intermediates tensor (selective_scan.cpp:313) at a finer grain. */
 #define MMU_STATE_STRIDE 64
 
 /* ---------------------------------------------------------------------------------------------
@@ -61,7 +61,7 @@ enum mmu_error {
  *   D, delta_bias   : (dim) fp32 or NULL;  z / out_z NULL when there is no gate
  *   out             : y*silu(z) when z != NULL, else y.  (The reference's separate pre-gate `out`
  *                     tensor is not produced: the backward recomputes it.)
- *   x               : (batch, dim, ceil(seqlen/MMU_STATE_STRIDE), dstate) fp32, contiguous; NULL allowed
+ *   x               : (batch, dim, ceil(seqlen/x_stride), dstate) fp32, contiguous; NULL allowed
  *                     for inference (no backward).
  *   last_state      : (batch, dim, dstate) fp32 or NULL
  *   workspace       : mmu_selective_scan_fwd_workspace() bytes (may be NULL when that is 0)
@@ -71,7 +71,7 @@ typedef struct mmu_scan_fwd_params {
     int32_t dtype;           /* enum mmu_dtype */
     int32_t delta_softplus;  /* 0/1 */
     int32_t reverse;         /* 0: scan l = 0..L-1.  1: scan l = L-1..0 (fused flip, mamba_simple.py:230) */
-    int32_t reserved;
+    int32_t x_stride;        /* tokens between saved states in x; 0 = MMU_STATE_STRIDE.  Use mmu_scan_state_stride() */
     const void *u, *delta, *z, *B, *C;
     const float *A, *D, *delta_bias;
     void *out;
@@ -90,6 +90,10 @@ typedef struct mmu_scan_fwd_params {
 
 size_t mmu_selective_scan_fwd_workspace(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate);
 int mmu_selective_scan_fwd(const mmu_scan_fwd_params *p, void *stream);
+/* Tokens between the states the backward wants in x for this problem: 8 for the wide (rows-in-lanes) kernels
+ * (dim >= 64, dstate <= 16, seqlen % 8 == 0, fp32 / bf16), MMU_STATE_STRIDE otherwise.  Pass it as x_stride to BOTH passes
+ * and size x as (batch, dim, ceil(seqlen / stride), dstate). */
+int32_t mmu_scan_state_stride(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate, int32_t dtype);
 
 /* ---------------------------------------------------------------------------------------------
  * selective scan backward.  replaces selective_scan_cuda.bwd  (selective_scan.cpp:338-492)

@@ -7,7 +7,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --expt-r
 mkdir -p build
 pids=()
 for f in capi selective_scan_fwd selective_scan_bwd causal_conv1d scan_order snake_sample group_norm; do
-  if [ ! -f build/$f.o ] || [ $f.cu -nt build/$f.o ] || [ common.cuh -nt build/$f.o ] || [ scan_tiles.cuh -nt build/$f.o ] || [ scan3.cuh -nt build/$f.o ] || [ scan3_fwd.cuh -nt build/$f.o ] || [ scan3_bwd.cuh -nt build/$f.o ] || [ ../../include/mmunet_b200.h -nt build/$f.o ]; then
+  if [ ! -f build/$f.o ] || [ $f.cu -nt build/$f.o ] || [ common.cuh -nt build/$f.o ] || [ scan_tiles.cuh -nt build/$f.o ] || [ scan3.cuh -nt build/$f.o ] || [ scan3_fwd.cuh -nt build/$f.o ] || [ scan3_bwd.cuh -nt build/$f.o ] || [ scan4.cuh -nt build/$f.o ] || [ scan4_bwd.cuh -nt build/$f.o ] || [ ../../include/mmunet_b200.h -nt build/$f.o ]; then
     nvcc $FLAGS -c $f.cu -o build/$f.o &
     pids+=($!)
   fi

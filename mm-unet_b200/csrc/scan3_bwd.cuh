@@ -578,7 +578,7 @@ __global__ void scan3_bwd_chain_kernel(const float *__restrict__ A, const float 
     float carry = 0.f;
     for (int s = nseg - 1; s >= 0; --s) {
         ein[(bd * nseg + s) * 16 + n] = carry;
-        carry = fmaf(ex2(a2 * seg_dsum[bd * nseg + s]), carry, seg_E[(bd * nseg + s) * 16 + n]);
+        if (s > 0) carry = fmaf(ex2(a2 * seg_dsum[bd * nseg + s]), carry, seg_E[(bd * nseg + s) * 16 + n]);
     }
 }
 

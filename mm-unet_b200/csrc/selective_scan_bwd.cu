@@ -18,6 +18,7 @@
 #include <cstdlib>
 
 #include "scan3_bwd.cuh"
+#include "scan4_bwd.cuh"
 #include "scan_tiles.cuh"
 
 namespace mmu {
@@ -709,11 +710,103 @@ template <typename IN_T> int run_bwd3(const mmu_scan_bwd_params *p, cudaStream_t
     return dispatch_bwd3<IN_T, false>(a, pl.W, rev, st);
 }
 
+
+// ---- v4 host side (scan4_bwd.cuh): wide problems, rows in lanes; needs x saved every 8 tokens ---------------------------------
+struct Bwd4Plan {
+    int nseg, sps, nstage, nrg;
+};
+
+Bwd4Plan plan_bwd4(int B, int D, int L) {
+    Bwd4Plan pl;
+    pl.nstage = L / 8;
+    pl.nrg = (D + kS4Rows - 1) / kS4Rows;
+    const int wps = B * pl.nrg;                                          // warps per segment
+    int nseg = (148 * env_int("MMU_V4_BWD_WPSM", 16) + wps - 1) / wps;   // about two waves of the 8 resident warps
+    nseg = std::min(nseg, std::max(1, pl.nstage / 4));                   // at least 32 tokens per segment
+    nseg = env_int("MMU_BWD_NSEG", nseg);
+    nseg = std::max(1, std::min(nseg, std::min(pl.nstage, kS4MaxSeg)));
+    pl.sps = (pl.nstage + nseg - 1) / nseg;
+    pl.nseg = (pl.nstage + pl.sps - 1) / pl.sps;
+    return pl;
+}
+
+template <typename IN_T> bool bwd4_eligible(const mmu_scan_bwd_params *p) {
+    const mmu_scan_fwd_params &f = p->f;
+    if (env_int("MMU_SCAN_V", 4) < 4 || env_int("MMU_BWD_V", 4) < 4) return false;
+    if (f.x_stride != 8 || f.dim < env_int("MMU_V4_MIN_DIM", 64)) return false;
+    if (f.seqlen > 8 && !f.x) return false;
+    return bwd3_eligible<IN_T>(p);
+}
+
+template <typename IN_T> int run_bwd4(const mmu_scan_bwd_params *p, cudaStream_t st) {
+    const mmu_scan_fwd_params &f = p->f;
+    const Bwd4Plan pl = plan_bwd4(f.batch, f.dim, f.seqlen);
+    Bwd4Args a{};
+    a.u = f.u, a.delta = f.delta, a.z = f.z, a.dout = p->dout, a.ysave = f.y, a.Bm = f.B, a.Cm = f.C;
+    a.A = f.A, a.Dv = f.D, a.dbias = f.delta_bias, a.x = f.x;
+    a.du = p->du, a.ddelta = p->ddelta, a.dz = p->dz;
+    a.dA = p->dA, a.dB = p->dB, a.dC = p->dC, a.dD = p->dD, a.ddbias = p->ddelta_bias;
+    a.u_bs = f.u_bs, a.u_ds = f.u_ds, a.dl_bs = f.delta_bs, a.dl_ds = f.delta_ds, a.z_bs = f.z_bs, a.z_ds = f.z_ds;
+    a.g_bs = p->dout_bs, a.g_ds = p->dout_ds, a.y_bs = f.y_bs, a.y_ds = f.y_ds;
+    a.B_bs = f.B_bs, a.B_ns = f.B_ns, a.C_bs = f.C_bs, a.C_ns = f.C_ns;
+    a.du_bs = p->du_bs, a.du_ds = p->du_ds, a.ddl_bs = p->ddelta_bs, a.ddl_ds = p->ddelta_ds;
+    a.dz_bs = p->dz_bs, a.dz_ds = p->dz_ds;
+    a.dB_bs = p->dB_bs ? p->dB_bs : (int64_t)f.dstate * f.seqlen, a.dC_bs = p->dC_bs ? p->dC_bs : (int64_t)f.dstate * f.seqlen;
+    a.dB_ns = p->dB_ns ? p->dB_ns : f.seqlen, a.dC_ns = p->dC_ns ? p->dC_ns : f.seqlen;
+    a.B = f.batch, a.D = f.dim, a.L = f.seqlen, a.N = f.dstate;
+    a.nseg = pl.nseg, a.sps = pl.sps, a.nstage = pl.nstage, a.nrg = pl.nrg;
+    a.nx = (f.seqlen + 7) / 8;
+    a.softplus = f.delta_softplus;
+    const bool rev = f.reverse != 0;
+    if (pl.nseg > 1) {
+        const size_t n_state = (size_t)a.B * a.D * pl.nseg * 16, n_row = (size_t)a.B * a.D * pl.nseg;
+        const size_t need = 2 * align256(n_state * 4) + 2 * align256(n_row * 4);
+        if (f.workspace == nullptr || f.workspace_bytes < need)
+            return set_error(MMU_ERR_WORKSPACE, "selective_scan_bwd: workspace %zu < %zu", f.workspace_bytes, need);
+        char *w = static_cast<char *>(f.workspace);
+        a.seg_E = reinterpret_cast<float *>(w);
+        float *ein = reinterpret_cast<float *>(w + align256(n_state * 4));
+        a.seg_dsum = reinterpret_cast<float *>(w + 2 * align256(n_state * 4));
+        a.ein = nullptr;
+        a.nitems = a.B * a.nrg * (pl.nseg - 1);
+        {
+            using Sm = S4Fwd<IN_T, 3>;
+            const size_t smem = (size_t)kS4W * Sm::kWarpBytes;
+            auto k = rev ? scan4_bwd_agg_kernel<IN_T, true> : scan4_bwd_agg_kernel<IN_T, false>;
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k<<<(a.nitems + kS4W - 1) / kS4W, 32 * kS4W, smem, st>>>(a);
+            count_launch();
+            int rc = check_launch("selective_scan_bwd(v4 aggregates)");
+            if (rc) return rc;
+        }
+        const int64_t tot = (int64_t)a.B * a.D * 16;
+        scan3_bwd_chain_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(a.A, a.seg_E, a.seg_dsum, ein, a.B, a.D, a.N, pl.nseg);
+        count_launch();
+        int rc = check_launch("scan3_bwd_chain");
+        if (rc) return rc;
+        a.ein = ein;
+    }
+    a.nitems = a.B * a.nrg * pl.nseg;
+    using Sm = S4Bwd<IN_T>;
+    const size_t smem = (size_t)kS4W * Sm::kWarpBytes;
+    auto k = rev ? scan4_bwd_kernel<IN_T, true> : scan4_bwd_kernel<IN_T, false>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<(a.nitems + kS4W - 1) / kS4W, 32 * kS4W, smem, st>>>(a);
+    count_launch();
+    return check_launch("selective_scan_bwd(v4)");
+}
+
 template <typename IN_T> struct HasV3 { static constexpr bool value = false; };
 template <> struct HasV3<float> { static constexpr bool value = true; };
 template <> struct HasV3<__nv_bfloat16> { static constexpr bool value = true; };
 
 template <typename IN_T> int run_bwd(const mmu_scan_bwd_params *p, cudaStream_t st) {
+    if constexpr (HasV3<IN_T>::value) {
+        if (bwd4_eligible<IN_T>(p)) return run_bwd4<IN_T>(p, st);
+    }
+    if (p->f.x_stride != 0 && p->f.x_stride != MMU_STATE_STRIDE)
+        return set_error(MMU_ERR_UNSUPPORTED, "selective_scan_bwd: x_stride %d needs the wide (v4) kernels (dim >= 64, dstate <= 16, "
+                         "seqlen %% 8 == 0, 16-byte aligned rows)", p->f.x_stride);
     if constexpr (HasV3<IN_T>::value) {
         if (bwd3_eligible<IN_T>(p)) return run_bwd3<IN_T>(p, st);
     }
@@ -780,7 +873,21 @@ extern "C" size_t mmu_selective_scan_bwd_workspace(int32_t batch, int32_t dim, i
     const int nchunks = (seqlen + 63) / 64;
     const size_t nseg = (size_t)std::max(1, std::min(nchunks, std::max(64, mmu::env_int("MMU_BWD_NSEG", 1))));
     const size_t n_state = (size_t)batch * dim * nseg * Ne, n_row = (size_t)batch * dim * nseg;
-    return 2 * mmu::align256(n_state * 4) + 2 * mmu::align256(n_row * 4);
+    size_t need = 2 * mmu::align256(n_state * 4) + 2 * mmu::align256(n_row * 4);
+    if (dstate <= 16 && seqlen % 8 == 0 && seqlen >= 8) {   // the wide (v4) plan
+        const mmu::Bwd4Plan pl = mmu::plan_bwd4(batch, dim, seqlen);
+        const size_t n4 = (size_t)batch * dim * pl.nseg * 16, r4 = (size_t)batch * dim * pl.nseg;
+        need = std::max(need, 2 * mmu::align256(n4 * 4) + 2 * mmu::align256(r4 * 4));
+    }
+    return need;
+}
+
+extern "C" int32_t mmu_scan_state_stride(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate, int32_t dtype) {
+    using namespace mmu;
+    (void)batch;
+    const bool v4 = env_int("MMU_SCAN_V", 4) >= 4 && env_int("MMU_BWD_V", 4) >= 4 && dim >= env_int("MMU_V4_MIN_DIM", 64) &&
+                    dstate <= 16 && seqlen % 8 == 0 && (dtype == MMU_F32 || dtype == MMU_BF16);
+    return v4 ? 8 : MMU_STATE_STRIDE;
 }
 
 extern "C" int mmu_selective_scan_bwd(const mmu_scan_bwd_params *p, void *stream) {
@@ -792,7 +899,7 @@ extern "C" int mmu_selective_scan_bwd(const mmu_scan_bwd_params *p, void *stream
     if (f.dstate > 256) return set_error(MMU_ERR_INVALID, "selective_scan only supports state dimension <= 256");
     if (!f.u || !f.delta || !f.A || !f.B || !f.C || !p->dout || !p->du || !p->ddelta || !p->dA || !p->dB || !p->dC)
         return set_error(MMU_ERR_INVALID, "selective_scan_bwd: null tensor pointer");
-    if (f.seqlen > MMU_STATE_STRIDE && !f.x)
+    if (f.seqlen > (f.x_stride ? f.x_stride : MMU_STATE_STRIDE) && !f.x)
         return set_error(MMU_ERR_INVALID, "selective_scan_bwd: x (saved states from the forward) is required");
     if ((f.z != nullptr) != (p->dz != nullptr)) return set_error(MMU_ERR_INVALID, "selective_scan_bwd: dz must be given iff z is");
     if ((f.D != nullptr && !p->dD) || (f.delta_bias != nullptr && !p->ddelta_bias))

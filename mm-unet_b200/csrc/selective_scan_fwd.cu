@@ -19,6 +19,7 @@
 #include <cstdlib>
 
 #include "scan3_fwd.cuh"
+#include "scan4.cuh"
 #include "scan_tiles.cuh"
 
 namespace mmu {
@@ -329,7 +330,7 @@ __global__ void scan_fwd_chain_kernel(const float *__restrict__ A, const float *
     float h = 0.f;
     for (int s = 0; s < nseg; ++s) {
         hin[(bd * nseg + s) * Ne + n] = h;
-        h = fmaf(ex2(a2 * seg_dsum[bd * nseg + s]), h, seg_hend[(bd * nseg + s) * Ne + n]);
+        if (s + 1 < nseg) h = fmaf(ex2(a2 * seg_dsum[bd * nseg + s]), h, seg_hend[(bd * nseg + s) * Ne + n]);
     }
 }
 
@@ -509,14 +510,98 @@ template <typename IN_T> int run_fwd3(const mmu_scan_fwd_params *p, cudaStream_t
     return dispatch_fwd3<IN_T, false>(a, pl, rev, st);
 }
 
+
+// ---- v4 host side (scan4.cuh): wide problems, rows in lanes ------------------------------------------------------------------
+struct Fwd4Plan {
+    int nseg, sps, nstage, nrg;
+};
+
+Fwd4Plan plan_fwd4(int B, int D, int L) {
+    Fwd4Plan pl;
+    pl.nstage = L / 8;
+    pl.nrg = (D + kS4Rows - 1) / kS4Rows;
+    const int wps = B * pl.nrg;                                          // warps per segment
+    int nseg = (148 * env_int("MMU_V4_WPSM", 12) + wps - 1) / wps;       // about one wave of resident warps
+    nseg = std::min(nseg, std::max(1, pl.nstage / 4));                   // at least 32 tokens per segment
+    nseg = env_int("MMU_FWD_NSEG", nseg);
+    nseg = std::max(1, std::min(nseg, std::min(pl.nstage, kS4MaxSeg)));
+    pl.sps = (pl.nstage + nseg - 1) / nseg;
+    pl.nseg = (pl.nstage + pl.sps - 1) / pl.sps;
+    return pl;
+}
+
+template <typename IN_T> bool fwd4_eligible(const mmu_scan_fwd_params *p) {
+    if (env_int("MMU_SCAN_V", 4) < 4) return false;
+    if (p->dim < env_int("MMU_V4_MIN_DIM", 64)) return false;
+    const int xs = p->x_stride ? p->x_stride : MMU_STATE_STRIDE;
+    if (xs != 8 && xs != 64) return false;
+    if (p->x && p->dstate == 16 && reinterpret_cast<uintptr_t>(p->x) % 16 != 0) return false;
+    return fwd3_eligible<IN_T>(p);
+}
+
+template <typename IN_T, bool REV, bool AGG> int launch_fwd4(const Fwd4Args &a, cudaStream_t st) {
+    using Sm = S4Fwd<IN_T, AGG ? 2 : 3>;
+    const size_t smem = (size_t)kS4W * Sm::kWarpBytes;
+    auto k = scan4_fwd_kernel<IN_T, REV, AGG>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<(a.nitems + kS4W - 1) / kS4W, 32 * kS4W, smem, st>>>(a);
+    count_launch();
+    return check_launch("selective_scan_fwd(v4)");
+}
+
+template <typename IN_T> int run_fwd4(const mmu_scan_fwd_params *p, cudaStream_t st) {
+    const Fwd4Plan pl = plan_fwd4(p->batch, p->dim, p->seqlen);
+    Fwd4Args a{};
+    a.u = p->u, a.delta = p->delta, a.z = p->z, a.Bm = p->B, a.Cm = p->C;
+    a.A = p->A, a.Dv = p->D, a.dbias = p->delta_bias;
+    a.out = p->out, a.ysave = p->z ? p->y : nullptr, a.x = p->x, a.last_state = p->last_state;
+    a.u_bs = p->u_bs, a.u_ds = p->u_ds, a.dl_bs = p->delta_bs, a.dl_ds = p->delta_ds;
+    a.z_bs = p->z_bs, a.z_ds = p->z_ds, a.o_bs = p->out_bs, a.o_ds = p->out_ds, a.y_bs = p->y_bs, a.y_ds = p->y_ds;
+    a.B_bs = p->B_bs, a.B_ns = p->B_ns, a.C_bs = p->C_bs, a.C_ns = p->C_ns;
+    a.B = p->batch, a.D = p->dim, a.L = p->seqlen, a.N = p->dstate;
+    a.nseg = pl.nseg, a.sps = pl.sps, a.nstage = pl.nstage, a.nrg = pl.nrg;
+    const int xs = p->x_stride ? p->x_stride : MMU_STATE_STRIDE;
+    a.xs8 = xs / 8, a.nx = (p->seqlen + xs - 1) / xs;
+    a.softplus = p->delta_softplus;
+    const bool rev = p->reverse != 0;
+    if (pl.nseg > 1) {
+        const size_t n_state = (size_t)a.B * a.D * pl.nseg * 16;
+        const size_t need = 2 * align256(n_state * 4) + align256((size_t)a.B * a.D * pl.nseg * 4);
+        if (p->workspace == nullptr || p->workspace_bytes < need)
+            return set_error(MMU_ERR_WORKSPACE, "selective_scan_fwd: workspace %zu < %zu", p->workspace_bytes, need);
+        char *w = static_cast<char *>(p->workspace);
+        a.seg_hend = reinterpret_cast<float *>(w);
+        float *hin = reinterpret_cast<float *>(w + align256(n_state * 4));
+        a.seg_dsum = reinterpret_cast<float *>(w + 2 * align256(n_state * 4));
+        a.hin = nullptr;
+        a.nitems = a.B * a.nrg * (pl.nseg - 1);                          // the last segment's aggregate is never used
+        int rc = rev ? launch_fwd4<IN_T, true, true>(a, st) : launch_fwd4<IN_T, false, true>(a, st);
+        if (rc) return rc;
+        const int64_t tot = (int64_t)a.B * a.D * 16;
+        scan_fwd_chain_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(a.A, a.seg_hend, a.seg_dsum, hin, a.B, a.D,
+                                                                             a.N, 16, pl.nseg);
+        count_launch();
+        rc = check_launch("scan_fwd_chain");
+        if (rc) return rc;
+        a.hin = hin;
+    }
+    a.nitems = a.B * a.nrg * pl.nseg;
+    return rev ? launch_fwd4<IN_T, true, false>(a, st) : launch_fwd4<IN_T, false, false>(a, st);
+}
+
 template <typename IN_T> struct HasV3 { static constexpr bool value = false; };
 template <> struct HasV3<float> { static constexpr bool value = true; };
 template <> struct HasV3<__nv_bfloat16> { static constexpr bool value = true; };
 
 template <typename IN_T> int run_fwd(const mmu_scan_fwd_params *p, cudaStream_t st) {
     if constexpr (HasV3<IN_T>::value) {
+        if (fwd4_eligible<IN_T>(p)) return run_fwd4<IN_T>(p, st);
+        if (p->x_stride != 0 && p->x_stride != MMU_STATE_STRIDE)
+            return set_error(MMU_ERR_UNSUPPORTED, "selective_scan_fwd: x_stride %d is only supported by the wide (v4) kernels", p->x_stride);
         if (fwd3_eligible<IN_T>(p)) return run_fwd3<IN_T>(p, st);
     }
+    if (p->x_stride != 0 && p->x_stride != MMU_STATE_STRIDE)
+        return set_error(MMU_ERR_UNSUPPORTED, "selective_scan_fwd: x_stride %d is only supported by the wide (v4) kernels", p->x_stride);
     const FwdPlan pl = plan_fwd(p->batch, p->dim, p->seqlen, p->dstate);
     FwdArgs a{};
     a.u = p->u, a.delta = p->delta, a.z = p->z, a.Bm = p->B, a.Cm = p->C;
@@ -572,7 +657,13 @@ extern "C" size_t mmu_selective_scan_fwd_workspace(int32_t batch, int32_t dim, i
     const int nchunks = (seqlen + 63) / 64;
     const size_t nseg = (size_t)std::max(1, std::min(nchunks, std::max(64, mmu::env_int("MMU_FWD_NSEG", 1))));
     const size_t n_state = (size_t)batch * dim * nseg * Ne;
-    return 2 * mmu::align256(n_state * 4) + mmu::align256((size_t)batch * dim * nseg * 4);
+    size_t need = 2 * mmu::align256(n_state * 4) + mmu::align256((size_t)batch * dim * nseg * 4);
+    if (dstate <= 16 && seqlen % 8 == 0 && seqlen >= 8) {   // the wide (v4) plan
+        const mmu::Fwd4Plan pl = mmu::plan_fwd4(batch, dim, seqlen);
+        const size_t n4 = (size_t)batch * dim * pl.nseg * 16;
+        need = std::max(need, 2 * mmu::align256(n4 * 4) + mmu::align256((size_t)batch * dim * pl.nseg * 4));
+    }
+    return need;
 }
 
 extern "C" int mmu_selective_scan_fwd(const mmu_scan_fwd_params *p, void *stream) {

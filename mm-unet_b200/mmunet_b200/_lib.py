@@ -20,7 +20,7 @@ _vp, _i32, _i64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
 
 class ScanFwdParams(C.Structure):
     _fields_ = (
-        [(n, _i32) for n in ("batch", "dim", "seqlen", "dstate", "dtype", "delta_softplus", "reverse", "reserved")]
+        [(n, _i32) for n in ("batch", "dim", "seqlen", "dstate", "dtype", "delta_softplus", "reverse", "x_stride")]
         + [(n, _vp) for n in ("u", "delta", "z", "B", "C", "A", "D", "delta_bias", "out", "x", "last_state")]
         + [(n, _i64) for n in ("u_bs", "u_ds", "delta_bs", "delta_ds", "z_bs", "z_ds", "out_bs", "out_ds",
                                "B_bs", "B_ns", "C_bs", "C_ns")]
@@ -51,7 +51,7 @@ class ConvParams(C.Structure):
 EXPORTS = (
     "mmu_version", "mmu_last_error", "mmu_launch_count",
     "mmu_selective_scan_fwd_workspace", "mmu_selective_scan_fwd",
-    "mmu_selective_scan_bwd_workspace", "mmu_selective_scan_bwd",
+    "mmu_selective_scan_bwd_workspace", "mmu_selective_scan_bwd", "mmu_scan_state_stride",
     "mmu_causal_conv1d_fwd", "mmu_causal_conv1d_bwd",
     "mmu_scan_order_gather", "mmu_scan_order_scatter", "mmu_scan_order_index",
     "mmu_snake_sample_fwd", "mmu_snake_sample_bwd",
@@ -77,6 +77,8 @@ def lib() -> C.CDLL:
     for n in ("mmu_selective_scan_fwd_workspace", "mmu_selective_scan_bwd_workspace"):
         getattr(L, n).restype = _sz
         getattr(L, n).argtypes = [_i32, _i32, _i32, _i32]
+    L.mmu_scan_state_stride.restype = _i32
+    L.mmu_scan_state_stride.argtypes = [_i32] * 5
     L.mmu_selective_scan_fwd.argtypes = [C.POINTER(ScanFwdParams), _vp]
     L.mmu_selective_scan_bwd.argtypes = [C.POINTER(ScanBwdParams), _vp]
     L.mmu_causal_conv1d_fwd.argtypes = [C.POINTER(ConvParams), _vp]

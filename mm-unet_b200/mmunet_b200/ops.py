@@ -123,18 +123,20 @@ def selective_scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta
     G = B.shape[1]
     A = A.contiguous()
     out = torch.empty_like(u, memory_format=torch.contiguous_format)
-    nx = (L + _lib.STATE_STRIDE - 1) // _lib.STATE_STRIDE
+    H = dim // G
+    L_ = _lib.lib()
+    xs = L_.mmu_scan_state_stride(batch, H, L, N, _DT[u.dtype]) if save_states else _lib.STATE_STRIDE
+    nx = (L + xs - 1) // xs
     x = torch.empty((batch, dim, nx, N), device=u.device, dtype=torch.float32) if save_states else None
     y = torch.empty_like(out) if (save_states and z is not None) else None
     last = torch.empty((batch, dim, N), device=u.device, dtype=torch.float32) if return_last_state else None
-    H = dim // G
-    L_ = _lib.lib()
     ws_bytes = L_.mmu_selective_scan_fwd_workspace(batch, H, L, N)
     ws = torch.empty(ws_bytes, device=u.device, dtype=torch.uint8) if ws_bytes else None
     with torch.cuda.device(u.device):
         for g in range(G):
             p = _lib.ScanFwdParams()
             _fill_fwd(p, u, delta, A, B, C, D, z, delta_bias, delta_softplus, reverse, g, G)
+            p.x_stride = xs
             p.out = out.data_ptr() + g * H * out.stride(1) * out.element_size()
             p.out_bs, p.out_ds = out.stride(0), out.stride(1)
             p.x = None if x is None else x.data_ptr() + g * H * x.stride(1) * 4
@@ -154,6 +156,12 @@ def selective_scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta
                 if last is not None:
                     last[:, g * H:(g + 1) * H] = lg
     return out, (ScanStates(x, y) if save_states else None), last
+
+
+def _x_stride(x, L):
+    """Token stride of the saved states, from the shape the forward allocated (see mmu_scan_state_stride)."""
+    n8, n64 = (L + 7) // 8, (L + _lib.STATE_STRIDE - 1) // _lib.STATE_STRIDE
+    return 8 if (x.shape[2] == n8 and n8 != n64) else _lib.STATE_STRIDE
 
 
 def selective_scan_bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softplus=False, reverse=False,
@@ -206,6 +214,7 @@ def selective_scan_bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softp
             _fill_fwd(p.f, u, delta, A, B, C, D, z, delta_bias, delta_softplus, reverse, g, G)
             xg = x if G == 1 else x[:, g * H:(g + 1) * H].contiguous()
             p.f.x = xg.data_ptr()
+            p.f.x_stride = _x_stride(x, L)
             if y is not None and z is not None:
                 p.f.y = y.data_ptr() + g * H * y.stride(1) * es
                 p.f.y_bs, p.f.y_ds = y.stride(0), y.stride(1)

@@ -226,6 +226,111 @@ def test_scan_generations_interoperate(fwd_v, bwd_v, monkeypatch):
     check("dB", g[3], rg["dB"][:, None] if rg["dB"].ndim == 3 else rg["dB"], 1e-3, 2e-3)
 
 
+# ---- v4: wide problems (dim >= 64), rows in lanes, states saved every 8 tokens (csrc/scan4.cuh, scan4_bwd.cuh) -----------------
+V4_SHAPES = [(2, 64, 256, 16), (1, 128, 1024, 16), (2, 130, 200, 16), (1, 96, 520, 8), (3, 70, 64, 5), (1, 64, 8, 16),
+             (2, 192, 4096, 16), (1, 65, 16, 1)]
+
+
+@pytest.mark.parametrize("ver", ["3", "4"])
+@pytest.mark.parametrize("shape", V4_SHAPES)
+def test_scan_v4_shapes(ver, shape, monkeypatch):
+    monkeypatch.setenv("MMU_SCAN_V", ver)
+    run_scan_case(*shape)
+    run_scan_case(*shape, reverse=True)
+
+
+def test_scan_v4_is_selected():
+    """The wide kernels are the ones that run: the forward saves a state every 8 tokens for them."""
+    assert _lib.lib().mmu_scan_state_stride(2, 128, 1024, 16, _lib.F32) == 8
+    assert _lib.lib().mmu_scan_state_stride(2, 6, 1024, 16, _lib.F32) == 64
+    cpu, gpu = make_scan_inputs(2, 128, 1024, 16)
+    n0 = _lib.launch_count()
+    out, st, _ = ops.selective_scan_fwd(*(gpu[k] for k in ("u", "delta", "A", "B", "C", "D", "z", "delta_bias")), True)
+    assert st.x.shape == (2, 128, 128, 16)
+    assert _lib.launch_count() - n0 == 3          # aggregates, chain, main pass
+
+
+@pytest.mark.parametrize("flags", [dict(has_z=False), dict(has_D=False), dict(has_bias=False),
+                                   dict(has_z=False, has_D=False, has_bias=False)])
+@pytest.mark.parametrize("softplus", [False, True])
+def test_scan_v4_optional_inputs(flags, softplus):
+    run_scan_case(2, 72, 520, 16, softplus=softplus, **flags)
+
+
+@pytest.mark.parametrize("reverse", [False, True])
+def test_scan_v4_bf16(reverse):
+    run_scan_case(2, 128, 1024, 16, dtype=torch.bfloat16, reverse=reverse)
+    run_scan_case(1, 66, 776, 16, dtype=torch.bfloat16, reverse=reverse)
+    run_scan_case(3, 64, 512, 16, dtype=torch.bfloat16, reverse=reverse, xz_layout=True)
+
+
+@pytest.mark.parametrize("nseg", [1, 2, 3, 7, 64])
+def test_scan_v4_sequence_split(nseg, monkeypatch):
+    """Any segment count (aggregate -> chain -> main in both passes) gives the single-segment answer."""
+    monkeypatch.setenv("MMU_FWD_NSEG", str(nseg))
+    monkeypatch.setenv("MMU_BWD_NSEG", str(nseg))
+    run_scan_case(2, 64, 2048, 16)
+    run_scan_case(1, 100, 4096, 16, reverse=True)
+    run_scan_case(2, 64, 1800, 16, dtype=torch.bfloat16)
+
+
+def test_scan_v4_xz_strided_layout():
+    run_scan_case(3, 64, 512, 16, xz_layout=True)
+    run_scan_case(2, 128, 264, 16, xz_layout=True, reverse=True)
+
+
+def _parity_report(name, rows):
+    """Per-tensor max-abs / max-rel errors, for BASELINE.md section 5 (written next to the other GPU artefacts)."""
+    import json
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        json.dump(rows, open(os.path.join(d, f"parity_{name}.json"), "w"), indent=1)
+    except OSError:
+        pass
+
+
+def _errs(got, ref):
+    got = got.detach().float().cpu().numpy().astype(np.float64)
+    ref = np.asarray(ref, np.float64).reshape(got.shape)
+    err = np.abs(got - ref)
+    return dict(max_abs=float(err.max()), max_abs_ref=float(np.abs(ref).max()),
+                max_rel=float((err / np.maximum(np.abs(ref), 1e-2 * np.abs(ref).max())).max()))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,D,L,N,tag", [(8, 384, 4096, 16, "config2"), (2, 128, 65536, 16, "rcg64k"), (2, 128, 4096, 64, "n64")])
+def test_scan_baseline_configs_vs_oracle(B, D, L, N, tag, dtype):
+    """The BASELINE configs themselves - config 2 (B8 D384 L4096 N16), an RCG-shaped long scan and d_state 64 - forward and all
+    eight gradients against the C oracle, with the reference's UNSCALED tolerances (test_selective_scan.py:45-51, 137-149:
+    out rtol/atol, du x2 atol, ddelta rtol x5 / atol x10, dA atol x5, weight grads widened to the activation tolerance because
+    of the gate).  bf16: the oracle sees the same bf16-rounded inputs."""
+    cpu, gpu = make_scan_inputs(B, D, L, N, dtype=dtype)
+    n = lambda t: None if t is None else t.numpy()
+    keys = ("u", "delta", "A", "B", "C", "D", "z", "delta_bias")
+    ro, rl = oracle.selective_scan_fwd(*(n(cpu[k]) for k in keys), True)
+    rg = oracle.selective_scan_bwd(*(n(cpu[k]) for k in keys), n(cpu["dout"]), True)
+    out, st, last = ops.selective_scan_fwd(*(gpu[k] for k in keys), True, return_last_state=True)
+    g = ops.selective_scan_bwd(*(gpu[k] for k in keys), gpu["dout"], st, True)
+    rtol, atol = {torch.float32: (6e-4, 2e-3), torch.bfloat16: (3e-2, 5e-2)}[dtype]
+    rep = {"out": _errs(out, ro), "last_state": _errs(last, rl)}
+    for k, t in zip(("du", "ddelta", "dA", "dB", "dC", "dD", "dz", "ddelta_bias"), g):
+        rep[k] = _errs(t, rg[k])
+    _parity_report(f"{tag}_{'fp32' if dtype == torch.float32 else 'bf16'}", rep)
+    # gradient sums over batch*L (dA, dD, ddelta_bias) and over dim (dB, dC) grow with the problem: their atol scales with
+    # the magnitude of the reference, as the reference's own `atolw = max(atolw, atol)` widening intends; activations are unscaled
+    check("out", out, ro, rtol, atol, scale_atol=False)
+    check("du", g[0], rg["du"], rtol, 2 * atol, scale_atol=False)
+    check("dz", g[6], rg["dz"], rtol, atol, scale_atol=False)
+    check("ddelta", g[1], rg["ddelta"], 5 * rtol, 10 * atol, scale_atol=False)
+    check("last_state", last, rl, max(rtol, 1e-3), atol)
+    check("dA", g[2], rg["dA"], max(rtol, 1e-3), 5 * atol)
+    check("dB", g[3], np.asarray(rg["dB"]).reshape(g[3].shape), max(rtol, 1e-3), atol)
+    check("dC", g[4], np.asarray(rg["dC"]).reshape(g[4].shape), max(rtol, 1e-3), atol)
+    check("dD", g[5], rg["dD"], max(rtol, 1e-3), atol)
+    check("ddelta_bias", g[7], rg["ddelta_bias"], 5 * max(rtol, 1e-3), 10 * atol)
+
+
 def test_scan_golden_fixtures():
     for name, c in load_golden("selective_scan.npz").items():
         t = lambda k: None if k not in c else torch.tensor(c[k], device=DEV)
