@@ -42,6 +42,15 @@ struct GnGeom {
 
 constexpr int kGnThreads = 256;
 
+// Shift of the one-pass variance: the group's own first sample (pixel 0, first channel), the same value in every block.
+// sums hold sum(x - K) and sum((x - K)^2); var = E[(x-K)^2] - E[x-K]^2 then cancels at the scale of (mean - K) ~ std
+// instead of |mean| (E[x^2] - mean^2 lost all digits for inputs like x + 100).
+template <typename TI> __device__ __forceinline__ float gn_shift(const TI *group_base) {
+    float v[4];
+    V4<TI>::ld(group_base, v);
+    return v[0];
+}
+
 // thread layout of the reduction kernels: tid = lane_p * G + g  (G | 256 or G >= 256 handled by the g loop)
 template <typename TI>
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const TI *__restrict__ x, float *__restrict__ sums, GnGeom g) {
@@ -53,10 +62,13 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const TI *__restri
         float s = 0.f, ss = 0.f;
         if (gi < G && lp < lanes) {
             const TI *xp = x + ((int64_t)b * g.HW) * g.C + 4 * gi;
+            const float K = gn_shift(xp);               // shifted sums: no cancellation when |mean| >> std
 #pragma unroll 4
             for (int p = p0 + lp; p < p1; p += lanes) {
                 float v[4];
                 V4<TI>::ld(xp + (int64_t)p * g.C, v);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] -= K;
                 s += (v[0] + v[1]) + (v[2] + v[3]);
                 ss += (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
             }
@@ -72,10 +84,11 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const TI *__restri
     }
 }
 
-__device__ __forceinline__ void gn_moments(const float *__restrict__ sums, int64_t bg, float n, float eps, float &mean, float &rstd) {
+__device__ __forceinline__ void gn_moments(const float *__restrict__ sums, int64_t bg, float n, float eps, float K, float &mean, float &rstd) {
     const float s = sums[bg * 2], ss = sums[bg * 2 + 1];
-    mean = s / n;
-    rstd = rsqrtf(fmaxf(ss / n - mean * mean, 0.f) + eps);
+    const float m = s / n;                              // mean of (x - K)
+    mean = K + m;
+    rstd = rsqrtf(fmaxf(ss / n - m * m, 0.f) + eps);
 }
 
 template <typename TI, typename TO>
@@ -88,7 +101,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const TI *__restrict__ x,
     const int gi = (int)(i - pix * (unsigned)g.G), b = blockIdx.y;
     const int64_t bp = (int64_t)b * g.HW + pix;
     float mean, rstd;
-    gn_moments(sums, (int64_t)b * g.G + gi, 4.f * g.HW, g.eps, mean, rstd);
+    gn_moments(sums, (int64_t)b * g.G + gi, 4.f * g.HW, g.eps, gn_shift(x + ((int64_t)b * g.HW) * g.C + 4 * gi), mean, rstd);
     if (pix == 0) mean_out[(int64_t)b * g.G + gi] = mean, rstd_out[(int64_t)b * g.G + gi] = rstd;
     float v[4], o[4];
     V4<TI>::ld(x + bp * g.C + 4 * gi, v);

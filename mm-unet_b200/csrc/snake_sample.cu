@@ -32,11 +32,12 @@ __device__ __forceinline__ void snake_coord(const SnakeGeom &g, const float *__r
     h = (int)(bh - (unsigned)b * (unsigned)g.H);
     const float yv = y[(((int64_t)b * g.K + k) * g.H + h) * g.W + w];
     const float hi = (float)(g.H - 1);
-    inside = yv >= 0.f && yv <= hi;
+    const bool is_nan = yv != yv;                // a NaN coordinate must poison the sample and its gradients, as torch.clamp +
+    inside = (yv >= 0.f && yv <= hi) || is_nan;  // grid_sample do (fminf/fmaxf alone would silently map it to row 0)
     const float yc = fminf(fmaxf(yv, 0.f), hi);
     const float fl = floorf(yc);
     r0 = (int)fl;
-    f = yc - fl;
+    f = is_nan ? yv : yc - fl;
     r1ok = r0 + 1 < g.H;
     xk = min(max(w + k - g.K / 2, 0), g.W - 1);
 }
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(256) snake_bwd_kernel(const TI *__restrict__ f
             acc = fmaf(gv, -v0, acc);       // zero padding below the last row
         }
     }
-    if (dy != nullptr && inside) atomicAdd(dy + (((int64_t)b * g.K + k) * g.H + h) * g.W + w, acc);
+    if (dy != nullptr && inside) atomicAdd(dy + (((int64_t)b * g.K + k) * g.H + h) * g.W + w, fmaf(f, 0.f, acc));   // NaN f -> NaN dy
 }
 
 // ---- channels-last (NHWC) variants: feat[b][r][x][c], out[b][h*K+k][w][c].  A thread owns 4 consecutive channels of one sample,
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(256) snake_bwd_nhwc_kernel(const TI *__restric
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc = fmaf(gv[i], v1[i] - v0[i], acc);
+        acc = fmaf(f, 0.f, acc);                 // NaN f -> NaN dy
         if (!inside) acc = 0.f;
     }
     // d_y: sum over the sample's channel threads.  cv is a power of two (checked by the host): groups of min(cv, 32) lanes

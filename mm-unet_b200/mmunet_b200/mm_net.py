@@ -56,6 +56,7 @@ class MMConv(nn.Module):
         self.kernel_size, self.extend_scope, self.morph, self.if_offset = K, extend_scope, morph, if_offset
         self.gn_offset = nn.GroupNorm(K, 2 * K)
         self.gn = nn.GroupNorm(out_channels // 4, out_channels)
+        self.gn_fp32_out = False     # channels-last path only: True = fp32 result under autocast, as torch's GroupNorm returns
         self.relu = nn.ReLU(inplace=False)
         self.tanh = nn.Tanh()
         self.offset_conv = nn.Conv2d(in_channels, 2 * K, 3, padding=1)
@@ -119,7 +120,7 @@ class MMConv(nn.Module):
         B, _, H, W = offset.shape
         K = self.kernel_size
         y = self.row_coordinates(offset)                                       # (B, K, H, W)
-        if _snake_sample is not None and self.morph == 0:
+        if _snake_sample is not None and self.morph == 0 and input.is_cuda and input.dtype in (torch.float32, torch.bfloat16):
             # fused clamp + row interpolation, written in the dtype the strided conv consumes (MMUNet.py:190-224)
             dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else input.dtype
             feat = _snake_sample(input, y, dt if dt in (torch.float32, torch.bfloat16) else torch.float32)
@@ -129,7 +130,9 @@ class MMConv(nn.Module):
         if _group_norm_nhwc is not None and out.is_cuda and ops.group_norm_nhwc_supported(out, self.gn.num_groups):
             # channels-last model: normalise in place of layout (ATen's GroupNorm would copy to NCHW, return NCHW and, under
             # autocast, fp32); the output keeps the conv's dtype, statistics are fp32
-            return _group_norm_nhwc(out, self.gn.num_groups, self.gn.weight, self.gn.bias, self.gn.eps)
+            # (MMConv.gn_fp32_out = True restores torch's autocast behaviour: an fp32 result)
+            return _group_norm_nhwc(out, self.gn.num_groups, self.gn.weight, self.gn.bias, self.gn.eps,
+                                    torch.float32 if self.gn_fp32_out else None)
         return self.gn(out)
 
 

@@ -135,6 +135,22 @@ def test_snake_sample_matches_grid_sample(no_tf32, shape, dtypes, channels_last)
     assert bad <= 2e-3, f"{bad:.4f} of d_y elements differ"
 
 
+def test_snake_sample_nan_and_fp16(no_tf32):
+    """A NaN row coordinate poisons the sample and its gradient (as torch.clamp + grid_sample do) instead of silently reading
+    row 0; fp16 feature maps (not supported by the fused sampler) take the reference formulation instead of raising."""
+    from mmunet_b200 import mm_net, ops
+    feat = torch.randn(1, 4, 6, 5, device="cuda", requires_grad=True)
+    y = torch.arange(6, device="cuda").view(1, 1, 6, 1).expand(1, 3, 6, 5).float().clone()
+    y[0, 1, 2, 3] = float("nan")
+    y.requires_grad_()
+    out = ops.snake_sample(feat, y)
+    assert torch.isnan(out[0, :, 2 * 3 + 1, 3]).all() and torch.isfinite(out[0, :, 0]).all()
+    out.nan_to_num().sum().backward()
+    conv = mm_net.MMConv(8, 8, kernel_size=3).cuda().half()
+    o16 = conv(torch.randn(1, 8, 6, 6, device="cuda", dtype=torch.float16))
+    assert o16.shape == (1, 8, 6, 6) and torch.isfinite(o16.float()).all()
+
+
 @pytest.mark.parametrize("shape", [(2, 64, 12, 10), (3, 16, 7, 9), (1, 512, 4, 4), (2, 128, 33, 17), (2, 8, 5, 5)])
 @pytest.mark.parametrize("dtypes", [("fp32", "fp32"), ("bf16", "bf16"), ("fp32", "bf16")])
 def test_group_norm_nhwc_matches_torch(shape, dtypes):
@@ -162,6 +178,11 @@ def test_group_norm_nhwc_matches_torch(shape, dtypes):
     gt = 2e-4 if (tin, tout) == (torch.float32, torch.float32) else 3e-2
     for got, want, name in ((x1.grad, x2.grad, "dx"), (w1.grad, w2.grad, "dgamma"), (b1.grad, b2.grad, "dbeta")):
         torch.testing.assert_close(got.float(), want, rtol=gt, atol=gt * float(want.abs().max()), msg=lambda m: f"{name}: {m}")
+    # statistics must survive a large common offset (one-pass E[x^2] - mean^2 would lose every digit here)
+    if tin == torch.float32:
+        xo = (x.float() + 300.0).contiguous(memory_format=torch.channels_last)
+        yo = ops.group_norm_nhwc(xo, G, w, b, 1e-5, torch.float32)
+        torch.testing.assert_close(yo, F.group_norm(xo.double(), G, w.double(), b.double(), 1e-5).float(), rtol=2e-3, atol=2e-3)
     # unsupported layouts are refused (the model then falls back to nn.GroupNorm)
     assert not ops.group_norm_nhwc_supported(x.contiguous(), G) or H * W == 1
     assert not ops.group_norm_nhwc_supported(x, G * 2)

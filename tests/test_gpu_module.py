@@ -71,6 +71,53 @@ def test_inner_no_out_proj_vs_torch_oracle(batch, d, L, N, R, reverse):
         close("d" + k, gpu[k].grad, cpu[k].grad, 5e-3, 5e-3)
 
 
+@pytest.mark.parametrize("batch,d,L,N,R,e", [(2, 8, 48, 4, 2, 4), (3, 6, 203, 16, 1, 3), (1, 128, 256, 16, 4, 64)])
+def test_bimamba_inner_fn_vs_torch_oracle(batch, d, L, N, R, e):
+    """bimamba_inner_fn (selective_scan_interface.py:437-603, 616-624) against bimamba_inner_ref's formulation
+    (:673-709, oracle/torch_ref.py:bimamba_inner): out = out_proj(scan(A) + flip(scan_flipped(A_b))), one conv / projection
+    shared by both directions.  Forward and every gradient, including dA_b, dD, ddelta_bias and the out_proj pair; ragged L."""
+    g = torch.Generator().manual_seed(11)
+    p = dict(xz=torch.randn(batch, 2 * d, L, generator=g), conv_w=torch.randn(d, 1, 4, generator=g) * 0.5,
+             conv_b=torch.randn(d, generator=g) * 0.5, x_proj_w=torch.randn(R + 2 * N, d, generator=g) * 0.3,
+             dt_proj_w=torch.randn(d, R, generator=g) * 0.3, out_proj_w=torch.randn(e, d, generator=g) * 0.3,
+             out_proj_b=torch.randn(e, generator=g) * 0.3, A=-0.5 * torch.rand(d, N, generator=g),
+             A_b=-0.5 * torch.rand(d, N, generator=g), D=torch.randn(d, generator=g), dt_bias=0.5 * torch.rand(d, generator=g))
+    dout = torch.randn(batch, L, e, generator=g)
+    cpu = {k: v.clone().requires_grad_() for k, v in p.items()}
+    ref = torch_ref.bimamba_inner(cpu["xz"], cpu["conv_w"], cpu["conv_b"], cpu["x_proj_w"], cpu["dt_proj_w"], cpu["out_proj_w"],
+                                  cpu["out_proj_b"], cpu["A"], cpu["A_b"], cpu["D"], cpu["dt_bias"])
+    ref.backward(dout)
+    gpu = {k: v.to(DEV).requires_grad_() for k, v in p.items()}
+    xz = gpu["xz"].detach().transpose(0, 1).contiguous().transpose(0, 1).requires_grad_()      # (l, b*l, 1) strides, as in_proj gives
+    out = ops.bimamba_inner_fn(xz, gpu["conv_w"], gpu["conv_b"], gpu["x_proj_w"], gpu["dt_proj_w"], gpu["out_proj_w"],
+                               gpu["out_proj_b"], gpu["A"], gpu["A_b"], None, None, gpu["D"], gpu["dt_bias"])
+    close("out", out, ref)
+    out.backward(dout.to(DEV))
+    close("dxz", xz.grad, cpu["xz"].grad, 5e-3, 5e-3)
+    for k in ("conv_w", "conv_b", "x_proj_w", "dt_proj_w", "out_proj_w", "out_proj_b", "A", "A_b", "D", "dt_bias"):
+        close("d" + k, gpu[k].grad, cpu[k].grad, 5e-3, 5e-3)
+
+
+def test_bimamba_inner_fn_bf16_autocast():
+    g = torch.Generator().manual_seed(12)
+    batch, d, L, N, R, e = 2, 64, 520, 16, 4, 32
+    p = dict(xz=torch.randn(batch, 2 * d, L, generator=g), conv_w=torch.randn(d, 1, 4, generator=g) * 0.5,
+             conv_b=torch.randn(d, generator=g) * 0.5, x_proj_w=torch.randn(R + 2 * N, d, generator=g) * 0.1,
+             dt_proj_w=torch.randn(d, R, generator=g) * 0.3, out_proj_w=torch.randn(e, d, generator=g) * 0.1,
+             A=-0.5 * torch.rand(d, N, generator=g), A_b=-0.5 * torch.rand(d, N, generator=g), D=torch.randn(d, generator=g),
+             dt_bias=0.5 * torch.rand(d, generator=g))
+    ref = torch_ref.bimamba_inner(p["xz"], p["conv_w"], p["conv_b"], p["x_proj_w"], p["dt_proj_w"], p["out_proj_w"], None,
+                                  p["A"], p["A_b"], p["D"], p["dt_bias"])
+    gpu = {k: v.to(DEV).requires_grad_() for k, v in p.items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = ops.bimamba_inner_fn(gpu["xz"].to(torch.bfloat16), gpu["conv_w"], gpu["conv_b"], gpu["x_proj_w"], gpu["dt_proj_w"],
+                                   gpu["out_proj_w"], None, gpu["A"], gpu["A_b"], None, None, gpu["D"], gpu["dt_bias"])
+    assert out.dtype == torch.bfloat16
+    close("out.bf16", out, ref, 3e-2, 5e-2)
+    out.float().sum().backward()
+    assert all(gpu[k].grad is not None and torch.isfinite(gpu[k].grad).all() for k in gpu if k != "xz")
+
+
 def _load_golden_module(bimamba_type):
     c = np.load(os.path.join(GOLDEN, "tfm_mamba.npz"))
     m = Mamba(d_model=8, d_state=4, d_conv=4, expand=2, bimamba_type=bimamba_type, nslices=4)

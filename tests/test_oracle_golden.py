@@ -101,3 +101,16 @@ def test_torch_inner_matches_reference():
     for k in t:
         scale = max(1.0, float(np.abs(c["d" + k]).max()))
         close(t[k].grad, c["d" + k], rtol=1e-3, atol=1e-3 * scale)
+
+
+def test_ref_fixtures_are_verbatim():
+    """tests/golden/_ref/ holds unmodified copies of two reference files (the "runs unchanged" GPU test loads them by path);
+    checked against the reference tree whenever it is present (build container)."""
+    import filecmp
+    import os
+    from conftest import GOLDEN
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present")
+    assert filecmp.cmp(os.path.join(GOLDEN, "_ref", "mamba_simple.py"), os.path.join(ref, "requirements", "mamba_simple.py"), shallow=False)
+    assert filecmp.cmp(os.path.join(GOLDEN, "_ref", "MMUNet.py"), os.path.join(ref, "src", "UM_Net", "MMUNet.py"), shallow=False)
