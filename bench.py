@@ -102,6 +102,30 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bind_to_gpu_numa(index):
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU BEFORE any pinned staging buffer is allocated:
+    first-touch then places the staging pages on the GPU's NUMA node, so the per-step H2D copies of N ranks do not all cross one
+    socket (e2e scaled 0.53 / 0.43 at 4 / 8 GPUs).  Returns a description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        numa = None
+        try:
+            bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+            numa = int(open(f"/sys/bus/pci/devices/{bus[-12:]}/numa_node").read())       # "00000000:1b:00.0" -> "0000:1b:00.0"
+        except Exception:
+            pass
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"cpus_bound": len(cpus), "first_cpu": cpus[0] if cpus else None, "gpu_numa_node": numa, "host_cpus": os.cpu_count()}
+    except Exception as exc:
+        return {"error": repr(exc)}
+
+
 def reduce_max_ms(ms, dist, device=None):
     """Timing rule of the bench contract: a multi-rank number is the MAX over ranks (backend-agnostic: NCCL or gloo)."""
     if dist is None or not dist.is_initialized():
@@ -302,6 +326,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    host_binding = bind_to_gpu_numa(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -460,7 +485,7 @@ def main():
                         "frac_of_peak": nbytes[n] / (per_kernel[n] * 1e-3) / 1e9 / peak} for n in names},
         "scan_fwd_bwd": {"us": (per_kernel["scan_fwd"] + per_kernel["scan_bwd"]) * 1e3,
                          "GBps": (nbytes["scan_fwd"] + nbytes["scan_bwd"]) / ((per_kernel["scan_fwd"] + per_kernel["scan_bwd"]) * 1e-3) / 1e9},
-        "clocks": sampler.summary(), "wall_s": wall,
+        "clocks": sampler.summary(), "wall_s": wall, "host_binding": host_binding,
     }
     if train is not None:
         line["train"] = train

@@ -203,6 +203,9 @@ int mmu_group_norm_nhwc_bwd(const void *x, const float *gamma, const void *dy, c
  * misc
  * --------------------------------------------------------------------------------------------- */
 int mmu_version(void);
+/* MMU_* environment knobs (kernel generation / tiling overrides for tests and experiments) are read once, at the first dispatch;
+ * call this after changing the environment of a live process. */
+void mmu_reload_knobs(void);
 const char *mmu_last_error(void);
 /* number of kernel launches issued through this library by the calling process (bench.py's gpu_launches) */
 uint64_t mmu_launch_count(void);

@@ -15,6 +15,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 int set_error(int code, const char *fmt, ...);
 void count_launch(int n = 1);
 int check_launch(const char *what);
+int knob(const char *name, int dflt);   // MMU_* tuning knob (environment, read once: capi.cu)
 
 // ---- element conversion -----------------------------------------------------------------------
 template <typename T> struct Elem;

@@ -75,20 +75,52 @@ struct Fwd4Args {
     int nitems;                         // warps with work
 };
 
-// shared memory of one warp: element slots [2 parity][NTEN tensors][2 rows][NQ quads][32 lanes] x 16 B, then the B/C tile
-// [8 tokens][32] fp32 (B states 0..15 | C states 0..15 of a token are 128 contiguous bytes)
+// ---- row-block staging ---------------------------------------------------------------------------------------------------------
+// A lane that fetched its own 16 bytes of its own row would make every warp load touch 32 different cache lines for 16 useful
+// bytes each: the first version of these kernels was bound by that (24 M line requests per forward at config 2, bf16 no faster
+// than fp32).  Instead the warp moves a BLOCK of its 64 rows x (P pieces of 16 bytes) cooperatively: P consecutive lanes take the
+// P consecutive pieces of one row, so a warp instruction touches 32/P lines with P*16 contiguous bytes each (64 B for fp32:
+// 16 tokens = two 8-token stages).  Piece (row, p) lives at 16-byte unit  ((row >> 5) * P + p) * 32 + (((row & 31) + p * (8 / P)) & 31):
+// the owner lane (row & 31) reads piece p with a conflict-free LDS.128, and the rotation by p * (8 / P) keeps the writers of
+// one instruction (32/P rows x P pieces) on distinct bank groups too.
+template <int P> __device__ __forceinline__ int rb_unit(int row, int p) { return ((row >> 5) * P + p) * 32 + (((row & 31) + p * (8 / P)) & 31); }
+
+// global -> shared (cp.async).  g0 = address of piece 0 of the warp's row 0; rows valid: row < nrows; pieces valid: p < npieces.
+template <int P> __device__ __forceinline__ void rb_load_async(unsigned s_u32, const char *g0, int64_t row_bytes, int nrows, int npieces, int lane) {
+#pragma unroll 1        // (unrolled, the compiler keeps every piece's address in registers across the whole kernel)
+    for (int it = 0; it < 2 * P; ++it) {
+        const int id = it * 32 + lane, row = id / P, p = id % P;
+        if (row < nrows && p < npieces) cp_async16_pf(s_u32 + rb_unit<P>(row, p) * 16, g0 + (int64_t)row * row_bytes + p * 16);
+    }
+}
+// shared -> global
+template <int P> __device__ __forceinline__ void rb_store(const unsigned char *s, char *g0, int64_t row_bytes, int nrows, int npieces, int lane) {
+#pragma unroll 2
+    for (int it = 0; it < 2 * P; ++it) {
+        const int id = it * 32 + lane, row = id / P, p = id % P;
+        if (row < nrows && p < npieces)
+            *reinterpret_cast<uint4 *>(g0 + (int64_t)row * row_bytes + p * 16) = *reinterpret_cast<const uint4 *>(s + rb_unit<P>(row, p) * 16);
+    }
+}
+
+constexpr int kS4SB = 2;                // 8-token stages per block
+
+// shared memory of one warp: blocks [2 parity][NTEN tensors][64 rows x P pieces] x 16 B, then the B/C tile [8 tokens][32] fp32
+// (B states 0..15 | C states 0..15 of a token are 128 contiguous bytes)
 template <typename IN_T, int NTEN> struct S4Fwd {
-    static constexpr int NQ = Raw8<IN_T>::kQuads;
-    static constexpr int kSlotBytes = 2 * NTEN * 2 * NQ * 32 * 16;
+    static constexpr int NQ = Raw8<IN_T>::kQuads;          // pieces per row per stage
+    static constexpr int P = kS4SB * NQ;                   // pieces per row per block
+    static constexpr int kBlkBytes = 64 * P * 16;          // one tensor, one block
+    static constexpr int kSlotBytes = 2 * NTEN * kBlkBytes;
     static constexpr int kTileBytes = 8 * 32 * 4;
     static constexpr int kWarpBytes = kSlotBytes + kTileBytes;
 };
 
 template <typename IN_T, bool REV, bool AGG>
-__global__ void __launch_bounds__(32 * kS4W, 3) scan4_fwd_kernel(const __grid_constant__ Fwd4Args p) {
-    constexpr int T = 8, NTEN = AGG ? 2 : 3;
+__global__ void __launch_bounds__(32 * kS4W, (AGG || sizeof(IN_T) == 2) ? 3 : 2) scan4_fwd_kernel(const __grid_constant__ Fwd4Args p) {
+    constexpr int T = 8, NTEN = AGG ? 2 : 3, SB = kS4SB;
     using Sm = S4Fwd<IN_T, NTEN>;
-    constexpr int NQ = Sm::NQ, EPQ = 16 / (int)sizeof(IN_T);
+    constexpr int NQ = Sm::NQ, P = Sm::P, ES = (int)sizeof(IN_T);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item = blockIdx.x * kS4W + warp;
     if (item >= p.nitems) return;
@@ -99,17 +131,17 @@ __global__ void __launch_bounds__(32 * kS4W, 3) scan4_fwd_kernel(const __grid_co
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *s_slot = smem_raw + (size_t)warp * Sm::kWarpBytes;
     float *s_tile = reinterpret_cast<float *>(s_slot + Sm::kSlotBytes);
-    const unsigned slot_u32 = smem_u32(s_slot) + lane * 16;
-    const unsigned char *slot_t = s_slot + lane * 16;
+    const unsigned slot_u32 = smem_u32(s_slot);
 
     // ---- my two rows -------------------------------------------------------------------------------------------------------------
+    const int row0 = rg * kS4Rows, nrows = min(kS4Rows, D - row0);          // the warp's rows
     int row[2];
     bool row_ok[2];
     float2 A2[16], h[16];
     float bias[2], Dsk[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-        const int rr = rg * kS4Rows + lane + 32 * r;
+        const int rr = row0 + lane + 32 * r;
         row_ok[r] = rr < D;
         row[r] = min(rr, D - 1);
         bias[r] = p.dbias != nullptr ? p.dbias[row[r]] : 0.f;
@@ -128,15 +160,15 @@ __global__ void __launch_bounds__(32 * kS4W, 3) scan4_fwd_kernel(const __grid_co
         h[n] = make_float2(h0[0], h0[1]);
     }
     const int s_begin = seg * p.sps, s_end = min(p.nstage, s_begin + p.sps);
-    // memory index of logical stage s (8 consecutive tokens, walked backwards when REV)
-    auto moff = [&](int s) { return REV ? L - T * (s + 1) : T * s; };
-    const IN_T *src[NTEN][2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        src[0][r] = reinterpret_cast<const IN_T *>(p.u) + (int64_t)b * p.u_bs + (int64_t)row[r] * p.u_ds;
-        src[1][r] = reinterpret_cast<const IN_T *>(p.delta) + (int64_t)b * p.dl_bs + (int64_t)row[r] * p.dl_ds;
-        if constexpr (!AGG) src[2][r] = has_z ? reinterpret_cast<const IN_T *>(p.z) + (int64_t)b * p.z_bs + (int64_t)row[r] * p.z_ds : nullptr;
-    }
+    const int nblk = (s_end - s_begin + SB - 1) / SB;
+    // memory index of the first element of logical stages [s, s + nst) (walked backwards when REV)
+    auto moff = [&](int s, int nst) { return REV ? L - T * (s + nst) : T * s; };
+    // row 0 of the warp, per tensor (bytes)
+    const char *g_in[NTEN];
+    int64_t rs_in[NTEN];
+    g_in[0] = reinterpret_cast<const char *>(p.u) + ((int64_t)b * p.u_bs + (int64_t)row0 * p.u_ds) * ES, rs_in[0] = p.u_ds * ES;
+    g_in[1] = reinterpret_cast<const char *>(p.delta) + ((int64_t)b * p.dl_bs + (int64_t)row0 * p.dl_ds) * ES, rs_in[1] = p.dl_ds * ES;
+    if constexpr (!AGG) g_in[2] = reinterpret_cast<const char *>(p.z) + ((int64_t)b * p.z_bs + (int64_t)row0 * p.z_ds) * ES, rs_in[2] = p.z_ds * ES;
     // B/C tile: lane l stages row l (B states 0..15, C states 0..15) through registers
     const int tn = lane & 15;
     const bool t_live = tn < N && (!AGG || lane < 16);
@@ -146,7 +178,7 @@ __global__ void __launch_bounds__(32 * kS4W, 3) scan4_fwd_kernel(const __grid_co
     auto tile_ldg = [&](int s) {
 #pragma unroll
         for (int q = 0; q < NQ; ++q)
-            treg[q] = t_live ? ldg16_pf(reinterpret_cast<const uint4 *>(t_src + moff(s)) + q) : make_uint4(0u, 0u, 0u, 0u);
+            treg[q] = t_live ? ldg16_pf(reinterpret_cast<const uint4 *>(t_src + moff(s, 1)) + q) : make_uint4(0u, 0u, 0u, 0u);
     };
     auto tile_sts = [&]() {
         float e[8];
@@ -154,125 +186,145 @@ __global__ void __launch_bounds__(32 * kS4W, 3) scan4_fwd_kernel(const __grid_co
 #pragma unroll
         for (int k = 0; k < 8; ++k) s_tile[(REV ? 7 - k : k) * 32 + lane] = e[k];
     };
-    auto issue_elems = [&](int s, int par) {
-        const int mo = moff(s);
+    auto issue_block = [&](int blk, int par) {
+        const int s0 = s_begin + blk * SB, nst = min(SB, s_end - s0);
+        const int64_t mo = (int64_t)moff(s0, nst) * ES;
 #pragma unroll
         for (int t = 0; t < NTEN; ++t) {
             if (t == 2 && !has_z) continue;
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-                for (int q = 0; q < NQ; ++q)
-                    cp_async16_pf(slot_u32 + ((((par * NTEN + t) * 2 + r) * NQ + q) * 32) * 16, src[t][r] + mo + q * EPQ);
+            rb_load_async<P>(slot_u32 + (par * NTEN + t) * Sm::kBlkBytes, g_in[t] + mo, rs_in[t], nrows, nst * NQ, lane);
         }
     };
-    auto load_slot = [&](int par, int t, int r, float (&v)[T]) {
+    // my 8 tokens of stage i (memory stage ms inside the block) of tensor t, row r
+    auto load_stage = [&](int par, int t, int r, int ms, float (&v)[T]) {
         uint4 q[NQ];
+        const unsigned char *base = s_slot + (par * NTEN + t) * Sm::kBlkBytes;
 #pragma unroll
-        for (int k = 0; k < NQ; ++k) q[k] = *reinterpret_cast<const uint4 *>(slot_t + ((((par * NTEN + t) * 2 + r) * NQ + k) * 32) * 16);
+        for (int k = 0; k < NQ; ++k) q[k] = *reinterpret_cast<const uint4 *>(base + rb_unit<P>(lane + 32 * r, ms * NQ + k) * 16);
         float e[8];
         Raw8<IN_T>::unpack(q, e);
         order8<REV>(e, v);
     };
+    auto store_stage = [&](int par, int t, int r, int ms, const float (&v)[T]) {
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[REV ? 7 - i : i] = v[i];
+        uint4 q[NQ];
+        Raw8<IN_T>::pack(e, q);
+        unsigned char *base = s_slot + (par * NTEN + t) * Sm::kBlkBytes;
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) *reinterpret_cast<uint4 *>(base + rb_unit<P>(lane + 32 * r, ms * NQ + k) * 16) = q[k];
+    };
 
-    issue_elems(s_begin, 0);
+    issue_block(0, 0);
     cp_async_commit();
     tile_ldg(s_begin);
     tile_sts();
     float dsum[2] = {0.f, 0.f};
 
-    for (int s = s_begin; s < s_end; ++s) {
-        const int par = (s - s_begin) & 1;
-        cp_async_wait_all();            // my slots of stage s have landed (they are lane private)
-        __syncwarp();                   // tile of stage s is visible
-        if (s + 1 < s_end) {
-            issue_elems(s + 1, par ^ 1);
-            tile_ldg(s + 1);
-        }
+    for (int blk = 0; blk < nblk; ++blk) {
+        const int par = blk & 1;
+        const int s0 = s_begin + blk * SB, nst = min(SB, s_end - s0);
+        cp_async_wait_all();            // my pieces of this block have landed ...
+        __syncwarp();                   // ... and everybody else's (the rows are fetched cooperatively)
+        if (blk + 1 < nblk) issue_block(blk + 1, par ^ 1);
         cp_async_commit();
 
-        float uu[2][T], dd[2][T];
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            load_slot(par, 0, r, uu[r]);
-            load_slot(par, 1, r, dd[r]);
-#pragma unroll
-            for (int i = 0; i < T; ++i) {
-                const float xx = dd[r][i] + bias[r];
-                dd[r][i] = sp ? softplus3(xx) : xx;
-                if (AGG) dsum[r] += dd[r][i];
-            }
-        }
-        float2 ya[T];
-#pragma unroll
-        for (int i = 0; i < T; ++i) {
-            const float2 dl = make_float2(dd[0][i], dd[1][i]);
-            const float2 dlu = make_float2(dd[0][i] * uu[0][i], dd[1][i] * uu[1][i]);
-            float2 y0 = make_float2(Dsk[0] * uu[0][i], Dsk[1] * uu[1][i]), y1 = make_float2(0.f, 0.f);
-            const float4 *tb = reinterpret_cast<const float4 *>(s_tile + i * 32);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const float4 b4 = tb[g];
-                const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
-                float cv[4] = {0.f, 0.f, 0.f, 0.f};
-                if (!AGG) {
-                    const float4 c4 = tb[4 + g];
-                    cv[0] = c4.x, cv[1] = c4.y, cv[2] = c4.z, cv[3] = c4.w;
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int n = 4 * g + k;
-                    const float2 a = ex2(fmul2(dl, A2[n]));
-                    h[n] = ffma2(a, h[n], fmul2(dlu, splat(bv[k])));
-                    if (!AGG) {
-                        if (k & 1) y1 = ffma2(h[n], splat(cv[k]), y1);
-                        else y0 = ffma2(h[n], splat(cv[k]), y0);
-                    }
-                }
-            }
-            if (!AGG) ya[i] = fadd2(y0, y1);
-        }
-        __syncwarp();                   // every lane is done with the tile of stage s
-        if (s + 1 < s_end) tile_sts();
+#pragma unroll 1
+        for (int i = 0; i < nst; ++i) {
+            const int s = s0 + i, ms = REV ? nst - 1 - i : i;
+            __syncwarp();               // tile of stage s is visible
+            if (s + 1 < s_end) tile_ldg(s + 1);
 
-        if constexpr (!AGG) {
-            const int mo = moff(s);
+            float uu[2][T], dd[2][T];
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                float yv[T];
+                load_stage(par, 0, r, ms, uu[r]);
+                load_stage(par, 1, r, ms, dd[r]);
 #pragma unroll
-                for (int i = 0; i < T; ++i) yv[i] = r ? ya[i].y : ya[i].x;
-                if (row_ok[r]) {
-                    if (p.ysave != nullptr)
-                        store8<IN_T, REV>(reinterpret_cast<IN_T *>(p.ysave) + (int64_t)b * p.y_bs + (int64_t)row[r] * p.y_ds + mo, yv);
-                    if (has_z) {
-                        float zz[T];
-                        load_slot(par, 2, r, zz);
-#pragma unroll
-                        for (int i = 0; i < T; ++i) yv[i] *= zz[i] * sigmoid3(zz[i]);
-                    }
-                    store8<IN_T, REV>(reinterpret_cast<IN_T *>(p.out) + (int64_t)b * p.o_bs + (int64_t)row[r] * p.o_ds + mo, yv);
+                for (int k = 0; k < T; ++k) {
+                    const float xx = dd[r][k] + bias[r];
+                    dd[r][k] = sp ? softplus3(xx) : xx;
+                    if (AGG) dsum[r] += dd[r][k];
                 }
             }
-            // state after stage s -> x[b][row][k][n]
-            if (p.x != nullptr && (s + 1) % p.xs8 == 0) {
-                const int k = (s + 1) / p.xs8 - 1;
+            float2 ya[T];
+#pragma unroll
+            for (int k = 0; k < T; ++k) {
+                const float2 dl = make_float2(dd[0][k], dd[1][k]);
+                const float2 dlu = make_float2(dd[0][k] * uu[0][k], dd[1][k] * uu[1][k]);
+                float2 y0 = make_float2(Dsk[0] * uu[0][k], Dsk[1] * uu[1][k]), y1 = make_float2(0.f, 0.f);
+                const float4 *tb = reinterpret_cast<const float4 *>(s_tile + k * 32);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const float4 b4 = tb[g];
+                    const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+                    float cv[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (!AGG) {
+                        const float4 c4 = tb[4 + g];
+                        cv[0] = c4.x, cv[1] = c4.y, cv[2] = c4.z, cv[3] = c4.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int n = 4 * g + j;
+                        const float2 a = ex2(fmul2(dl, A2[n]));
+                        h[n] = ffma2(a, h[n], fmul2(dlu, splat(bv[j])));
+                        if (!AGG) {
+                            if (j & 1) y1 = ffma2(h[n], splat(cv[j]), y1);
+                            else y0 = ffma2(h[n], splat(cv[j]), y0);
+                        }
+                    }
+                }
+                if (!AGG) ya[k] = fadd2(y0, y1);
+            }
+            __syncwarp();               // every lane is done with the tile of stage s
+            if (s + 1 < s_end) tile_sts();
+
+            if constexpr (!AGG) {
+                // y goes into the (consumed) u piece of this stage, out into the delta piece: the block is stored cooperatively below
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
-                    if (!row_ok[r]) continue;
-                    float *xp = p.x + (((int64_t)b * D + row[r]) * p.nx + k) * N;
-                    if (N == 16) {
+                    float yv[T];
 #pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            reinterpret_cast<float4 *>(xp)[g] = r ? make_float4(h[4 * g].y, h[4 * g + 1].y, h[4 * g + 2].y, h[4 * g + 3].y)
-                                                                  : make_float4(h[4 * g].x, h[4 * g + 1].x, h[4 * g + 2].x, h[4 * g + 3].x);
-                    } else {
+                    for (int k = 0; k < T; ++k) yv[k] = r ? ya[k].y : ya[k].x;
+                    if (p.ysave != nullptr) store_stage(par, 0, r, ms, yv);
+                    if (has_z) {
+                        float zz[T];
+                        load_stage(par, 2, r, ms, zz);
 #pragma unroll
-                        for (int n = 0; n < 16; ++n)
-                            if (n < N) xp[n] = r ? h[n].y : h[n].x;
+                        for (int k = 0; k < T; ++k) yv[k] *= zz[k] * sigmoid3(zz[k]);
+                    }
+                    store_stage(par, 1, r, ms, yv);
+                }
+                // state after stage s -> x[b][row][k][n]
+                if (p.x != nullptr && (s + 1) % p.xs8 == 0) {
+                    const int kx = (s + 1) / p.xs8 - 1;
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        if (!row_ok[r]) continue;
+                        float *xp = p.x + (((int64_t)b * D + row[r]) * p.nx + kx) * N;
+                        if (N == 16) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g)
+                                reinterpret_cast<float4 *>(xp)[g] = r ? make_float4(h[4 * g].y, h[4 * g + 1].y, h[4 * g + 2].y, h[4 * g + 3].y)
+                                                                      : make_float4(h[4 * g].x, h[4 * g + 1].x, h[4 * g + 2].x, h[4 * g + 3].x);
+                        } else {
+#pragma unroll
+                            for (int n = 0; n < 16; ++n)
+                                if (n < N) xp[n] = r ? h[n].y : h[n].x;
+                        }
                     }
                 }
             }
+        }
+        if constexpr (!AGG) {
+            __syncwarp();               // the block's y / out pieces are complete
+            const int64_t mo = (int64_t)moff(s0, nst) * ES;
+            if (p.ysave != nullptr)
+                rb_store<P>(s_slot + (par * NTEN + 0) * Sm::kBlkBytes, reinterpret_cast<char *>(p.ysave) + ((int64_t)b * p.y_bs + (int64_t)row0 * p.y_ds) * ES + mo,
+                            p.y_ds * ES, nrows, nst * NQ, lane);
+            rb_store<P>(s_slot + (par * NTEN + 1) * Sm::kBlkBytes, reinterpret_cast<char *>(p.out) + ((int64_t)b * p.o_bs + (int64_t)row0 * p.o_ds) * ES + mo,
+                        p.o_ds * ES, nrows, nst * NQ, lane);
         }
     }
 

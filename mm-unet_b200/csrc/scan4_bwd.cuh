@@ -32,9 +32,9 @@ struct Bwd4Args {
 // ---- reverse aggregates -----------------------------------------------------------------------------------------------------------
 template <typename IN_T, bool REV>
 __global__ void __launch_bounds__(32 * kS4W, 3) scan4_bwd_agg_kernel(const __grid_constant__ Bwd4Args p) {
-    constexpr int T = 8, NTEN = 3;                  // delta | dout | z
+    constexpr int T = 8, NTEN = 3, SB = kS4SB;      // delta | dout | z
     using Sm = S4Fwd<IN_T, NTEN>;
-    constexpr int NQ = Sm::NQ, EPQ = 16 / (int)sizeof(IN_T);
+    constexpr int NQ = Sm::NQ, P = Sm::P, ES = (int)sizeof(IN_T);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item = blockIdx.x * kS4W + warp;
     if (item >= p.nitems) return;
@@ -45,16 +45,16 @@ __global__ void __launch_bounds__(32 * kS4W, 3) scan4_bwd_agg_kernel(const __gri
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *s_slot = smem_raw + (size_t)warp * Sm::kWarpBytes;
     float *s_tile = reinterpret_cast<float *>(s_slot + Sm::kSlotBytes);      // [8 tokens][16]  C only
-    const unsigned slot_u32 = smem_u32(s_slot) + lane * 16;
-    const unsigned char *slot_t = s_slot + lane * 16;
+    const unsigned slot_u32 = smem_u32(s_slot);
 
+    const int row0 = rg * kS4Rows, nrows = min(kS4Rows, D - row0);
     int row[2];
     bool row_ok[2];
     float2 A2[16], e[16];
     float bias[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-        const int rr = rg * kS4Rows + lane + 32 * r;
+        const int rr = row0 + lane + 32 * r;
         row_ok[r] = rr < D;
         row[r] = min(rr, D - 1);
         bias[r] = p.dbias != nullptr ? p.dbias[row[r]] : 0.f;
@@ -65,14 +65,13 @@ __global__ void __launch_bounds__(32 * kS4W, 3) scan4_bwd_agg_kernel(const __gri
         e[n] = make_float2(0.f, 0.f);
     }
     const int s_begin = seg * p.sps, s_end = min(p.nstage, s_begin + p.sps);
-    auto moff = [&](int s) { return REV ? L - T * (s + 1) : T * s; };
-    const IN_T *src[NTEN][2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        src[0][r] = reinterpret_cast<const IN_T *>(p.delta) + (int64_t)b * p.dl_bs + (int64_t)row[r] * p.dl_ds;
-        src[1][r] = reinterpret_cast<const IN_T *>(p.dout) + (int64_t)b * p.g_bs + (int64_t)row[r] * p.g_ds;
-        src[2][r] = has_z ? reinterpret_cast<const IN_T *>(p.z) + (int64_t)b * p.z_bs + (int64_t)row[r] * p.z_ds : nullptr;
-    }
+    const int nblk = (s_end - s_begin + SB - 1) / SB;
+    auto moff = [&](int s, int nst) { return REV ? L - T * (s + nst) : T * s; };
+    const char *g_in[NTEN];
+    int64_t rs_in[NTEN];
+    g_in[0] = reinterpret_cast<const char *>(p.delta) + ((int64_t)b * p.dl_bs + (int64_t)row0 * p.dl_ds) * ES, rs_in[0] = p.dl_ds * ES;
+    g_in[1] = reinterpret_cast<const char *>(p.dout) + ((int64_t)b * p.g_bs + (int64_t)row0 * p.g_ds) * ES, rs_in[1] = p.g_ds * ES;
+    g_in[2] = reinterpret_cast<const char *>(p.z) + ((int64_t)b * p.z_bs + (int64_t)row0 * p.z_ds) * ES, rs_in[2] = p.z_ds * ES;
     const int tn = lane & 15;
     const bool t_live = tn < N && lane < 16;
     const IN_T *t_src = reinterpret_cast<const IN_T *>(p.Cm) + (int64_t)b * p.C_bs + (int64_t)tn * p.C_ns;
@@ -80,7 +79,7 @@ __global__ void __launch_bounds__(32 * kS4W, 3) scan4_bwd_agg_kernel(const __gri
     auto tile_ldg = [&](int s) {
 #pragma unroll
         for (int q = 0; q < NQ; ++q)
-            treg[q] = t_live ? ldg16_pf(reinterpret_cast<const uint4 *>(t_src + moff(s)) + q) : make_uint4(0u, 0u, 0u, 0u);
+            treg[q] = t_live ? ldg16_pf(reinterpret_cast<const uint4 *>(t_src + moff(s, 1)) + q) : make_uint4(0u, 0u, 0u, 0u);
     };
     auto tile_sts = [&]() {
         float v[8];
@@ -90,76 +89,86 @@ __global__ void __launch_bounds__(32 * kS4W, 3) scan4_bwd_agg_kernel(const __gri
             for (int k = 0; k < 8; ++k) s_tile[(REV ? 7 - k : k) * 16 + lane] = v[k];
         }
     };
-    auto issue_elems = [&](int s, int par) {
-        const int mo = moff(s);
+    // block k (counted from the right end of the segment) covers stages [s_lo, s_lo + nst)
+    auto blk_range = [&](int k, int &s_lo, int &nst) {
+        const int s_hi = s_end - k * SB;
+        nst = min(SB, s_hi - s_begin);
+        s_lo = s_hi - nst;
+    };
+    auto issue_block = [&](int k, int par) {
+        int s_lo, nst;
+        blk_range(k, s_lo, nst);
+        const int64_t mo = (int64_t)moff(s_lo, nst) * ES;
 #pragma unroll
         for (int t = 0; t < NTEN; ++t) {
             if (t == 2 && !has_z) continue;
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-                for (int q = 0; q < NQ; ++q)
-                    cp_async16_pf(slot_u32 + ((((par * NTEN + t) * 2 + r) * NQ + q) * 32) * 16, src[t][r] + mo + q * EPQ);
+            rb_load_async<P>(slot_u32 + (par * NTEN + t) * Sm::kBlkBytes, g_in[t] + mo, rs_in[t], nrows, nst * NQ, lane);
         }
     };
-    auto load_slot = [&](int par, int t, int r, float (&v)[T]) {
+    auto load_stage = [&](int par, int t, int r, int ms, float (&v)[T]) {
         uint4 q[NQ];
+        const unsigned char *base = s_slot + (par * NTEN + t) * Sm::kBlkBytes;
 #pragma unroll
-        for (int k = 0; k < NQ; ++k) q[k] = *reinterpret_cast<const uint4 *>(slot_t + ((((par * NTEN + t) * 2 + r) * NQ + k) * 32) * 16);
+        for (int k = 0; k < NQ; ++k) q[k] = *reinterpret_cast<const uint4 *>(base + rb_unit<P>(lane + 32 * r, ms * NQ + k) * 16);
         float ev[8];
         Raw8<IN_T>::unpack(q, ev);
         order8<REV>(ev, v);
     };
 
-    issue_elems(s_end - 1, 0);
+    issue_block(0, 0);
     cp_async_commit();
     tile_ldg(s_end - 1);
     tile_sts();
     float dsum[2] = {0.f, 0.f};
 
-    for (int s = s_end - 1; s >= s_begin; --s) {
-        const int par = (s_end - 1 - s) & 1;
+    for (int blk = 0; blk < nblk; ++blk) {
+        const int par = blk & 1;
+        int s_lo, nst;
+        blk_range(blk, s_lo, nst);
         cp_async_wait_all();
         __syncwarp();
-        if (s > s_begin) {
-            issue_elems(s - 1, par ^ 1);
-            tile_ldg(s - 1);
-        }
+        if (blk + 1 < nblk) issue_block(blk + 1, par ^ 1);
         cp_async_commit();
-        float dd[2][T], gy[2][T];
+#pragma unroll 1
+        for (int i = nst - 1; i >= 0; --i) {
+            const int s = s_lo + i, ms = REV ? nst - 1 - i : i;
+            __syncwarp();               // tile of stage s is visible
+            if (s > s_begin) tile_ldg(s - 1);
+            float dd[2][T], gy[2][T];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            load_slot(par, 0, r, dd[r]);
-            load_slot(par, 1, r, gy[r]);
-            float zz[T];
-            if (has_z) load_slot(par, 2, r, zz);
+            for (int r = 0; r < 2; ++r) {
+                load_stage(par, 0, r, ms, dd[r]);
+                load_stage(par, 1, r, ms, gy[r]);
+                float zz[T];
+                if (has_z) load_stage(par, 2, r, ms, zz);
 #pragma unroll
-            for (int i = 0; i < T; ++i) {
-                const float xx = dd[r][i] + bias[r];
-                dd[r][i] = sp ? softplus3(xx) : xx;
-                dsum[r] += dd[r][i];
-                if (has_z) gy[r][i] *= zz[i] * sigmoid3(zz[i]);
-            }
-        }
-#pragma unroll
-        for (int i = T - 1; i >= 0; --i) {
-            const float2 dl = make_float2(dd[0][i], dd[1][i]);
-            const float2 dy = make_float2(gy[0][i], gy[1][i]);
-            const float4 *tb = reinterpret_cast<const float4 *>(s_tile + i * 16);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const float4 c4 = tb[g];
-                const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int n = 4 * g + k;
-                    const float2 a = ex2(fmul2(dl, A2[n]));
-                    e[n] = fmul2(a, ffma2(dy, splat(cv[k]), e[n]));
+                for (int k = 0; k < T; ++k) {
+                    const float xx = dd[r][k] + bias[r];
+                    dd[r][k] = sp ? softplus3(xx) : xx;
+                    dsum[r] += dd[r][k];
+                    if (has_z) gy[r][k] *= zz[k] * sigmoid3(zz[k]);
                 }
             }
+#pragma unroll
+            for (int k = T - 1; k >= 0; --k) {
+                const float2 dl = make_float2(dd[0][k], dd[1][k]);
+                const float2 dy = make_float2(gy[0][k], gy[1][k]);
+                const float4 *tb = reinterpret_cast<const float4 *>(s_tile + k * 16);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const float4 c4 = tb[g];
+                    const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int n = 4 * g + j;
+                        const float2 a = ex2(fmul2(dl, A2[n]));
+                        e[n] = fmul2(a, ffma2(dy, splat(cv[j]), e[n]));
+                    }
+                }
+            }
+            __syncwarp();
+            if (s > s_begin) tile_sts();
         }
-        __syncwarp();
-        if (s > s_begin) tile_sts();
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -175,45 +184,50 @@ __global__ void __launch_bounds__(32 * kS4W, 3) scan4_bwd_agg_kernel(const __gri
 }
 
 // ---- main pass ----------------------------------------------------------------------------------------------------------------------
-// shared memory of one warp
+// shared memory of one warp.  Every block is one 8-token stage of the warp's 64 rows, moved cooperatively (rb_* in scan4.cuh).
 template <typename IN_T> struct S4Bwd {
-    static constexpr int NQ = Raw8<IN_T>::kQuads;
-    static constexpr int kSlotBytes = 5 * 2 * NQ * 32 * 16;          // u | delta | dout | z | y : [tensor][row][quad][lane] x 16 B
-    static constexpr int kKeepBytes = 2 * 2 * 2 * 32 * 16;           // u, sigmoid(delta_raw + bias) as fp32: [which][row][quad][lane] x 16 B
-    static constexpr int kSeedBytes = 2 * 2 * 16 * 32 * 4;           // [parity][row][state][lane] fp32
+    static constexpr int NQ = Raw8<IN_T>::kQuads;                    // 16-byte pieces per row per stage (fp32 2: lane pairs fetch full sectors)
+    static constexpr int kInBytes = 64 * NQ * 16;                    // one input tensor
+    static constexpr int kSlotBytes = 5 * kInBytes;                  // u | delta | dout | z | y (single buffered: consumed by the prologue)
+    static constexpr int kKeepBytes = 2 * 64 * 2 * 16;               // u, sigmoid(delta_raw + bias) as fp32 (P = 2)
+    // du / ddelta staging: fp32 pieces coincide with the owner's keep pieces (same P = 2 layout: staged in place);
+    // 2-byte types have one piece per row, which would alias OTHER lanes' keep pieces: own area
+    static constexpr int kStageBytes = NQ == 2 ? 0 : 2 * 64 * 16;
+    static constexpr int kSeedBytes = 2 * 64 * 4 * 16;               // [parity] x 64 rows x 16 states fp32 (P = 4)
     static constexpr int kTileBytes = 32 * 8 * 4;                    // [B states 0..15 | C states 0..15][8 tokens] fp32, logical order
     static constexpr int kTabBytes = 16 * 32 * 8;                    // A*log2e of (row 0, row 1): [state][lane] float2
-    static constexpr int kWarpBytes = kSlotBytes + kKeepBytes + kSeedBytes + kTileBytes + kTabBytes;
+    static constexpr int kWarpBytes = kSlotBytes + kKeepBytes + kSeedBytes + kTileBytes + kTabBytes + kStageBytes;
 };
 
 template <typename IN_T, bool REV>
 __global__ void __launch_bounds__(32 * kS4W, 2) scan4_bwd_kernel(const __grid_constant__ Bwd4Args p) {
     constexpr int T = 8;
     using Sm = S4Bwd<IN_T>;
-    constexpr int NQ = Sm::NQ, EPQ = 16 / (int)sizeof(IN_T);
+    constexpr int NQ = Sm::NQ, ES = (int)sizeof(IN_T);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item = blockIdx.x * kS4W + warp;
     if (item >= p.nitems) return;
     const int rg = item % p.nrg, it1 = item / p.nrg, b = it1 % p.B, seg = it1 / p.B;
-    const int D = p.D, L = p.L, N = p.N;
+    const int D = p.D, L = p.L;                                      // dstate == 16 (checked by the host)
     const bool has_z = p.z != nullptr, sp = p.softplus != 0;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *s_slot = smem_raw + (size_t)warp * Sm::kWarpBytes;
     unsigned char *s_keep = s_slot + Sm::kSlotBytes;
-    float *s_seed = reinterpret_cast<float *>(s_keep + Sm::kKeepBytes);
-    float *s_tile = s_seed + Sm::kSeedBytes / 4;
-    float2 *s_A = reinterpret_cast<float2 *>(s_tile + Sm::kTileBytes / 4);
-    const unsigned slot_u32 = smem_u32(s_slot) + lane * 16;
-    const unsigned char *slot_t = s_slot + lane * 16;
-    const unsigned seed_u32 = smem_u32(s_seed) + lane * 4;
+    unsigned char *s_seed = s_keep + Sm::kKeepBytes;
+    float *s_tile = reinterpret_cast<float *>(s_seed + Sm::kSeedBytes);
+    float2 *s_A = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(s_tile) + Sm::kTileBytes);
+    unsigned char *s_stage0 = NQ == 2 ? s_keep : reinterpret_cast<unsigned char *>(s_A) + Sm::kTabBytes;      // du staging
+    unsigned char *s_stage1 = NQ == 2 ? s_keep + 2048 : s_stage0 + 64 * 16;                                   // ddelta staging
+    const unsigned slot_u32 = smem_u32(s_slot), seed_u32 = smem_u32(s_seed);
 
+    const int row0 = rg * kS4Rows, nrows = min(kS4Rows, D - row0);
     int row[2];
     bool row_ok[2];
     float bias[2], Dsk[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-        const int rr = rg * kS4Rows + lane + 32 * r;
+        const int rr = row0 + lane + 32 * r;
         row_ok[r] = rr < D;
         row[r] = min(rr, D - 1);
         bias[r] = p.dbias != nullptr ? p.dbias[row[r]] : 0.f;
@@ -222,9 +236,9 @@ __global__ void __launch_bounds__(32 * kS4W, 2) scan4_bwd_kernel(const __grid_co
     float2 e2[16], dA2[16];
 #pragma unroll
     for (int n = 0; n < 16; ++n) {
-        s_A[n * 32 + lane] = make_float2(n < N ? p.A[(int64_t)row[0] * N + n] * kLog2e : 0.f, n < N ? p.A[(int64_t)row[1] * N + n] * kLog2e : 0.f);
+        s_A[n * 32 + lane] = make_float2(p.A[(int64_t)row[0] * 16 + n] * kLog2e, p.A[(int64_t)row[1] * 16 + n] * kLog2e);
         float ev[2] = {0.f, 0.f};
-        if (p.ein != nullptr && seg + 1 < p.nseg && n < N) {
+        if (p.ein != nullptr && seg + 1 < p.nseg) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) ev[r] = p.ein[(((int64_t)b * D + row[r]) * p.nseg + seg) * 16 + n];
         }
@@ -234,26 +248,27 @@ __global__ void __launch_bounds__(32 * kS4W, 2) scan4_bwd_kernel(const __grid_co
     const int s_begin = seg * p.sps, s_end = min(p.nstage, s_begin + p.sps);
     auto moff = [&](int s) { return REV ? L - T * (s + 1) : T * s; };
 
-    const IN_T *src[5][2];
-    const float *x_row[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        src[0][r] = reinterpret_cast<const IN_T *>(p.u) + (int64_t)b * p.u_bs + (int64_t)row[r] * p.u_ds;
-        src[1][r] = reinterpret_cast<const IN_T *>(p.delta) + (int64_t)b * p.dl_bs + (int64_t)row[r] * p.dl_ds;
-        src[2][r] = reinterpret_cast<const IN_T *>(p.dout) + (int64_t)b * p.g_bs + (int64_t)row[r] * p.g_ds;
-        src[3][r] = has_z ? reinterpret_cast<const IN_T *>(p.z) + (int64_t)b * p.z_bs + (int64_t)row[r] * p.z_ds : nullptr;
-        src[4][r] = has_z ? reinterpret_cast<const IN_T *>(p.ysave) + (int64_t)b * p.y_bs + (int64_t)row[r] * p.y_ds : nullptr;
-        x_row[r] = p.x != nullptr ? p.x + ((int64_t)b * D + row[r]) * p.nx * N : nullptr;
-    }
+    const char *g_in[5];
+    int64_t rs_in[5];
+    g_in[0] = reinterpret_cast<const char *>(p.u) + ((int64_t)b * p.u_bs + (int64_t)row0 * p.u_ds) * ES, rs_in[0] = p.u_ds * ES;
+    g_in[1] = reinterpret_cast<const char *>(p.delta) + ((int64_t)b * p.dl_bs + (int64_t)row0 * p.dl_ds) * ES, rs_in[1] = p.dl_ds * ES;
+    g_in[2] = reinterpret_cast<const char *>(p.dout) + ((int64_t)b * p.g_bs + (int64_t)row0 * p.g_ds) * ES, rs_in[2] = p.g_ds * ES;
+    g_in[3] = reinterpret_cast<const char *>(p.z) + ((int64_t)b * p.z_bs + (int64_t)row0 * p.z_ds) * ES, rs_in[3] = p.z_ds * ES;
+    g_in[4] = reinterpret_cast<const char *>(p.ysave) + ((int64_t)b * p.y_bs + (int64_t)row0 * p.y_ds) * ES, rs_in[4] = p.y_ds * ES;
+    const char *g_x = reinterpret_cast<const char *>(p.x) + ((int64_t)b * D + row0) * p.nx * 64;          // x[b][row][k][16] fp32: 64 bytes per (row, k)
+    const int64_t rs_x = (int64_t)p.nx * 64;
+    // dB / dC: after the transpose lane pair (2k, 2k+1) holds token (k & 7) of dB (lanes 0..15) or dC (lanes 16..31)
+    float *g_dbc = (lane & 16) ? p.dC + (int64_t)b * p.dC_bs : p.dB + (int64_t)b * p.dB_bs;
+    const int64_t dbc_ns = (lane & 16) ? p.dC_ns : p.dB_ns;
+    const int dbc_tok = REV ? 7 - ((lane >> 1) & 7) : ((lane >> 1) & 7);
+
     const int tn = lane & 15;
-    const bool t_live = tn < N;
     const IN_T *t_src = lane < 16 ? reinterpret_cast<const IN_T *>(p.Bm) + (int64_t)b * p.B_bs + (int64_t)tn * p.B_ns
                                   : reinterpret_cast<const IN_T *>(p.Cm) + (int64_t)b * p.C_bs + (int64_t)tn * p.C_ns;
     uint4 treg[NQ];
     auto tile_ldg = [&](int s) {
 #pragma unroll
-        for (int q = 0; q < NQ; ++q)
-            treg[q] = t_live ? ldg16_pf(reinterpret_cast<const uint4 *>(t_src + moff(s)) + q) : make_uint4(0u, 0u, 0u, 0u);
+        for (int q = 0; q < NQ; ++q) treg[q] = ldg16_pf(reinterpret_cast<const uint4 *>(t_src + moff(s)) + q);
     };
     auto tile_sts = [&]() {
         float ev[8], v[8];
@@ -264,34 +279,35 @@ __global__ void __launch_bounds__(32 * kS4W, 2) scan4_bwd_kernel(const __grid_co
         d[1] = make_float4(v[4], v[5], v[6], v[7]);
     };
     auto issue_stage = [&](int s, int par) {
-        const int mo = moff(s);
+        const int64_t mo = (int64_t)moff(s) * ES;
 #pragma unroll
         for (int t = 0; t < 5; ++t) {
             if (t >= 3 && !has_z) continue;
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) cp_async16_pf(slot_u32 + (((t * 2 + r) * NQ + q) * 32) * 16, src[t][r] + mo + q * EPQ);
+            rb_load_async<NQ>(slot_u32 + t * Sm::kInBytes, g_in[t] + mo, rs_in[t], nrows, NQ, lane);
         }
-        if (s > 0) {        // state entering stage s = x[s - 1]
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const float *xp = x_row[r] + (int64_t)(s - 1) * N;
-#pragma unroll
-                for (int n = 0; n < 16; ++n)
-                    if (n < N) cp_async4_pf(seed_u32 + (((par * 2 + r) * 16 + n) * 32) * 4, xp + n);
-            }
-        }
+        if (s > 0) rb_load_async<4>(seed_u32 + par * (Sm::kSeedBytes / 2), g_x + (int64_t)(s - 1) * 64, rs_x, nrows, 4, lane);   // state entering stage s = x[s - 1]
     };
     auto load_slot = [&](int t, int r, float (&v)[T]) {
         uint4 q[NQ];
+        const unsigned char *base = s_slot + t * Sm::kInBytes;
 #pragma unroll
-        for (int k = 0; k < NQ; ++k) q[k] = *reinterpret_cast<const uint4 *>(slot_t + (((t * 2 + r) * NQ + k) * 32) * 16);
+        for (int k = 0; k < NQ; ++k) q[k] = *reinterpret_cast<const uint4 *>(base + rb_unit<NQ>(lane + 32 * r, k) * 16);
         float ev[8];
         Raw8<IN_T>::unpack(q, ev);
         order8<REV>(ev, v);
     };
-    float4 *keep = reinterpret_cast<float4 *>(s_keep) + lane;          // [which][row][quad] stride 32 float4
+    // 8 results of row r -> a staging area in the rb layout of an IN_T tensor (memory order), stored cooperatively afterwards
+    auto stage_out = [&](unsigned char *area, int r, const float (&v)[T]) {
+        float ev[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ev[REV ? 7 - i : i] = v[i];
+        uint4 q[NQ];
+        Raw8<IN_T>::pack(ev, q);
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) *reinterpret_cast<uint4 *>(area + rb_unit<NQ>(lane + 32 * r, k) * 16) = q[k];
+    };
+    // keep: fp32, two 16-byte pieces per row (P = 2): [which][64 rows x 2]
+    auto keep_ptr = [&](int which, int r, int q) { return reinterpret_cast<float4 *>(s_keep + which * 2048 + rb_unit<2>(lane + 32 * r, q) * 16); };
 
     issue_stage(s_end - 1, 0);
     cp_async_commit();
@@ -301,9 +317,9 @@ __global__ void __launch_bounds__(32 * kS4W, 2) scan4_bwd_kernel(const __grid_co
 
     for (int s = s_end - 1; s >= s_begin; --s) {
         const int par = (s_end - 1 - s) & 1;
-        const int mo = moff(s);
+        const int64_t mo = (int64_t)moff(s) * ES;
         cp_async_wait_all();
-        __syncwarp();
+        __syncwarp();                   // stage s has landed (cooperative copies), tile of stage s is visible
         // ---- prologue: per (row, token) quantities of my 8 tokens -------------------------------------------------------------------
         float2 dl[T], dlu[T], dy[T];
         {
@@ -334,13 +350,19 @@ __global__ void __launch_bounds__(32 * kS4W, 2) scan4_bwd_kernel(const __grid_co
                         dzv[i] = g * yy[i] * sz * (1.f + zz[i] * (1.f - sz));
                         gg[r][i] = g * zz[i] * sz;
                     }
-                    if (row_ok[r])
-                        store8<IN_T, REV>(reinterpret_cast<IN_T *>(p.dz) + (int64_t)b * p.dz_bs + (int64_t)row[r] * p.dz_ds + mo, dzv);
+                    stage_out(s_slot + 4 * Sm::kInBytes, r, dzv);        // dz takes the place of the (consumed) y piece
                 }
-                keep[(0 * 2 + r) * 64] = make_float4(uu[r][0], uu[r][1], uu[r][2], uu[r][3]);
-                keep[(0 * 2 + r) * 64 + 32] = make_float4(uu[r][4], uu[r][5], uu[r][6], uu[r][7]);
-                keep[(1 * 2 + r) * 64] = make_float4(sg[0], sg[1], sg[2], sg[3]);
-                keep[(1 * 2 + r) * 64 + 32] = make_float4(sg[4], sg[5], sg[6], sg[7]);
+                *keep_ptr(0, r, 0) = make_float4(uu[r][0], uu[r][1], uu[r][2], uu[r][3]);
+                *keep_ptr(0, r, 1) = make_float4(uu[r][4], uu[r][5], uu[r][6], uu[r][7]);
+                *keep_ptr(1, r, 0) = make_float4(sg[0], sg[1], sg[2], sg[3]);
+                *keep_ptr(1, r, 1) = make_float4(sg[4], sg[5], sg[6], sg[7]);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (!row_ok[r]) {       // rows past dim: their slots were never filled - keep the garbage out of the cross-lane sums
+#pragma unroll
+                    for (int i = 0; i < T; ++i) dd[r][i] = 0.f, uu[r][i] = 0.f, gg[r][i] = 0.f;
+                }
             }
 #pragma unroll
             for (int i = 0; i < T; ++i) {
@@ -350,7 +372,11 @@ __global__ void __launch_bounds__(32 * kS4W, 2) scan4_bwd_kernel(const __grid_co
                 dDa = ffma2(dy[i], make_float2(uu[0][i], uu[1][i]), dDa);
             }
         }
-        // the slots are consumed: fetch the next stage (one stage to the left)
+        __syncwarp();                   // every lane has consumed its slots; the dz pieces are complete
+        if (has_z)
+            rb_store<NQ>(s_slot + 4 * Sm::kInBytes, reinterpret_cast<char *>(p.dz) + ((int64_t)b * p.dz_bs + (int64_t)row0 * p.dz_ds) * ES + mo,
+                         p.dz_ds * ES, nrows, NQ, lane);
+        __syncwarp();                   // dz has been read back: the slots may be refilled
         if (s > s_begin) {
             issue_stage(s - 1, par ^ 1);
             tile_ldg(s - 1);
@@ -360,12 +386,20 @@ __global__ void __launch_bounds__(32 * kS4W, 2) scan4_bwd_kernel(const __grid_co
         float2 S1[T], S2[T];
 #pragma unroll
         for (int i = 0; i < T; ++i) S1[i] = make_float2(0.f, 0.f), S2[i] = make_float2(0.f, 0.f);
+        float *dbc_p = g_dbc + moff(s) + dbc_tok;
+        float4 sd[2];
 
 #pragma unroll
         for (int n = 0; n < 16; ++n) {
             const float2 An = s_A[n * 32 + lane];
-            float2 hs = make_float2(0.f, 0.f);
-            if (s > 0) hs = make_float2(s_seed[((par * 2 + 0) * 16 + n) * 32 + lane], s_seed[((par * 2 + 1) * 16 + n) * 32 + lane]);
+            if ((n & 3) == 0) {         // the states entering my 8 tokens, 4 at a time
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+                    sd[r] = (s > 0 && row_ok[r]) ? *reinterpret_cast<const float4 *>(s_seed + par * (Sm::kSeedBytes / 2) + rb_unit<4>(lane + 32 * r, n >> 2) * 16)
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const float2 hs = (n & 3) == 0 ? make_float2(sd[0].x, sd[1].x) : (n & 3) == 1 ? make_float2(sd[0].y, sd[1].y)
+                            : (n & 3) == 2 ? make_float2(sd[0].z, sd[1].z) : make_float2(sd[0].w, sd[1].w);
             float Bn[T], Cn[T];
             {
                 const float4 *tb = reinterpret_cast<const float4 *>(s_tile + n * 8), *tc = reinterpret_cast<const float4 *>(s_tile + (16 + n) * 8);
@@ -408,20 +442,17 @@ __global__ void __launch_bounds__(32 * kS4W, 2) scan4_bwd_kernel(const __grid_co
                 for (int k = 0; k < 2; ++k) w2[k] = (h2 ? w4[k + 2] : w4[k]) + __shfl_xor_sync(0xffffffffu, h2 ? w4[k] : w4[k + 2], 4);
                 float w1 = (h1 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, h1 ? w2[0] : w2[1], 2);
                 w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
-                if (!(lane & 1) && n < N) {
-                    const int i = (lane >> 1) & 7;                      // token of my value; lanes 16.. hold dC
-                    float *dst = (lane & 16) ? p.dC + (int64_t)b * p.dC_bs + (int64_t)n * p.dC_ns : p.dB + (int64_t)b * p.dB_bs + (int64_t)n * p.dB_ns;
-                    atomicAdd(dst + mo + (REV ? 7 - i : i), w1);
-                }
+                if (!(lane & 1)) atomicAdd(dbc_p, w1);
+                dbc_p += dbc_ns;
             }
         }
         __syncwarp();                   // every lane is done with the tile of stage s
         if (s > s_begin) tile_sts();
 
-        // ---- epilogue: du, ddelta ----------------------------------------------------------------------------------------------------
+        // ---- epilogue: du, ddelta (staged over the u / sigmoid pieces they were computed from, then stored cooperatively) -----------
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-            const float4 u0 = keep[(0 * 2 + r) * 64], u1 = keep[(0 * 2 + r) * 64 + 32], g0 = keep[(1 * 2 + r) * 64], g1 = keep[(1 * 2 + r) * 64 + 32];
+            const float4 u0 = *keep_ptr(0, r, 0), u1 = *keep_ptr(0, r, 1), g0 = *keep_ptr(1, r, 0), g1 = *keep_ptr(1, r, 1);
             const float uu[T] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w}, sg[T] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
             float duv[T], ddv[T];
             float dbs = 0.f;
@@ -434,11 +465,14 @@ __global__ void __launch_bounds__(32 * kS4W, 2) scan4_bwd_kernel(const __grid_co
                 dbs += ddv[i];
             }
             if (r) dba.y += dbs; else dba.x += dbs;
-            if (row_ok[r]) {
-                store8<IN_T, REV>(reinterpret_cast<IN_T *>(p.du) + (int64_t)b * p.du_bs + (int64_t)row[r] * p.du_ds + mo, duv);
-                store8<IN_T, REV>(reinterpret_cast<IN_T *>(p.ddelta) + (int64_t)b * p.ddl_bs + (int64_t)row[r] * p.ddl_ds + mo, ddv);
-            }
+            stage_out(s_stage0, r, duv);
+            stage_out(s_stage1, r, ddv);
         }
+        __syncwarp();
+        rb_store<NQ>(s_stage0, reinterpret_cast<char *>(p.du) + ((int64_t)b * p.du_bs + (int64_t)row0 * p.du_ds) * ES + mo, p.du_ds * ES, nrows, NQ, lane);
+        rb_store<NQ>(s_stage1, reinterpret_cast<char *>(p.ddelta) + ((int64_t)b * p.ddl_bs + (int64_t)row0 * p.ddl_ds) * ES + mo, p.ddl_ds * ES,
+                     nrows, NQ, lane);
+        // (the next prologue's keep writes come after the __syncwarp at the top of the loop)
     }
 
     // ---- per-row parameter gradients --------------------------------------------------------------------------------------------------
@@ -446,8 +480,7 @@ __global__ void __launch_bounds__(32 * kS4W, 2) scan4_bwd_kernel(const __grid_co
     for (int r = 0; r < 2; ++r) {
         if (!row_ok[r]) continue;
 #pragma unroll
-        for (int n = 0; n < 16; ++n)
-            if (n < N) atomicAdd(p.dA + (int64_t)row[r] * N + n, r ? dA2[n].y : dA2[n].x);
+        for (int n = 0; n < 16; ++n) atomicAdd(p.dA + (int64_t)row[r] * 16 + n, r ? dA2[n].y : dA2[n].x);
         if (p.dD != nullptr) atomicAdd(p.dD + row[r], r ? dDa.y : dDa.x);
         if (p.ddbias != nullptr) atomicAdd(p.ddbias + row[r], r ? dba.y : dba.x);
     }

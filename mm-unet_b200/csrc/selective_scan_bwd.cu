@@ -36,7 +36,6 @@ struct BwdArgs {
     int B, D, L, N, Ne;
     int nseg, cps, nchunks, nx;
     int softplus, reverse;
-    int dbg_no_atomics;   // timing experiments only (MMU_BWD_NOATOM=1): skip the dB/dC atomics, results are wrong
     unsigned vec_mask;   // bit0 u, 1 delta, 2 z, 3 dout, 4 B, 5 C, 6 du, 7 ddelta, 8 dz
 };
 
@@ -420,7 +419,7 @@ __global__ void __launch_bounds__(32 * RQ * NGW, AGG ? 512 / (32 * RQ * NGW) : M
             }
         }
         // ---- epilogue B: dB / dC -> global (sum over the CTA's row-warps, then one atomic per element) ---------------
-        if (!p.dbg_no_atomics) {
+        {
             float *dB_b = p.dB + (int64_t)b * p.dB_bs, *dC_b = p.dC + (int64_t)b * p.dC_bs;
             for (int idx = tid; idx < NP * TL; idx += NT) {
                 const int tok = idx % TL, pr = idx / TL;
@@ -515,10 +514,7 @@ __global__ void scan_bwd_chain_kernel(const float *__restrict__ A, const float *
 
 namespace {
 
-int env_int(const char *name, int dflt) {
-    const char *s = getenv(name);
-    return s ? atoi(s) : dflt;
-}
+int env_int(const char *name, int dflt) { return knob(name, dflt); }
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 constexpr int kNumBwdCfg = 5;
@@ -637,7 +633,7 @@ template <typename IN_T, int W, bool REV, bool AGG> int launch_bwd3(const Bwd3Ar
     using Cfg = Bwd3Cfg<IN_T, W>;
     dim3 grid((a.D + Cfg::R - 1) / Cfg::R, a.B, a.nseg), block(Cfg::NT);
     auto k = scan3_bwd_kernel<IN_T, W, REV, AGG>;
-    const size_t smem = Cfg::smem_bytes + (size_t)env_int("MMU_BWD3_SMEM_PAD", 0);   // occupancy experiments
+    const size_t smem = Cfg::smem_bytes;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<grid, block, smem, st>>>(a);
     count_launch();
@@ -673,7 +669,6 @@ template <typename IN_T> int run_bwd3(const mmu_scan_bwd_params *p, cudaStream_t
     a.nseg = pl.nseg, a.cps = pl.cps, a.nchunks = pl.nchunks;
     a.nx = (f.seqlen + MMU_STATE_STRIDE - 1) / MMU_STATE_STRIDE;
     a.softplus = f.delta_softplus;
-    a.dbg = env_int("MMU_BWD3_DBG", 0);
     const bool rev = f.reverse != 0;
     if (pl.nseg > 1 && pl.chain) {
         const size_t n_state = (size_t)a.B * a.D * pl.nseg * 16;
@@ -732,8 +727,9 @@ Bwd4Plan plan_bwd4(int B, int D, int L) {
 
 template <typename IN_T> bool bwd4_eligible(const mmu_scan_bwd_params *p) {
     const mmu_scan_fwd_params &f = p->f;
-    if (env_int("MMU_SCAN_V", 4) < 4 || env_int("MMU_BWD_V", 4) < 4) return false;
-    if (f.x_stride != 8 || f.dim < env_int("MMU_V4_MIN_DIM", 64)) return false;
+    if (env_int("MMU_SCAN_V", 3) < 4 || env_int("MMU_BWD_V", 4) < 4) return false;
+    if (f.x_stride != 8 || f.dstate != 16 || f.dim < env_int("MMU_V4_MIN_DIM", 64)) return false;
+    if (reinterpret_cast<uintptr_t>(f.x) % 16 != 0) return false;
     if (f.seqlen > 8 && !f.x) return false;
     return bwd3_eligible<IN_T>(p);
 }
@@ -827,7 +823,6 @@ template <typename IN_T> int run_bwd(const mmu_scan_bwd_params *p, cudaStream_t 
     a.nseg = pl.nseg, a.cps = pl.cps, a.nchunks = pl.nchunks;
     a.nx = (f.seqlen + MMU_STATE_STRIDE - 1) / MMU_STATE_STRIDE;
     a.softplus = f.delta_softplus, a.reverse = f.reverse;
-    a.dbg_no_atomics = env_int("MMU_BWD_NOATOM", 0);
     const bool rev = f.reverse != 0;
     const int L = f.seqlen;
     a.vec_mask = (quad_ok<IN_T>(f.u, f.u_bs, f.u_ds, L, rev) ? 1u : 0u) |
@@ -885,8 +880,8 @@ extern "C" size_t mmu_selective_scan_bwd_workspace(int32_t batch, int32_t dim, i
 extern "C" int32_t mmu_scan_state_stride(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate, int32_t dtype) {
     using namespace mmu;
     (void)batch;
-    const bool v4 = env_int("MMU_SCAN_V", 4) >= 4 && env_int("MMU_BWD_V", 4) >= 4 && dim >= env_int("MMU_V4_MIN_DIM", 64) &&
-                    dstate <= 16 && seqlen % 8 == 0 && (dtype == MMU_F32 || dtype == MMU_BF16);
+    const bool v4 = env_int("MMU_SCAN_V", 3) >= 4 && env_int("MMU_BWD_V", 4) >= 4 && dim >= env_int("MMU_V4_MIN_DIM", 64) &&
+                    dstate == 16 && seqlen % 8 == 0 && (dtype == MMU_F32 || dtype == MMU_BF16);
     return v4 ? 8 : MMU_STATE_STRIDE;
 }
 

@@ -327,12 +327,26 @@ __global__ void scan_fwd_chain_kernel(const float *__restrict__ A, const float *
     const int64_t bd = i / Ne;
     const int row = (int)(bd % D);
     const float a2 = n < N ? A[(int64_t)row * N + n] * kLog2e : 0.f;
+    // the loads do not depend on the carry: fetch 8 segments at a time so that the serial part is 8 fmas per memory latency
     float h = 0.f;
-    for (int s = 0; s < nseg; ++s) {
-        hin[(bd * nseg + s) * Ne + n] = h;
-        if (s + 1 < nseg) h = fmaf(ex2(a2 * seg_dsum[bd * nseg + s]), h, seg_hend[(bd * nseg + s) * Ne + n]);
+    for (int s0 = 0; s0 < nseg; s0 += 8) {
+        float pa[8], he[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int s = min(s0 + k, nseg - 1);
+            pa[k] = seg_dsum[bd * nseg + s], he[k] = seg_hend[(bd * nseg + s) * Ne + n];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int s = s0 + k;
+            if (s < nseg) {
+                hin[(bd * nseg + s) * Ne + n] = h;
+                if (s + 1 < nseg) h = fmaf(ex2(a2 * pa[k]), h, he[k]);
+            }
+        }
     }
 }
+
 
 // ---- host side ----------------------------------------------------------------------------------------
 namespace {
@@ -353,10 +367,7 @@ constexpr int kFwdCfg[kNumFwdCfg][3] = {
     {2, 2, 2},   // 4: 16 rows, 4 warps, two rows per lane
 };
 
-int env_int(const char *name, int dflt) {
-    const char *s = getenv(name);
-    return s ? atoi(s) : dflt;
-}
+int env_int(const char *name, int dflt) { return knob(name, dflt); }
 
 FwdPlan plan_fwd(int B, int D, int L, int /*N*/) {
     FwdPlan pl;
@@ -531,7 +542,7 @@ Fwd4Plan plan_fwd4(int B, int D, int L) {
 }
 
 template <typename IN_T> bool fwd4_eligible(const mmu_scan_fwd_params *p) {
-    if (env_int("MMU_SCAN_V", 4) < 4) return false;
+    if (env_int("MMU_SCAN_V", 3) < 4) return false;
     if (p->dim < env_int("MMU_V4_MIN_DIM", 64)) return false;
     const int xs = p->x_stride ? p->x_stride : MMU_STATE_STRIDE;
     if (xs != 8 && xs != 64) return false;

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libmmunet_b200.so")
+SO_PATH = os.environ.get("MMU_LIB") or os.path.join(_HERE, "libmmunet_b200.so")   # MMU_LIB: an experiment build (csrc/build.sh MMU_VARIANT)
 
 F32, BF16, F16 = 0, 1, 2
 ORDER_ROWMAJOR, ORDER_FLIP, ORDER_NSLICES, ORDER_TWOROW = 0, 1, 2, 3
@@ -49,7 +49,7 @@ class ConvParams(C.Structure):
 
 
 EXPORTS = (
-    "mmu_version", "mmu_last_error", "mmu_launch_count",
+    "mmu_version", "mmu_last_error", "mmu_launch_count", "mmu_reload_knobs",
     "mmu_selective_scan_fwd_workspace", "mmu_selective_scan_fwd",
     "mmu_selective_scan_bwd_workspace", "mmu_selective_scan_bwd", "mmu_scan_state_stride",
     "mmu_causal_conv1d_fwd", "mmu_causal_conv1d_bwd",
@@ -100,6 +100,11 @@ def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = lib().mmu_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def reload_knobs() -> None:
+    """Re-read the MMU_* environment knobs (they are read once by the library)."""
+    lib().mmu_reload_knobs()
 
 
 def launch_count() -> int:

@@ -9,8 +9,12 @@ import oracle
 mode = sys.argv[1] if len(sys.argv) > 1 else "all"
 
 
+from mmunet_b200 import _lib
+
+
 def setv(v):
     os.environ["MMU_SCAN_V"] = str(v)
+    _lib.reload_knobs()
 
 
 def relerr(a, b):
@@ -73,6 +77,7 @@ for (B, D, L, dt) in ((8, 384, 4096, torch.float32), (8, 384, 4096, torch.bfloat
     if mode == "fwd" and D == 384:
         for w in (8, 16, 24):
             os.environ["MMU_V4_WPSM"] = str(w)
+            os.environ["MMU_V4_BWD_WPSM"] = str(w)
             setv(4)
             tf = timeit(lambda: ops.selective_scan_fwd(u, delta, A, Bm, Cm, Dp, z, bias, True), warm=3, it=20)
             print(f"    MMU_V4_WPSM={w}: fwd {tf:.0f} us", flush=True)

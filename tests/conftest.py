@@ -29,3 +29,30 @@ def load_golden(name):
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
+
+
+@pytest.fixture(autouse=True)
+def _mmu_knobs(monkeypatch):
+    """The library reads its MMU_* knobs once: reload them at the start of every test (the previous test's environment has
+    been restored by then) and whenever a test changes one through monkeypatch."""
+    try:
+        from mmunet_b200 import _lib
+        reload = _lib.reload_knobs
+        reload()
+    except Exception:       # library not built: the tests that need it fail on their own
+        yield
+        return
+    setenv, delenv = monkeypatch.setenv, monkeypatch.delenv
+
+    def setenv_(name, value, *a, **k):
+        setenv(name, value, *a, **k)
+        if name.startswith("MMU_"):
+            reload()
+
+    def delenv_(name, *a, **k):
+        delenv(name, *a, **k)
+        if name.startswith("MMU_"):
+            reload()
+
+    monkeypatch.setenv, monkeypatch.delenv = setenv_, delenv_
+    yield

@@ -22,12 +22,13 @@ def tol(dtype):
     return {torch.float32: (1e-3, 2e-3), torch.bfloat16: (2e-2, 5e-2), torch.float16: (3e-3, 5e-3)}[dtype]
 
 
-def check(name, got, ref, rtol, atol, scale_atol=True):
+def check(name, got, ref, rtol, atol, scale_atol=True, floor=0.0):
     got = got.detach().float().cpu().numpy().astype(np.float64)
     ref = np.asarray(ref, np.float64)
     assert got.shape == ref.shape, (name, got.shape, ref.shape)
     if scale_atol:
         atol = atol * max(1.0, float(np.abs(ref).max()))
+    atol = atol + floor * float(np.abs(ref).max())
     err = np.abs(got - ref)
     bound = atol + rtol * np.abs(ref)
     worst = float((err / bound).max()) if err.size else 0.0
@@ -239,8 +240,11 @@ def test_scan_v4_shapes(ver, shape, monkeypatch):
     run_scan_case(*shape, reverse=True)
 
 
-def test_scan_v4_is_selected():
-    """The wide kernels are the ones that run: the forward saves a state every 8 tokens for them."""
+def test_scan_v4_is_selected(monkeypatch):
+    """MMU_SCAN_V=4 selects the experimental wide kernels (opt-in: they do not beat v3, profiles/r2_v4_rows_in_lanes.md): the
+    forward then saves a state every 8 tokens for them."""
+    assert _lib.lib().mmu_scan_state_stride(2, 128, 1024, 16, _lib.F32) == 64
+    monkeypatch.setenv("MMU_SCAN_V", "4")
     assert _lib.lib().mmu_scan_state_stride(2, 128, 1024, 16, _lib.F32) == 8
     assert _lib.lib().mmu_scan_state_stride(2, 6, 1024, 16, _lib.F32) == 64
     cpu, gpu = make_scan_inputs(2, 128, 1024, 16)
@@ -253,12 +257,14 @@ def test_scan_v4_is_selected():
 @pytest.mark.parametrize("flags", [dict(has_z=False), dict(has_D=False), dict(has_bias=False),
                                    dict(has_z=False, has_D=False, has_bias=False)])
 @pytest.mark.parametrize("softplus", [False, True])
-def test_scan_v4_optional_inputs(flags, softplus):
+def test_scan_v4_optional_inputs(flags, softplus, monkeypatch):
+    monkeypatch.setenv("MMU_SCAN_V", "4")
     run_scan_case(2, 72, 520, 16, softplus=softplus, **flags)
 
 
 @pytest.mark.parametrize("reverse", [False, True])
-def test_scan_v4_bf16(reverse):
+def test_scan_v4_bf16(reverse, monkeypatch):
+    monkeypatch.setenv("MMU_SCAN_V", "4")
     run_scan_case(2, 128, 1024, 16, dtype=torch.bfloat16, reverse=reverse)
     run_scan_case(1, 66, 776, 16, dtype=torch.bfloat16, reverse=reverse)
     run_scan_case(3, 64, 512, 16, dtype=torch.bfloat16, reverse=reverse, xz_layout=True)
@@ -267,6 +273,7 @@ def test_scan_v4_bf16(reverse):
 @pytest.mark.parametrize("nseg", [1, 2, 3, 7, 64])
 def test_scan_v4_sequence_split(nseg, monkeypatch):
     """Any segment count (aggregate -> chain -> main in both passes) gives the single-segment answer."""
+    monkeypatch.setenv("MMU_SCAN_V", "4")
     monkeypatch.setenv("MMU_FWD_NSEG", str(nseg))
     monkeypatch.setenv("MMU_BWD_NSEG", str(nseg))
     run_scan_case(2, 64, 2048, 16)
@@ -274,7 +281,8 @@ def test_scan_v4_sequence_split(nseg, monkeypatch):
     run_scan_case(2, 64, 1800, 16, dtype=torch.bfloat16)
 
 
-def test_scan_v4_xz_strided_layout():
+def test_scan_v4_xz_strided_layout(monkeypatch):
+    monkeypatch.setenv("MMU_SCAN_V", "4")
     run_scan_case(3, 64, 512, 16, xz_layout=True)
     run_scan_case(2, 128, 264, 16, xz_layout=True, reverse=True)
 
@@ -317,12 +325,20 @@ def test_scan_baseline_configs_vs_oracle(B, D, L, N, tag, dtype):
     for k, t in zip(("du", "ddelta", "dA", "dB", "dC", "dD", "dz", "ddelta_bias"), g):
         rep[k] = _errs(t, rg[k])
     _parity_report(f"{tag}_{'fp32' if dtype == torch.float32 else 'bf16'}", rep)
-    # gradient sums over batch*L (dA, dD, ddelta_bias) and over dim (dB, dC) grow with the problem: their atol scales with
-    # the magnitude of the reference, as the reference's own `atolw = max(atolw, atol)` widening intends; activations are unscaled
-    check("out", out, ro, rtol, atol, scale_atol=False)
-    check("du", g[0], rg["du"], rtol, 2 * atol, scale_atol=False)
-    check("dz", g[6], rg["dz"], rtol, atol, scale_atol=False)
-    check("ddelta", g[1], rg["ddelta"], 5 * rtol, 10 * atol, scale_atol=False)
+    # Activations: the reference's UNSCALED atol (2e-3 fp32) plus an fp32 accumulation floor of 3e-5 * max|ref|.  At these sizes
+    # |out| reaches 7e2 (config 2) / 3e3 (L = 65 536): one fp32 ulp there is 6e-5 / 2.4e-4, and the reference's own CUDA kernel
+    # differs from the fp64-accumulating oracle by 9e-3 at config 2 (profiles/r2_reference_cuda_kernels.md), so 2e-3 alone is
+    # below what ANY fp32 implementation can meet; the per-tensor raw errors are written to gpurun_out/parity_*.json.
+    # Gradient sums over batch*L (dA, dD, ddelta_bias) and over dim (dB, dC) grow with the problem: their atol scales with the
+    # magnitude of the reference, as the reference's own `atolw = max(atolw, atol)` widening intends.
+    fl = 3e-5 if dtype == torch.float32 else 0.0
+    for k in rep:
+        rep[k]["within_unscaled_reference_tolerance"] = bool(rep[k]["max_abs"] <= atol) if k in ("out", "dz") else None
+    _parity_report(f"{tag}_{'fp32' if dtype == torch.float32 else 'bf16'}", rep)
+    check("out", out, ro, rtol, atol, scale_atol=False, floor=fl)
+    check("du", g[0], rg["du"], rtol, 2 * atol, scale_atol=False, floor=fl)
+    check("dz", g[6], rg["dz"], rtol, atol, scale_atol=False, floor=fl)
+    check("ddelta", g[1], rg["ddelta"], 5 * rtol, 10 * atol, scale_atol=False, floor=fl)
     check("last_state", last, rl, max(rtol, 1e-3), atol)
     check("dA", g[2], rg["dA"], max(rtol, 1e-3), 5 * atol)
     check("dB", g[3], np.asarray(rg["dB"]).reshape(g[3].shape), max(rtol, 1e-3), atol)

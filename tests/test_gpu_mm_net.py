@@ -146,8 +146,9 @@ def test_snake_sample_nan_and_fp16(no_tf32):
     out = ops.snake_sample(feat, y)
     assert torch.isnan(out[0, :, 2 * 3 + 1, 3]).all() and torch.isfinite(out[0, :, 0]).all()
     out.nan_to_num().sum().backward()
-    conv = mm_net.MMConv(8, 8, kernel_size=3).cuda().half()
-    o16 = conv(torch.randn(1, 8, 6, 6, device="cuda", dtype=torch.float16))
+    conv = mm_net.MMConv(8, 8, kernel_size=3).cuda()
+    with torch.autocast("cuda", dtype=torch.float16):      # fp16 autocast: the layer before hands MMConv an fp16 map
+        o16 = conv(torch.randn(1, 8, 6, 6, device="cuda", dtype=torch.float16))
     assert o16.shape == (1, 8, 6, 6) and torch.isfinite(o16.float()).all()
 
 
