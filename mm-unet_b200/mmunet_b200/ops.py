@@ -114,10 +114,49 @@ class ScanStates(tuple):
     y = property(lambda self: self[1])
 
 
+def _wide_state_groups(u, A, B):
+    """d_state > 16 on the fast kernels: the register-resident kernels walk at most 16 states, and the recurrences of different
+    states are independent - y = sum_n C_n h_n is a sum over state groups, every gradient either a sum over groups (du, ddelta,
+    ddelta_bias) or group-local (dA, dB, dC).  So a wide state dimension runs as ceil(dstate/16) passes of the dstate <= 16 kernels
+    over 16-state slices of A / B / C, with the D skip in the first pass and the gate applied once to the summed y (the
+    reference walks `for state_idx < dstate` inside one kernel, selective_scan_fwd_kernel.cuh:163).  Needs what those kernels
+    need (seqlen % 8 == 0, fp32 / bf16, n_groups == 1); anything else stays on the generic kernels."""
+    N = A.shape[1]
+    if N <= 16 or B.shape[1] != 1 or u.shape[-1] % 8 != 0 or u.dtype not in (torch.float32, torch.bfloat16):
+        return None
+    return [(n0, min(n0 + 16, N)) for n0 in range(0, N, 16)]
+
+
+def _silu_parts(z):
+    zf = z.float()
+    sg = torch.sigmoid(zf)
+    return zf * sg, sg * (1.0 + zf * (1.0 - sg))          # silu(z), d silu / dz
+
+
 def selective_scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, reverse=False,
                        save_states=True, return_last_state=False):
     """-> (out, states, last_state).  out is y*silu(z) when z is given; states is a ScanStates (or None)."""
     _scan_checks(u, delta, A, B, C, D, z, delta_bias)
+    groups = _wide_state_groups(u, A, B)
+    if groups is None:
+        return _selective_scan_fwd_single(u, delta, A, B, C, D, z, delta_bias, delta_softplus, reverse, save_states, return_last_state)
+    y32, xs, lasts = None, [], []
+    for gi, (n0, n1) in enumerate(groups):
+        yg, st, last = _selective_scan_fwd_single(u, delta, A[:, n0:n1].contiguous(), B[:, :, n0:n1], C[:, :, n0:n1], D if gi == 0 else None,
+                                                   None, delta_bias, delta_softplus, reverse, save_states, return_last_state)
+        y32 = yg.float() if y32 is None else y32.add_(yg)
+        if save_states:
+            xs.append(st.x)
+        if return_last_state:
+            lasts.append(last)
+    y = y32.to(u.dtype)
+    out = y if z is None else (y32 * _silu_parts(z)[0]).to(u.dtype)
+    states = ScanStates(xs, y if z is not None else None) if save_states else None     # x: one saved-state tensor per state group
+    return out, states, (torch.cat(lasts, dim=-1) if return_last_state else None)
+
+
+def _selective_scan_fwd_single(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, reverse=False,
+                               save_states=True, return_last_state=False):
     batch, dim, L = u.shape
     N = A.shape[1]
     G = B.shape[1]
@@ -166,6 +205,51 @@ def _x_stride(x, L):
 
 def selective_scan_bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softplus=False, reverse=False,
                        du=None, ddelta=None, dz=None, dBC=None):
+    """-> (du, ddelta, dA, dB, dC, dD, dz, ddelta_bias); see _selective_scan_bwd_single.  A saved-state LIST (one tensor per group
+    of 16 states, from the grouped forward) selects the grouped backward."""
+    xs = x.x if isinstance(x, ScanStates) else x
+    if not isinstance(xs, (list, tuple)):
+        return _selective_scan_bwd_single(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softplus, reverse, du, ddelta, dz, dBC)
+    _scan_checks(u, delta, A, B, C, D, z, delta_bias)
+    groups = _wide_state_groups(u, A, B)
+    batch, dim, L = u.shape
+    N = A.shape[1]
+    if dout.stride(-1) != 1 and L > 1:
+        dout = dout.contiguous()
+    dy = dout
+    if z is not None:
+        y = x.y
+        silu, dsilu = _silu_parts(z)
+        g32 = dout.float()
+        dz_val = (g32 * y.float() * dsilu).to(u.dtype)
+        dz = dz_val if dz is None else dz.copy_(dz_val)
+        dy = (g32 * silu).to(u.dtype)
+    if dBC is None:
+        dB = torch.zeros((batch, 1, N, L), device=u.device, dtype=torch.float32)
+        dC = torch.zeros_like(dB)
+        dB3, dC3 = dB[:, 0], dC[:, 0]
+    else:
+        dB3, dC3 = dBC
+        dB, dC = dB3.unsqueeze(1), dC3.unsqueeze(1)
+    dA = torch.empty((dim, N), device=u.device, dtype=torch.float32)
+    du32 = dd32 = dD = dbias = None
+    for gi, (n0, n1) in enumerate(groups):
+        g = _selective_scan_bwd_single(u, delta, A[:, n0:n1].contiguous(), B[:, :, n0:n1], C[:, :, n0:n1], D if gi == 0 else None, None,
+                                       delta_bias, dy, ScanStates(xs[gi], None), delta_softplus, reverse, dBC=(dB3[:, n0:n1], dC3[:, n0:n1]))
+        du32 = g[0].float() if du32 is None else du32.add_(g[0])
+        dd32 = g[1].float() if dd32 is None else dd32.add_(g[1])
+        dA[:, n0:n1] = g[2]
+        if gi == 0:
+            dD = g[5]
+        if g[7] is not None:
+            dbias = g[7] if dbias is None else dbias + g[7]
+    du = du32.to(u.dtype) if du is None else du.copy_(du32)
+    ddelta = dd32.to(u.dtype) if ddelta is None else ddelta.copy_(dd32)
+    return du, ddelta, dA, dB, dC, dD, dz, dbias
+
+
+def _selective_scan_bwd_single(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softplus=False, reverse=False,
+                               du=None, ddelta=None, dz=None, dBC=None):
     """-> (du, ddelta, dA, dB, dC, dD, dz, ddelta_bias); dA/dB/dC/dD/ddelta_bias fp32.
     du / ddelta / dz may be pre-allocated views (e.g. halves of dxz, as selective_scan_interface.py:244-248).
     dBC: optional pair (dB, dC) of ZERO-FILLED fp32 (batch, dstate, L) views with unit sequence stride and free batch / state
@@ -308,6 +392,27 @@ def causal_conv1d_bwd(x, weight, bias, dout, silu=False, dx=None, reverse=False)
 # autograd functions with the reference's signatures
 # ----------------------------------------------------------------------------------------------------------
 
+def _save(ctx, saved):
+    """ctx.save_for_backward for a tuple whose entries are None, tensors or lists of tensors (grouped saved states)."""
+    flat, spec = [], []
+    for t in saved:
+        if t is None:
+            spec.append(None)
+        elif isinstance(t, (list, tuple)):
+            spec.append(len(t))
+            flat.extend(t)
+        else:
+            spec.append(-1)
+            flat.append(t)
+    ctx.save_for_backward(*flat)
+    ctx.saved_spec = spec
+
+
+def _load(ctx):
+    it = iter(ctx.saved_tensors)
+    return tuple(None if k is None else (next(it) if k == -1 else [next(it) for _ in range(k)]) for k in ctx.saved_spec)
+
+
 class SelectiveScanFn(torch.autograd.Function):
     """selective_scan_interface.py:14-74."""
 
@@ -336,12 +441,12 @@ class SelectiveScanFn(torch.autograd.Function):
                                           save_states=True, return_last_state=return_last_state)
         ctx.delta_softplus = delta_softplus
         ctx.has_z = z is not None
-        ctx.save_for_backward(u, delta, A, B, C, D, z, delta_bias, x.x, x.y)
+        _save(ctx, (u, delta, A, B, C, D, z, delta_bias, x.x, x.y))
         return out if not return_last_state else (out, last)
 
     @staticmethod
     def backward(ctx, dout, *args):
-        u, delta, A, B, C, D, z, delta_bias, x, y = ctx.saved_tensors
+        u, delta, A, B, C, D, z, delta_bias, x, y = _load(ctx)
         du, ddelta, dA, dB, dC, dD, dz, ddelta_bias = selective_scan_bwd(
             u, delta, A, B, C, D, z, delta_bias, dout, ScanStates(x, y), ctx.delta_softplus)
         dB = (dB.squeeze(1) if ctx.squeeze_B else dB).to(B.dtype)
@@ -521,15 +626,13 @@ class MambaInnerFnNoOutProj(torch.autograd.Function):
                                           delta_bias, B_proj_bias, C_proj_bias, delta_softplus, reverse=reverse)
         ctx.delta_softplus = delta_softplus
         ctx.reverse = reverse
-        ctx.save_for_backward(*[t for t in saved if t is not None])
-        ctx.mask = [t is not None for t in saved]
+        _save(ctx, saved)
         return out_z
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dout):
-        it = iter(ctx.saved_tensors)
-        saved = tuple(next(it) if m else None for m in ctx.mask)
+        saved = _load(ctx)
         dxz, dcw, dcb, dxw, ddw, dA, dD, ddb = _InnerCore.backward(saved, dout, ctx.delta_softplus, reverse=ctx.reverse)
         return (dxz, dcw, dcb, dxw, ddw, dA, None, None, dD, ddb, None, None, None, None, None)
 
@@ -549,15 +652,13 @@ class MambaInnerFn(torch.autograd.Function):
         ctx.delta_softplus = delta_softplus
         ctx.out_proj_bias_is_None = out_proj_bias is None
         saved = saved + (out_proj_weight, out_z)
-        ctx.save_for_backward(*[t for t in saved if t is not None])
-        ctx.mask = [t is not None for t in saved]
+        _save(ctx, saved)
         return _out_proj(out_z, out_proj_weight, out_proj_bias)
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dout):
-        it = iter(ctx.saved_tensors)
-        saved = tuple(next(it) if m else None for m in ctx.mask)
+        saved = _load(ctx)
         out_proj_weight, out_z = saved[-2], saved[-1]
         dout_y, dout_proj_w, dout_proj_b = _out_proj_bwd(dout, out_z, out_proj_weight, not ctx.out_proj_bias_is_None)
         dxz, dcw, dcb, dxw, ddw, dA, dD, ddb = _InnerCore.backward(saved[:-2], dout_y, ctx.delta_softplus)
@@ -588,15 +689,13 @@ class BiMambaInnerFn(torch.autograd.Function):
         ctx.delta_softplus = delta_softplus
         ctx.out_proj_bias_is_None = out_proj_bias is None
         saved = saved + (out_proj_weight, out_z, A_b, xs_b.x, xs_b.y)
-        ctx.save_for_backward(*[t for t in saved if t is not None])
-        ctx.mask = [t is not None for t in saved]
+        _save(ctx, saved)
         return _out_proj(out_z, out_proj_weight, out_proj_bias)
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dout):
-        it = iter(ctx.saved_tensors)
-        saved = tuple(next(it) if m else None for m in ctx.mask)
+        saved = _load(ctx)
         out_proj_weight, out_z, A_b, xs_bx, xs_by = saved[-5:]
         core = saved[:-5]
         (xz, conv_w, conv_b, x_dbl, xw, dw, conv_st, delta, A, _, _, D, dbias, xs_fx, xs_fy) = core

@@ -287,6 +287,36 @@ def test_scan_v4_xz_strided_layout(monkeypatch):
     run_scan_case(2, 128, 264, 16, xz_layout=True, reverse=True)
 
 
+@pytest.mark.parametrize("B,D,L,N", [(2, 20, 264, 64), (1, 9, 136, 40), (2, 6, 2048, 32), (1, 128, 512, 64)])
+@pytest.mark.parametrize("reverse", [False, True])
+def test_scan_wide_state_runs_on_fast_kernels(B, D, L, N, reverse):
+    """d_state > 16 (BASELINE configs[4] sweeps 16 / 64): ceil(N/16) passes of the dstate <= 16 kernels over 16-state slices
+    (ops._wide_state_groups), y summed over the groups and gated once; a ragged last group (N = 40) included."""
+    n0 = _lib.launch_count()
+    run_scan_case(B, D, L, N, reverse=reverse)
+    assert _lib.launch_count() - n0 >= 2 * ((N + 15) // 16)          # one forward + one backward pass per state group
+    run_scan_case(B, D, L, N, reverse=reverse, dtype=torch.bfloat16)
+
+
+def test_scan_wide_state_autograd_and_optional_inputs():
+    run_scan_case(2, 12, 520, 48, has_z=False)
+    run_scan_case(2, 12, 520, 48, has_D=False, has_bias=False, softplus=False)
+    cpu, gpu = make_scan_inputs(2, 8, 256, 64)
+    t = {k: (None if v is None else v.clone().requires_grad_()) for k, v in gpu.items() if k != "dout"}
+    out, last = ops.selective_scan_fn(t["u"], t["delta"], t["A"], t["B"], t["C"], t["D"], t["z"], t["delta_bias"], True, True)
+    out.backward(gpu["dout"])
+    n = lambda v: v.numpy()
+    keys = ("u", "delta", "A", "B", "C", "D", "z", "delta_bias")
+    ro, rl = oracle.selective_scan_fwd(*(n(cpu[k]) for k in keys), True)
+    rg = oracle.selective_scan_bwd(*(n(cpu[k]) for k in keys), n(cpu["dout"]), True)
+    check("out", out, ro, 1e-3, 2e-3)
+    check("last_state", last, rl, 1e-3, 2e-3)
+    check("dA", t["A"].grad, rg["dA"], 1e-3, 1e-2)
+    check("dB", t["B"].grad, np.asarray(rg["dB"]).reshape(t["B"].grad.shape), 1e-3, 2e-3)
+    check("ddelta", t["delta"].grad, rg["ddelta"], 5e-3, 2e-2)
+    check("dz", t["z"].grad, rg["dz"], 1e-3, 2e-3)
+
+
 def _parity_report(name, rows):
     """Per-tensor max-abs / max-rel errors, for BASELINE.md section 5 (written next to the other GPU artefacts)."""
     import json
