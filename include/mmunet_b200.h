@@ -86,6 +86,13 @@ typedef struct mmu_scan_fwd_params {
      * backward recomputes it.  Ignored when z == NULL (then out == y). */
     void *y;
     int64_t y_bs, y_ds;
+    /* Fused scan order (enum mmu_order; 0 = none).  NSLICES / TWOROW: logical token l of the scan lives at memory index idx(l)
+     * (the index map of mmu_scan_order_*) in the GATE and OUTPUT tensors - z and out in the forward, z, dout and dz in the
+     * backward - i.e. those tensors stay in the image's natural token order and are permuted by the kernels' own loads and
+     * stores (requirements/mamba_simple.py:245-247, 263; src/UM_Net/MMUNet.py:68-121), while u, delta, B, C, y, x, du, ddelta,
+     * dB, dC are in scan order (they are produced / consumed in that order by the conv and the projections).  Only where
+     * mmu_scan_order_fusable() says so; FLIP is the `reverse` flag. */
+    int32_t order, order_h, order_w, order_ns;
 } mmu_scan_fwd_params;
 
 size_t mmu_selective_scan_fwd_workspace(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate);
@@ -142,6 +149,9 @@ typedef struct mmu_conv_params {
     void *dx;
     float *dweight, *dbias;
     int64_t dout_bs, dout_ds, dx_bs, dx_ds;
+    /* Fused scan order (0 = none): x (and dx) are addressed through idx(l), i.e. they stay in natural token order, while out /
+     * dout are in scan order: out[l] = act(bias + sum_k w[k] x[idx(l - (W-1-k))]).  Not combined with `reverse`. */
+    int32_t order, order_h, order_w, order_ns;
 } mmu_conv_params;
 
 int mmu_causal_conv1d_fwd(const mmu_conv_params *p, void *stream);
@@ -165,6 +175,10 @@ int mmu_scan_order_gather(const void *src, void *dst, int32_t dtype, int64_t row
 int mmu_scan_order_scatter(const void *src, void *dst, int32_t dtype, int64_t rows, int64_t src_rs, int64_t dst_rs,
                            int32_t order, int32_t H, int32_t W, int32_t nslices, void *stream);
 int mmu_scan_order_index(int64_t *idx_dev, int32_t order, int32_t H, int32_t W, int32_t nslices, void *stream);
+/* 1 when the conv / scan kernels can apply `order` themselves for a sequence of H*W tokens (their `order` fields): 8-token groups
+ * must map to simple strides - NSLICES: nslices % 8 == 0, (L / nslices) even; TWOROW: W % 4 == 0 - and the scan must run on the
+ * dstate <= 16 kernels (seqlen % 8 == 0, fp32 / bf16).  Otherwise permute with mmu_scan_order_gather / _scatter. */
+int32_t mmu_scan_order_fusable(int32_t order, int32_t H, int32_t W, int32_t nslices, int32_t dstate, int32_t dtype);
 
 /* ---------------------------------------------------------------------------------------------
  * snake row sampler of MMConv (the caller of the Mamba block).  replaces the

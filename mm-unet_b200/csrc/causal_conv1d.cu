@@ -23,6 +23,7 @@ struct ConvArgs {
     int B, D, L, W;
     int silu, reverse;
     unsigned vec_mask;   // bit0 x, bit1 out/dx, bit2 dout
+    OrdMap ord;          // fused scan order: x / dx live at ord(l), out / dout at l
 };
 
 constexpr int kConvNT = 128;
@@ -44,6 +45,12 @@ __device__ __forceinline__ void loadv(const IN_T *rp, int t, int L, bool vec, bo
 #pragma unroll
         for (int k = 0; k < VT; ++k) v[k] = (t + k < L) ? Elem<IN_T>::to_f(rp[mpos(t + k, L, rev)]) : 0.f;
     }
+}
+
+// x addressed through the scan-order map (element-wise: the map scatters consecutive tokens)
+template <typename IN_T, int N> __device__ __forceinline__ void load_ord(const IN_T *rp, int t, int L, const OrdMap &ord, float *v) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = (t + k >= 0 && t + k < L) ? Elem<IN_T>::to_f(rp[ord(t + k)]) : 0.f;
 }
 
 template <typename OUT_T, int VT>
@@ -82,9 +89,13 @@ template <typename IN_T> __global__ void __launch_bounds__(kConvNT) conv1d_fwd_k
     const IN_T *xr = reinterpret_cast<const IN_T *>(p.x) + (int64_t)b * p.x_bs + (int64_t)d * p.x_ds;
     float xv[kConvVT + 3];
     const bool rev = p.reverse != 0;
+    if (p.ord.kind != MMU_ORDER_ROWMAJOR) {
+        load_ord<IN_T, kConvVT + 3>(xr, t - 3, p.L, p.ord, xv);
+    } else {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) xv[k] = (t - 3 + k >= 0) ? Elem<IN_T>::to_f(xr[mpos(t - 3 + k, p.L, rev)]) : 0.f;
-    loadv<IN_T, kConvVT>(xr, t, p.L, p.vec_mask & 1u, rev, xv + 3);
+        for (int k = 0; k < 3; ++k) xv[k] = (t - 3 + k >= 0) ? Elem<IN_T>::to_f(xr[mpos(t - 3 + k, p.L, rev)]) : 0.f;
+        loadv<IN_T, kConvVT>(xr, t, p.L, p.vec_mask & 1u, rev, xv + 3);
+    }
     float o[kConvVT];
 #pragma unroll
     for (int i = 0; i < kConvVT; ++i) {
@@ -109,14 +120,19 @@ template <typename IN_T> __global__ void __launch_bounds__(kConvNT) conv1d_bwd_k
         const IN_T *xr = reinterpret_cast<const IN_T *>(p.x) + (int64_t)b * p.x_bs + (int64_t)d * p.x_ds;
         const IN_T *gr = reinterpret_cast<const IN_T *>(p.dout) + (int64_t)b * p.g_bs + (int64_t)d * p.g_ds;
         float xv[kConvVT + 6], gv[kConvVT + 3];   // x[t-3 .. t+10], dout[t .. t+10]
+        const bool ordered = p.ord.kind != MMU_ORDER_ROWMAJOR;
+        if (ordered) {
+            load_ord<IN_T, kConvVT + 6>(xr, t - 3, p.L, p.ord, xv);
+        } else {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) xv[k] = (t - 3 + k >= 0) ? Elem<IN_T>::to_f(xr[mpos(t - 3 + k, p.L, rev)]) : 0.f;
-        loadv<IN_T, kConvVT>(xr, t, p.L, p.vec_mask & 1u, rev, xv + 3);
+            for (int k = 0; k < 3; ++k) xv[k] = (t - 3 + k >= 0) ? Elem<IN_T>::to_f(xr[mpos(t - 3 + k, p.L, rev)]) : 0.f;
+            loadv<IN_T, kConvVT>(xr, t, p.L, p.vec_mask & 1u, rev, xv + 3);
+        }
         loadv<IN_T, kConvVT>(gr, t, p.L, p.vec_mask & 4u, rev, gv);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const int tt = t + kConvVT + k;
-            xv[3 + kConvVT + k] = tt < p.L ? Elem<IN_T>::to_f(xr[mpos(tt, p.L, rev)]) : 0.f;
+            if (!ordered) xv[3 + kConvVT + k] = tt < p.L ? Elem<IN_T>::to_f(xr[mpos(tt, p.L, rev)]) : 0.f;
             gv[kConvVT + k] = tt < p.L ? Elem<IN_T>::to_f(gr[mpos(tt, p.L, rev)]) : 0.f;
         }
         float dpre[kConvVT + 3];
@@ -143,8 +159,14 @@ template <typename IN_T> __global__ void __launch_bounds__(kConvNT) conv1d_bwd_k
 #pragma unroll
             for (int k = 0; k < 4; ++k) part[k] = fmaf(xv[i + k], dpre[i], part[k]);
         }
-        storev<IN_T, kConvVT>(reinterpret_cast<IN_T *>(p.dx) + (int64_t)b * p.dx_bs + (int64_t)d * p.dx_ds, t, p.L, p.vec_mask & 2u,
-                     rev, dxv);
+        IN_T *dxr = reinterpret_cast<IN_T *>(p.dx) + (int64_t)b * p.dx_bs + (int64_t)d * p.dx_ds;
+        if (ordered) {
+#pragma unroll
+            for (int k = 0; k < kConvVT; ++k)
+                if (t + k < p.L) dxr[p.ord(t + k)] = Elem<IN_T>::from_f(dxv[k]);
+        } else {
+            storev<IN_T, kConvVT>(dxr, t, p.L, p.vec_mask & 2u, rev, dxv);
+        }
     }
     // block reduce -> one atomic per (channel, tap) per CTA
     __shared__ float red[kConvNT / 32][5];
@@ -177,6 +199,10 @@ template <typename IN_T> int run_conv(const mmu_conv_params *p, bool bwd, cudaSt
     a.x_bs = p->x_bs, a.x_ds = p->x_ds, a.o_bs = p->out_bs, a.o_ds = p->out_ds, a.w_ds = p->w_ds, a.w_ws = p->w_ws;
     a.g_bs = p->dout_bs, a.g_ds = p->dout_ds, a.dx_bs = p->dx_bs, a.dx_ds = p->dx_ds;
     a.B = p->batch, a.D = p->dim, a.L = p->seqlen, a.W = p->width, a.silu = p->silu, a.reverse = p->reverse;
+    if (!make_ordmap(a.ord, p->order, p->order_h, p->order_w, p->order_ns, p->seqlen) || (p->order == MMU_ORDER_FLIP) ||
+        (p->order != MMU_ORDER_ROWMAJOR && p->reverse))
+        return set_error(MMU_ERR_INVALID, "causal_conv1d: bad scan order %d (H=%d W=%d nslices=%d, L=%d, reverse=%d)", p->order, p->order_h,
+                         p->order_w, p->order_ns, p->seqlen, p->reverse);
     const int L = p->seqlen;
     const bool rv = p->reverse != 0;
     a.vec_mask = quad_ok<IN_T>(p->x, p->x_bs, p->x_ds, L, rv) ? 1u : 0u;

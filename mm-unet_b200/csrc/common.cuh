@@ -73,6 +73,66 @@ __device__ __forceinline__ float2 shfl_down2(float2 v, int delta, int width) {
                        __shfl_down_sync(0xffffffffu, v.y, delta, width));
 }
 
+// ---- scan-order index map -------------------------------------------------------------------------------------------------
+// idx(l) = memory index of logical (scan-order) token l; the closed forms of the reference's permutations
+// (NSLICES: requirements/mamba_simple.py:245-247, 263;  TWOROW: src/UM_Net/MMUNet.py:68-121).  Shared by the standalone gather /
+// scatter kernels, the conv kernels (x / dx addressed through it) and the scan kernels (gate z, out, dout, dz addressed through it).
+struct OrdMap {
+    int kind;                 // MMU_ORDER_ROWMAJOR / FLIP / NSLICES / TWOROW
+    int W, ns, L, Ls, even_tokens;   // Ls = L / ns, even_tokens = 2*(H/2)*W
+    __device__ __forceinline__ int operator()(int l) const {
+        switch (kind) {
+            case MMU_ORDER_FLIP: return L - 1 - l;
+            case MMU_ORDER_NSLICES: {
+                const int jj = l / ns, s = l - jj * ns;
+                return s * Ls + jj;
+            }
+            case MMU_ORDER_TWOROW: {
+                if (l >= even_tokens) return l;   // odd tail row, appended row-major
+                const int pair = l / (2 * W), rem = l - pair * 2 * W;
+                return (2 * pair + (rem & 1)) * W + (rem >> 1);
+            }
+            default: return l;
+        }
+    }
+    // 8 consecutive logical tokens t0 .. t0+7 with t0 % 8 == 0, for the fusable cases (NSLICES: ns % 8 == 0; TWOROW: W % 4 == 0, so
+    // that a group never straddles a slice round / a row pair): one division per group
+    __device__ __forceinline__ void idx8(int t0, int (&m)[8]) const {
+        if (kind == MMU_ORDER_NSLICES) {
+            const int jj = t0 / ns, s0 = t0 - jj * ns;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m[i] = (s0 + i) * Ls + jj;
+        } else if (kind == MMU_ORDER_TWOROW && t0 < even_tokens) {
+            const int pair = t0 / (2 * W), rem = t0 - pair * 2 * W, base = 2 * pair * W + (rem >> 1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m[i] = base + (i & 1) * W + (i >> 1);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m[i] = t0 + i;
+        }
+    }
+};
+// host: fill the map; returns false when the arguments are inconsistent
+inline bool make_ordmap(OrdMap &m, int order, int H, int W, int ns, int L) {
+    m = OrdMap{order, W > 0 ? W : 1, ns > 0 ? ns : 1, L, 0, 0};
+    if (order == MMU_ORDER_NSLICES) {
+        if (ns <= 0 || L % ns != 0) return false;
+        m.Ls = L / ns;
+    } else if (order == MMU_ORDER_TWOROW) {
+        if (H <= 0 || W <= 0 || (int64_t)H * W != L) return false;
+        m.even_tokens = 2 * (H / 2) * W;
+    }
+    return true;
+}
+// the scan / conv kernels fuse an order only where 8-token groups map to simple strides (otherwise the caller permutes explicitly)
+inline bool ordmap_fusable(int order, int H, int W, int ns, int L) {
+    if (order == MMU_ORDER_ROWMAJOR) return true;
+    if (L % 8 != 0) return false;
+    if (order == MMU_ORDER_NSLICES) return ns > 0 && ns % 8 == 0 && L % ns == 0 && (L / ns) % 2 == 0;
+    if (order == MMU_ORDER_TWOROW) return H > 0 && W > 0 && (int64_t)H * W == L && W % 4 == 0;
+    return false;
+}
+
 // ---- shared-memory tile addressing ---------------------------------------------------------------
 // A tile row holds TL fp32 tokens.  Thread j of a row-group reads T consecutive tokens with LDS.128; the
 // 16-byte chunk index is XOR-swizzled so that the 8 lanes of a quarter-warp hit 8 distinct bank groups.

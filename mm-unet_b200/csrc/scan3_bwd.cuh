@@ -29,6 +29,7 @@ struct Bwd3Args {
     int B, D, L, N;
     int nseg, cps, nchunks, nx;
     int softplus;
+    OrdMap ord;                    // ORD kernels: z, dout and dz live at ord(l) (natural token order), everything else at l
 };
 
 template <typename IN_T, int W> struct Bwd3Cfg {
@@ -44,15 +45,19 @@ template <typename IN_T, int W> struct Bwd3Cfg {
     static constexpr int kSlabBytes = 2 * W * 2 * 2 * 32 * 16;            // dB | dC partials of one state: [buf][warp][tensor][quad][lane] float4
     static constexpr int kSeedBytes = 2 * W * NCK * 16 * 8;               // x seeds [buf][warp][ck][state] float2
     static constexpr int kTabBytes = 2 * NRP * 16 * 8;                    // A*log2e | e carry
-    static constexpr size_t smem_bytes = (size_t)BcTile<LPR>::kBytes + kRawBytes + kLandBytes + kZfBytes + kDABytes + kSlabBytes + kSeedBytes + kTabBytes;
+    static constexpr int kOrdBytes = kF32 ? 0 : 2 * 2 * NT * 16;          // ordered z / dout of 2-byte types: second quad [tensor][row][thread]
+    static constexpr size_t smem_bytes = (size_t)BcTile<LPR>::kBytes + kRawBytes + kLandBytes + kZfBytes + kDABytes + kSlabBytes + kSeedBytes + kTabBytes + kOrdBytes;
 };
 
 __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <typename IN_T, int W, bool REV, bool AGG>
+// ORD: fused scan order (NSLICES / TWOROW): z and dout are gathered, dz is scattered through p.ord (4-byte accesses; a 2-byte
+// element comes with its neighbour and is picked by the parity of its index); never together with REV.
+template <typename IN_T, int W, bool REV, bool AGG, bool ORD = false>
 __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(const __grid_constant__ Bwd3Args p) {
+    static_assert(!ORD || !REV, "ordered gate / output gradient: forward direction only");
     using Cfg = Bwd3Cfg<IN_T, W>;
     constexpr int LPR = 32;
     using Tl = BcTile<LPR>;
@@ -91,6 +96,7 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
     float2 *s_seed = reinterpret_cast<float2 *>(s_zf + Cfg::kZfBytes + Cfg::kDABytes + Cfg::kSlabBytes);   // [2][W][NCK][16]
     float2 *s_A = s_seed + 2 * W * NCK * 16;                               // [NRP][16]  A*log2e of (row A, row B)
     float2 *s_ec = s_A + NRP * 16;                                         // [NRP][16]  e entering the chunk from the right
+    [[maybe_unused]] unsigned char *s_ordx = reinterpret_cast<unsigned char *>(s_ec + NRP * 16);   // [2 tensors][2 rows][NT] x 16 B (2-byte types)
 
     for (int i = tid; i < (int)((Tl::kBytes + Cfg::kRawBytes + Cfg::kLandBytes + Cfg::kZfBytes + Cfg::kDABytes + Cfg::kSlabBytes + Cfg::kSeedBytes) / 16); i += NT)
         reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -145,6 +151,18 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
         bias[r] = p.dbias != nullptr ? p.dbias[row] : 0.f;
         Dsk[r] = p.Dv != nullptr ? p.Dv[row] : 0.f;
     }
+    [[maybe_unused]] const IN_T *z_row[2], *g_row[2];
+    [[maybe_unused]] IN_T *dz_row[2];
+    if constexpr (ORD) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int row = min(rowA + r, D - 1);
+            z_row[r] = has_z ? reinterpret_cast<const IN_T *>(p.z) + (int64_t)b * p.z_bs + (int64_t)row * p.z_ds : nullptr;
+            g_row[r] = reinterpret_cast<const IN_T *>(p.dout) + (int64_t)b * p.g_bs + (int64_t)row * p.g_ds;
+            dz_row[r] = (AGG || !has_z) ? nullptr : reinterpret_cast<IN_T *>(p.dz) + (int64_t)b * p.dz_bs + (int64_t)row * p.dz_ds;
+        }
+    }
+    [[maybe_unused]] int tin = tl + CH;      // ORD: first logical token of my 8 in the chunk being prefetched (one step behind, like the pointers)
     const IN_T *B_b = reinterpret_cast<const IN_T *>(p.Bm) + (int64_t)b * p.B_bs;
     const IN_T *C_b = reinterpret_cast<const IN_T *>(p.Cm) + (int64_t)b * p.C_bs;
     float *dB_b = AGG ? nullptr : p.dB + (int64_t)b * p.dB_bs;
@@ -164,6 +182,12 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
     float2 dDacc = make_float2(0.f, 0.f), dbacc = make_float2(0.f, 0.f);
     float dsum[2] = {0.f, 0.f};
 
+    [[maybe_unused]] const unsigned s_ordx_u32 = smem_u32(s_ordx) + tid * 16;
+    // word i (4 bytes) of my slot of ordered tensor `which` (2 = z, 3 = dout), row r
+    auto ordword_u32 = [&](int which, int r, int i) {
+        if constexpr (kF32) return s_land_u32 + ((which * 2 + r) * NQ + (i >> 2)) * NT * 16 + (i & 3) * 4;
+        else return (i < 4 ? s_land_u32 + (which * 2 + r) * NT * 16 : s_ordx_u32 + ((which - 2) * 2 + r) * NT * 16) + (i & 3) * 4;
+    };
     auto issue_tile = [&](int c) {
         if constexpr (kF32) {
             tile_async_f32<LPR, NT, REV, true>(s_tile_u32, reinterpret_cast<const float *>(B_b), reinterpret_cast<const float *>(C_b), p.B_ns,
@@ -181,17 +205,39 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
             if (has_z) z_p[r] += STEP;
             if (!AGG && has_z) y_p[r] += STEP;
         }
+        if constexpr (ORD) tin -= CH;
         if (in_seq) {
 #pragma unroll
             for (int r = 0; r < 2; ++r)
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) {
                     cp_async16(s_land_u32 + ((1 * 2 + r) * NQ + q) * NT * 16, d_p[r] + q * EPQ);
-                    cp_async16(s_land_u32 + ((3 * 2 + r) * NQ + q) * NT * 16, g_p[r] + q * EPQ);
+                    if (!ORD) cp_async16(s_land_u32 + ((3 * 2 + r) * NQ + q) * NT * 16, g_p[r] + q * EPQ);
                     if (!AGG) cp_async16(s_land_u32 + ((0 * 2 + r) * NQ + q) * NT * 16, u_p[r] + q * EPQ);
-                    if (has_z) cp_async16(s_land_u32 + ((2 * 2 + r) * NQ + q) * NT * 16, z_p[r] + q * EPQ);
+                    if (!ORD && has_z) cp_async16(s_land_u32 + ((2 * 2 + r) * NQ + q) * NT * 16, z_p[r] + q * EPQ);
                     if (!AGG && has_z) cp_async16(s_land_u32 + ((4 * 2 + r) * NQ + q) * NT * 16, y_p[r] + q * EPQ);
                 }
+            if constexpr (ORD) {
+                int m[8];
+                p.ord.idx8(tin, m);
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        cp_async4(ordword_u32(3, r, i), g_row[r] + (kF32 ? m[i] : (m[i] & ~1)));
+                        if (has_z) cp_async4(ordword_u32(2, r, i), z_row[r] + (kF32 ? m[i] : (m[i] & ~1)));
+                    }
+            }
+        }
+    };
+    // ordered tensor `which` (2 = z, 3 = dout), row r, logical order: 8 words; 2-byte types pick the half by the parity of the index
+    auto load_ord8 = [&](int which, int r, const int (&m)[8], float (&v)[T]) {
+#pragma unroll
+        for (int i = 0; i < T; ++i) {
+            const unsigned char *q0 = kF32 ? s_land_t + ((which * 2 + r) * NQ + (i >> 2)) * NT * 16
+                                           : (i < 4 ? s_land_t + (which * 2 + r) * NT * 16 : s_ordx + tid * 16 + ((which - 2) * 2 + r) * NT * 16);
+            const unsigned w = *reinterpret_cast<const unsigned *>(q0 + (i & 3) * 4);
+            v[i] = kF32 ? __uint_as_float(w) : __uint_as_float((m[i] & 1) ? (w & 0xffff0000u) : (w << 16));
         }
     };
     auto load_land = [&](int which, int r, float (&v)[T]) {
@@ -237,14 +283,18 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
         float2 dl[T], dlu[T], dy[T];
         {
             float uu[2][T], dd[2][T], gg[2][T], zf[2][T];
+            [[maybe_unused]] int mo[8];
+            if constexpr (ORD) p.ord.idx8(tl, mo);
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 load_land(1, r, dd[r]);
-                load_land(3, r, gg[r]);
+                if constexpr (ORD) load_ord8(3, r, mo, gg[r]);
+                else load_land(3, r, gg[r]);
                 if (!AGG) load_land(0, r, uu[r]);
                 if (has_z) {
                     float zz[T], yv[T];
-                    load_land(2, r, zz);
+                    if constexpr (ORD) load_ord8(2, r, mo, zz);
+                    else load_land(2, r, zz);
                     if (!AGG) load_land(4, r, yv);
 #pragma unroll
                     for (int i = 0; i < T; ++i) {
@@ -256,7 +306,14 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
                     // dz needs nothing from the state loop: store it now, so that neither y nor the gate factor has to be kept
                     if (!AGG) {
                         dz_p[r] += STEP;
-                        if (ok && row_ok[r]) store8<IN_T, REV>(dz_p[r], zf[r]);
+                        if (ok && row_ok[r]) {
+                            if constexpr (ORD) {
+#pragma unroll
+                                for (int i = 0; i < T; ++i) dz_row[r][mo[i]] = Elem<IN_T>::from_f(zf[r][i]);
+                            } else {
+                                store8<IN_T, REV>(dz_p[r], zf[r]);
+                            }
+                        }
                     }
                 }
 #pragma unroll

@@ -33,6 +33,7 @@ struct Fwd3Args {
     int B, D, L, N;
     int nseg, cps, nchunks, nx;    // cps = chunks per segment
     int softplus;
+    OrdMap ord;                    // ORD kernels: the gate z and the output live at ord(l) (natural token order), everything else at l
 };
 
 template <typename IN_T, int LPR, int W> struct Fwd3Cfg {
@@ -43,11 +44,15 @@ template <typename IN_T, int LPR, int W> struct Fwd3Cfg {
     static constexpr int NQ = Raw8<IN_T>::kQuads;
     static constexpr int kElemBytes = 3 * 2 * NQ * NT * 16;               // u | delta | z : [tensor][row][quad][thread] x 16 B
     static constexpr int kTabBytes = (1 + NCK) * NRP * 16 * (int)sizeof(float2);   // A*log2e | states after every 64 tokens
-    static constexpr size_t smem_bytes = (size_t)BcTile<LPR>::kBytes + kRawBytes + kElemBytes + kTabBytes;
+    static constexpr int kZxBytes = kF32 ? 0 : 2 * NT * 16;               // ordered z of 2-byte types: 8 pair-words need a second quad per row
+    static constexpr size_t smem_bytes = (size_t)BcTile<LPR>::kBytes + kRawBytes + kElemBytes + kTabBytes + kZxBytes;
 };
 
-template <typename IN_T, int LPR, int W, bool REV, bool AGG>
+// ORD: fused scan order (NSLICES / TWOROW) - z is gathered and out scattered through p.ord, 4 bytes at a time (a 2-byte element
+// comes with its neighbour and is picked by the parity of its index); never together with REV or AGG.
+template <typename IN_T, int LPR, int W, bool REV, bool AGG, bool ORD = false>
 __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) scan3_fwd_kernel(const __grid_constant__ Fwd3Args p) {
+    static_assert(!ORD || (!REV && !AGG), "ordered gate / output: forward direction, main pass only");
     using Cfg = Fwd3Cfg<IN_T, LPR, W>;
     using Tl = BcTile<LPR>;
     constexpr int CH = Cfg::CH, RPW = Cfg::RPW, R = Cfg::R, NT = Cfg::NT, NRP = Cfg::NRP, T = kS3T, NQ = Cfg::NQ, NCK = Cfg::NCK;
@@ -70,6 +75,7 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
     float2 *s_A = reinterpret_cast<float2 *>(s_elem + Cfg::kElemBytes);                // [NRP][16]  A*log2e of (row A, row B)
     float2 *s_ck = s_A + NRP * 16;                                                     // [NRP][NCK][16]  state after every 64th token;
                                                                                        // slot NCK-1 = state entering the next chunk
+    [[maybe_unused]] unsigned char *s_zx = reinterpret_cast<unsigned char *>(s_ck + NRP * NCK * 16);   // [2 rows][NT] x 16 B (2-byte types)
     // ---- one-time initialisation -----------------------------------------------------------------------------------------
     for (int i = tid; i < (int)((Tl::kBytes + Cfg::kRawBytes + Cfg::kElemBytes) / 16); i += NT)
         reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -112,6 +118,17 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
         Dsk[r] = p.Dv != nullptr ? p.Dv[row] : 0.f;
     }
     constexpr int STEP = REV ? -CH : CH;
+    [[maybe_unused]] const IN_T *z_row[2];
+    [[maybe_unused]] IN_T *o_row[2];
+    if constexpr (ORD) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int row = min(rowA + r, D - 1);
+            z_row[r] = has_z ? reinterpret_cast<const IN_T *>(p.z) + (int64_t)b * p.z_bs + (int64_t)row * p.z_ds : nullptr;
+            o_row[r] = reinterpret_cast<IN_T *>(p.out) + (int64_t)b * p.o_bs + (int64_t)row * p.o_ds;
+        }
+    }
+    [[maybe_unused]] int tz = tl;        // ORD: first logical token of my 8 in the chunk whose z is being prefetched
     const IN_T *B_b = reinterpret_cast<const IN_T *>(p.Bm) + (int64_t)b * p.B_bs;
     const IN_T *C_b = reinterpret_cast<const IN_T *>(p.Cm) + (int64_t)b * p.C_bs;
 
@@ -162,7 +179,25 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
 #pragma unroll
         for (int r = 0; r < 2; ++r) u_p[r] += STEP, d_p[r] += STEP;
     };
+    [[maybe_unused]] const unsigned s_zx_u32 = smem_u32(s_zx) + tid * 16;
+    // word i (4 bytes) of my ordered-z slot of row r: fp32 = element i; 2-byte types = the aligned pair holding element i
+    auto zword_u32 = [&](int r, int i) {
+        if constexpr (kF32) return s_elem_u32 + ((2 * 2 + r) * NQ + (i >> 2)) * NT * 16 + (i & 3) * 4;
+        else return (i < 4 ? s_elem_u32 + (2 * 2 + r) * NT * 16 : s_zx_u32 + r * NT * 16) + (i & 3) * 4;
+    };
     auto issue_z = [&](bool in_seq) {
+        if constexpr (ORD) {
+            if (has_z && in_seq) {
+                int m[8];
+                p.ord.idx8(tz, m);
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) cp_async4(zword_u32(r, i), z_row[r] + (kF32 ? m[i] : (m[i] & ~1)));
+            }
+            tz += CH;
+            return;
+        }
         if (!AGG && has_z) {
             if (in_seq) {
 #pragma unroll
@@ -297,7 +332,21 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
             if (c + 1 < c_end) issue_tile(c + 1);
             // ---- epilogue: gate and store ---------------------------------------------------------------------------------------
             float zz[2][T];
-            if (has_z) {
+            [[maybe_unused]] int mo[8];
+            if constexpr (ORD) {
+                p.ord.idx8(tl, mo);
+                if (has_z) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r)
+#pragma unroll
+                        for (int i = 0; i < T; ++i) {
+                            const unsigned w = *reinterpret_cast<const unsigned *>(
+                                (kF32 ? s_elem_t + ((2 * 2 + r) * NQ + (i >> 2)) * NT * 16 : (i < 4 ? s_elem_t + (2 * 2 + r) * NT * 16 : s_zx + tid * 16 + r * NT * 16)) +
+                                (i & 3) * 4);
+                            zz[r][i] = kF32 ? __uint_as_float(w) : __uint_as_float((mo[i] & 1) ? (w & 0xffff0000u) : (w << 16));
+                        }
+                }
+            } else if (has_z) {
                 load_elem(2, 0, zz[0]);
                 load_elem(2, 1, zz[1]);
             }
@@ -315,7 +364,12 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
 #pragma unroll
                             for (int i = 0; i < T; ++i) yv[i] *= zz[r][i] * sigmoid3(zz[r][i]);
                         }
-                        store8<IN_T, REV>(o_p[r], yv);
+                        if constexpr (ORD) {
+#pragma unroll
+                            for (int i = 0; i < T; ++i) o_row[r][mo[i]] = Elem<IN_T>::from_f(yv[i]);
+                        } else {
+                            store8<IN_T, REV>(o_p[r], yv);
+                        }
                     }
                 }
             }

@@ -13,24 +13,7 @@
 
 namespace mmu {
 
-struct OrderMap {
-    int order, W, ns, L, Ls, even_tokens;   // Ls = L / ns, even_tokens = 2*(H/2)*W
-    __device__ __forceinline__ int operator()(int l) const {
-        switch (order) {
-            case MMU_ORDER_FLIP: return L - 1 - l;
-            case MMU_ORDER_NSLICES: {
-                const int jj = l / ns, s = l - jj * ns;
-                return s * Ls + jj;
-            }
-            case MMU_ORDER_TWOROW: {
-                if (l >= even_tokens) return l;   // odd tail row, appended row-major
-                const int pair = l / (2 * W), rem = l - pair * 2 * W;
-                return (2 * pair + (rem & 1)) * W + (rem >> 1);
-            }
-            default: return l;
-        }
-    }
-};
+using OrderMap = OrdMap;   // common.cuh
 
 template <typename T, bool SCATTER>
 __global__ void __launch_bounds__(256) scan_order_kernel(const T *__restrict__ src, T *__restrict__ dst, int64_t rows,
@@ -101,7 +84,7 @@ int make_map(OrderMap &m, int order, int H, int W, int ns) {
     if (H <= 0 || W <= 0) return set_error(MMU_ERR_INVALID, "scan_order: empty map %dx%d", H, W);
     if ((int64_t)H * W > INT32_MAX) return set_error(MMU_ERR_UNSUPPORTED, "scan_order: H*W exceeds int32");
     if (order < MMU_ORDER_ROWMAJOR || order > MMU_ORDER_TWOROW) return set_error(MMU_ERR_INVALID, "scan_order: order %d", order);
-    m.order = order, m.W = W, m.L = H * W, m.ns = 1, m.Ls = m.L, m.even_tokens = 2 * (H / 2) * W;
+    m.kind = order, m.W = W, m.L = H * W, m.ns = 1, m.Ls = m.L, m.even_tokens = 2 * (H / 2) * W;
     if (order == MMU_ORDER_NSLICES) {
         if (ns <= 0 || m.L % ns != 0) return set_error(MMU_ERR_INVALID, "scan_order: L=%d not divisible by nslices=%d", m.L, ns);
         m.ns = ns, m.Ls = m.L / ns;

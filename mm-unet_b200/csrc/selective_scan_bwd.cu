@@ -601,10 +601,11 @@ struct Bwd3Plan {
     bool chain;     // segments are chained CTAs (no aggregate pass)
 };
 
-Bwd3Plan plan_bwd3(int B, int D, int L) {
+Bwd3Plan plan_bwd3(int B, int D, int L, bool ordered = false) {
     Bwd3Plan pl;
     pl.W = env_int("MMU_BWD3_W", D <= 2 ? 1 : (D <= 4 ? 2 : 4));   // W = 3 (6 rows) measured slower than 4 with idle lanes
     if (pl.W != 8 && (pl.W < 1 || pl.W > 4)) pl.W = 4;
+    if (ordered && pl.W == 8) pl.W = 4;
     const int R = 2 * pl.W;
     pl.nchunks = (L + 255) / 256;
     const int warps = B * ((D + R - 1) / R) * pl.W;
@@ -629,10 +630,10 @@ Bwd3Plan plan_bwd3(int B, int D, int L) {
     return pl;
 }
 
-template <typename IN_T, int W, bool REV, bool AGG> int launch_bwd3(const Bwd3Args &a, cudaStream_t st) {
+template <typename IN_T, int W, bool REV, bool AGG, bool ORD = false> int launch_bwd3(const Bwd3Args &a, cudaStream_t st) {
     using Cfg = Bwd3Cfg<IN_T, W>;
     dim3 grid((a.D + Cfg::R - 1) / Cfg::R, a.B, a.nseg), block(Cfg::NT);
-    auto k = scan3_bwd_kernel<IN_T, W, REV, AGG>;
+    auto k = scan3_bwd_kernel<IN_T, W, REV, AGG, ORD>;
     const size_t smem = Cfg::smem_bytes;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<grid, block, smem, st>>>(a);
@@ -641,6 +642,12 @@ template <typename IN_T, int W, bool REV, bool AGG> int launch_bwd3(const Bwd3Ar
 }
 
 template <typename IN_T, bool AGG> int dispatch_bwd3(const Bwd3Args &a, int W, bool rev, cudaStream_t st) {
+    if (a.ord.kind != MMU_ORDER_ROWMAJOR) {         // fused scan order: z / dout / dz permuted by the kernel (never with rev)
+        if (W == 1) return launch_bwd3<IN_T, 1, false, AGG, true>(a, st);
+        if (W == 2) return launch_bwd3<IN_T, 2, false, AGG, true>(a, st);
+        if (W == 3) return launch_bwd3<IN_T, 3, false, AGG, true>(a, st);
+        return launch_bwd3<IN_T, 4, false, AGG, true>(a, st);
+    }
 #define MMU_B3(W_) (rev ? launch_bwd3<IN_T, W_, true, AGG>(a, st) : launch_bwd3<IN_T, W_, false, AGG>(a, st))
     if (W == 1) return MMU_B3(1);
     if (W == 2) return MMU_B3(2);
@@ -652,8 +659,9 @@ template <typename IN_T, bool AGG> int dispatch_bwd3(const Bwd3Args &a, int W, b
 
 template <typename IN_T> int run_bwd3(const mmu_scan_bwd_params *p, cudaStream_t st) {
     const mmu_scan_fwd_params &f = p->f;
-    const Bwd3Plan pl = plan_bwd3(f.batch, f.dim, f.seqlen);
+    const Bwd3Plan pl = plan_bwd3(f.batch, f.dim, f.seqlen, f.order != MMU_ORDER_ROWMAJOR);
     Bwd3Args a{};
+    make_ordmap(a.ord, f.order, f.order_h, f.order_w, f.order_ns, f.seqlen);
     a.u = f.u, a.delta = f.delta, a.z = f.z, a.dout = p->dout, a.ysave = f.y, a.Bm = f.B, a.Cm = f.C;
     a.A = f.A, a.Dv = f.D, a.dbias = f.delta_bias, a.x = f.x;
     a.du = p->du, a.ddelta = p->ddelta, a.dz = p->dz;
@@ -797,6 +805,17 @@ template <> struct HasV3<float> { static constexpr bool value = true; };
 template <> struct HasV3<__nv_bfloat16> { static constexpr bool value = true; };
 
 template <typename IN_T> int run_bwd(const mmu_scan_bwd_params *p, cudaStream_t st) {
+    if (p->f.order != MMU_ORDER_ROWMAJOR) {      // fused scan order: only on the dstate <= 16 kernels, only for the fusable maps
+        const mmu_scan_fwd_params &f = p->f;
+        bool ok = f.order != MMU_ORDER_FLIP && !f.reverse && ordmap_fusable(f.order, f.order_h, f.order_w, f.order_ns, f.seqlen) &&
+                  (f.x_stride == 0 || f.x_stride == MMU_STATE_STRIDE);
+        if constexpr (HasV3<IN_T>::value) ok = ok && bwd3_eligible<IN_T>(p);
+        else ok = false;
+        if (!ok)
+            return set_error(MMU_ERR_UNSUPPORTED, "selective_scan_bwd: scan order %d (H=%d W=%d nslices=%d) cannot be fused for this problem "
+                             "(see mmu_scan_order_fusable)", f.order, f.order_h, f.order_w, f.order_ns);
+        if constexpr (HasV3<IN_T>::value) return run_bwd3<IN_T>(p, st);
+    }
     if constexpr (HasV3<IN_T>::value) {
         if (bwd4_eligible<IN_T>(p)) return run_bwd4<IN_T>(p, st);
     }

@@ -442,9 +442,9 @@ struct Fwd3Plan {
     int LPR, W, nseg, cps, nchunks;
 };
 
-Fwd3Plan plan_fwd3(int B, int D, int L) {
+Fwd3Plan plan_fwd3(int B, int D, int L, bool ordered = false) {
     Fwd3Plan pl;
-    pl.LPR = env_int("MMU_FWD3_LPR", 32) == 16 ? 16 : 32;
+    pl.LPR = (!ordered && env_int("MMU_FWD3_LPR", 32) == 16) ? 16 : 32;
     if (pl.LPR == 16) {
         pl.W = 4;
     } else {
@@ -464,10 +464,10 @@ Fwd3Plan plan_fwd3(int B, int D, int L) {
     return pl;
 }
 
-template <typename IN_T, int LPR, int W, bool REV, bool AGG> int launch_fwd3(const Fwd3Args &a, cudaStream_t st) {
+template <typename IN_T, int LPR, int W, bool REV, bool AGG, bool ORD = false> int launch_fwd3(const Fwd3Args &a, cudaStream_t st) {
     using Cfg = Fwd3Cfg<IN_T, LPR, W>;
     dim3 grid((a.D + Cfg::R - 1) / Cfg::R, a.B, a.nseg), block(Cfg::NT);
-    auto k = scan3_fwd_kernel<IN_T, LPR, W, REV, AGG>;
+    auto k = scan3_fwd_kernel<IN_T, LPR, W, REV, AGG, ORD>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
     k<<<grid, block, Cfg::smem_bytes, st>>>(a);
     count_launch();
@@ -475,6 +475,14 @@ template <typename IN_T, int LPR, int W, bool REV, bool AGG> int launch_fwd3(con
 }
 
 template <typename IN_T, bool AGG> int dispatch_fwd3(const Fwd3Args &a, const Fwd3Plan &pl, bool rev, cudaStream_t st) {
+    if constexpr (!AGG) {
+        if (a.ord.kind != MMU_ORDER_ROWMAJOR) {     // fused scan order: gate / output permuted by the kernel (never with rev)
+            if (pl.W == 1) return launch_fwd3<IN_T, 32, 1, false, false, true>(a, st);
+            if (pl.W == 2) return launch_fwd3<IN_T, 32, 2, false, false, true>(a, st);
+            if (pl.W == 3) return launch_fwd3<IN_T, 32, 3, false, false, true>(a, st);
+            return launch_fwd3<IN_T, 32, 4, false, false, true>(a, st);
+        }
+    }
 #define MMU_F3(LPR_, W_) (rev ? launch_fwd3<IN_T, LPR_, W_, true, AGG>(a, st) : launch_fwd3<IN_T, LPR_, W_, false, AGG>(a, st))
     if (pl.LPR == 16) return MMU_F3(16, 4);
     if (pl.W == 1) return MMU_F3(32, 1);
@@ -485,8 +493,9 @@ template <typename IN_T, bool AGG> int dispatch_fwd3(const Fwd3Args &a, const Fw
 }
 
 template <typename IN_T> int run_fwd3(const mmu_scan_fwd_params *p, cudaStream_t st) {
-    const Fwd3Plan pl = plan_fwd3(p->batch, p->dim, p->seqlen);
+    const Fwd3Plan pl = plan_fwd3(p->batch, p->dim, p->seqlen, p->order != MMU_ORDER_ROWMAJOR);
     Fwd3Args a{};
+    make_ordmap(a.ord, p->order, p->order_h, p->order_w, p->order_ns, p->seqlen);
     a.u = p->u, a.delta = p->delta, a.z = p->z, a.Bm = p->B, a.Cm = p->C;
     a.A = p->A, a.Dv = p->D, a.dbias = p->delta_bias;
     a.out = p->out, a.ysave = p->z ? p->y : nullptr, a.x = p->x, a.last_state = p->last_state;
@@ -605,6 +614,15 @@ template <> struct HasV3<float> { static constexpr bool value = true; };
 template <> struct HasV3<__nv_bfloat16> { static constexpr bool value = true; };
 
 template <typename IN_T> int run_fwd(const mmu_scan_fwd_params *p, cudaStream_t st) {
+    if (p->order != MMU_ORDER_ROWMAJOR) {        // fused scan order: only on the dstate <= 16 kernels, only for the fusable maps
+        bool ok = p->order != MMU_ORDER_FLIP && !p->reverse && ordmap_fusable(p->order, p->order_h, p->order_w, p->order_ns, p->seqlen);
+        if constexpr (HasV3<IN_T>::value) ok = ok && fwd3_eligible<IN_T>(p);
+        else ok = false;
+        if (!ok)
+            return set_error(MMU_ERR_UNSUPPORTED, "selective_scan_fwd: scan order %d (H=%d W=%d nslices=%d) cannot be fused for this problem "
+                             "(see mmu_scan_order_fusable); permute with mmu_scan_order_gather / _scatter", p->order, p->order_h, p->order_w, p->order_ns);
+        if constexpr (HasV3<IN_T>::value) return run_fwd3<IN_T>(p, st);
+    }
     if constexpr (HasV3<IN_T>::value) {
         if (fwd4_eligible<IN_T>(p)) return run_fwd4<IN_T>(p, st);
         if (p->x_stride != 0 && p->x_stride != MMU_STATE_STRIDE)
@@ -675,6 +693,17 @@ extern "C" size_t mmu_selective_scan_fwd_workspace(int32_t batch, int32_t dim, i
         need = std::max(need, 2 * mmu::align256(n4 * 4) + mmu::align256((size_t)batch * dim * pl.nseg * 4));
     }
     return need;
+}
+
+extern "C" int32_t mmu_scan_order_fusable(int32_t order, int32_t H, int32_t W, int32_t nslices, int32_t dstate, int32_t dtype) {
+    using namespace mmu;
+    if (order == MMU_ORDER_ROWMAJOR) return 1;
+    if (order == MMU_ORDER_FLIP) return 0;        // the `reverse` flag
+    if (env_int("MMU_FUSE", 1) == 0 || env_int("MMU_SCAN_V", 3) < 3) return 0;
+    if (dstate > 16 || (dtype != MMU_F32 && dtype != MMU_BF16)) return 0;
+    const int64_t L = (int64_t)H * W;
+    if (H <= 0 || W <= 0 || L > INT32_MAX) return 0;
+    return ordmap_fusable(order, H, W, nslices, (int)L) ? 1 : 0;
 }
 
 extern "C" int mmu_selective_scan_fwd(const mmu_scan_fwd_params *p, void *stream) {

@@ -25,6 +25,7 @@ class ScanFwdParams(C.Structure):
         + [(n, _i64) for n in ("u_bs", "u_ds", "delta_bs", "delta_ds", "z_bs", "z_ds", "out_bs", "out_ds",
                                "B_bs", "B_ns", "C_bs", "C_ns")]
         + [("workspace", _vp), ("workspace_bytes", _sz), ("y", _vp), ("y_bs", _i64), ("y_ds", _i64)]
+        + [(n, _i32) for n in ("order", "order_h", "order_w", "order_ns")]
     )
 
 
@@ -45,6 +46,7 @@ class ConvParams(C.Structure):
         + [(n, _i64) for n in ("x_bs", "x_ds", "out_bs", "out_ds", "w_ds", "w_ws")]
         + [(n, _vp) for n in ("dout", "dx", "dweight", "dbias")]
         + [(n, _i64) for n in ("dout_bs", "dout_ds", "dx_bs", "dx_ds")]
+        + [(n, _i32) for n in ("order", "order_h", "order_w", "order_ns")]
     )
 
 
@@ -53,7 +55,7 @@ EXPORTS = (
     "mmu_selective_scan_fwd_workspace", "mmu_selective_scan_fwd",
     "mmu_selective_scan_bwd_workspace", "mmu_selective_scan_bwd", "mmu_scan_state_stride",
     "mmu_causal_conv1d_fwd", "mmu_causal_conv1d_bwd",
-    "mmu_scan_order_gather", "mmu_scan_order_scatter", "mmu_scan_order_index",
+    "mmu_scan_order_gather", "mmu_scan_order_scatter", "mmu_scan_order_index", "mmu_scan_order_fusable",
     "mmu_snake_sample_fwd", "mmu_snake_sample_bwd",
     "mmu_group_norm_nhwc_fwd", "mmu_group_norm_nhwc_bwd",
 )
@@ -86,6 +88,8 @@ def lib() -> C.CDLL:
     for n in ("mmu_scan_order_gather", "mmu_scan_order_scatter"):
         getattr(L, n).argtypes = [_vp, _vp, _i32, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp]
     L.mmu_scan_order_index.argtypes = [_vp, _i32, _i32, _i32, _i32, _vp]
+    L.mmu_scan_order_fusable.restype = _i32
+    L.mmu_scan_order_fusable.argtypes = [_i32] * 6
     L.mmu_snake_sample_fwd.argtypes = [_vp, _vp, _vp] + [_i32] * 8 + [_vp]
     L.mmu_snake_sample_bwd.argtypes = [_vp, _vp, _vp, _vp, _vp] + [_i32] * 8 + [_vp]
     L.mmu_group_norm_nhwc_fwd.argtypes = [_vp] * 7 + [_i32] * 6 + [C.c_float, _vp]

@@ -107,9 +107,14 @@ class Mamba(nn.Module):
             return ops.mamba_inner_fn_no_out_proj_reversed(*args, D=D, delta_bias=db, delta_softplus=True)
         return ops.mamba_inner_fn_no_out_proj(*args, None, None, D, delta_bias=db, delta_softplus=True)
 
-    def forward(self, hidden_states, inference_params=None):
+    def forward(self, hidden_states, inference_params=None, scan_order=None):
+        """scan_order = (kind, H, W, nslices) (extension, single-direction types only): the tokens of hidden_states are in natural
+        order and the block scans them in that order, returning natural order - what MMConv gets from flatten -> Mamba ->
+        inverse flatten (src/UM_Net/MMUNet.py:178-183), with the permutation inside the conv / scan kernels' addressing."""
         if inference_params is not None:
             raise NotImplementedError("mmunet_b200.Mamba: decode / inference_params is outside the training hot path")
+        if scan_order is not None and (not self.use_fast_path or self.bimamba_type in ("v2", "v3")):
+            raise NotImplementedError("mmunet_b200.Mamba: scan_order is for the single-direction fast path")
         batch, seqlen, dim = hidden_states.shape
         # in_proj and BLD -> BDL in one go (mamba_simple.py:201-205).  MM-UNet's token tensors are transposed views of
         # channel-major (b, d_model, l) maps (MMUNet.py:180, 405): then xz = W @ X[b] is a contiguous (b, 2d, l) batched
@@ -133,8 +138,12 @@ class Mamba(nn.Module):
                                    "(torch.stack fails in the reference, mamba_simple.py:245-246)")
 
             def slice_direction():
-                xz_s = ops.scan_order_gather(xz, _lib.ORDER_NSLICES, 1, seqlen, ns)
-                return ops.scan_order_scatter(self._inner(xz_s, "_s"), _lib.ORDER_NSLICES, 1, seqlen, ns)
+                # xz_s = stack(xz.chunk(ns, -1), -1).flatten(-2); out_s scattered back (mamba_simple.py:245-247, 263): the index
+                # map is applied by the conv / scan kernels' own loads and stores (explicit gather / scatter if not fusable)
+                conv, dtp = self.conv1d_s, self.dt_proj_s
+                return ops.mamba_inner_fn_no_out_proj_ordered(xz, conv.weight, conv.bias, self.x_proj_s.weight, dtp.weight,
+                                                              -torch.exp(self.A_s_log.float()), self.D_s.float(), dtp.bias.float(), True,
+                                                              order=(_lib.ORDER_NSLICES, 1, seqlen, ns))
 
             if self.concurrent_directions and xz.is_cuda:
                 # The directions are independent until the sum: run them on side streams so that their kernels share the GPU
@@ -167,9 +176,14 @@ class Mamba(nn.Module):
             out = ops._out_proj_autograd(total, self.out_proj.weight, self.out_proj.bias)
         else:
             A = -torch.exp(self.A_log.float())
-            out = ops.mamba_inner_fn(xz, self.conv1d.weight, self.conv1d.bias, self.x_proj.weight, self.dt_proj.weight,
-                                     self.out_proj.weight, self.out_proj.bias, A, None, None, self.D.float(),
-                                     delta_bias=self.dt_proj.bias.float(), delta_softplus=True)
+            if scan_order is not None:
+                out = ops.mamba_inner_fn_ordered(xz, self.conv1d.weight, self.conv1d.bias, self.x_proj.weight, self.dt_proj.weight,
+                                                 self.out_proj.weight, self.out_proj.bias, A, self.D.float(), self.dt_proj.bias.float(), True,
+                                                 order=scan_order)
+            else:
+                out = ops.mamba_inner_fn(xz, self.conv1d.weight, self.conv1d.bias, self.x_proj.weight, self.dt_proj.weight,
+                                         self.out_proj.weight, self.out_proj.bias, A, None, None, self.D.float(),
+                                         delta_bias=self.dt_proj.bias.float(), delta_softplus=True)
         return out, o_1, o_2, o_3
 
     def _slow_path(self, xz, seqlen):

@@ -38,6 +38,7 @@ _flatten_two_row = ops.two_row_flatten
 _unflatten_two_row = ops.two_row_unflatten
 _snake_sample = ops.snake_sample          # None -> the reference's torch formulation (grid rescale + F.grid_sample)
 _group_norm_nhwc = ops.group_norm_nhwc    # None -> always nn.GroupNorm
+_fuse_scan_order = True                   # False -> always materialise the two-row flatten / inverse around the Mamba block
 
 
 class MMConv(nn.Module):
@@ -99,9 +100,16 @@ class MMConv(nn.Module):
         K = self.kernel_size
         dy = offset[:, :K]                                    # the second K channels (x offsets) are unused (:136)
         rows, _ = self._base_grids(H, W, offset.device)
-        tokens = _flatten_two_row(dy.contiguous())            # (B, K, L) in morph scan order        (:178)
-        refined = self.mamba(tokens.transpose(-1, -2))[0]     # (B, L, K)                             (:180-181)
-        refined = _unflatten_two_row(refined.transpose(-1, -2), H, W)          # (B, K, H, W)         (:182-183)
+        if _fuse_scan_order and dy.is_cuda and isinstance(self.mamba, Mamba) and self.mamba.bimamba_type not in ("v2", "v3"):
+            # the morph (two-row) order is applied inside the conv / scan kernels' addressing: the tokens stay in natural order,
+            # no flatten / inverse-flatten copies (:178-183); explicit gather / scatter kernels where the map cannot be fused
+            from . import _lib
+            refined = self.mamba(dy.reshape(B, K, H * W).transpose(-1, -2), scan_order=(_lib.ORDER_TWOROW, H, W, 1))[0]
+            refined = refined.transpose(-1, -2).reshape(B, K, H, W)
+        else:
+            tokens = _flatten_two_row(dy.contiguous())            # (B, K, L) in morph scan order        (:178)
+            refined = self.mamba(tokens.transpose(-1, -2))[0]     # (B, L, K)                             (:180-181)
+            refined = _unflatten_two_row(refined.transpose(-1, -2), H, W)      # (B, K, H, W)         (:182-183)
         gain = torch.clamp(F.softplus(self.altho), min=0.01)                   #                      (:186-187)
         return gain * refined.float() + (rows + self._snake_offsets(dy).float() * self.extend_scope)
 

@@ -101,6 +101,22 @@ def _fill_fwd(p, u, delta, A, B, C, D, z, delta_bias, softplus, reverse, g, G):
     p.B_bs, p.B_ns, p.C_bs, p.C_ns = B.stride(0), B.stride(2), C.stride(0), C.stride(2)
 
 
+def order_fusable(order, dstate, dtype):
+    """order = (kind, H, W, nslices) or None.  True when the conv / scan kernels can apply the scan order themselves
+    (mmu_scan_order_fusable): the gate / output tensors then stay in natural token order and no gather / scatter copy runs."""
+    if order is None or order[0] == _lib.ORDER_ROWMAJOR:
+        return True
+    if dtype not in _DT:
+        return False
+    kind, H, W, ns = order
+    return bool(_lib.lib().mmu_scan_order_fusable(kind, H, W, max(1, ns), dstate, _DT[dtype]))
+
+
+def _set_order(p, order):
+    if order is not None:
+        p.order, p.order_h, p.order_w, p.order_ns = order[0], order[1], order[2], max(1, order[3])
+
+
 class ScanStates(tuple):
     """What the forward saves for the backward: x = fp32 states after every 64th token (batch, dim, ceil(L/64), dstate),
     y = pre-gate output C.h + D*u (input dtype; None without a gate) - the role of the reference's `scan_intermediates`
@@ -134,12 +150,22 @@ def _silu_parts(z):
 
 
 def selective_scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, reverse=False,
-                       save_states=True, return_last_state=False):
-    """-> (out, states, last_state).  out is y*silu(z) when z is given; states is a ScanStates (or None)."""
+                       save_states=True, return_last_state=False, order=None):
+    """-> (out, states, last_state).  out is y*silu(z) when z is given; states is a ScanStates (or None).
+    order = (kind, H, W, nslices): fused scan order - z and out are in natural token order and permuted by the kernel, u, delta,
+    B, C in scan order (only where order_fusable() holds)."""
     _scan_checks(u, delta, A, B, C, D, z, delta_bias)
-    groups = _wide_state_groups(u, A, B)
+    if order is not None and order[0] == _lib.ORDER_ROWMAJOR:
+        order = None
+    groups = _wide_state_groups(u, A, B) if order is None else None
     if groups is None:
-        return _selective_scan_fwd_single(u, delta, A, B, C, D, z, delta_bias, delta_softplus, reverse, save_states, return_last_state)
+        return _selective_scan_fwd_single(u, delta, A, B, C, D, z, delta_bias, delta_softplus, reverse, save_states, return_last_state,
+                                          order)
+    io_dtype = u.dtype
+    if io_dtype != torch.float32:
+        # the per-group partial sums of y cancel against each other: rounding each of them to bf16 first would cost ~3 digits of
+        # the total, so 2-byte inputs run the group passes in fp32 on the same (rounded) values and round the result once
+        u, delta, B, C = u.float(), delta.float(), B.float(), C.float()
     y32, xs, lasts = None, [], []
     for gi, (n0, n1) in enumerate(groups):
         yg, st, last = _selective_scan_fwd_single(u, delta, A[:, n0:n1].contiguous(), B[:, :, n0:n1], C[:, :, n0:n1], D if gi == 0 else None,
@@ -149,14 +175,14 @@ def selective_scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta
             xs.append(st.x)
         if return_last_state:
             lasts.append(last)
-    y = y32.to(u.dtype)
-    out = y if z is None else (y32 * _silu_parts(z)[0]).to(u.dtype)
+    y = y32.to(io_dtype)
+    out = y if z is None else (y32 * _silu_parts(z)[0]).to(io_dtype)
     states = ScanStates(xs, y if z is not None else None) if save_states else None     # x: one saved-state tensor per state group
     return out, states, (torch.cat(lasts, dim=-1) if return_last_state else None)
 
 
 def _selective_scan_fwd_single(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, reverse=False,
-                               save_states=True, return_last_state=False):
+                               save_states=True, return_last_state=False, order=None):
     batch, dim, L = u.shape
     N = A.shape[1]
     G = B.shape[1]
@@ -164,7 +190,7 @@ def _selective_scan_fwd_single(u, delta, A, B, C, D=None, z=None, delta_bias=Non
     out = torch.empty_like(u, memory_format=torch.contiguous_format)
     H = dim // G
     L_ = _lib.lib()
-    xs = L_.mmu_scan_state_stride(batch, H, L, N, _DT[u.dtype]) if save_states else _lib.STATE_STRIDE
+    xs = L_.mmu_scan_state_stride(batch, H, L, N, _DT[u.dtype]) if (save_states and order is None) else _lib.STATE_STRIDE
     nx = (L + xs - 1) // xs
     x = torch.empty((batch, dim, nx, N), device=u.device, dtype=torch.float32) if save_states else None
     y = torch.empty_like(out) if (save_states and z is not None) else None
@@ -176,6 +202,7 @@ def _selective_scan_fwd_single(u, delta, A, B, C, D=None, z=None, delta_bias=Non
             p = _lib.ScanFwdParams()
             _fill_fwd(p, u, delta, A, B, C, D, z, delta_bias, delta_softplus, reverse, g, G)
             p.x_stride = xs
+            _set_order(p, order)
             p.out = out.data_ptr() + g * H * out.stride(1) * out.element_size()
             p.out_bs, p.out_ds = out.stride(0), out.stride(1)
             p.x = None if x is None else x.data_ptr() + g * H * x.stride(1) * 4
@@ -204,26 +231,32 @@ def _x_stride(x, L):
 
 
 def selective_scan_bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softplus=False, reverse=False,
-                       du=None, ddelta=None, dz=None, dBC=None):
+                       du=None, ddelta=None, dz=None, dBC=None, order=None):
     """-> (du, ddelta, dA, dB, dC, dD, dz, ddelta_bias); see _selective_scan_bwd_single.  A saved-state LIST (one tensor per group
-    of 16 states, from the grouped forward) selects the grouped backward."""
+    of 16 states, from the grouped forward) selects the grouped backward.  order: as the forward (z, dout, dz in natural order)."""
     xs = x.x if isinstance(x, ScanStates) else x
+    if order is not None and order[0] == _lib.ORDER_ROWMAJOR:
+        order = None
     if not isinstance(xs, (list, tuple)):
-        return _selective_scan_bwd_single(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softplus, reverse, du, ddelta, dz, dBC)
+        return _selective_scan_bwd_single(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softplus, reverse, du, ddelta, dz, dBC, order)
     _scan_checks(u, delta, A, B, C, D, z, delta_bias)
     groups = _wide_state_groups(u, A, B)
     batch, dim, L = u.shape
     N = A.shape[1]
+    io_dtype = u.dtype
     if dout.stride(-1) != 1 and L > 1:
         dout = dout.contiguous()
-    dy = dout
+    dy = dout.float()
     if z is not None:
         y = x.y
         silu, dsilu = _silu_parts(z)
-        g32 = dout.float()
-        dz_val = (g32 * y.float() * dsilu).to(u.dtype)
+        dz_val = (dy * y.float() * dsilu).to(io_dtype)
         dz = dz_val if dz is None else dz.copy_(dz_val)
-        dy = (g32 * silu).to(u.dtype)
+        dy = dy * silu
+    if io_dtype != torch.float32:       # as the forward: the group passes run in fp32 on the rounded inputs
+        u, delta, B, C = u.float(), delta.float(), B.float(), C.float()
+    else:
+        dy = dy.contiguous()
     if dBC is None:
         dB = torch.zeros((batch, 1, N, L), device=u.device, dtype=torch.float32)
         dC = torch.zeros_like(dB)
@@ -243,13 +276,13 @@ def selective_scan_bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softp
             dD = g[5]
         if g[7] is not None:
             dbias = g[7] if dbias is None else dbias + g[7]
-    du = du32.to(u.dtype) if du is None else du.copy_(du32)
-    ddelta = dd32.to(u.dtype) if ddelta is None else ddelta.copy_(dd32)
+    du = du32.to(io_dtype) if du is None else du.copy_(du32)
+    ddelta = dd32.to(io_dtype) if ddelta is None else ddelta.copy_(dd32)
     return du, ddelta, dA, dB, dC, dD, dz, dbias
 
 
 def _selective_scan_bwd_single(u, delta, A, B, C, D, z, delta_bias, dout, x, delta_softplus=False, reverse=False,
-                               du=None, ddelta=None, dz=None, dBC=None):
+                               du=None, ddelta=None, dz=None, dBC=None, order=None):
     """-> (du, ddelta, dA, dB, dC, dD, dz, ddelta_bias); dA/dB/dC/dD/ddelta_bias fp32.
     du / ddelta / dz may be pre-allocated views (e.g. halves of dxz, as selective_scan_interface.py:244-248).
     dBC: optional pair (dB, dC) of ZERO-FILLED fp32 (batch, dstate, L) views with unit sequence stride and free batch / state
@@ -299,6 +332,7 @@ def _selective_scan_bwd_single(u, delta, A, B, C, D, z, delta_bias, dout, x, del
             xg = x if G == 1 else x[:, g * H:(g + 1) * H].contiguous()
             p.f.x = xg.data_ptr()
             p.f.x_stride = _x_stride(x, L)
+            _set_order(p.f, order)
             if y is not None and z is not None:
                 p.f.y = y.data_ptr() + g * H * y.stride(1) * es
                 p.f.y_bs, p.f.y_ds = y.stride(0), y.stride(1)
@@ -329,7 +363,7 @@ def _selective_scan_bwd_single(u, delta, A, B, C, D, z, delta_bias, dout, x, del
     return du, ddelta, dA, dB, dC, dD, dz, dbias
 
 
-def _conv_params(x, weight, bias, silu, reverse=False):
+def _conv_params(x, weight, bias, silu, reverse=False, order=None):
     _require_cuda(x, weight, bias)
     if x.dtype not in _DT:
         raise RuntimeError("causal_conv1d: input type must be float32, float16 or bfloat16")
@@ -344,17 +378,19 @@ def _conv_params(x, weight, bias, silu, reverse=False):
     p.width, p.dtype, p.silu, p.reverse = weight.shape[1], _DT[x.dtype], int(bool(silu)), int(bool(reverse))
     p.x, p.weight, p.bias = x.data_ptr(), weight.data_ptr(), _ptr(bias)
     p.x_bs, p.x_ds, p.w_ds, p.w_ws = x.stride(0), x.stride(1), weight.stride(0), weight.stride(1)
+    _set_order(p, order)
     return p
 
 
-def causal_conv1d_fwd(x, weight, bias=None, silu=False, reverse=False, out=None):
+def causal_conv1d_fwd(x, weight, bias=None, silu=False, reverse=False, out=None, order=None):
     """x (B,D,L) with stride(-1)==1; weight (D,W) / bias (D) are used in fp32.  `out`: optional pre-allocated (B,D,L) result
-    with unit sequence stride and free batch / channel strides."""
+    with unit sequence stride and free batch / channel strides.  order = (kind, H, W, nslices): x is read through the scan-order
+    index map (it stays in natural token order), out is written in scan order."""
     if x.stride(-1) != 1 and x.shape[-1] > 1:
         x = x.contiguous()
     weight = weight.float()
     bias = None if bias is None else bias.float().contiguous()
-    p = _conv_params(x, weight, bias, silu, reverse)
+    p = _conv_params(x, weight, bias, silu, reverse, order)
     if out is None:
         out = torch.empty_like(x, memory_format=torch.contiguous_format)
     elif out.shape != x.shape or out.dtype != x.dtype or (out.stride(-1) != 1 and out.shape[-1] > 1):
@@ -365,8 +401,8 @@ def causal_conv1d_fwd(x, weight, bias=None, silu=False, reverse=False, out=None)
     return out
 
 
-def causal_conv1d_bwd(x, weight, bias, dout, silu=False, dx=None, reverse=False):
-    """-> (dx, dweight fp32 (D,W), dbias fp32 or None)."""
+def causal_conv1d_bwd(x, weight, bias, dout, silu=False, dx=None, reverse=False, order=None):
+    """-> (dx, dweight fp32 (D,W), dbias fp32 or None).  order: x / dx in natural token order, dout in scan order."""
     if x.stride(-1) != 1 and x.shape[-1] > 1:
         x = x.contiguous()
     if dout.stride(-1) != 1 and dout.shape[-1] > 1:
@@ -376,7 +412,7 @@ def causal_conv1d_bwd(x, weight, bias, dout, silu=False, dx=None, reverse=False)
         raise RuntimeError("causal_conv1d_bwd: dout must match x in dtype and shape")
     weight = weight.float()
     bias = None if bias is None else bias.float().contiguous()
-    p = _conv_params(x, weight, bias, silu, reverse)
+    p = _conv_params(x, weight, bias, silu, reverse, order)
     dx = torch.empty_like(x, memory_format=torch.contiguous_format) if dx is None else dx
     dw = torch.zeros(weight.shape, device=x.device, dtype=torch.float32)
     db = torch.zeros(x.shape[1], device=x.device, dtype=torch.float32) if bias is not None else None
@@ -510,7 +546,11 @@ class _InnerCore:
 
     @staticmethod
     def forward(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C, D, delta_bias,
-                B_proj_bias, C_proj_bias, delta_softplus, reverse=False):
+                B_proj_bias, C_proj_bias, delta_softplus, reverse=False, order=None):
+        """order = (kind, H, W, nslices): the scan runs over xz in that token order WITHOUT permuted copies - the conv reads x
+        through the index map and writes conv_out in scan order, the projections work on scan-order tensors (they are per-token),
+        the scan reads the gate z and writes its output through the map: out_z comes back in natural token order
+        (== scatter(inner(gather(xz))), requirements/mamba_simple.py:245-263, src/UM_Net/MMUNet.py:178-183)."""
         if B is not None or C is not None or B_proj_bias is not None or C_proj_bias is not None:
             raise NotImplementedError("mmunet_b200: only input-dependent B/C without projection bias are supported "
                                       "(the only form MM-UNet's Mamba uses)")
@@ -526,14 +566,14 @@ class _InnerCore:
         x, z = xz.chunk(2, dim=1)
         conv_b = conv1d_bias.contiguous() if conv1d_bias is not None else None
         conv_st, conv_out = _InnerCore._cbl(d, batch, L, xz)
-        causal_conv1d_fwd(x, conv_w, conv_b, True, reverse=reverse, out=conv_out)
+        causal_conv1d_fwd(x, conv_w, conv_b, True, reverse=reverse, out=conv_out, order=order)
         x_dbl = torch.mm(x_proj_weight, conv_st.view(d, batch * L))                 # (R+2N, b*l)     (:181)
         delta = torch.mm(delta_proj_weight, x_dbl[:R]).view(d, batch, L).permute(1, 0, 2)      # (b, d, l) view    (:182)
         x3 = x_dbl.view(-1, batch, L)
         Bm = x3[R:R + N].permute(1, 0, 2).unsqueeze(1)                              # (b, 1, n, l) views of x_dbl
         Cm = x3[R + N:].permute(1, 0, 2).unsqueeze(1)
         D = D.contiguous() if D is not None else None
-        out_z, xs, _ = selective_scan_fwd(conv_out, delta, A, Bm, Cm, D, z, delta_bias, delta_softplus, reverse=reverse)
+        out_z, xs, _ = selective_scan_fwd(conv_out, delta, A, Bm, Cm, D, z, delta_bias, delta_softplus, reverse=reverse, order=order)
         saved = (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, conv_st, delta, A, None, None, D, delta_bias,
                  xs.x, xs.y)
         return out_z, saved
@@ -554,7 +594,7 @@ class _InnerCore:
         return dconv.view(d, batch, L).permute(1, 0, 2), dx_proj_w, ddt_proj_w
 
     @staticmethod
-    def backward(saved, dout_y, delta_softplus, reverse=False):
+    def backward(saved, dout_y, delta_softplus, reverse=False, order=None):
         """dout_y: (b, d, l).  Returns (dxz, dconv_w (d,1,w), dconv_b, dx_proj_w, ddt_proj_w, dA, dD, ddelta_bias)."""
         (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, conv_st, delta, A, _, _, D, delta_bias, xs_x, xs_y) = saved
         xs = ScanStates(xs_x, xs_y)
@@ -573,10 +613,10 @@ class _InnerCore:
         dBC = (dBC_st[:N].permute(1, 0, 2), dBC_st[N:].permute(1, 0, 2))
         _, _, dA, _, _, dD, dz, ddelta_bias = selective_scan_bwd(
             conv_out, delta, A, Bm, Cm, D, z, delta_bias, dout_y, xs, delta_softplus, reverse=reverse, dz=dz, dBC=dBC,
-            du=du, ddelta=ddl)
+            du=du, ddelta=ddl, order=order)
         dconv_out, dx_proj_w, ddt_proj_w = _InnerCore.project_grads(x_dbl, x_proj_weight, delta_proj_weight, conv_st, ddl_st,
                                                                     dBC_st, du_st)
-        _, dconv_w, dconv_b = causal_conv1d_bwd(x, conv_w, conv_b, dconv_out, True, dx=dx, reverse=reverse)
+        _, dconv_w, dconv_b = causal_conv1d_bwd(x, conv_w, conv_b, dconv_out, True, dx=dx, reverse=reverse, order=order)
         return dxz, dconv_w.unsqueeze(1), dconv_b, dx_proj_w, ddt_proj_w, dA, dD, ddelta_bias
 
 
@@ -620,12 +660,13 @@ class MambaInnerFnNoOutProj(torch.autograd.Function):
     @torch.amp.custom_fwd(device_type="cuda")
     def forward(ctx, xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B=None, C=None, D=None,
                 delta_bias=None, B_proj_bias=None, C_proj_bias=None, delta_softplus=True, checkpoint_lvl=1,
-                reverse=False):
+                reverse=False, order=None):
         x_proj_weight, delta_proj_weight = _cast_proj(x_proj_weight, delta_proj_weight)
         out_z, saved = _InnerCore.forward(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C, D,
-                                          delta_bias, B_proj_bias, C_proj_bias, delta_softplus, reverse=reverse)
+                                          delta_bias, B_proj_bias, C_proj_bias, delta_softplus, reverse=reverse, order=order)
         ctx.delta_softplus = delta_softplus
         ctx.reverse = reverse
+        ctx.order = order
         _save(ctx, saved)
         return out_z
 
@@ -633,8 +674,8 @@ class MambaInnerFnNoOutProj(torch.autograd.Function):
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dout):
         saved = _load(ctx)
-        dxz, dcw, dcb, dxw, ddw, dA, dD, ddb = _InnerCore.backward(saved, dout, ctx.delta_softplus, reverse=ctx.reverse)
-        return (dxz, dcw, dcb, dxw, ddw, dA, None, None, dD, ddb, None, None, None, None, None)
+        dxz, dcw, dcb, dxw, ddw, dA, dD, ddb = _InnerCore.backward(saved, dout, ctx.delta_softplus, reverse=ctx.reverse, order=ctx.order)
+        return (dxz, dcw, dcb, dxw, ddw, dA, None, None, dD, ddb, None, None, None, None, None, None)
 
 
 class MambaInnerFn(torch.autograd.Function):
@@ -644,12 +685,13 @@ class MambaInnerFn(torch.autograd.Function):
     @torch.amp.custom_fwd(device_type="cuda")
     def forward(ctx, xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias,
                 A, B=None, C=None, D=None, delta_bias=None, B_proj_bias=None, C_proj_bias=None, delta_softplus=True,
-                checkpoint_lvl=1):
+                checkpoint_lvl=1, order=None):
         x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias = _cast_proj(
             x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias)
         out_z, saved = _InnerCore.forward(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C, D,
-                                          delta_bias, B_proj_bias, C_proj_bias, delta_softplus)
+                                          delta_bias, B_proj_bias, C_proj_bias, delta_softplus, order=order)
         ctx.delta_softplus = delta_softplus
+        ctx.order = order
         ctx.out_proj_bias_is_None = out_proj_bias is None
         saved = saved + (out_proj_weight, out_z)
         _save(ctx, saved)
@@ -661,8 +703,8 @@ class MambaInnerFn(torch.autograd.Function):
         saved = _load(ctx)
         out_proj_weight, out_z = saved[-2], saved[-1]
         dout_y, dout_proj_w, dout_proj_b = _out_proj_bwd(dout, out_z, out_proj_weight, not ctx.out_proj_bias_is_None)
-        dxz, dcw, dcb, dxw, ddw, dA, dD, ddb = _InnerCore.backward(saved[:-2], dout_y, ctx.delta_softplus)
-        return (dxz, dcw, dcb, dxw, ddw, dout_proj_w, dout_proj_b, dA, None, None, dD, ddb, None, None, None, None)
+        dxz, dcw, dcb, dxw, ddw, dA, dD, ddb = _InnerCore.backward(saved[:-2], dout_y, ctx.delta_softplus, order=ctx.order)
+        return (dxz, dcw, dcb, dxw, ddw, dout_proj_w, dout_proj_b, dA, None, None, dD, ddb, None, None, None, None, None)
 
 
 class BiMambaInnerFn(torch.autograd.Function):
@@ -747,6 +789,35 @@ def mamba_inner_fn_no_out_proj(xz, conv1d_weight, conv1d_bias, x_proj_weight, de
                                D=None, delta_bias=None, B_proj_bias=None, C_proj_bias=None, delta_softplus=True):
     return MambaInnerFnNoOutProj.apply(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C, D,
                                        delta_bias, B_proj_bias, C_proj_bias, delta_softplus)
+
+
+def mamba_inner_fn_ordered(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias, A, D=None,
+                           delta_bias=None, delta_softplus=True, order=None):
+    """mamba_inner_fn over the tokens of xz taken in `order` = (kind, H, W, nslices), result in natural token order:
+    == scatter(mamba_inner_fn(gather(xz), ...)) of MMConv (src/UM_Net/MMUNet.py:178-183) without the two permuted copies.
+    Falls back to explicit gather / scatter kernels where the order cannot be fused."""
+    N = A.shape[-1]
+    if order is None or order_fusable(order, N, xz.dtype):
+        return MambaInnerFn.apply(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias, A,
+                                  None, None, D, delta_bias, None, None, delta_softplus, 1, order)
+    kind, H, W, ns = order
+    out = MambaInnerFn.apply(scan_order_gather(xz, kind, H, W, ns), conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
+                             out_proj_weight, out_proj_bias, A, None, None, D, delta_bias, None, None, delta_softplus)
+    return scan_order_scatter(out.transpose(1, 2), kind, H, W, ns).transpose(1, 2)
+
+
+def mamba_inner_fn_no_out_proj_ordered(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, D=None, delta_bias=None,
+                                       delta_softplus=True, order=None):
+    """== scatter(mamba_inner_fn_no_out_proj(gather(xz), ...)) (requirements/mamba_simple.py:245-263) with the scan order fused into
+    the conv / scan kernels' addressing; explicit gather / scatter where it cannot be fused."""
+    N = A.shape[-1]
+    if order is None or order_fusable(order, N, xz.dtype):
+        return MambaInnerFnNoOutProj.apply(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, None, None, D, delta_bias,
+                                           None, None, delta_softplus, 1, False, order)
+    kind, H, W, ns = order
+    out = MambaInnerFnNoOutProj.apply(scan_order_gather(xz, kind, H, W, ns), conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
+                                      A, None, None, D, delta_bias, None, None, delta_softplus)
+    return scan_order_scatter(out, kind, H, W, ns)
 
 
 def mamba_inner_fn_no_out_proj_reversed(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, D=None,

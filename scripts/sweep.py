@@ -1,13 +1,17 @@
 """BASELINE.json configs[4]: scan roofline sweep.  L 1k-64k x d_state 16/64 x 4 scan orders x {fwd, bwd} x {fp32, bf16}, wide
 (B=8, D=384) and MM-UNet-narrow (B=16, D=6) regimes.  Prints a markdown table (algorithmic GB/s and fraction of the measured
-HBM peak per point).  Scan orders:  forward = plain;  flip = the kernels' `reverse` flag (no copy);  nslices / two-row = the
-gather kernel on (u, delta, z, B, C) [as the module does on xz] + scan + scatter of the output (bwd: + their adjoints on dout / du).
+HBM peak per point).  Scan orders:  forward = plain;  flip = the kernels' `reverse` flag (no copy);  nslices / two-row = the order
+FUSED into the scan kernels' addressing where mmu_scan_order_fusable() allows it (the gate z, out, dout and dz stay in natural
+token order and are permuted by the kernel's own loads / stores; u, delta, B, C arrive in scan order, as the conv and the
+projections produce them inside the fused inner functions) - marked "fused" in the order column; otherwise (d_state 64: grouped
+passes) the round-1 form: gather kernel on (u, delta, z, B, C) + scan + scatter of the output (bwd: + their adjoints).
    python scripts/sweep.py [quick] > profiles/rN_sweep.md"""
 import json, os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "mm-unet_b200")); sys.path.insert(0, ROOT)
 from mmunet_b200 import _lib, ops
 from scripts.probe_scan import make, timeit
+s_guard = lambda dt: 4 if dt == torch.float32 else 2
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 quick = "quick" in sys.argv
 Ls = [1024, 4096, 16384, 65536] if quick else [1024, 2048, 4096, 8192, 16384, 32768, 65536]
@@ -17,7 +21,7 @@ for (B, D, regime) in ((8, 384, "wide B8 D384"), (16, 6, "narrow B16 D6")):
     for dt in (torch.float32, torch.bfloat16):
         for N in (16, 64):
             for L in Ls:
-                if B * D * L * N * 4 > 8e9:
+                if B * D * L * s_guard(dt) * 16 > 40e9:      # ~16 activation-sized tensors alive per point
                     continue
                 u, delta, A, Bm, Cm, Dp, z, bias, dout = make(B, D, L, N, dt)
                 s = u.element_size()
@@ -31,6 +35,12 @@ for (B, D, regime) in ((8, 384, "wide B8 D384"), (16, 6, "narrow B16 D6")):
                         f = lambda: ops.selective_scan_fwd(u, delta, A, Bm, Cm, Dp, z, bias, True, reverse=rev)
                         out, xs, _ = f()
                         b = lambda: ops.selective_scan_bwd(u, delta, A, Bm, Cm, Dp, z, bias, dout, xs, True, reverse=rev)
+                    elif ops.order_fusable((_lib.ORDER_NSLICES, 1, L, 16) if order == "nslices" else (_lib.ORDER_TWOROW, H, W, 1), N, dt):
+                        od = (_lib.ORDER_NSLICES, 1, L, 16) if order == "nslices" else (_lib.ORDER_TWOROW, H, W, 1)
+                        order = order + " (fused)"
+                        f = lambda: ops.selective_scan_fwd(u, delta, A, Bm, Cm, Dp, z, bias, True, order=od)
+                        out, xs, _ = f()
+                        b = lambda: ops.selective_scan_bwd(u, delta, A, Bm, Cm, Dp, z, bias, dout, xs, True, order=od)
                     else:
                         oid = _lib.ORDER_NSLICES if order == "nslices" else _lib.ORDER_TWOROW
                         g = lambda t: ops.scan_order_gather(t, oid, H, W, 16)

@@ -558,6 +558,66 @@ def test_scan_order_golden_and_errors():
     assert torch.equal(x.grad, torch.ones_like(x))
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# scan order fused into the conv / scan kernels' addressing (requirements/mamba_simple.py:245-263, MMUNet.py:68-121, 178-183)
+# ---------------------------------------------------------------------------------------------------------------
+FUSED_ORDERS = [((2, 1, 512, 16), 2, 8), ((2, 1, 1024, 64), 1, 72), ((2, 1, 4096, 32), 2, 6), ((3, 8, 16, 1), 2, 6), ((3, 6, 8, 1), 1, 2),
+                ((3, 5, 8, 1), 2, 6), ((3, 32, 64, 1), 1, 128)]
+
+
+@pytest.mark.parametrize("order,B,D", FUSED_ORDERS)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_scan_order_matches_explicit_permutation(order, B, D, dtype):
+    """conv + scan with the order fused (x / z / out / dout / dz addressed through idx(l)) against the same kernels run on
+    explicitly gathered tensors with the result scattered back: identical arithmetic, so forward results must be bit-equal and
+    the atomically accumulated gradients equal up to summation order."""
+    kind, H, W, ns = order
+    L, N = H * W, 16
+    assert ops.order_fusable(order, N, dtype)
+    gth = lambda t: ops.scan_order_gather(t, kind, H, W, ns)
+    sct = lambda t: ops.scan_order_scatter(t, kind, H, W, ns)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, D, L, generator=g).to(DEV, dtype)
+    z = torch.randn(B, D, L, generator=g).to(DEV, dtype)
+    w, cb = torch.randn(D, 4, generator=g).to(DEV), torch.randn(D, generator=g).to(DEV)
+    # conv: natural x in, scan-order out
+    u_f = ops.causal_conv1d_fwd(x, w, cb, True, order=order)
+    u_e = ops.causal_conv1d_fwd(gth(x), w, cb, True)
+    assert torch.equal(u_f, u_e)
+    du_s = torch.randn(B, D, L, generator=g).to(DEV, dtype)
+    dx_f, dw_f, db_f = ops.causal_conv1d_bwd(x, w, cb, du_s, True, order=order)
+    dx_e, dw_e, db_e = ops.causal_conv1d_bwd(gth(x), w, cb, du_s, True)
+    assert torch.equal(dx_f, sct(dx_e))
+    torch.testing.assert_close(dw_f, dw_e, rtol=1e-4, atol=1e-3)
+    # scan: u, delta, B, C in scan order; z / out / dout / dz natural
+    delta = (0.5 * torch.rand(B, D, L, generator=g)).to(DEV, dtype)
+    A = (-0.5 * torch.rand(D, N, generator=g)).to(DEV)
+    Bm, Cm = (torch.randn(B, 1, N, L, generator=g).to(DEV, dtype) for _ in range(2))
+    Dp, bias = torch.randn(D, generator=g).to(DEV), (0.5 * torch.rand(D, generator=g)).to(DEV)
+    dout = torch.randn(B, D, L, generator=g).to(DEV, dtype)
+    o_f, st_f, l_f = ops.selective_scan_fwd(u_f, delta, A, Bm, Cm, Dp, z, bias, True, return_last_state=True, order=order)
+    o_e, st_e, l_e = ops.selective_scan_fwd(u_f, delta, A, Bm, Cm, Dp, gth(z), bias, True, return_last_state=True)
+    assert torch.equal(o_f, sct(o_e)) and torch.equal(l_f, l_e) and torch.equal(st_f.y, st_e.y) and torch.equal(st_f.x, st_e.x)
+    g_f = ops.selective_scan_bwd(u_f, delta, A, Bm, Cm, Dp, z, bias, dout, st_f, True, order=order)
+    g_e = ops.selective_scan_bwd(u_f, delta, A, Bm, Cm, Dp, gth(z), bias, gth(dout), st_e, True)
+    assert torch.equal(g_f[0], g_e[0]) and torch.equal(g_f[1], g_e[1])          # du, ddelta: scan order in both
+    assert torch.equal(g_f[6], sct(g_e[6]))                                      # dz back in natural order
+    for a, b_ in zip(g_f[2:6] + g_f[7:], g_e[2:6] + g_e[7:]):                     # dA, dB, dC, dD, ddelta_bias: atomics
+        torch.testing.assert_close(a, b_, rtol=1e-4, atol=1e-3 * float(b_.abs().max()))
+
+
+def test_fused_scan_order_refused_when_not_fusable():
+    assert not ops.order_fusable((_lib.ORDER_NSLICES, 1, 512, 4), 16, torch.float32)         # nslices % 8 != 0
+    assert not ops.order_fusable((_lib.ORDER_TWOROW, 12, 10, 1), 16, torch.float32)          # W % 4 != 0
+    assert not ops.order_fusable((_lib.ORDER_NSLICES, 1, 512, 16), 64, torch.float32)        # wide state: grouped passes
+    assert not ops.order_fusable((_lib.ORDER_NSLICES, 1, 512, 16), 16, torch.float16)
+    u = torch.randn(1, 8, 512, device=DEV)
+    A = -torch.rand(8, 16, device=DEV)
+    Bm = torch.randn(1, 1, 16, 512, device=DEV)
+    with pytest.raises(RuntimeError, match="cannot be fused"):
+        ops.selective_scan_fwd(u, u, A, Bm, Bm, None, u, None, True, order=(_lib.ORDER_NSLICES, 1, 512, 4))
+
+
 def test_error_behaviour():
     u = torch.randn(1, 4, 16, device=DEV)
     A = -torch.rand(4, 8, device=DEV)

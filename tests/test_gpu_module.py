@@ -185,6 +185,42 @@ def test_tfm_mamba_vs_torch_oracle(bimamba_type, d_model, L, ns):
             close("grad." + k, p.grad, ref_grads[k], 5e-3, 5e-3)
 
 
+@pytest.mark.parametrize("bimamba_type,d_model,L,ns,order", [("v3", 64, 512, 16, None), ("v3", 8, 1024, 64, None),
+                                                            ("v1", 3, 48, 1, (3, 6, 8, 1)), ("v1", 3, 1024, 1, (3, 32, 32, 1)),
+                                                            ("v1", 1, 160, 1, (3, 10, 16, 1))])
+@pytest.mark.parametrize("autocast", [False, True])
+def test_mamba_fused_scan_order_equals_explicit(bimamba_type, d_model, L, ns, order, autocast, monkeypatch):
+    """The module with the scan order fused into the kernels (v3's nslices direction; MMConv's two-row order through the
+    scan_order keyword) against the same module with MMU_FUSE=0 (explicit gather / scatter kernels): same outputs, same grads."""
+    from mmunet_b200 import _lib
+    torch.manual_seed(9)
+    m = Mamba(d_model=d_model, d_state=16, d_conv=4, expand=2, bimamba_type=bimamba_type, nslices=ns).to(DEV)
+    x = torch.randn(2, L, d_model, device=DEV)
+    dout = torch.randn(2, L, d_model, device=DEV)
+
+    def run():
+        m.zero_grad()
+        xi = x.clone().requires_grad_()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            out = m(xi, scan_order=order)[0] if order is not None else m(xi)[0]
+        out.float().backward(dout)
+        return out.float().detach(), xi.grad.clone(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+
+    n0 = _lib.launch_count()
+    o1, dx1, g1 = run()
+    fused_launches = _lib.launch_count() - n0
+    monkeypatch.setenv("MMU_FUSE", "0")
+    n0 = _lib.launch_count()
+    o2, dx2, g2 = run()
+    assert _lib.launch_count() - n0 >= fused_launches + 4          # the explicit path adds gather + scatter launches, both passes
+    tol = dict(rtol=2e-2, atol=2e-2) if autocast else dict(rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(o1, o2, **tol)
+    torch.testing.assert_close(dx1, dx2, rtol=tol["rtol"], atol=tol["atol"] * float(dx2.abs().max()))
+    assert g1.keys() == g2.keys()
+    for k in g1:
+        torch.testing.assert_close(g1[k], g2[k], rtol=5 * tol["rtol"], atol=5 * tol["atol"] * max(1.0, float(g2[k].abs().max())), msg=lambda s_: f"{k}: {s_}")
+
+
 def test_tfm_mamba_bf16_autocast():
     torch.manual_seed(5)
     m = Mamba(d_model=64, d_state=16, bimamba_type="v3", nslices=16)
