@@ -80,11 +80,12 @@ __device__ __forceinline__ float2 shfl_down2(float2 v, int delta, int width) {
 struct OrdMap {
     int kind;                 // MMU_ORDER_ROWMAJOR / FLIP / NSLICES / TWOROW
     int W, ns, L, Ls, even_tokens;   // Ls = L / ns, even_tokens = 2*(H/2)*W
+    int ns_shift;                    // log2(ns) when ns is a power of two, else -1 (a runtime integer division costs ~25 instructions)
     __device__ __forceinline__ int operator()(int l) const {
         switch (kind) {
             case MMU_ORDER_FLIP: return L - 1 - l;
             case MMU_ORDER_NSLICES: {
-                const int jj = l / ns, s = l - jj * ns;
+                const int jj = ns_shift >= 0 ? l >> ns_shift : l / ns, s = l - jj * ns;
                 return s * Ls + jj;
             }
             case MMU_ORDER_TWOROW: {
@@ -99,7 +100,7 @@ struct OrdMap {
     // that a group never straddles a slice round / a row pair): one division per group
     __device__ __forceinline__ void idx8(int t0, int (&m)[8]) const {
         if (kind == MMU_ORDER_NSLICES) {
-            const int jj = t0 / ns, s0 = t0 - jj * ns;
+            const int jj = ns_shift >= 0 ? t0 >> ns_shift : t0 / ns, s0 = t0 - jj * ns;
 #pragma unroll
             for (int i = 0; i < 8; ++i) m[i] = (s0 + i) * Ls + jj;
         } else if (kind == MMU_ORDER_TWOROW && t0 < even_tokens) {
@@ -114,10 +115,12 @@ struct OrdMap {
 };
 // host: fill the map; returns false when the arguments are inconsistent
 inline bool make_ordmap(OrdMap &m, int order, int H, int W, int ns, int L) {
-    m = OrdMap{order, W > 0 ? W : 1, ns > 0 ? ns : 1, L, 0, 0};
+    m = OrdMap{order, W > 0 ? W : 1, ns > 0 ? ns : 1, L, 0, 0, -1};
     if (order == MMU_ORDER_NSLICES) {
         if (ns <= 0 || L % ns != 0) return false;
         m.Ls = L / ns;
+        if ((ns & (ns - 1)) == 0)
+            for (m.ns_shift = 0; (1 << m.ns_shift) < ns; ++m.ns_shift) {}
     } else if (order == MMU_ORDER_TWOROW) {
         if (H <= 0 || W <= 0 || (int64_t)H * W != L) return false;
         m.even_tokens = 2 * (H / 2) * W;

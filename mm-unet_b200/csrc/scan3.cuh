@@ -83,6 +83,9 @@ __device__ __forceinline__ void cp_async16(unsigned dst, const void *src) {
 __device__ __forceinline__ void cp_async4(unsigned dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async8(unsigned dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_but_last() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }   // all but the newest group
@@ -113,6 +116,67 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
         "MBAR_DONE_%=:\n\t}" ::"r"(mbar),
         "r"(parity)
         : "memory");
+}
+
+// ---- fused scan order: my 8 consecutive logical tokens t0 .. t0+7 of a tensor that lives in NATURAL token order ----------------
+// (the gate z, out, dout, dz; OrdMap in common.cuh).  The slot is the lane's usual landing slot (two 16-byte quads for fp32, one
+// for 2-byte types), filled in a memory-friendly element order:
+//   TWOROW, row-pair part:  [row 2r: cols c..c+3 | row 2r+1: cols c..c+3]  - two vector copies; token i = element (i&1)*4 + (i>>1)
+//   TWOROW, odd tail row :  8 contiguous elements                            - token i = element i
+//   NSLICES (fp32 only)  :  element i = token i, eight 4-byte copies at stride L/ns (2-byte types would need 2-byte copies: the
+//                           host does not fuse them, mmu_scan_order_fusable)
+template <typename IN_T> __device__ __forceinline__ void ord_issue8(const OrdMap &o, int t0, const IN_T *row, unsigned q0, unsigned q1) {
+    constexpr bool kF32 = sizeof(IN_T) == 4;
+    if (o.kind == MMU_ORDER_TWOROW) {
+        if (t0 < o.even_tokens) {
+            const int pair = t0 / (2 * o.W), rem = t0 - pair * 2 * o.W, base = 2 * pair * o.W + (rem >> 1);
+            if constexpr (kF32) cp_async16(q0, row + base), cp_async16(q1, row + base + o.W);
+            else cp_async8(q0, row + base), cp_async8(q0 + 8, row + base + o.W);
+        } else {
+            if constexpr (kF32) cp_async16(q0, row + t0), cp_async16(q1, row + t0 + 4);
+            else cp_async16(q0, row + t0);
+        }
+    } else if constexpr (kF32) {        // NSLICES
+        const int jj = o.ns_shift >= 0 ? t0 >> o.ns_shift : t0 / o.ns, s0 = t0 - jj * o.ns;
+        const IN_T *src = row + (int64_t)s0 * o.Ls + jj;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cp_async4((i < 4 ? q0 : q1) + (i & 3) * 4, src + (int64_t)i * o.Ls);
+    }
+}
+// e[] = the slot's 8 elements (memory-friendly order) -> v[] in logical token order
+__device__ __forceinline__ void ord_to_tokens(const OrdMap &o, int t0, const float (&e)[8], float (&v)[8]) {
+    const bool inter = o.kind == MMU_ORDER_TWOROW && t0 < o.even_tokens;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = inter ? e[(i & 1) * 4 + (i >> 1)] : e[i];
+}
+template <typename IN_T> __device__ __forceinline__ void ord_store8(const OrdMap &o, int t0, IN_T *row, const float (&v)[8]) {
+    constexpr bool kF32 = sizeof(IN_T) == 4;
+    if (o.kind == MMU_ORDER_TWOROW) {
+        float e[8];
+        const bool inter = t0 < o.even_tokens;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[inter ? (i & 1) * 4 + (i >> 1) : i] = v[i];
+        uint4 q[Raw8<IN_T>::kQuads];
+        Raw8<IN_T>::pack(e, q);
+        if (inter) {
+            const int pair = t0 / (2 * o.W), rem = t0 - pair * 2 * o.W, base = 2 * pair * o.W + (rem >> 1);
+            if constexpr (kF32) {
+                *reinterpret_cast<uint4 *>(row + base) = q[0];
+                *reinterpret_cast<uint4 *>(row + base + o.W) = q[1];
+            } else {
+                *reinterpret_cast<uint2 *>(row + base) = make_uint2(q[0].x, q[0].y);
+                *reinterpret_cast<uint2 *>(row + base + o.W) = make_uint2(q[0].z, q[0].w);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < Raw8<IN_T>::kQuads; ++k) reinterpret_cast<uint4 *>(row + t0)[k] = q[k];
+        }
+    } else {                             // NSLICES: element-wise
+        const int jj = o.ns_shift >= 0 ? t0 >> o.ns_shift : t0 / o.ns, s0 = t0 - jj * o.ns;
+        IN_T *dst = row + (int64_t)s0 * o.Ls + jj;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[(int64_t)i * o.Ls] = Elem<IN_T>::from_f(v[i]);
+    }
 }
 
 __device__ __forceinline__ float lg2_fast(float x) {

@@ -45,16 +45,15 @@ template <typename IN_T, int W> struct Bwd3Cfg {
     static constexpr int kSlabBytes = 2 * W * 2 * 2 * 32 * 16;            // dB | dC partials of one state: [buf][warp][tensor][quad][lane] float4
     static constexpr int kSeedBytes = 2 * W * NCK * 16 * 8;               // x seeds [buf][warp][ck][state] float2
     static constexpr int kTabBytes = 2 * NRP * 16 * 8;                    // A*log2e | e carry
-    static constexpr int kOrdBytes = kF32 ? 0 : 2 * 2 * NT * 16;          // ordered z / dout of 2-byte types: second quad [tensor][row][thread]
-    static constexpr size_t smem_bytes = (size_t)BcTile<LPR>::kBytes + kRawBytes + kLandBytes + kZfBytes + kDABytes + kSlabBytes + kSeedBytes + kTabBytes + kOrdBytes;
+    static constexpr size_t smem_bytes = (size_t)BcTile<LPR>::kBytes + kRawBytes + kLandBytes + kZfBytes + kDABytes + kSlabBytes + kSeedBytes + kTabBytes;
 };
 
 __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// ORD: fused scan order (NSLICES / TWOROW): z and dout are gathered, dz is scattered through p.ord (4-byte accesses; a 2-byte
-// element comes with its neighbour and is picked by the parity of its index); never together with REV.
+// ORD: fused scan order (NSLICES / TWOROW): z and dout are gathered, dz is scattered through p.ord (ord_issue8 / ord_store8 in
+// scan3.cuh); never together with REV.
 template <typename IN_T, int W, bool REV, bool AGG, bool ORD = false>
 __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(const __grid_constant__ Bwd3Args p) {
     static_assert(!ORD || !REV, "ordered gate / output gradient: forward direction only");
@@ -96,7 +95,6 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
     float2 *s_seed = reinterpret_cast<float2 *>(s_zf + Cfg::kZfBytes + Cfg::kDABytes + Cfg::kSlabBytes);   // [2][W][NCK][16]
     float2 *s_A = s_seed + 2 * W * NCK * 16;                               // [NRP][16]  A*log2e of (row A, row B)
     float2 *s_ec = s_A + NRP * 16;                                         // [NRP][16]  e entering the chunk from the right
-    [[maybe_unused]] unsigned char *s_ordx = reinterpret_cast<unsigned char *>(s_ec + NRP * 16);   // [2 tensors][2 rows][NT] x 16 B (2-byte types)
 
     for (int i = tid; i < (int)((Tl::kBytes + Cfg::kRawBytes + Cfg::kLandBytes + Cfg::kZfBytes + Cfg::kDABytes + Cfg::kSlabBytes + Cfg::kSeedBytes) / 16); i += NT)
         reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -182,12 +180,6 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
     float2 dDacc = make_float2(0.f, 0.f), dbacc = make_float2(0.f, 0.f);
     float dsum[2] = {0.f, 0.f};
 
-    [[maybe_unused]] const unsigned s_ordx_u32 = smem_u32(s_ordx) + tid * 16;
-    // word i (4 bytes) of my slot of ordered tensor `which` (2 = z, 3 = dout), row r
-    auto ordword_u32 = [&](int which, int r, int i) {
-        if constexpr (kF32) return s_land_u32 + ((which * 2 + r) * NQ + (i >> 2)) * NT * 16 + (i & 3) * 4;
-        else return (i < 4 ? s_land_u32 + (which * 2 + r) * NT * 16 : s_ordx_u32 + ((which - 2) * 2 + r) * NT * 16) + (i & 3) * 4;
-    };
     auto issue_tile = [&](int c) {
         if constexpr (kF32) {
             tile_async_f32<LPR, NT, REV, true>(s_tile_u32, reinterpret_cast<const float *>(B_b), reinterpret_cast<const float *>(C_b), p.B_ns,
@@ -218,27 +210,23 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
                     if (!AGG && has_z) cp_async16(s_land_u32 + ((4 * 2 + r) * NQ + q) * NT * 16, y_p[r] + q * EPQ);
                 }
             if constexpr (ORD) {
-                int m[8];
-                p.ord.idx8(tin, m);
 #pragma unroll
-                for (int r = 0; r < 2; ++r)
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        cp_async4(ordword_u32(3, r, i), g_row[r] + (kF32 ? m[i] : (m[i] & ~1)));
-                        if (has_z) cp_async4(ordword_u32(2, r, i), z_row[r] + (kF32 ? m[i] : (m[i] & ~1)));
-                    }
+                for (int r = 0; r < 2; ++r) {
+                    ord_issue8<IN_T>(p.ord, tin, g_row[r], s_land_u32 + ((3 * 2 + r) * NQ) * NT * 16, s_land_u32 + ((3 * 2 + r) * NQ + NQ - 1) * NT * 16);
+                    if (has_z)
+                        ord_issue8<IN_T>(p.ord, tin, z_row[r], s_land_u32 + ((2 * 2 + r) * NQ) * NT * 16, s_land_u32 + ((2 * 2 + r) * NQ + NQ - 1) * NT * 16);
+                }
             }
         }
     };
-    // ordered tensor `which` (2 = z, 3 = dout), row r, logical order: 8 words; 2-byte types pick the half by the parity of the index
-    auto load_ord8 = [&](int which, int r, const int (&m)[8], float (&v)[T]) {
+    // ordered tensor `which` (2 = z, 3 = dout), row r -> logical token order
+    auto load_ord8 = [&](int which, int r, int t0, float (&v)[T]) {
+        uint4 q[NQ];
 #pragma unroll
-        for (int i = 0; i < T; ++i) {
-            const unsigned char *q0 = kF32 ? s_land_t + ((which * 2 + r) * NQ + (i >> 2)) * NT * 16
-                                           : (i < 4 ? s_land_t + (which * 2 + r) * NT * 16 : s_ordx + tid * 16 + ((which - 2) * 2 + r) * NT * 16);
-            const unsigned w = *reinterpret_cast<const unsigned *>(q0 + (i & 3) * 4);
-            v[i] = kF32 ? __uint_as_float(w) : __uint_as_float((m[i] & 1) ? (w & 0xffff0000u) : (w << 16));
-        }
+        for (int k = 0; k < NQ; ++k) q[k] = *reinterpret_cast<const uint4 *>(s_land_t + ((which * 2 + r) * NQ + k) * NT * 16);
+        float e[8];
+        Raw8<IN_T>::unpack(q, e);
+        ord_to_tokens(p.ord, t0, e, v);
     };
     auto load_land = [&](int which, int r, float (&v)[T]) {
         uint4 q[NQ];
@@ -283,17 +271,15 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
         float2 dl[T], dlu[T], dy[T];
         {
             float uu[2][T], dd[2][T], gg[2][T], zf[2][T];
-            [[maybe_unused]] int mo[8];
-            if constexpr (ORD) p.ord.idx8(tl, mo);
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 load_land(1, r, dd[r]);
-                if constexpr (ORD) load_ord8(3, r, mo, gg[r]);
+                if constexpr (ORD) load_ord8(3, r, tl, gg[r]);
                 else load_land(3, r, gg[r]);
                 if (!AGG) load_land(0, r, uu[r]);
                 if (has_z) {
                     float zz[T], yv[T];
-                    if constexpr (ORD) load_ord8(2, r, mo, zz);
+                    if constexpr (ORD) load_ord8(2, r, tl, zz);
                     else load_land(2, r, zz);
                     if (!AGG) load_land(4, r, yv);
 #pragma unroll
@@ -308,8 +294,7 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
                         dz_p[r] += STEP;
                         if (ok && row_ok[r]) {
                             if constexpr (ORD) {
-#pragma unroll
-                                for (int i = 0; i < T; ++i) dz_row[r][mo[i]] = Elem<IN_T>::from_f(zf[r][i]);
+                                ord_store8<IN_T>(p.ord, tl, dz_row[r], zf[r]);
                             } else {
                                 store8<IN_T, REV>(dz_p[r], zf[r]);
                             }

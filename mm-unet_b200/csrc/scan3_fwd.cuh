@@ -19,6 +19,15 @@
 #ifndef MMU_BULK_TILE
 #define MMU_BULK_TILE 0
 #endif
+// experiment knobs (csrc/build.sh MMU_VARIANT builds): registers per thread the launch bounds aim at, state-loop unroll
+#ifndef MMU_FWD3_REGS
+#define MMU_FWD3_REGS 168
+#endif
+#ifndef MMU_FWD3_UNROLL
+#define MMU_FWD3_UNROLL 2
+#endif
+#define MMU_PRAGMA_(x) _Pragma(#x)
+#define MMU_UNROLL(n) MMU_PRAGMA_(unroll n)
 
 namespace mmu {
 
@@ -44,14 +53,13 @@ template <typename IN_T, int LPR, int W> struct Fwd3Cfg {
     static constexpr int NQ = Raw8<IN_T>::kQuads;
     static constexpr int kElemBytes = 3 * 2 * NQ * NT * 16;               // u | delta | z : [tensor][row][quad][thread] x 16 B
     static constexpr int kTabBytes = (1 + NCK) * NRP * 16 * (int)sizeof(float2);   // A*log2e | states after every 64 tokens
-    static constexpr int kZxBytes = kF32 ? 0 : 2 * NT * 16;               // ordered z of 2-byte types: 8 pair-words need a second quad per row
-    static constexpr size_t smem_bytes = (size_t)BcTile<LPR>::kBytes + kRawBytes + kElemBytes + kTabBytes + kZxBytes;
+    static constexpr size_t smem_bytes = (size_t)BcTile<LPR>::kBytes + kRawBytes + kElemBytes + kTabBytes;
 };
 
-// ORD: fused scan order (NSLICES / TWOROW) - z is gathered and out scattered through p.ord, 4 bytes at a time (a 2-byte element
-// comes with its neighbour and is picked by the parity of its index); never together with REV or AGG.
+// ORD: fused scan order (NSLICES / TWOROW) - z is gathered and out scattered through p.ord (ord_issue8 / ord_store8 in scan3.cuh);
+// never together with REV or AGG.
 template <typename IN_T, int LPR, int W, bool REV, bool AGG, bool ORD = false>
-__global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) scan3_fwd_kernel(const __grid_constant__ Fwd3Args p) {
+__global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * MMU_FWD3_REGS))) scan3_fwd_kernel(const __grid_constant__ Fwd3Args p) {
     static_assert(!ORD || (!REV && !AGG), "ordered gate / output: forward direction, main pass only");
     using Cfg = Fwd3Cfg<IN_T, LPR, W>;
     using Tl = BcTile<LPR>;
@@ -75,7 +83,6 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
     float2 *s_A = reinterpret_cast<float2 *>(s_elem + Cfg::kElemBytes);                // [NRP][16]  A*log2e of (row A, row B)
     float2 *s_ck = s_A + NRP * 16;                                                     // [NRP][NCK][16]  state after every 64th token;
                                                                                        // slot NCK-1 = state entering the next chunk
-    [[maybe_unused]] unsigned char *s_zx = reinterpret_cast<unsigned char *>(s_ck + NRP * NCK * 16);   // [2 rows][NT] x 16 B (2-byte types)
     // ---- one-time initialisation -----------------------------------------------------------------------------------------
     for (int i = tid; i < (int)((Tl::kBytes + Cfg::kRawBytes + Cfg::kElemBytes) / 16); i += NT)
         reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -179,21 +186,12 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
 #pragma unroll
         for (int r = 0; r < 2; ++r) u_p[r] += STEP, d_p[r] += STEP;
     };
-    [[maybe_unused]] const unsigned s_zx_u32 = smem_u32(s_zx) + tid * 16;
-    // word i (4 bytes) of my ordered-z slot of row r: fp32 = element i; 2-byte types = the aligned pair holding element i
-    auto zword_u32 = [&](int r, int i) {
-        if constexpr (kF32) return s_elem_u32 + ((2 * 2 + r) * NQ + (i >> 2)) * NT * 16 + (i & 3) * 4;
-        else return (i < 4 ? s_elem_u32 + (2 * 2 + r) * NT * 16 : s_zx_u32 + r * NT * 16) + (i & 3) * 4;
-    };
     auto issue_z = [&](bool in_seq) {
         if constexpr (ORD) {
             if (has_z && in_seq) {
-                int m[8];
-                p.ord.idx8(tz, m);
 #pragma unroll
                 for (int r = 0; r < 2; ++r)
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) cp_async4(zword_u32(r, i), z_row[r] + (kF32 ? m[i] : (m[i] & ~1)));
+                    ord_issue8<IN_T>(p.ord, tz, z_row[r], s_elem_u32 + ((2 * 2 + r) * NQ) * NT * 16, s_elem_u32 + ((2 * 2 + r) * NQ + NQ - 1) * NT * 16);
             }
             tz += CH;
             return;
@@ -259,7 +257,7 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
         // u / delta of the next chunk (the staging slots are private to this thread and were just consumed)
         if (c + 1 < c_end) issue_ud(tl + CH < L);
 
-#pragma unroll 2
+MMU_UNROLL(MMU_FWD3_UNROLL)
         for (int n0 = 0; n0 < NS; n0 += 2) {
             const float4 A4 = *reinterpret_cast<const float4 *>(s_A + rpg * 16 + n0);
             const float4 car4 = *reinterpret_cast<const float4 *>(s_ck + (rpg * NCK + NCK - 1) * 16 + n0);
@@ -332,19 +330,17 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
             if (c + 1 < c_end) issue_tile(c + 1);
             // ---- epilogue: gate and store ---------------------------------------------------------------------------------------
             float zz[2][T];
-            [[maybe_unused]] int mo[8];
             if constexpr (ORD) {
-                p.ord.idx8(tl, mo);
                 if (has_z) {
 #pragma unroll
-                    for (int r = 0; r < 2; ++r)
+                    for (int r = 0; r < 2; ++r) {
+                        uint4 q[NQ];
 #pragma unroll
-                        for (int i = 0; i < T; ++i) {
-                            const unsigned w = *reinterpret_cast<const unsigned *>(
-                                (kF32 ? s_elem_t + ((2 * 2 + r) * NQ + (i >> 2)) * NT * 16 : (i < 4 ? s_elem_t + (2 * 2 + r) * NT * 16 : s_zx + tid * 16 + r * NT * 16)) +
-                                (i & 3) * 4);
-                            zz[r][i] = kF32 ? __uint_as_float(w) : __uint_as_float((mo[i] & 1) ? (w & 0xffff0000u) : (w << 16));
-                        }
+                        for (int k = 0; k < NQ; ++k) q[k] = *reinterpret_cast<const uint4 *>(s_elem_t + ((2 * 2 + r) * NQ + k) * NT * 16);
+                        float e[8];
+                        Raw8<IN_T>::unpack(q, e);
+                        ord_to_tokens(p.ord, tl, e, zz[r]);
+                    }
                 }
             } else if (has_z) {
                 load_elem(2, 0, zz[0]);
@@ -365,8 +361,7 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * 168))) sc
                             for (int i = 0; i < T; ++i) yv[i] *= zz[r][i] * sigmoid3(zz[r][i]);
                         }
                         if constexpr (ORD) {
-#pragma unroll
-                            for (int i = 0; i < T; ++i) o_row[r][mo[i]] = Elem<IN_T>::from_f(yv[i]);
+                            ord_store8<IN_T>(p.ord, tl, o_row[r], yv);
                         } else {
                             store8<IN_T, REV>(o_p[r], yv);
                         }

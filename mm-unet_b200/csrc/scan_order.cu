@@ -84,7 +84,7 @@ int make_map(OrderMap &m, int order, int H, int W, int ns) {
     if (H <= 0 || W <= 0) return set_error(MMU_ERR_INVALID, "scan_order: empty map %dx%d", H, W);
     if ((int64_t)H * W > INT32_MAX) return set_error(MMU_ERR_UNSUPPORTED, "scan_order: H*W exceeds int32");
     if (order < MMU_ORDER_ROWMAJOR || order > MMU_ORDER_TWOROW) return set_error(MMU_ERR_INVALID, "scan_order: order %d", order);
-    m.kind = order, m.W = W, m.L = H * W, m.ns = 1, m.Ls = m.L, m.even_tokens = 2 * (H / 2) * W;
+    m.kind = order, m.W = W, m.L = H * W, m.ns = 1, m.Ls = m.L, m.even_tokens = 2 * (H / 2) * W, m.ns_shift = -1;
     if (order == MMU_ORDER_NSLICES) {
         if (ns <= 0 || m.L % ns != 0) return set_error(MMU_ERR_INVALID, "scan_order: L=%d not divisible by nslices=%d", m.L, ns);
         m.ns = ns, m.Ls = m.L / ns;
