@@ -221,6 +221,22 @@ template <int LPR> struct BcTile {
     static __device__ __forceinline__ int quad_off(int q) { return 16 * q + 16 * (q >> 3); }
 };
 
+// Dense variant for the tensor-map (TMA 2-D tile) experiment (MMU_TMA_TILE): rows of CH fp32 tokens back to back, which is what a
+// cp.async.bulk.tensor box without swizzle writes; the lanes' 32-byte reads then take 2-way bank conflicts (a 128B-swizzled box
+// would put the eight 32-token boxes of a row on the same banks: 8-way).
+template <int LPR> struct BcTileDense {
+    static constexpr int CH = LPR * kS3T;
+    static constexpr int kRowBytes = CH * 4;
+    static constexpr int kBytes = 2 * 16 * kRowBytes;
+    static __device__ __forceinline__ int quad_off(int q) { return 16 * q; }
+};
+// one 3-D box {CH tokens, 16 states, 1 batch element} of a (L, dstate, batch) tensor map -> shared memory, completion on the mbarrier
+__device__ __forceinline__ void tma_tile_3d(unsigned dst, const void *tmap, int x, int y, int z, unsigned mbar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+                 "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(mbar)
+                 : "memory");
+}
+
 // Tile of logical tokens [t0, t0 + CH): lane `lane` of the issuing warp owns row `lane` (rows 0..15 = B states, 16..31 = C states).
 // fp32: the row is copied in 128-byte pieces into the padded layout (quad_off); 2-byte types: one copy of the raw row (widened
 // later).  Pieces outside [0, L) are skipped (those lanes run with delta = 0).  The mbarrier must have been initialised with a

@@ -7,6 +7,8 @@
 // which gives every lane the true state hs before its first token, and y_i += cp_i * hs closes the recurrence without a
 // second serial pass.  One MUFU.EX2 per (row, token, state).
 #pragma once
+#include <type_traits>
+
 #include "scan3.cuh"
 
 // MMU_BULK_TILE=1 loads the B/C tile with TMA 1-D bulk copies (cp.async.bulk + mbarrier, scan3.cuh:tile_bulk_issue) issued by
@@ -18,6 +20,11 @@
 // use - together 173 -> 180 us here.)
 #ifndef MMU_BULK_TILE
 #define MMU_BULK_TILE 0
+#endif
+// MMU_TMA_TILE=1 (fp32 only, experiment): the B/C tile of a chunk is TWO cp.async.bulk.tensor copies (tensor maps built by the host
+// per call, UTMALDG in the SASS) into a dense tile instead of ~1 100 per-thread LDGSTS into the padded one.
+#ifndef MMU_TMA_TILE
+#define MMU_TMA_TILE 0
 #endif
 // experiment knobs (csrc/build.sh MMU_VARIANT builds): registers per thread the launch bounds aim at, state-loop unroll
 #ifndef MMU_FWD3_REGS
@@ -43,6 +50,9 @@ struct Fwd3Args {
     int nseg, cps, nchunks, nx;    // cps = chunks per segment
     int softplus;
     OrdMap ord;                    // ORD kernels: the gate z and the output live at ord(l) (natural token order), everything else at l
+#if MMU_TMA_TILE
+    alignas(64) unsigned char tmB[128], tmC[128];   // CUtensorMap of B and C: (L, dstate, batch) fp32, box {256, 16, 1}
+#endif
 };
 
 template <typename IN_T, int LPR, int W> struct Fwd3Cfg {
@@ -62,11 +72,12 @@ template <typename IN_T, int LPR, int W, bool REV, bool AGG, bool ORD = false>
 __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * MMU_FWD3_REGS))) scan3_fwd_kernel(const __grid_constant__ Fwd3Args p) {
     static_assert(!ORD || (!REV && !AGG), "ordered gate / output: forward direction, main pass only");
     using Cfg = Fwd3Cfg<IN_T, LPR, W>;
-    using Tl = BcTile<LPR>;
+    constexpr bool kF32 = Cfg::kF32;
+    constexpr bool kTmaTile = MMU_TMA_TILE != 0 && kF32 && LPR == 32;   // B/C tile by two tensor-map copies into a dense tile
+    using Tl = typename std::conditional<kTmaTile, BcTileDense<LPR>, BcTile<LPR>>::type;
     constexpr int CH = Cfg::CH, RPW = Cfg::RPW, R = Cfg::R, NT = Cfg::NT, NRP = Cfg::NRP, T = kS3T, NQ = Cfg::NQ, NCK = Cfg::NCK;
     constexpr int EPQ = 16 / (int)sizeof(IN_T);          // elements per 16-byte piece
-    constexpr bool kF32 = Cfg::kF32;
-    constexpr bool kBulkTile = MMU_BULK_TILE != 0;       // B/C tile by cp.async.bulk (TMA) instead of per-thread cp.async
+    constexpr bool kBulkTile = MMU_BULK_TILE != 0 && !kTmaTile;   // B/C tile by cp.async.bulk (TMA) instead of per-thread cp.async
     constexpr int NSTEP = LPR == 32 ? 5 : (LPR == 16 ? 4 : 3);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rp = lane / LPR, j = lane % LPR;
@@ -76,15 +87,15 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * MMU_FWD3_
     const bool has_z = p.z != nullptr, sp = p.softplus != 0;
     const int NS = min(16, (N + 1) & ~1);               // states walked (two at a time)
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned char *s_tile = smem_raw;                                                  // [Tl::kBytes]
-    unsigned char *s_rawbc = s_tile + Tl::kBytes;                                      // bf16 only
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *s_tile = smem_raw;                                                  // [Tl::kBytes] (the allocation is sized for the padded tile)
+    unsigned char *s_rawbc = s_tile + BcTile<LPR>::kBytes;                             // bf16 only
     unsigned char *s_elem = s_rawbc + Cfg::kRawBytes;                                  // [3][2][NQ][NT] x 16 B
     float2 *s_A = reinterpret_cast<float2 *>(s_elem + Cfg::kElemBytes);                // [NRP][16]  A*log2e of (row A, row B)
     float2 *s_ck = s_A + NRP * 16;                                                     // [NRP][NCK][16]  state after every 64th token;
                                                                                        // slot NCK-1 = state entering the next chunk
     // ---- one-time initialisation -----------------------------------------------------------------------------------------
-    for (int i = tid; i < (int)((Tl::kBytes + Cfg::kRawBytes + Cfg::kElemBytes) / 16); i += NT)
+    for (int i = tid; i < (int)((BcTile<LPR>::kBytes + Cfg::kRawBytes + Cfg::kElemBytes) / 16); i += NT)
         reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = tid; i < NRP * 16; i += NT) {
         const int g = i >> 4, n = i & 15;
@@ -153,13 +164,25 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * MMU_FWD3_
     __shared__ __align__(8) unsigned long long s_mbar;       // used by the bulk-copy variant only
     const unsigned mbar = smem_u32(&s_mbar);
     [[maybe_unused]] unsigned tile_phase = 0;
-    if constexpr (kBulkTile) {
+    if constexpr (kBulkTile || kTmaTile) {
         if (tid == 0) {
-            mbar_init(mbar, 32);
+            mbar_init(mbar, kTmaTile ? 1 : 32);
             fence_mbar_init();
         }
     }
     auto issue_tile = [&](int c) {
+#if MMU_TMA_TILE
+        if constexpr (kTmaTile) {       // one thread: expect the tile's bytes, then one box per tensor (out-of-range tokens / states read as 0)
+            if (tid == 0) {
+                const int m0 = REV ? L - (c + 1) * CH : c * CH;
+                fence_proxy_async();
+                mbar_arrive_expect_tx(mbar, (AGG ? 1u : 2u) * 16u * CH * 4u);
+                tma_tile_3d(s_tile_u32, p.tmB, m0, 0, b, mbar);
+                if (!AGG) tma_tile_3d(s_tile_u32 + 16 * Tl::kRowBytes, p.tmC, m0, 0, b, mbar);
+            }
+            return;
+        }
+#endif
         if constexpr (kBulkTile) {      // TMA bulk copies issued by warp 0, completion on the mbarrier
             if (warp == 0)
                 tile_bulk_issue<IN_T, LPR, REV, !AGG>(kF32 ? s_tile_u32 : s_raw_u32, mbar, B_b, C_b, p.B_ns, p.C_ns, N, c * CH, L, lane);
@@ -225,7 +248,7 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : (65536 / (32 * W * MMU_FWD3_
     for (int c = c_begin; c < c_end; ++c, tl += CH) {
         const bool ok = tl < L;
         cp_async_wait_all();
-        if constexpr (kBulkTile) mbar_wait(mbar, tile_phase++ & 1u);
+        if constexpr (kBulkTile || kTmaTile) mbar_wait(mbar, tile_phase++ & 1u);
         __syncthreads();                // chunk c has landed
         if constexpr (!kF32) {
             widen_bf16_tile<LPR, NT, !AGG>(s_tile, s_rawbc, tid);
