@@ -11,6 +11,9 @@
 // shared memory 128 B/clk of delivered bytes, SHFL 1 clk.
 #pragma once
 #include "common.cuh"
+#ifndef MMU_TMA_TILE
+#define MMU_TMA_TILE 0          // 1: fp32 B/C tiles by cp.async.bulk.tensor (scan3_fwd.cuh)
+#endif
 
 namespace mmu {
 

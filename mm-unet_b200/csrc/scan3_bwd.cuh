@@ -11,6 +11,8 @@
 //                       S2 = sum_n dh a h_prev A (registers, per token), dA (lane-private shared accumulators).
 // The per (row, token) epilogue turns S1, S2 into du, ddelta, and uses the pre-gate y saved by the forward for dz.
 #pragma once
+#include <type_traits>
+
 #include "scan3.cuh"
 
 namespace mmu {
@@ -30,6 +32,9 @@ struct Bwd3Args {
     int nseg, cps, nchunks, nx;
     int softplus;
     OrdMap ord;                    // ORD kernels: z, dout and dz live at ord(l) (natural token order), everything else at l
+#if MMU_TMA_TILE
+    alignas(64) unsigned char tmB[128], tmC[128];   // CUtensorMap of B and C (see Fwd3Args)
+#endif
 };
 
 template <typename IN_T, int W> struct Bwd3Cfg {
@@ -59,7 +64,8 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
     static_assert(!ORD || !REV, "ordered gate / output gradient: forward direction only");
     using Cfg = Bwd3Cfg<IN_T, W>;
     constexpr int LPR = 32;
-    using Tl = BcTile<LPR>;
+    constexpr bool kTmaTile = MMU_TMA_TILE != 0 && sizeof(IN_T) == 4 && LPR == 32;   // B/C tile by two tensor-map copies (scan3_fwd.cuh)
+    using Tl = typename std::conditional<kTmaTile, BcTileDense<LPR>, BcTile<LPR>>::type;
     constexpr int CH = Cfg::CH, R = Cfg::R, NT = Cfg::NT, NRP = Cfg::NRP, T = kS3T, NQ = Cfg::NQ, NCK = Cfg::NCK;
     constexpr int EPQ = 16 / (int)sizeof(IN_T);
     constexpr bool kF32 = Cfg::kF32;
@@ -85,9 +91,9 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
     const int row0 = bx * R;
     const int NS = (N + 1) & ~1;           // states are walked two at a time (a padding state has A = B = C = 0)
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *s_tile = smem_raw;
-    unsigned char *s_rawbc = s_tile + Tl::kBytes;
+    unsigned char *s_rawbc = s_tile + BcTile<LPR>::kBytes;
     unsigned char *s_land = s_rawbc + Cfg::kRawBytes;
     unsigned char *s_zf = s_land + Cfg::kLandBytes;
     float2 *s_dA = reinterpret_cast<float2 *>(s_zf + Cfg::kZfBytes);       // [16][W][8]
@@ -96,7 +102,7 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
     float2 *s_A = s_seed + 2 * W * NCK * 16;                               // [NRP][16]  A*log2e of (row A, row B)
     float2 *s_ec = s_A + NRP * 16;                                         // [NRP][16]  e entering the chunk from the right
 
-    for (int i = tid; i < (int)((Tl::kBytes + Cfg::kRawBytes + Cfg::kLandBytes + Cfg::kZfBytes + Cfg::kDABytes + Cfg::kSlabBytes + Cfg::kSeedBytes) / 16); i += NT)
+    for (int i = tid; i < (int)((BcTile<LPR>::kBytes + Cfg::kRawBytes + Cfg::kLandBytes + Cfg::kZfBytes + Cfg::kDABytes + Cfg::kSlabBytes + Cfg::kSeedBytes) / 16); i += NT)
         reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (chained && seg + 1 < p.nseg) {
         if (tid == 0) {
@@ -180,7 +186,28 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
     float2 dDacc = make_float2(0.f, 0.f), dbacc = make_float2(0.f, 0.f);
     float dsum[2] = {0.f, 0.f};
 
+    __shared__ __align__(8) unsigned long long s_mbar;       // tensor-map variant only
+    const unsigned mbar = smem_u32(&s_mbar);
+    [[maybe_unused]] unsigned tile_phase = 0;
+    if constexpr (kTmaTile) {
+        if (tid == 0) {
+            mbar_init(mbar, 1);
+            fence_mbar_init();
+        }
+    }
     auto issue_tile = [&](int c) {
+#if MMU_TMA_TILE
+        if constexpr (kTmaTile) {
+            if (tid == 0) {
+                const int m0 = REV ? L - (c + 1) * CH : c * CH;
+                fence_proxy_async();
+                mbar_arrive_expect_tx(mbar, 2u * 16u * CH * 4u);
+                tma_tile_3d(s_tile_u32, p.tmB, m0, 0, b, mbar);
+                tma_tile_3d(s_tile_u32 + 16 * Tl::kRowBytes, p.tmC, m0, 0, b, mbar);
+            }
+            return;
+        }
+#endif
         if constexpr (kF32) {
             tile_async_f32<LPR, NT, REV, true>(s_tile_u32, reinterpret_cast<const float *>(B_b), reinterpret_cast<const float *>(C_b), p.B_ns,
                                                p.C_ns, N, c * CH, L, tid);
@@ -328,6 +355,7 @@ __global__ void __launch_bounds__(32 * W, AGG ? 1 : 8 / W) scan3_bwd_kernel(cons
         // inputs of the next chunk (c-1): the landing slots are private to this thread and were just consumed
         cp_async_wait_all();            // group B: the B/C tile (and everybody's seeds) of this chunk
         __syncthreads();
+        if constexpr (kTmaTile) mbar_wait(mbar, tile_phase++ & 1u);
         if constexpr (!kF32) {
             widen_bf16_tile<LPR, NT, true>(s_tile, s_rawbc, tid);
             __syncthreads();

@@ -23,9 +23,6 @@
 #endif
 // MMU_TMA_TILE=1 (fp32 only, experiment): the B/C tile of a chunk is TWO cp.async.bulk.tensor copies (tensor maps built by the host
 // per call, UTMALDG in the SASS) into a dense tile instead of ~1 100 per-thread LDGSTS into the padded one.
-#ifndef MMU_TMA_TILE
-#define MMU_TMA_TILE 0
-#endif
 // experiment knobs (csrc/build.sh MMU_VARIANT builds): registers per thread the launch bounds aim at, state-loop unroll
 #ifndef MMU_FWD3_REGS
 #define MMU_FWD3_REGS 168

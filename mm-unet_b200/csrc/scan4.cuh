@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(32 * kS4W, (AGG || sizeof(IN_T) == 2) ? 3 : 2)
     const int D = p.D, L = p.L, N = p.N;
     const bool has_z = !AGG && p.z != nullptr, sp = p.softplus != 0;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *s_slot = smem_raw + (size_t)warp * Sm::kWarpBytes;
     float *s_tile = reinterpret_cast<float *>(s_slot + Sm::kSlotBytes);
     const unsigned slot_u32 = smem_u32(s_slot);

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(32 * kS4W, 3) scan4_bwd_agg_kernel(const __gri
     const int D = p.D, L = p.L, N = p.N;
     const bool has_z = p.z != nullptr, sp = p.softplus != 0;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *s_slot = smem_raw + (size_t)warp * Sm::kWarpBytes;
     float *s_tile = reinterpret_cast<float *>(s_slot + Sm::kSlotBytes);      // [8 tokens][16]  C only
     const unsigned slot_u32 = smem_u32(s_slot);
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(32 * kS4W, 2) scan4_bwd_kernel(const __grid_co
     const int D = p.D, L = p.L;                                      // dstate == 16 (checked by the host)
     const bool has_z = p.z != nullptr, sp = p.softplus != 0;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *s_slot = smem_raw + (size_t)warp * Sm::kWarpBytes;
     unsigned char *s_keep = s_slot + Sm::kSlotBytes;
     unsigned char *s_seed = s_keep + Sm::kKeepBytes;

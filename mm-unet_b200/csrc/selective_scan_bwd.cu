@@ -18,6 +18,7 @@
 #include <cstdlib>
 
 #include "scan3_bwd.cuh"
+#include "tma_map.cuh"
 #include "scan4_bwd.cuh"
 #include "scan_tiles.cuh"
 
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(32 * RQ * NGW, AGG ? 512 / (32 * RQ * NGW) : M
     const int N = p.N, Ne = p.Ne, NP = Ne >> 1, D = p.D, L = p.L;
     const bool has_z = p.z != nullptr, rev = p.reverse != 0, sp = p.softplus != 0;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_u = reinterpret_cast<float *>(smem_raw);   // [R][TL]  u, later du
     float *s_dl = s_u + R * TL;                          // [R][TL]  softplus(delta+bias), later ddelta
     float *s_z = s_dl + R * TL;                          // [R][TL]  z -> dz factor -> dz
@@ -678,6 +679,12 @@ template <typename IN_T> int run_bwd3(const mmu_scan_bwd_params *p, cudaStream_t
     a.nx = (f.seqlen + MMU_STATE_STRIDE - 1) / MMU_STATE_STRIDE;
     a.softplus = f.delta_softplus;
     const bool rev = f.reverse != 0;
+#if MMU_TMA_TILE
+    if constexpr (sizeof(IN_T) == 4) {
+        if (int rc = encode_bc_map(a.tmB, f.B, f.seqlen, f.dstate, f.batch, f.B_ns, f.B_bs)) return rc;
+        if (int rc = encode_bc_map(a.tmC, f.C, f.seqlen, f.dstate, f.batch, f.C_ns, f.C_bs)) return rc;
+    }
+#endif
     if (pl.nseg > 1 && pl.chain) {
         const size_t n_state = (size_t)a.B * a.D * pl.nseg * 16;
         const size_t n_flags = (size_t)a.B * ((a.D + 2 * pl.W - 1) / (2 * pl.W)) * pl.nseg + 1;

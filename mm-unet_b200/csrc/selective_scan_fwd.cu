@@ -18,11 +18,8 @@
 #include <algorithm>
 #include <cstdlib>
 
-#if defined(MMU_TMA_TILE) && MMU_TMA_TILE
-#include <cuda.h>
-#include <cudaTypedefs.h>
-#endif
 #include "scan3_fwd.cuh"
+#include "tma_map.cuh"
 #include "scan4.cuh"
 #include "scan_tiles.cuh"
 
@@ -62,7 +59,7 @@ __global__ void __launch_bounds__(32 * RQ * NGW, 512 / (32 * RQ * NGW)) scan_fwd
     const int N = p.N, Ne = p.Ne, NP = Ne >> 1, D = p.D, L = p.L;
     const bool has_z = p.z != nullptr;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_u = reinterpret_cast<float *>(smem_raw);   // [R][TL]
     float *s_dl = s_u + R * TL;                          // [R][TL]  softplus(delta + bias)
     float *s_z = s_dl + R * TL;                          // [R][TL]
@@ -495,26 +492,6 @@ template <typename IN_T, bool AGG> int dispatch_fwd3(const Fwd3Args &a, const Fw
     return MMU_F3(32, 4);
 #undef MMU_F3
 }
-
-#if MMU_TMA_TILE
-// tensor maps of B / C for the TMA tile experiment: (L, dstate, batch) fp32, box {256 tokens, 16 states, 1}
-int encode_bc_map(void *out, const void *base, int L, int N, int B, int64_t ns, int64_t bs) {
-    static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
-        void *f = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q);
-        return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(f);
-    }();
-    if (fn == nullptr) return set_error(MMU_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
-    const cuuint64_t dims[3] = {(cuuint64_t)L, (cuuint64_t)N, (cuuint64_t)B};
-    const cuuint64_t strides[2] = {(cuuint64_t)ns * 4, (cuuint64_t)bs * 4};
-    const cuuint32_t box[3] = {256, 16, 1}, es[3] = {1, 1, 1};
-    const CUresult rc = fn(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(base), dims, strides, box, es,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return rc == CUDA_SUCCESS ? MMU_OK : set_error(MMU_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled failed: %d", (int)rc);
-}
-#endif
 
 template <typename IN_T> int run_fwd3(const mmu_scan_fwd_params *p, cudaStream_t st) {
     const Fwd3Plan pl = plan_fwd3(p->batch, p->dim, p->seqlen, p->order != MMU_ORDER_ROWMAJOR);
