@@ -153,6 +153,7 @@ def cpu_baseline_port(sample_batch=B, min_seconds=10.0, max_reps=8):
     """The oracle's C port (OpenMP over all host cores) on a bounded sample of the same step: the full batch, repeated
     until about 10 s of CPU work have been timed."""
     import oracle
+    oracle.set_num_threads(len(os.sched_getaffinity(0)))
     t, w = make_inputs(sample_batch, torch.float32, "cpu")
     n = {k: v.numpy() for k, v in {**t, **w}.items()}
     reps, t0, scan_s = 0, time.perf_counter(), 0.0
@@ -180,6 +181,9 @@ def run_reference(args):
         return
     import oracle
     from oracle import torch_ref
+    host_cores = len(os.sched_getaffinity(0))       # torchrun exports OMP_NUM_THREADS=1: use every core this process may run on
+    torch.set_num_threads(host_cores)
+    oracle.set_num_threads(host_cores)
     t, w = make_inputs(B, torch.float32, "cpu")
     n = {k: v.numpy() for k, v in {**t, **w}.items()}
     nb = algo_bytes(B, 4)
@@ -204,7 +208,6 @@ def run_reference(args):
     val = (nb["scan_fwd"] + nb["scan_bwd"]) / scan_s / 1e9
 
     # the reference's own pure-PyTorch arithmetic on a bounded sample (batch 1 of 8, all 384 channels), 2 steps
-    torch.set_num_threads(os.cpu_count() or 1)
     ts, ws = make_inputs(1, torch.float32, "cpu")
     pt = []
     for _ in range(2):
@@ -471,7 +474,7 @@ def main():
         "config": workload_config(args.dtype),
         "value_basis": "scan fwd+bwd algorithmic bytes (11D+6N)BLs / (scan fwd + scan bwd time inside the step, CUDA events); "
                        "ms_per_step is the whole 4-kernel step",
-        "block": {"value": whole_job_gbps(world, nbytes["step"], ms), "unit": "GB/s", "what": "whole step incl. causal_conv1d fwd/bwd (818 MB fp32)"},
+        "block": {"value": whole_job_gbps(world, nbytes["step"], ms), "unit": "GB/s", "what": "whole step incl. causal_conv1d fwd/bwd (%d MB algorithmic per rank)" % round(nbytes["step"] / 1e6)},
         "e2e": {"value": whole_job_gbps(world, nbytes["scan_fwd"] + nbytes["scan_bwd"], e2e_ms), "unit": "GB/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
                 "api": "causal_conv1d_fn + selective_scan_fn (autograd), pinned host inputs (H2D of step i+1 on a copy stream overlaps "

@@ -214,6 +214,54 @@ int mmu_group_norm_nhwc_bwd(const void *x, const float *gamma, const void *dy, c
                             int32_t G, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Narrow Mamba block (d_model = 3, d_inner = 6, dt_rank = 1, d_state = 16, d_conv = 4: the Mamba inside every MMConv,
+ * src/UM_Net/MMUNet.py:56, 178-183) - SURVEY.md section 8 row f3.  Replaces, around the selective scan, the separate
+ * in_proj / causal_conv1d / x_proj / dt_proj / out_proj ops of requirements/mamba_simple.py:201-270 and
+ * mamba_ssm/ops/selective_scan_interface.py:181-207 (backward :256-277) by one kernel each way:
+ *   pre_fwd  : hidden -> pre   = rows [u (d_inner) | delta (d_inner) | z (d_inner) | B (d_state) | C (d_state)] in SCAN order;
+ *              the caller then runs mmu_selective_scan_fwd on row views of `pre` (delta bias + softplus inside the scan)
+ *   post_fwd : out_z (scan order, the gated scan output) -> out = out_proj(out_z) in natural token order
+ *   post_bwd : dout (natural order) -> dout_y (scan order);  d(out_proj.weight) accumulated
+ *   pre_bwd  : gpre = rows [du | ddelta | dz] and dBC = rows [dB | dC] (fp32) from mmu_selective_scan_bwd -> dhidden (natural
+ *              order) and the in_proj / conv / x_proj / dt_proj weight gradients accumulated
+ * hidden, out, dout, dhidden: (batch, d_model, L), token stride 1, tokens in NATURAL order; the scan visits them in the order
+ * idx(l) (order fields as in mmu_conv_params; 0 = natural order).  pre (batch, mmu_mamba_narrow_rows(), L), out_z / dout_y
+ * (batch, d_inner, L), gpre (batch, 3*d_inner, L), dBC (batch, 2*d_state, L) fp32: contiguous.  Weights fp32 contiguous, no in_proj /
+ * out_proj bias.  dweights: fp32, caller zero-fills, mmu_mamba_narrow_weight_floats() long, laid out
+ * [in_proj (2*d_inner, d_model) | conv_w (d_inner, d_conv) | conv_b (d_inner) | x_proj (dt_rank + 2*d_state, d_inner) |
+ *  dt_proj (d_inner, dt_rank) | out_proj (d_model, d_inner)].
+ * --------------------------------------------------------------------------------------------- */
+typedef struct mmu_narrow_params {
+    int32_t dtype;
+    int32_t batch, seqlen;
+    int32_t d_model, d_inner, d_state, dt_rank, d_conv;
+    int32_t order, order_h, order_w, order_ns;
+    const float *in_proj_w, *conv_w, *conv_b /* or NULL */, *x_proj_w, *dt_proj_w, *out_proj_w;
+    const void *hidden;
+    int64_t hidden_bs, hidden_cs;
+    void *pre;               /* written by pre_fwd, read by pre_bwd */
+    const void *out_z;       /* post_fwd, post_bwd */
+    void *out;
+    int64_t out_bs, out_cs;
+    const void *dout;
+    int64_t dout_bs, dout_cs;
+    void *dout_y;
+    const void *gpre;
+    const float *dBC;
+    void *dhidden;
+    int64_t dhidden_bs, dhidden_cs;
+    float *dweights;
+} mmu_narrow_params;
+
+int32_t mmu_mamba_narrow_supported(int32_t d_model, int32_t d_inner, int32_t d_state, int32_t dt_rank, int32_t d_conv, int32_t dtype);
+int32_t mmu_mamba_narrow_rows(int32_t d_inner, int32_t d_state);
+int32_t mmu_mamba_narrow_weight_floats(int32_t d_model, int32_t d_inner, int32_t d_state, int32_t dt_rank, int32_t d_conv);
+int mmu_mamba_narrow_pre_fwd(const mmu_narrow_params *p, void *stream);
+int mmu_mamba_narrow_post_fwd(const mmu_narrow_params *p, void *stream);
+int mmu_mamba_narrow_post_bwd(const mmu_narrow_params *p, void *stream);
+int mmu_mamba_narrow_pre_bwd(const mmu_narrow_params *p, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * misc
  * --------------------------------------------------------------------------------------------- */
 int mmu_version(void);

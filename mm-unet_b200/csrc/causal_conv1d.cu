@@ -98,15 +98,16 @@ __device__ __forceinline__ void load_taps(const ConvArgs &p, int d, float w4[4],
     bias = p.bias != nullptr ? p.bias[d] : 0.f;
 }
 
-template <typename IN_T> __global__ void __launch_bounds__(kConvNT) conv1d_fwd_kernel(const __grid_constant__ ConvArgs p) {
+// ORD = false: the plain / reversed path only (no tile, no index map in the instruction stream)
+template <typename IN_T, bool ORD> __global__ void __launch_bounds__(kConvNT) conv1d_fwd_kernel(const __grid_constant__ ConvArgs p) {
     constexpr int kConvVT = ConvVT<IN_T>::value;
     const int d = blockIdx.y, b = blockIdx.z;
     const int t = (blockIdx.x * kConvNT + threadIdx.x) * kConvVT;
     const IN_T *xr = reinterpret_cast<const IN_T *>(p.x) + (int64_t)b * p.x_bs + (int64_t)d * p.x_ds;
     float xv[kConvVT + 3];
-    __shared__ IN_T s_x[OrdTile<IN_T>::kElems];
+    __shared__ IN_T s_x[ORD ? OrdTile<IN_T>::kElems : 1];
     __shared__ float s_halo[3];
-    const bool tiled = ord_tiled(p.ord, OrdTile<IN_T>::TB);
+    const bool tiled = ORD && ord_tiled(p.ord, OrdTile<IN_T>::TB);
     if (tiled) {       // block-uniform
         constexpr int TB = OrdTile<IN_T>::TB;
         const int sh = p.ord.ns_shift, RL = TB >> sh, rsh = 31 - __clz(RL), T0 = blockIdx.x * TB, j0 = T0 >> sh;
@@ -127,7 +128,7 @@ template <typename IN_T> __global__ void __launch_bounds__(kConvNT) conv1d_fwd_k
     load_taps(p, d, w4, bias);
     const bool rev = p.reverse != 0;
     if (tiled) {
-    } else if (p.ord.kind != MMU_ORDER_ROWMAJOR) {
+    } else if (ORD && p.ord.kind != MMU_ORDER_ROWMAJOR) {
         load_ord<IN_T, kConvVT + 3>(xr, t - 3, p.L, p.ord, xv);
     } else {
 #pragma unroll
@@ -146,7 +147,7 @@ template <typename IN_T> __global__ void __launch_bounds__(kConvNT) conv1d_fwd_k
                  rev, o);
 }
 
-template <typename IN_T> __global__ void __launch_bounds__(kConvNT) conv1d_bwd_kernel(const __grid_constant__ ConvArgs p) {
+template <typename IN_T, bool ORD> __global__ void __launch_bounds__(kConvNT) conv1d_bwd_kernel(const __grid_constant__ ConvArgs p) {
     constexpr int kConvVT = ConvVT<IN_T>::value;
     const int d = blockIdx.y, b = blockIdx.z;
     const int t = (blockIdx.x * kConvNT + threadIdx.x) * kConvVT;
@@ -154,10 +155,10 @@ template <typename IN_T> __global__ void __launch_bounds__(kConvNT) conv1d_bwd_k
     load_taps(p, d, w4, bias);
     float part[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // dw4[0..3], dbias
     const bool rev = p.reverse != 0;
-    __shared__ IN_T s_x[OrdTile<IN_T>::kElems];
-    __shared__ IN_T s_dx[OrdTile<IN_T>::kElems];
+    __shared__ IN_T s_x[ORD ? OrdTile<IN_T>::kElems : 1];
+    __shared__ IN_T s_dx[ORD ? OrdTile<IN_T>::kElems : 1];
     __shared__ float s_halo[6];
-    const bool tiled = ord_tiled(p.ord, OrdTile<IN_T>::TB);
+    const bool tiled = ORD && ord_tiled(p.ord, OrdTile<IN_T>::TB);
     if (tiled) {       // block-uniform: x of logical tokens [T0 - 3, T0 + TB + 3)
         constexpr int TB = OrdTile<IN_T>::TB;
         const IN_T *xr = reinterpret_cast<const IN_T *>(p.x) + (int64_t)b * p.x_bs + (int64_t)d * p.x_ds;
@@ -176,7 +177,7 @@ template <typename IN_T> __global__ void __launch_bounds__(kConvNT) conv1d_bwd_k
         const IN_T *xr = reinterpret_cast<const IN_T *>(p.x) + (int64_t)b * p.x_bs + (int64_t)d * p.x_ds;
         const IN_T *gr = reinterpret_cast<const IN_T *>(p.dout) + (int64_t)b * p.g_bs + (int64_t)d * p.g_ds;
         float xv[kConvVT + 6], gv[kConvVT + 3];   // x[t-3 .. t+10], dout[t .. t+10]
-        const bool ordered = p.ord.kind != MMU_ORDER_ROWMAJOR;
+        const bool ordered = ORD && p.ord.kind != MMU_ORDER_ROWMAJOR;
         if (tiled) {
 #pragma unroll
             for (int k = 0; k < kConvVT + 6; ++k) {
@@ -292,8 +293,14 @@ template <typename IN_T> int run_conv(const mmu_conv_params *p, bool bwd, cudaSt
     const int per_block = kConvNT * ConvVT<IN_T>::value;
     dim3 grid((L + per_block - 1) / per_block, p->dim, p->batch);
     if (grid.y > 65535 || grid.z > 65535) return set_error(MMU_ERR_UNSUPPORTED, "causal_conv1d: dim/batch > 65535");
-    if (bwd) conv1d_bwd_kernel<IN_T><<<grid, kConvNT, 0, st>>>(a);
-    else conv1d_fwd_kernel<IN_T><<<grid, kConvNT, 0, st>>>(a);
+    const bool ord = p->order != MMU_ORDER_ROWMAJOR;
+    if (bwd) {
+        if (ord) conv1d_bwd_kernel<IN_T, true><<<grid, kConvNT, 0, st>>>(a);
+        else conv1d_bwd_kernel<IN_T, false><<<grid, kConvNT, 0, st>>>(a);
+    } else {
+        if (ord) conv1d_fwd_kernel<IN_T, true><<<grid, kConvNT, 0, st>>>(a);
+        else conv1d_fwd_kernel<IN_T, false><<<grid, kConvNT, 0, st>>>(a);
+    }
     count_launch();
     return check_launch(bwd ? "causal_conv1d_bwd" : "causal_conv1d_fwd");
 }

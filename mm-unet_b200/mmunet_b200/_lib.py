@@ -50,6 +50,23 @@ class ConvParams(C.Structure):
     )
 
 
+class NarrowParams(C.Structure):
+    """mmu_narrow_params (include/mmunet_b200.h)."""
+    _fields_ = (
+        [(n, _i32) for n in ("dtype", "batch", "seqlen", "d_model", "d_inner", "d_state", "dt_rank", "d_conv",
+                             "order", "order_h", "order_w", "order_ns")]
+        + [(n, _vp) for n in ("in_proj_w", "conv_w", "conv_b", "x_proj_w", "dt_proj_w", "out_proj_w", "hidden")]
+        + [(n, _i64) for n in ("hidden_bs", "hidden_cs")]
+        + [(n, _vp) for n in ("pre", "out_z", "out")]
+        + [(n, _i64) for n in ("out_bs", "out_cs")]
+        + [("dout", _vp)]
+        + [(n, _i64) for n in ("dout_bs", "dout_cs")]
+        + [(n, _vp) for n in ("dout_y", "gpre", "dBC", "dhidden")]
+        + [(n, _i64) for n in ("dhidden_bs", "dhidden_cs")]
+        + [("dweights", _vp)]
+    )
+
+
 EXPORTS = (
     "mmu_version", "mmu_last_error", "mmu_launch_count", "mmu_reload_knobs",
     "mmu_selective_scan_fwd_workspace", "mmu_selective_scan_fwd",
@@ -58,6 +75,8 @@ EXPORTS = (
     "mmu_scan_order_gather", "mmu_scan_order_scatter", "mmu_scan_order_index", "mmu_scan_order_fusable",
     "mmu_snake_sample_fwd", "mmu_snake_sample_bwd",
     "mmu_group_norm_nhwc_fwd", "mmu_group_norm_nhwc_bwd",
+    "mmu_mamba_narrow_supported", "mmu_mamba_narrow_rows", "mmu_mamba_narrow_weight_floats",
+    "mmu_mamba_narrow_pre_fwd", "mmu_mamba_narrow_post_fwd", "mmu_mamba_narrow_post_bwd", "mmu_mamba_narrow_pre_bwd",
 )
 
 _lib = None
@@ -94,6 +113,14 @@ def lib() -> C.CDLL:
     L.mmu_snake_sample_bwd.argtypes = [_vp, _vp, _vp, _vp, _vp] + [_i32] * 8 + [_vp]
     L.mmu_group_norm_nhwc_fwd.argtypes = [_vp] * 7 + [_i32] * 6 + [C.c_float, _vp]
     L.mmu_group_norm_nhwc_bwd.argtypes = [_vp] * 8 + [_i32] * 6 + [_vp]
+    L.mmu_mamba_narrow_supported.restype = _i32
+    L.mmu_mamba_narrow_supported.argtypes = [_i32] * 6
+    L.mmu_mamba_narrow_rows.restype = _i32
+    L.mmu_mamba_narrow_rows.argtypes = [_i32] * 2
+    L.mmu_mamba_narrow_weight_floats.restype = _i32
+    L.mmu_mamba_narrow_weight_floats.argtypes = [_i32] * 5
+    for n in ("mmu_mamba_narrow_pre_fwd", "mmu_mamba_narrow_post_fwd", "mmu_mamba_narrow_post_bwd", "mmu_mamba_narrow_pre_bwd"):
+        getattr(L, n).argtypes = [C.POINTER(NarrowParams), _vp]
     for n in EXPORTS:      # fail loudly on a stale library
         getattr(L, n)
     _lib = L

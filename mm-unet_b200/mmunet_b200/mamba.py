@@ -120,6 +120,15 @@ class Mamba(nn.Module):
         # channel-major (b, d_model, l) maps (MMUNet.py:180, 405): then xz = W @ X[b] is a contiguous (b, 2d, l) batched
         # matmul with no copy; otherwise the reference's "d (b l)" form, a (b, 2d, l) view with strides (l, b*l, 1).
         tokens_cm = hidden_states.transpose(1, 2)
+        if (self.use_fast_path and self.bimamba_type not in ("v2", "v3") and hidden_states.is_cuda and self.in_proj.bias is None
+                and self.out_proj.bias is None
+                and ops.mamba_narrow_supported(self.d_model, self.d_inner, self.d_state, self.dt_rank, self.d_conv,
+                                               ops._autocast_dtype() or hidden_states.dtype)):
+            # narrow block (MMConv's d_model = 3 Mamba): in_proj .. dt_proj and out_proj run inside two fused kernels around the scan
+            out = ops.mamba_narrow_fn(tokens_cm, self.in_proj.weight, self.conv1d.weight, self.conv1d.bias, self.x_proj.weight,
+                                      self.dt_proj.weight, self.out_proj.weight, -torch.exp(self.A_log.float()), self.D.float(),
+                                      self.dt_proj.bias.float(), order=scan_order)
+            return out.transpose(1, 2), None, None, None
         if tokens_cm.stride(-1) == 1 or seqlen == 1:
             xz = torch.matmul(self.in_proj.weight, tokens_cm)
         else:

@@ -832,6 +832,113 @@ def mamba_inner_fn_no_out_proj_reversed(xz, conv1d_weight, conv1d_bias, x_proj_w
 # scan-order permutations (bit-exact index maps)
 # ----------------------------------------------------------------------------------------------------------
 
+# ---- narrow Mamba block: fused prologue / epilogue around the scan ----------------------------------
+def mamba_narrow_supported(d_model, d_inner, d_state, dt_rank, d_conv, dtype) -> bool:
+    """True for the block shape the fused narrow kernels are built for (MMConv's Mamba: d_model 3, expand 2, d_state 16, dt_rank 1,
+    d_conv 4; fp32 / bf16).  MMU_NARROW=0 in the environment disables them (the generic inner functions run instead)."""
+    import os
+    if os.environ.get("MMU_NARROW", "1") == "0" or dtype not in (torch.float32, torch.bfloat16):
+        return False
+    return bool(_lib.lib().mmu_mamba_narrow_supported(d_model, d_inner, d_state, dt_rank, d_conv, _DT[dtype]))
+
+
+def _narrow_params(io, batch, L, dims, order, weights):
+    p = _lib.NarrowParams()
+    p.dtype, p.batch, p.seqlen = _DT[io], batch, L
+    p.d_model, p.d_inner, p.d_state, p.dt_rank, p.d_conv = dims
+    _set_order(p, order)
+    p.in_proj_w, p.conv_w, p.conv_b, p.x_proj_w, p.dt_proj_w, p.out_proj_w = [_ptr(w) for w in weights]
+    return p
+
+
+class MambaNarrowFn(torch.autograd.Function):
+    """The whole narrow Mamba block, requirements/mamba_simple.py:201-270 with bimamba_type "v1" (in_proj -> mamba_inner_fn ->
+    out_proj, selective_scan_interface.py:292-434), on channel-major tokens: hidden (b, d_model, l) in NATURAL token order ->
+    (b, d_model, l) in natural order, scanned in `order` = (kind, H, W, nslices) or None.  Three launches forward (prologue, scan,
+    epilogue) and four backward instead of the separate projection / conv / cast ops; no in_proj / out_proj bias."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, hidden, in_w, conv_w, conv_b, x_w, dt_w, out_w, A, D, dt_bias, order):
+        io = _autocast_dtype() or hidden.dtype
+        _require_cuda(hidden, in_w, conv_w, conv_b, x_w, dt_w, out_w, A, D, dt_bias)
+        batch, dm, L = hidden.shape
+        di, N, R, kw = conv_w.shape[0], A.shape[1], dt_w.shape[1], conv_w.shape[-1]
+        dims = (dm, di, N, R, kw)
+        if not mamba_narrow_supported(*dims, io):
+            raise RuntimeError(f"mamba_narrow_fn: unsupported block shape {dims} / dtype {io}")
+        if order is not None and order[0] == _lib.ORDER_ROWMAJOR:
+            order = None
+        hidden = hidden.to(io)
+        if hidden.stride(-1) != 1:
+            hidden = hidden.contiguous()
+        weights = [w if w is None else w.detach().float().contiguous() for w in (in_w, conv_w.reshape(di, kw), conv_b, x_w, dt_w, out_w)]
+        A, D, dt_bias = A.float().contiguous(), D.float().contiguous(), dt_bias.float().contiguous()
+        L_ = _lib.lib()
+        rows = L_.mmu_mamba_narrow_rows(di, N)
+        pre = torch.empty((batch, rows, L), device=hidden.device, dtype=io)
+        out = torch.empty((batch, dm, L), device=hidden.device, dtype=io)
+        with torch.cuda.device(hidden.device):
+            p = _narrow_params(io, batch, L, dims, order, weights)
+            p.hidden, p.hidden_bs, p.hidden_cs, p.pre = hidden.data_ptr(), hidden.stride(0), hidden.stride(1), pre.data_ptr()
+            _lib.check(L_.mmu_mamba_narrow_pre_fwd(ct.byref(p), _stream()), "mamba_narrow_pre_fwd")
+            u, delta, z = pre[:, :di], pre[:, di:2 * di], pre[:, 2 * di:3 * di]
+            Bm, Cm = pre[:, 3 * di:3 * di + N].unsqueeze(1), pre[:, 3 * di + N:].unsqueeze(1)
+            out_z, xs, _ = selective_scan_fwd(u, delta, A, Bm, Cm, D, z, dt_bias, True)
+            p.out_z, p.out, p.out_bs, p.out_cs = out_z.data_ptr(), out.data_ptr(), out.stride(0), out.stride(1)
+            _lib.check(L_.mmu_mamba_narrow_post_fwd(ct.byref(p), _stream()), "mamba_narrow_post_fwd")
+        ctx.dims, ctx.order, ctx.io, ctx.has_conv_b = dims, order, io, conv_b is not None
+        ctx.wdtypes = [None if w is None else w.dtype for w in (in_w, conv_w, conv_b, x_w, dt_w, out_w)]
+        ctx.conv_w_shape = conv_w.shape
+        ctx.save_for_backward(hidden, pre, out_z, xs.x, xs.y, A, D, dt_bias, *[w for w in weights if w is not None])
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        hidden, pre, out_z, xs_x, xs_y, A, D, dt_bias, *ws = ctx.saved_tensors
+        if not ctx.has_conv_b:
+            ws.insert(2, None)
+        dm, di, N, R, kw = ctx.dims
+        io = ctx.io
+        batch, _, L = hidden.shape
+        dout = dout.to(io)
+        if dout.stride(-1) != 1:
+            dout = dout.contiguous()
+        L_ = _lib.lib()
+        dW = torch.zeros(L_.mmu_mamba_narrow_weight_floats(dm, di, N, R, kw), device=hidden.device, dtype=torch.float32)
+        dout_y = torch.empty((batch, di, L), device=hidden.device, dtype=io)
+        gpre = torch.empty((batch, 3 * di, L), device=hidden.device, dtype=io)
+        dBC = torch.zeros((batch, 2 * N, L), device=hidden.device, dtype=torch.float32)
+        dhidden = torch.empty_like(hidden)
+        with torch.cuda.device(hidden.device):
+            p = _narrow_params(io, batch, L, ctx.dims, ctx.order, ws)
+            p.out_z, p.dout, p.dout_bs, p.dout_cs = out_z.data_ptr(), dout.data_ptr(), dout.stride(0), dout.stride(1)
+            p.dout_y, p.dweights = dout_y.data_ptr(), dW.data_ptr()
+            _lib.check(L_.mmu_mamba_narrow_post_bwd(ct.byref(p), _stream()), "mamba_narrow_post_bwd")
+            u, delta, z = pre[:, :di], pre[:, di:2 * di], pre[:, 2 * di:3 * di]
+            Bm, Cm = pre[:, 3 * di:3 * di + N].unsqueeze(1), pre[:, 3 * di + N:].unsqueeze(1)
+            _, _, dA, _, _, dD, _, ddt_bias = selective_scan_bwd(
+                u, delta, A, Bm, Cm, D, z, dt_bias, dout_y, ScanStates(xs_x, xs_y), True, du=gpre[:, :di], ddelta=gpre[:, di:2 * di],
+                dz=gpre[:, 2 * di:], dBC=(dBC[:, :N], dBC[:, N:]))
+            p.hidden, p.hidden_bs, p.hidden_cs, p.pre = hidden.data_ptr(), hidden.stride(0), hidden.stride(1), pre.data_ptr()
+            p.gpre, p.dBC = gpre.data_ptr(), dBC.data_ptr()
+            p.dhidden, p.dhidden_bs, p.dhidden_cs = dhidden.data_ptr(), dhidden.stride(0), dhidden.stride(1)
+            _lib.check(L_.mmu_mamba_narrow_pre_bwd(ct.byref(p), _stream()), "mamba_narrow_pre_bwd")
+        sizes = (2 * di * dm, di * kw, di, (R + 2 * N) * di, di * R, dm * di)
+        g_in, g_cw, g_cb, g_x, g_dt, g_out = torch.split(dW, sizes)
+        wd = ctx.wdtypes
+        return (dhidden, g_in.view(2 * di, dm).to(wd[0]), g_cw.view(ctx.conv_w_shape).to(wd[1]), g_cb.to(wd[2]) if ctx.has_conv_b else None,
+                g_x.view(R + 2 * N, di).to(wd[3]), g_dt.view(di, R).to(wd[4]), g_out.view(dm, di).to(wd[5]), dA, dD, ddt_bias, None)
+
+
+def mamba_narrow_fn(hidden, in_proj_weight, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight, A, D,
+                    delta_bias, order=None):
+    """hidden (b, d_model, l), natural token order -> (b, d_model, l); see MambaNarrowFn."""
+    return MambaNarrowFn.apply(hidden, in_proj_weight, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight,
+                               A, D, delta_bias, order)
+
+
 def _order_call(fn_name, src, order, H, W, nslices):
     _require_cuda(src)
     if src.dtype not in _DT:

@@ -65,6 +65,12 @@ def num_threads() -> int:
     return int(lib().oracle_num_threads())
 
 
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the C oracle (torchrun exports OMP_NUM_THREADS=1 to its workers); returns the count now in effect."""
+    lib().oracle_set_num_threads(int(n))
+    return num_threads()
+
+
 def selective_scan_fwd(u, delta, A, Bm, Cm, D=None, z=None, delta_bias=None, delta_softplus=False):
     """-> (out (B,D,L), last_state (B,D,N)).  selective_scan_interface.py:86-152."""
     u, delta, A = _f32(u), _f32(delta), _f32(A)

@@ -279,3 +279,14 @@ int oracle_num_threads(void)
     return 1;
 #endif
 }
+
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the benchmark's CPU legs set the thread count explicitly. */
+void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    extern void omp_set_num_threads(int);
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

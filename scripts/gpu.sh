@@ -1,8 +1,8 @@
 #!/bin/bash
-# gpurun with retry on "busy" (exit 3): scripts/gpu.sh <timeout_s> '<command>'
+# gpurun with retry on "busy" (exit 3): [GPUS=n] scripts/gpu.sh <timeout_s> '<command>'
 T=$1; shift
-for i in $(seq 1 30); do
-  /usr/local/graft/bin/gpurun --timeout $T -- "$@"
+for i in $(seq 1 40); do
+  /usr/local/graft/bin/gpurun --timeout $T ${GPUS:+--gpus $GPUS} -- "$@"
   rc=$?
   if [ $rc -ne 3 ]; then exit $rc; fi
   sleep 90

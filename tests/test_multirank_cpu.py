@@ -129,3 +129,24 @@ def test_ddp_trainer_two_ranks_gloo():
     assert moved0 > 0 and np.isfinite(l0 + l1).all()
     assert xs0 != xs1, "ranks must train on different shards"
     assert nfrozen0 == nfrozen1 == 47 * (2 + 14), "dsc_conv_y (2) + the _b/_s Mamba sets (2 x 7 tensors) of the 47 MMConvs are frozen"
+
+
+def test_reference_arm_uses_all_cores_under_torchrun_env(monkeypatch, capfd):
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm (rank 0 only) must still run the C oracle on every
+    core the process may use, and the other ranks must print nothing.  Shapes shrunk so the test takes seconds."""
+    import argparse, json, os, sys
+    sys.path.insert(0, ROOT)
+    import bench, oracle
+    monkeypatch.setattr(bench, "B", 2); monkeypatch.setattr(bench, "D", 16); monkeypatch.setattr(bench, "L", 256)
+    args = argparse.Namespace(gpus=2, steps=1, warmup=0)
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")
+    oracle.set_num_threads(1)                                   # what a worker started by torchrun sees
+    monkeypatch.setenv("RANK", "1")
+    bench.run_reference(args)
+    assert capfd.readouterr().out.strip() == ""
+    monkeypatch.setenv("RANK", "0")
+    bench.run_reference(args)
+    line = json.loads(capfd.readouterr().out.strip().splitlines()[-1])
+    cores = len(os.sched_getaffinity(0))
+    assert line["impl"] == "reference" and line["cpu_baseline"]["cores"] == cores and line["n_gpus"] == 2
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
