@@ -229,7 +229,7 @@ int mmu_group_norm_nhwc_bwd(const void *x, const float *gamma, const void *dy, c
  * (batch, d_inner, L), gpre (batch, 3*d_inner, L), dBC (batch, 2*d_state, L) fp32: contiguous.  Weights fp32 contiguous, no in_proj /
  * out_proj bias.  dweights: fp32, caller zero-fills, mmu_mamba_narrow_weight_floats() long, laid out
  * [in_proj (2*d_inner, d_model) | conv_w (d_inner, d_conv) | conv_b (d_inner) | x_proj (dt_rank + 2*d_state, d_inner) |
- *  dt_proj (d_inner, dt_rank) | out_proj (d_model, d_inner)].
+ *  dt_proj (d_inner, dt_rank) | out_proj (d_model, d_inner) | d(altho) (1, coord_mode only)].
  * --------------------------------------------------------------------------------------------- */
 typedef struct mmu_narrow_params {
     int32_t dtype;
@@ -251,6 +251,16 @@ typedef struct mmu_narrow_params {
     void *dhidden;
     int64_t dhidden_bs, dhidden_cs;
     float *dweights;
+    int32_t hidden_dtype;    /* dtype of hidden / dhidden: equal to `dtype`, or MMU_F32 with dtype MMU_BF16 (autocast) */
+    /* MMConv coordinate epilogue (src/UM_Net/MMUNet.py:156-188), coord_mode = 1:  post_fwd writes, instead of `out`,
+     *   coords[b][k][h*map_w + w] = gain * refined + h + snake_offsets(hidden)[k] * extend_scope      (fp32, (batch, d_model, L))
+     * with gain = max(softplus(*altho), 0.01) and refined the block's output; post_bwd reads dcoords (fp32, same shape) instead of
+     * dout and accumulates d(altho) into the LAST float of dweights; pre_bwd adds the offsets' gradient to dhidden. */
+    int32_t coord_mode, map_h, map_w;
+    float extend_scope;
+    const float *altho;
+    float *coords;
+    const float *dcoords;
 } mmu_narrow_params;
 
 int32_t mmu_mamba_narrow_supported(int32_t d_model, int32_t d_inner, int32_t d_state, int32_t dt_rank, int32_t d_conv, int32_t dtype);

@@ -13,7 +13,11 @@
 //              Per 256-token tile: (1) per token d(x_dbl), d(u) and d(conv pre-activation) (+3 halo tokens), (2) conv transposed,
 //              in_proj transposed, (3) the x_proj / dt_proj / in_proj weight gradients as sums over the tile of products of two
 //              entries of a per-token record kept in shared memory (one accumulator per thread, one atomic per accumulator and tile).
-// All arithmetic in fp32 from fp32 weights; activations in the I/O dtype.
+// MMConv epilogue (coord_mode): the block's output is consumed only as  y = gain * refined + rows + snake_offsets(dy) * extend_scope
+// (src/UM_Net/MMUNet.py:156-188: gain = clamp(softplus(altho), 0.01), rows = the row index h, offsets = cumulative sums of dy away
+// from the centre tap, dy = the block's own input).  post_fwd writes y (fp32) instead of the block output, post_bwd takes d(y) and
+// accumulates d(altho), pre_bwd adds the offsets' gradient to d(hidden): ~35 element-wise launches per MMConv disappear.
+// All arithmetic in fp32 from fp32 weights; scan-side activations in the I/O dtype IN_T, hidden / d(hidden) in HID_T.
 #include "scan_tiles.cuh"
 
 namespace mmu {
@@ -42,7 +46,37 @@ struct NarArgs {
     int64_t h_bs, h_cs, o_bs, o_cs, g_bs, g_cs, dh_bs, dh_cs;
     int B, L;
     OrdMap ord;
+    // MMConv coordinate epilogue
+    int coord_mode, map_w;
+    float scope;
+    const float *altho, *dcoords;
+    float *coords;
 };
+
+__device__ __forceinline__ float coord_gain(float altho, float *dgain_daltho = nullptr) {
+    const float sp = altho > 20.f ? altho : log1pf(__expf(altho));        // F.softplus (threshold 20)
+    if (dgain_daltho != nullptr) *dgain_daltho = sp > 0.01f ? sigmoid_f(altho) : 0.f;
+    return fmaxf(sp, 0.01f);
+}
+// cumulative offsets away from the centre tap (MMUNet.py:156-174) and the transposed map for gradients
+template <int DM> __device__ __forceinline__ void snake_offsets(const float (&dy)[DM], float (&off)[DM]) {
+    constexpr int c = DM / 2;
+    off[c] = 0.f;
+#pragma unroll
+    for (int k = c + 1; k < DM; ++k) off[k] = off[k - 1] + dy[k];
+#pragma unroll
+    for (int k = c - 1; k >= 0; --k) off[k] = off[k + 1] + dy[k];
+}
+template <int DM> __device__ __forceinline__ void snake_offsets_t(const float (&g)[DM], float (&d)[DM]) {
+    constexpr int c = DM / 2;
+    d[c] = 0.f;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = DM - 1; k > c; --k) acc += g[k], d[k] = acc;
+    acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < c; ++k) acc += g[k], d[k] = acc;
+}
 
 template <int DM> __device__ __forceinline__ void load_weights(const NarArgs &p, float *s_w) {
     using C = Nar<DM>;
@@ -59,15 +93,15 @@ template <int DM> __device__ __forceinline__ void load_weights(const NarArgs &p,
 }
 
 // hidden of the 4 conv taps of scan token l (tap k = scan token l-3+k; zeros before the sequence start)
-template <typename IN_T, int DM>
+template <typename HID_T, int DM>
 __device__ __forceinline__ void load_taps_hidden(const NarArgs &p, int b, int l, float (&h)[4][DM]) {
-    const IN_T *hp = reinterpret_cast<const IN_T *>(p.hidden) + (int64_t)b * p.h_bs;
+    const HID_T *hp = reinterpret_cast<const HID_T *>(p.hidden) + (int64_t)b * p.h_bs;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int lt = l - 3 + k;
         const int m = lt >= 0 ? p.ord(lt) : 0;
 #pragma unroll
-        for (int c = 0; c < DM; ++c) h[k][c] = lt >= 0 ? Elem<IN_T>::to_f(hp[(int64_t)c * p.h_cs + m]) : 0.f;
+        for (int c = 0; c < DM; ++c) h[k][c] = lt >= 0 ? Elem<HID_T>::to_f(hp[(int64_t)c * p.h_cs + m]) : 0.f;
     }
 }
 
@@ -90,7 +124,7 @@ __device__ __forceinline__ void conv_pre(const float *s_w, const float (&h)[4][D
     }
 }
 
-template <typename IN_T, int DM> __global__ void __launch_bounds__(kNarT) narrow_pre_fwd_kernel(const __grid_constant__ NarArgs p) {
+template <typename IN_T, typename HID_T, int DM> __global__ void __launch_bounds__(kNarT) narrow_pre_fwd_kernel(const __grid_constant__ NarArgs p) {
     using C = Nar<DM>;
     __shared__ float s_w[C::kNW];
     load_weights<DM>(p, s_w);
@@ -98,7 +132,7 @@ template <typename IN_T, int DM> __global__ void __launch_bounds__(kNarT) narrow
     const int b = blockIdx.y, l = blockIdx.x * kNarT + threadIdx.x;
     if (l >= p.L) return;
     float h[4][DM], pre[C::DI], xtap[4][C::DI];
-    load_taps_hidden<IN_T, DM>(p, b, l, h);
+    load_taps_hidden<HID_T, DM>(p, b, l, h);
     conv_pre<DM>(s_w, h, pre, xtap);
     IN_T *P = reinterpret_cast<IN_T *>(p.pre) + (int64_t)b * C::kPreRows * p.L + l;
     float u[C::DI];
@@ -126,7 +160,7 @@ template <typename IN_T, int DM> __global__ void __launch_bounds__(kNarT) narrow
     }
 }
 
-template <typename IN_T, int DM> __global__ void __launch_bounds__(kNarT) narrow_post_fwd_kernel(const __grid_constant__ NarArgs p) {
+template <typename IN_T, typename HID_T, int DM> __global__ void __launch_bounds__(kNarT) narrow_post_fwd_kernel(const __grid_constant__ NarArgs p) {
     using C = Nar<DM>;
     __shared__ float s_wo[DM * C::DI];
     for (int i = threadIdx.x; i < DM * C::DI; i += kNarT) s_wo[i] = p.out_w[i];
@@ -137,14 +171,29 @@ template <typename IN_T, int DM> __global__ void __launch_bounds__(kNarT) narrow
     float y[C::DI];
 #pragma unroll
     for (int d = 0; d < C::DI; ++d) y[d] = Elem<IN_T>::to_f(oz[(int64_t)d * p.L]);
-    IN_T *op = reinterpret_cast<IN_T *>(p.out) + (int64_t)b * p.o_bs + p.ord(l);
+    const int m = p.ord(l);
+    float v[DM];
 #pragma unroll
     for (int e = 0; e < DM; ++e) {
-        float v = 0.f;
+        v[e] = 0.f;
 #pragma unroll
-        for (int d = 0; d < C::DI; ++d) v = fmaf(s_wo[e * C::DI + d], y[d], v);
-        op[(int64_t)e * p.o_cs] = Elem<IN_T>::from_f(v);
+        for (int d = 0; d < C::DI; ++d) v[e] = fmaf(s_wo[e * C::DI + d], y[d], v[e]);
     }
+    if (p.coord_mode) {       // y coordinates of the K snake taps at pixel m = (h, w)
+        const HID_T *hp = reinterpret_cast<const HID_T *>(p.hidden) + (int64_t)b * p.h_bs + m;
+        float dyv[DM], off[DM];
+#pragma unroll
+        for (int c = 0; c < DM; ++c) dyv[c] = Elem<HID_T>::to_f(hp[(int64_t)c * p.h_cs]);
+        snake_offsets<DM>(dyv, off);
+        const float gain = coord_gain(*p.altho), row = (float)(m / p.map_w);
+        float *cp = p.coords + (int64_t)b * DM * p.L + m;
+#pragma unroll
+        for (int e = 0; e < DM; ++e) cp[(int64_t)e * p.L] = fmaf(gain, v[e], fmaf(off[e], p.scope, row));
+        return;
+    }
+    IN_T *op = reinterpret_cast<IN_T *>(p.out) + (int64_t)b * p.o_bs + m;
+#pragma unroll
+    for (int e = 0; e < DM; ++e) op[(int64_t)e * p.o_cs] = Elem<IN_T>::from_f(v[e]);
 }
 
 // sum of v[i] over the block -> one atomicAdd per i
@@ -168,35 +217,54 @@ template <int NV> __device__ __forceinline__ void block_sum_atomic(float (&v)[NV
 template <typename IN_T, int DM> __global__ void __launch_bounds__(kNarT) narrow_post_bwd_kernel(const __grid_constant__ NarArgs p) {
     using C = Nar<DM>;
     __shared__ float s_wo[DM * C::DI];
-    __shared__ float s_red[(kNarT / 32) * DM * C::DI];
+    __shared__ float s_red[(kNarT / 32) * (DM * C::DI + 1)];
     for (int i = threadIdx.x; i < DM * C::DI; i += kNarT) s_wo[i] = p.out_w[i];
     __syncthreads();
     const int b = blockIdx.y, l = blockIdx.x * kNarT + threadIdx.x;
-    float dw[DM * C::DI];
+    float dw[DM * C::DI + 1];       // out_proj weight gradient | d(altho) (coord_mode; the two are adjacent in the accumulator)
 #pragma unroll
-    for (int i = 0; i < DM * C::DI; ++i) dw[i] = 0.f;
+    for (int i = 0; i < DM * C::DI + 1; ++i) dw[i] = 0.f;
+    float gain = 1.f, dgain_daltho = 0.f;
+    if (p.coord_mode) gain = coord_gain(*p.altho, &dgain_daltho);
     if (l < p.L) {
-        const IN_T *gp = reinterpret_cast<const IN_T *>(p.dout) + (int64_t)b * p.g_bs + p.ord(l);
+        const int m = p.ord(l);
         const IN_T *oz = reinterpret_cast<const IN_T *>(p.out_z) + (int64_t)b * C::DI * p.L + l;
         IN_T *dy = reinterpret_cast<IN_T *>(p.dout_y) + (int64_t)b * C::DI * p.L + l;
-        float g[DM];
+        float g[DM], y[C::DI];
 #pragma unroll
-        for (int e = 0; e < DM; ++e) g[e] = Elem<IN_T>::to_f(gp[(int64_t)e * p.g_cs]);
+        for (int d = 0; d < C::DI; ++d) y[d] = Elem<IN_T>::to_f(oz[(int64_t)d * p.L]);
+        if (p.coord_mode) {       // d(refined) = gain * d(coords);  d(gain) = sum d(coords) * refined
+            const float *gc = p.dcoords + (int64_t)b * DM * p.L + m;
+            float dgain = 0.f;
+#pragma unroll
+            for (int e = 0; e < DM; ++e) {
+                const float gce = gc[(int64_t)e * p.L];
+                float refined = 0.f;
+#pragma unroll
+                for (int d = 0; d < C::DI; ++d) refined = fmaf(s_wo[e * C::DI + d], y[d], refined);
+                dgain = fmaf(gce, refined, dgain);
+                g[e] = gain * gce;
+            }
+            dw[DM * C::DI] = dgain * dgain_daltho;
+        } else {
+            const IN_T *gp = reinterpret_cast<const IN_T *>(p.dout) + (int64_t)b * p.g_bs + m;
+#pragma unroll
+            for (int e = 0; e < DM; ++e) g[e] = Elem<IN_T>::to_f(gp[(int64_t)e * p.g_cs]);
+        }
 #pragma unroll
         for (int d = 0; d < C::DI; ++d) {
             float v = 0.f;
 #pragma unroll
             for (int e = 0; e < DM; ++e) v = fmaf(s_wo[e * C::DI + d], g[e], v);
             dy[(int64_t)d * p.L] = Elem<IN_T>::from_f(v);
-            const float y = Elem<IN_T>::to_f(oz[(int64_t)d * p.L]);
 #pragma unroll
-            for (int e = 0; e < DM; ++e) dw[e * C::DI + d] = g[e] * y;
+            for (int e = 0; e < DM; ++e) dw[e * C::DI + d] = g[e] * y[d];
         }
     }
-    block_sum_atomic<DM * C::DI>(dw, p.dW + C::oWout, s_red);
+    block_sum_atomic<DM * C::DI + 1>(dw, p.dW + C::oWout, s_red);       // slot kNW = d(altho)
 }
 
-template <typename IN_T, int DM> __global__ void __launch_bounds__(kNarT) narrow_pre_bwd_kernel(const __grid_constant__ NarArgs p) {
+template <typename IN_T, typename HID_T, int DM> __global__ void __launch_bounds__(kNarT) narrow_pre_bwd_kernel(const __grid_constant__ NarArgs p) {
     using C = Nar<DM>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *s_w = reinterpret_cast<float *>(smem_raw);                 // [kNW]
@@ -236,7 +304,7 @@ template <typename IN_T, int DM> __global__ void __launch_bounds__(kNarT) narrow
 #pragma unroll
             for (int r = 0; r < 2 * C::N; ++r) dxd[C::R + r] = BC[(int64_t)r * p.L + l];
             float h[4][DM], pre[C::DI], xtap[4][C::DI];
-            load_taps_hidden<IN_T, DM>(p, b, l, h);
+            load_taps_hidden<HID_T, DM>(p, b, l, h);
             conv_pre<DM>(s_w, h, pre, xtap);
 #pragma unroll
             for (int d = 0; d < C::DI; ++d) {
@@ -286,13 +354,24 @@ template <typename IN_T, int DM> __global__ void __launch_bounds__(kNarT) narrow
             rec[C::qDxz + d] = acc;
             dxz[C::DI + d] = rec[C::qDxz + C::DI + d];
         }
-        IN_T *dh = reinterpret_cast<IN_T *>(p.dhidden) + (int64_t)b * p.dh_bs + p.ord(l);
+        const int m = p.ord(l);
+        float doff[DM];
+#pragma unroll
+        for (int c = 0; c < DM; ++c) doff[c] = 0.f;
+        if (p.coord_mode) {       // the snake offsets' path from d(coords) straight back to dy = hidden
+            const float *gc = p.dcoords + (int64_t)b * DM * p.L + m;
+            float g[DM];
+#pragma unroll
+            for (int c = 0; c < DM; ++c) g[c] = gc[(int64_t)c * p.L] * p.scope;
+            snake_offsets_t<DM>(g, doff);
+        }
+        HID_T *dh = reinterpret_cast<HID_T *>(p.dhidden) + (int64_t)b * p.dh_bs + m;
 #pragma unroll
         for (int c = 0; c < DM; ++c) {
-            float v = 0.f;
+            float v = doff[c];
 #pragma unroll
             for (int j = 0; j < 2 * C::DI; ++j) v = fmaf(s_w[C::oWin + j * DM + c], dxz[j], v);
-            dh[(int64_t)c * p.dh_cs] = Elem<IN_T>::from_f(v);
+            dh[(int64_t)c * p.dh_cs] = Elem<HID_T>::from_f(v);
         }
     }
     // conv weight / bias gradients: block sum of the per-token partials
@@ -329,15 +408,15 @@ template <int DM> constexpr size_t pre_bwd_smem() {
 
 enum NarKernel { kPreFwd, kPostFwd, kPostBwd, kPreBwd };
 
-template <typename IN_T> int launch_narrow(const NarArgs &a, NarKernel which, cudaStream_t st) {
+template <typename IN_T, typename HID_T> int launch_narrow(const NarArgs &a, NarKernel which, cudaStream_t st) {
     constexpr int DM = 3;
     dim3 grid((a.L + kNarT - 1) / kNarT, a.B);
     switch (which) {
-        case kPreFwd: narrow_pre_fwd_kernel<IN_T, DM><<<grid, kNarT, 0, st>>>(a); break;
-        case kPostFwd: narrow_post_fwd_kernel<IN_T, DM><<<grid, kNarT, 0, st>>>(a); break;
+        case kPreFwd: narrow_pre_fwd_kernel<IN_T, HID_T, DM><<<grid, kNarT, 0, st>>>(a); break;
+        case kPostFwd: narrow_post_fwd_kernel<IN_T, HID_T, DM><<<grid, kNarT, 0, st>>>(a); break;
         case kPostBwd: narrow_post_bwd_kernel<IN_T, DM><<<grid, kNarT, 0, st>>>(a); break;
         case kPreBwd: {
-            auto k = narrow_pre_bwd_kernel<IN_T, DM>;
+            auto k = narrow_pre_bwd_kernel<IN_T, HID_T, DM>;
             constexpr size_t smem = pre_bwd_smem<DM>();
             cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             k<<<grid, kNarT, smem, st>>>(a);
@@ -364,20 +443,25 @@ int narrow_entry(const mmu_narrow_params *p, NarKernel which, void *stream) {
     if (!make_ordmap(a.ord, p->order, p->order_h, p->order_w, p->order_ns, p->seqlen) || p->order == MMU_ORDER_FLIP)
         return set_error(MMU_ERR_INVALID, "mamba_narrow: bad scan order %d (H=%d W=%d nslices=%d, L=%d)", p->order, p->order_h, p->order_w,
                          p->order_ns, p->seqlen);
+    a.coord_mode = p->coord_mode, a.map_w = p->map_w, a.scope = p->extend_scope, a.altho = p->altho, a.dcoords = p->dcoords, a.coords = p->coords;
+    const bool cm = p->coord_mode != 0;
+    if (cm && (p->map_h <= 0 || p->map_w <= 0 || (int64_t)p->map_h * p->map_w != p->seqlen || p->altho == nullptr))
+        return set_error(MMU_ERR_INVALID, "mamba_narrow: coord_mode needs map_h * map_w == seqlen and altho");
     bool ok = true;
     switch (which) {
         case kPreFwd: ok = a.in_w && a.conv_w && a.x_w && a.dt_w && a.hidden && a.pre; break;
-        case kPostFwd: ok = a.out_w && a.out_z && a.out; break;
-        case kPostBwd: ok = a.out_w && a.out_z && a.dout && a.dout_y && a.dW; break;
-        case kPreBwd: ok = a.in_w && a.conv_w && a.x_w && a.dt_w && a.hidden && a.pre && a.gpre && a.dBC && a.dhidden && a.dW; break;
+        case kPostFwd: ok = a.out_w && a.out_z && (cm ? (a.coords && a.hidden) : a.out != nullptr); break;
+        case kPostBwd: ok = a.out_w && a.out_z && (cm ? a.dcoords != nullptr : a.dout != nullptr) && a.dout_y && a.dW; break;
+        case kPreBwd:
+            ok = a.in_w && a.conv_w && a.x_w && a.dt_w && a.hidden && a.pre && a.gpre && a.dBC && a.dhidden && a.dW && (!cm || a.dcoords);
+            break;
     }
     if (!ok) return set_error(MMU_ERR_INVALID, "mamba_narrow: null tensor pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    switch (p->dtype) {
-        case MMU_F32: return launch_narrow<float>(a, which, st);
-        case MMU_BF16: return launch_narrow<__nv_bfloat16>(a, which, st);
-        default: return set_error(MMU_ERR_UNSUPPORTED, "mamba_narrow: dtype %d", p->dtype);
-    }
+    if (p->dtype == MMU_F32 && p->hidden_dtype == MMU_F32) return launch_narrow<float, float>(a, which, st);
+    if (p->dtype == MMU_BF16 && p->hidden_dtype == MMU_BF16) return launch_narrow<__nv_bfloat16, __nv_bfloat16>(a, which, st);
+    if (p->dtype == MMU_BF16 && p->hidden_dtype == MMU_F32) return launch_narrow<__nv_bfloat16, float>(a, which, st);
+    return set_error(MMU_ERR_UNSUPPORTED, "mamba_narrow: dtype %d with hidden dtype %d", p->dtype, p->hidden_dtype);
 }
 }  // namespace
 }  // namespace mmu
@@ -387,7 +471,7 @@ extern "C" int32_t mmu_mamba_narrow_supported(int32_t d_model, int32_t d_inner, 
 }
 extern "C" int32_t mmu_mamba_narrow_rows(int32_t d_inner, int32_t d_state) { return 3 * d_inner + 2 * d_state; }
 extern "C" int32_t mmu_mamba_narrow_weight_floats(int32_t d_model, int32_t d_inner, int32_t d_state, int32_t dt_rank, int32_t d_conv) {
-    return 2 * d_inner * d_model + d_inner * d_conv + d_inner + (dt_rank + 2 * d_state) * d_inner + d_inner * dt_rank + d_model * d_inner;
+    return 2 * d_inner * d_model + d_inner * d_conv + d_inner + (dt_rank + 2 * d_state) * d_inner + d_inner * dt_rank + d_model * d_inner + 1;
 }
 extern "C" int mmu_mamba_narrow_pre_fwd(const mmu_narrow_params *p, void *stream) { return mmu::narrow_entry(p, mmu::kPreFwd, stream); }
 extern "C" int mmu_mamba_narrow_post_fwd(const mmu_narrow_params *p, void *stream) { return mmu::narrow_entry(p, mmu::kPostFwd, stream); }

@@ -64,6 +64,9 @@ class NarrowParams(C.Structure):
         + [(n, _vp) for n in ("dout_y", "gpre", "dBC", "dhidden")]
         + [(n, _i64) for n in ("dhidden_bs", "dhidden_cs")]
         + [("dweights", _vp)]
+        + [(n, _i32) for n in ("hidden_dtype", "coord_mode", "map_h", "map_w")]
+        + [("extend_scope", C.c_float)]
+        + [(n, _vp) for n in ("altho", "coords", "dcoords")]
     )
 
 

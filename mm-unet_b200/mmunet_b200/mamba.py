@@ -107,7 +107,7 @@ class Mamba(nn.Module):
             return ops.mamba_inner_fn_no_out_proj_reversed(*args, D=D, delta_bias=db, delta_softplus=True)
         return ops.mamba_inner_fn_no_out_proj(*args, None, None, D, delta_bias=db, delta_softplus=True)
 
-    def forward(self, hidden_states, inference_params=None, scan_order=None):
+    def forward(self, hidden_states, inference_params=None, scan_order=None, coord_epilogue=None):
         """scan_order = (kind, H, W, nslices) (extension, single-direction types only): the tokens of hidden_states are in natural
         order and the block scans them in that order, returning natural order - what MMConv gets from flatten -> Mamba ->
         inverse flatten (src/UM_Net/MMUNet.py:178-183), with the permutation inside the conv / scan kernels' addressing."""
@@ -120,15 +120,15 @@ class Mamba(nn.Module):
         # channel-major (b, d_model, l) maps (MMUNet.py:180, 405): then xz = W @ X[b] is a contiguous (b, 2d, l) batched
         # matmul with no copy; otherwise the reference's "d (b l)" form, a (b, 2d, l) view with strides (l, b*l, 1).
         tokens_cm = hidden_states.transpose(1, 2)
-        if (self.use_fast_path and self.bimamba_type not in ("v2", "v3") and hidden_states.is_cuda and self.in_proj.bias is None
-                and self.out_proj.bias is None
-                and ops.mamba_narrow_supported(self.d_model, self.d_inner, self.d_state, self.dt_rank, self.d_conv,
-                                               ops._autocast_dtype() or hidden_states.dtype)):
+        if self.narrow_block_available(hidden_states):
             # narrow block (MMConv's d_model = 3 Mamba): in_proj .. dt_proj and out_proj run inside two fused kernels around the scan
+            altho, coord = (coord_epilogue[0], tuple(coord_epilogue[1:])) if coord_epilogue is not None else (None, None)
             out = ops.mamba_narrow_fn(tokens_cm, self.in_proj.weight, self.conv1d.weight, self.conv1d.bias, self.x_proj.weight,
                                       self.dt_proj.weight, self.out_proj.weight, -torch.exp(self.A_log.float()), self.D.float(),
-                                      self.dt_proj.bias.float(), order=scan_order)
+                                      self.dt_proj.bias.float(), order=scan_order, altho=altho, coord=coord)
             return out.transpose(1, 2), None, None, None
+        if coord_epilogue is not None:
+            raise NotImplementedError("mmunet_b200.Mamba: coord_epilogue needs the fused narrow block (see narrow_block_available)")
         if tokens_cm.stride(-1) == 1 or seqlen == 1:
             xz = torch.matmul(self.in_proj.weight, tokens_cm)
         else:
@@ -194,6 +194,13 @@ class Mamba(nn.Module):
                                          self.out_proj.weight, self.out_proj.bias, A, None, None, self.D.float(),
                                          delta_bias=self.dt_proj.bias.float(), delta_softplus=True)
         return out, o_1, o_2, o_3
+
+    def narrow_block_available(self, like) -> bool:
+        """True when forward() runs `like`-shaped CUDA inputs through the fused narrow block (and so accepts coord_epilogue)."""
+        return bool(self.use_fast_path and self.bimamba_type not in ("v2", "v3") and like.is_cuda and self.in_proj.bias is None
+                    and self.out_proj.bias is None
+                    and ops.mamba_narrow_supported(self.d_model, self.d_inner, self.d_state, self.dt_rank, self.d_conv,
+                                                   ops._autocast_dtype() or like.dtype))
 
     def _slow_path(self, xz, seqlen):
         """use_fast_path=False (mamba_simple.py:319-361): un-fused ops, single direction."""

@@ -100,6 +100,13 @@ class MMConv(nn.Module):
         K = self.kernel_size
         dy = offset[:, :K]                                    # the second K channels (x offsets) are unused (:136)
         rows, _ = self._base_grids(H, W, offset.device)
+        if (_fuse_scan_order and dy.is_cuda and isinstance(self.mamba, Mamba) and self.morph == 0 and dy.dtype in (torch.float32, torch.bfloat16)
+                and self.mamba.narrow_block_available(dy)):
+            # narrow fused block with the coordinate arithmetic below as its epilogue: offset map in, y coordinates out
+            from . import _lib
+            y = self.mamba(dy.reshape(B, K, H * W).transpose(-1, -2), scan_order=(_lib.ORDER_TWOROW, H, W, 1),
+                           coord_epilogue=(self.altho, self.extend_scope, H, W))[0]
+            return y.transpose(-1, -2).reshape(B, K, H, W)
         if _fuse_scan_order and dy.is_cuda and isinstance(self.mamba, Mamba) and self.mamba.bimamba_type not in ("v2", "v3"):
             # the morph (two-row) order is applied inside the conv / scan kernels' addressing: the tokens stay in natural order,
             # no flatten / inverse-flatten copies (:178-183); explicit gather / scatter kernels where the map cannot be fused

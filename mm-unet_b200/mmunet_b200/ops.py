@@ -842,12 +842,15 @@ def mamba_narrow_supported(d_model, d_inner, d_state, dt_rank, d_conv, dtype) ->
     return bool(_lib.lib().mmu_mamba_narrow_supported(d_model, d_inner, d_state, dt_rank, d_conv, _DT[dtype]))
 
 
-def _narrow_params(io, batch, L, dims, order, weights):
+def _narrow_params(io, hid_dtype, batch, L, dims, order, weights, coord):
     p = _lib.NarrowParams()
-    p.dtype, p.batch, p.seqlen = _DT[io], batch, L
+    p.dtype, p.hidden_dtype, p.batch, p.seqlen = _DT[io], _DT[hid_dtype], batch, L
     p.d_model, p.d_inner, p.d_state, p.dt_rank, p.d_conv = dims
     _set_order(p, order)
     p.in_proj_w, p.conv_w, p.conv_b, p.x_proj_w, p.dt_proj_w, p.out_proj_w = [_ptr(w) for w in weights]
+    if coord is not None:
+        altho, scope, H, W = coord
+        p.coord_mode, p.map_h, p.map_w, p.extend_scope, p.altho = 1, H, W, float(scope), altho.data_ptr()
     return p
 
 
@@ -855,13 +858,15 @@ class MambaNarrowFn(torch.autograd.Function):
     """The whole narrow Mamba block, requirements/mamba_simple.py:201-270 with bimamba_type "v1" (in_proj -> mamba_inner_fn ->
     out_proj, selective_scan_interface.py:292-434), on channel-major tokens: hidden (b, d_model, l) in NATURAL token order ->
     (b, d_model, l) in natural order, scanned in `order` = (kind, H, W, nslices) or None.  Three launches forward (prologue, scan,
-    epilogue) and four backward instead of the separate projection / conv / cast ops; no in_proj / out_proj bias."""
+    epilogue) and four backward instead of the separate projection / conv / cast ops; no in_proj / out_proj bias.
+    coord = (altho, extend_scope, H, W): MMConv's coordinate epilogue (src/UM_Net/MMUNet.py:156-188) - the result is the fp32 map
+    gain * block(hidden) + row index + snake_offsets(hidden) * extend_scope with gain = clamp(softplus(altho), 0.01)."""
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda")
-    def forward(ctx, hidden, in_w, conv_w, conv_b, x_w, dt_w, out_w, A, D, dt_bias, order):
+    def forward(ctx, hidden, in_w, conv_w, conv_b, x_w, dt_w, out_w, A, D, dt_bias, order, altho, coord):
         io = _autocast_dtype() or hidden.dtype
-        _require_cuda(hidden, in_w, conv_w, conv_b, x_w, dt_w, out_w, A, D, dt_bias)
+        _require_cuda(hidden, in_w, conv_w, conv_b, x_w, dt_w, out_w, A, D, dt_bias, altho)
         batch, dm, L = hidden.shape
         di, N, R, kw = conv_w.shape[0], A.shape[1], dt_w.shape[1], conv_w.shape[-1]
         dims = (dm, di, N, R, kw)
@@ -869,52 +874,71 @@ class MambaNarrowFn(torch.autograd.Function):
             raise RuntimeError(f"mamba_narrow_fn: unsupported block shape {dims} / dtype {io}")
         if order is not None and order[0] == _lib.ORDER_ROWMAJOR:
             order = None
-        hidden = hidden.to(io)
+        if not (hidden.dtype == io or (hidden.dtype == torch.float32 and io == torch.bfloat16)):
+            hidden = hidden.to(io)
         if hidden.stride(-1) != 1:
             hidden = hidden.contiguous()
         weights = [w if w is None else w.detach().float().contiguous() for w in (in_w, conv_w.reshape(di, kw), conv_b, x_w, dt_w, out_w)]
         A, D, dt_bias = A.float().contiguous(), D.float().contiguous(), dt_bias.float().contiguous()
+        if coord is not None:
+            coord = (altho.detach().float().contiguous(),) + tuple(coord)
+            if coord[2] * coord[3] != L:
+                raise RuntimeError("mamba_narrow_fn: coord = (extend_scope, H, W) needs H * W == seqlen")
         L_ = _lib.lib()
         rows = L_.mmu_mamba_narrow_rows(di, N)
         pre = torch.empty((batch, rows, L), device=hidden.device, dtype=io)
-        out = torch.empty((batch, dm, L), device=hidden.device, dtype=io)
+        out = torch.empty((batch, dm, L), device=hidden.device, dtype=torch.float32 if coord is not None else io)
         with torch.cuda.device(hidden.device):
-            p = _narrow_params(io, batch, L, dims, order, weights)
+            p = _narrow_params(io, hidden.dtype, batch, L, dims, order, weights, coord)
             p.hidden, p.hidden_bs, p.hidden_cs, p.pre = hidden.data_ptr(), hidden.stride(0), hidden.stride(1), pre.data_ptr()
             _lib.check(L_.mmu_mamba_narrow_pre_fwd(ct.byref(p), _stream()), "mamba_narrow_pre_fwd")
             u, delta, z = pre[:, :di], pre[:, di:2 * di], pre[:, 2 * di:3 * di]
             Bm, Cm = pre[:, 3 * di:3 * di + N].unsqueeze(1), pre[:, 3 * di + N:].unsqueeze(1)
             out_z, xs, _ = selective_scan_fwd(u, delta, A, Bm, Cm, D, z, dt_bias, True)
-            p.out_z, p.out, p.out_bs, p.out_cs = out_z.data_ptr(), out.data_ptr(), out.stride(0), out.stride(1)
+            p.out_z = out_z.data_ptr()
+            if coord is not None:
+                p.coords = out.data_ptr()
+            else:
+                p.out, p.out_bs, p.out_cs = out.data_ptr(), out.stride(0), out.stride(1)
             _lib.check(L_.mmu_mamba_narrow_post_fwd(ct.byref(p), _stream()), "mamba_narrow_post_fwd")
         ctx.dims, ctx.order, ctx.io, ctx.has_conv_b = dims, order, io, conv_b is not None
         ctx.wdtypes = [None if w is None else w.dtype for w in (in_w, conv_w, conv_b, x_w, dt_w, out_w)]
         ctx.conv_w_shape = conv_w.shape
-        ctx.save_for_backward(hidden, pre, out_z, xs.x, xs.y, A, D, dt_bias, *[w for w in weights if w is not None])
+        ctx.coord = None if coord is None else coord[1:]
+        ctx.altho_dtype = None if altho is None else altho.dtype
+        ctx.save_for_backward(hidden, pre, out_z, xs.x, xs.y, A, D, dt_bias, coord[0] if coord is not None else None,
+                              *[w for w in weights if w is not None])
         return out
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dout):
-        hidden, pre, out_z, xs_x, xs_y, A, D, dt_bias, *ws = ctx.saved_tensors
+        hidden, pre, out_z, xs_x, xs_y, A, D, dt_bias, altho, *ws = ctx.saved_tensors
         if not ctx.has_conv_b:
             ws.insert(2, None)
         dm, di, N, R, kw = ctx.dims
         io = ctx.io
+        coord = None if ctx.coord is None else (altho,) + tuple(ctx.coord)
         batch, _, L = hidden.shape
-        dout = dout.to(io)
-        if dout.stride(-1) != 1:
+        dout = dout.to(torch.float32 if coord is not None else io)
+        if coord is not None:
+            dout = dout.contiguous()
+        elif dout.stride(-1) != 1:
             dout = dout.contiguous()
         L_ = _lib.lib()
-        dW = torch.zeros(L_.mmu_mamba_narrow_weight_floats(dm, di, N, R, kw), device=hidden.device, dtype=torch.float32)
+        nW = L_.mmu_mamba_narrow_weight_floats(dm, di, N, R, kw)
+        acc = torch.zeros(nW + batch * 2 * N * L, device=hidden.device, dtype=torch.float32)      # one fill: weight grads | dB | dC
+        dW, dBC = acc[:nW], acc[nW:].view(batch, 2 * N, L)
         dout_y = torch.empty((batch, di, L), device=hidden.device, dtype=io)
         gpre = torch.empty((batch, 3 * di, L), device=hidden.device, dtype=io)
-        dBC = torch.zeros((batch, 2 * N, L), device=hidden.device, dtype=torch.float32)
         dhidden = torch.empty_like(hidden)
         with torch.cuda.device(hidden.device):
-            p = _narrow_params(io, batch, L, ctx.dims, ctx.order, ws)
-            p.out_z, p.dout, p.dout_bs, p.dout_cs = out_z.data_ptr(), dout.data_ptr(), dout.stride(0), dout.stride(1)
-            p.dout_y, p.dweights = dout_y.data_ptr(), dW.data_ptr()
+            p = _narrow_params(io, hidden.dtype, batch, L, ctx.dims, ctx.order, ws, coord)
+            p.out_z, p.dout_y, p.dweights = out_z.data_ptr(), dout_y.data_ptr(), dW.data_ptr()
+            if coord is not None:
+                p.dcoords = dout.data_ptr()
+            else:
+                p.dout, p.dout_bs, p.dout_cs = dout.data_ptr(), dout.stride(0), dout.stride(1)
             _lib.check(L_.mmu_mamba_narrow_post_bwd(ct.byref(p), _stream()), "mamba_narrow_post_bwd")
             u, delta, z = pre[:, :di], pre[:, di:2 * di], pre[:, 2 * di:3 * di]
             Bm, Cm = pre[:, 3 * di:3 * di + N].unsqueeze(1), pre[:, 3 * di + N:].unsqueeze(1)
@@ -925,18 +949,21 @@ class MambaNarrowFn(torch.autograd.Function):
             p.gpre, p.dBC = gpre.data_ptr(), dBC.data_ptr()
             p.dhidden, p.dhidden_bs, p.dhidden_cs = dhidden.data_ptr(), dhidden.stride(0), dhidden.stride(1)
             _lib.check(L_.mmu_mamba_narrow_pre_bwd(ct.byref(p), _stream()), "mamba_narrow_pre_bwd")
-        sizes = (2 * di * dm, di * kw, di, (R + 2 * N) * di, di * R, dm * di)
-        g_in, g_cw, g_cb, g_x, g_dt, g_out = torch.split(dW, sizes)
+        sizes = (2 * di * dm, di * kw, di, (R + 2 * N) * di, di * R, dm * di, 1)
+        g_in, g_cw, g_cb, g_x, g_dt, g_out, g_al = torch.split(dW, sizes)
         wd = ctx.wdtypes
+        d_altho = g_al.reshape(()).to(ctx.altho_dtype) if coord is not None else None
         return (dhidden, g_in.view(2 * di, dm).to(wd[0]), g_cw.view(ctx.conv_w_shape).to(wd[1]), g_cb.to(wd[2]) if ctx.has_conv_b else None,
-                g_x.view(R + 2 * N, di).to(wd[3]), g_dt.view(di, R).to(wd[4]), g_out.view(dm, di).to(wd[5]), dA, dD, ddt_bias, None)
+                g_x.view(R + 2 * N, di).to(wd[3]), g_dt.view(di, R).to(wd[4]), g_out.view(dm, di).to(wd[5]), dA, dD, ddt_bias, None,
+                d_altho, None)
 
 
 def mamba_narrow_fn(hidden, in_proj_weight, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight, A, D,
-                    delta_bias, order=None):
-    """hidden (b, d_model, l), natural token order -> (b, d_model, l); see MambaNarrowFn."""
+                    delta_bias, order=None, altho=None, coord=None):
+    """hidden (b, d_model, l), natural token order -> (b, d_model, l); see MambaNarrowFn.  coord = (extend_scope, H, W) with the
+    parameter altho selects MMConv's coordinate epilogue (fp32 result)."""
     return MambaNarrowFn.apply(hidden, in_proj_weight, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight,
-                               A, D, delta_bias, order)
+                               A, D, delta_bias, order, altho, coord)
 
 
 def _order_call(fn_name, src, order, H, W, nslices):
