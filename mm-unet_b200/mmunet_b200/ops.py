@@ -927,8 +927,9 @@ class MambaNarrowFn(torch.autograd.Function):
             dout = dout.contiguous()
         L_ = _lib.lib()
         nW = L_.mmu_mamba_narrow_weight_floats(dm, di, N, R, kw)
-        acc = torch.zeros(nW + batch * 2 * N * L, device=hidden.device, dtype=torch.float32)      # one fill: weight grads | dB | dC
-        dW, dBC = acc[:nW], acc[nW:].view(batch, 2 * N, L)
+        nBC = batch * 2 * N * L
+        acc = torch.zeros(nBC + nW, device=hidden.device, dtype=torch.float32)      # one fill: dB | dC (16-byte aligned rows) | weight grads
+        dBC, dW = acc[:nBC].view(batch, 2 * N, L), acc[nBC:]
         dout_y = torch.empty((batch, di, L), device=hidden.device, dtype=io)
         gpre = torch.empty((batch, 3 * di, L), device=hidden.device, dtype=io)
         dhidden = torch.empty_like(hidden)
