@@ -360,3 +360,36 @@ def test_narrow_mamba_coordinate_epilogue(H, W, autocast):
     torch.testing.assert_close(da1, da2, rtol=5 * tol, atol=5 * tol * max(1.0, float(da2.abs())))
     for k in g1:
         torch.testing.assert_close(g1[k], g2[k], rtol=5 * tol, atol=5 * tol * max(1.0, float(g2[k].abs().max())), msg=lambda s_: f"{k}: {s_}")
+
+
+@pytest.mark.parametrize("d_model,L,ns,heads", [(48, 512, 64, 1), (96, 256, 32, 2)])
+def test_v3_directional_outputs_feed_attention_like_consumer(d_model, L, ns, heads):
+    """sibling users of the same boundary consume the three directional outputs, not only `out` -
+    HWAUNETR's MFABlock turns (o_1, o_2, o_3) into q / k / v of a channel attention (src/model/HWAUNETR.py:202-270; dims 48 / 96,
+    num_slices 64 / 32).  A consumer of that shape (restated here, not the reference module) must get the oracle's values and the
+    oracle's gradients THROUGH o_1..o_3 as well as through out."""
+    torch.manual_seed(17)
+    m = Mamba(d_model=d_model, d_state=16, d_conv=4, expand=2, bimamba_type="v3", nslices=ns)
+    x = torch.randn(2, L, d_model)
+    w = torch.randn(2, L, d_model)
+
+    def consumer(out, q, k, v):
+        q, k, v = q.unsqueeze(1), k.unsqueeze(1), v.unsqueeze(1)             # (b, 1, d_inner, l)
+        attn = (q.transpose(-2, -1) @ k / q.shape[-2]).softmax(-1)           # (b, 1, l, l)
+        out_a = (v @ attn.transpose(-2, -1))[:, 0, :d_model]                 # (b, d_model, l)
+        return ((out + out_a.transpose(-1, -2)) * w.to(out.device)).sum()
+
+    xc = x.clone().requires_grad_()
+    consumer(*torch_ref.mamba_forward(m, xc)).backward()
+    ref_dx = xc.grad.clone()
+    ref_grads = {k: (None if p.grad is None else p.grad.clone()) for k, p in m.named_parameters()}
+    m.zero_grad()
+    m = m.to(DEV)
+    xg = x.to(DEV).requires_grad_()
+    consumer(*m(xg)).backward()
+    close("dx", xg.grad, ref_dx, 5e-3, 5e-3)
+    for k, p in m.named_parameters():
+        if ref_grads[k] is None:
+            assert p.grad is None, k
+        else:
+            close("grad." + k, p.grad, ref_grads[k], 5e-3, 5e-3)
