@@ -32,14 +32,16 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header(tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mmunet_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mmunet_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(mmu_scan_fwd_params),sizeof(mmu_scan_bwd_params),sizeof(mmu_conv_params),'
-                   'offsetof(mmu_scan_fwd_params,u_bs),offsetof(mmu_conv_params,dout));return 0;}\n')
+                   'offsetof(mmu_scan_fwd_params,u_bs),offsetof(mmu_conv_params,dout),'
+                   'sizeof(mmu_narrow_params),offsetof(mmu_narrow_params,dweights),offsetof(mmu_narrow_params,altho));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = list(map(int, subprocess.check_output([str(exe)]).split()))
     want = [ctypes.sizeof(_lib.ScanFwdParams), ctypes.sizeof(_lib.ScanBwdParams), ctypes.sizeof(_lib.ConvParams),
-            _lib.ScanFwdParams.u_bs.offset, _lib.ConvParams.dout.offset]
+            _lib.ScanFwdParams.u_bs.offset, _lib.ConvParams.dout.offset,
+            ctypes.sizeof(_lib.NarrowParams), _lib.NarrowParams.dweights.offset, _lib.NarrowParams.altho.offset]
     assert got == want
 
 
@@ -64,6 +66,25 @@ def test_argument_errors_without_gpu():
     c.width = 7
     assert lib.mmu_causal_conv1d_fwd(ctypes.byref(c), None) == -1
     assert b"width" in lib.mmu_last_error()
+
+
+def test_narrow_block_queries_and_argument_errors_without_gpu():
+    """The narrow-block entry points: host-side shape queries, and argument validation before any CUDA call."""
+    lib = _lib.lib()
+    assert lib.mmu_mamba_narrow_supported(3, 6, 16, 1, 4, _lib.F32) == 1 and lib.mmu_mamba_narrow_supported(3, 6, 16, 1, 4, _lib.BF16) == 1
+    assert lib.mmu_mamba_narrow_supported(64, 128, 16, 4, 4, _lib.BF16) == 0 and lib.mmu_mamba_narrow_supported(3, 6, 16, 1, 4, _lib.F16) == 0
+    assert lib.mmu_mamba_narrow_rows(6, 16) == 3 * 6 + 2 * 16
+    assert lib.mmu_mamba_narrow_weight_floats(3, 6, 16, 1, 4) == 12 * 3 + 6 * 4 + 6 + 33 * 6 + 6 + 3 * 6 + 1
+    p = _lib.NarrowParams()
+    p.d_model, p.d_inner, p.d_state, p.dt_rank, p.d_conv = 64, 128, 16, 4, 4
+    assert lib.mmu_mamba_narrow_pre_fwd(ctypes.byref(p), None) != 0 and b"not a narrow block" in lib.mmu_last_error()
+    p.d_model, p.d_inner, p.d_state, p.dt_rank, p.d_conv = 3, 6, 16, 1, 4
+    assert lib.mmu_mamba_narrow_pre_fwd(ctypes.byref(p), None) == -1 and b"bad shape" in lib.mmu_last_error()
+    p.batch, p.seqlen, p.order, p.order_h, p.order_w = 1, 12, _lib.ORDER_TWOROW, 3, 5          # 3 * 5 != 12
+    assert lib.mmu_mamba_narrow_post_fwd(ctypes.byref(p), None) == -1 and b"scan order" in lib.mmu_last_error()
+    p.order = 0
+    assert lib.mmu_mamba_narrow_pre_bwd(ctypes.byref(p), None) == -1 and b"null tensor" in lib.mmu_last_error()
+    assert ops.mamba_narrow_supported(3, 6, 16, 1, 4, torch.float16) is False
 
 
 def test_no_cpu_fallback():
