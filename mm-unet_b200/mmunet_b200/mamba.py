@@ -132,8 +132,10 @@ class Mamba(nn.Module):
         if tokens_cm.stride(-1) == 1 or seqlen == 1:
             xz = torch.matmul(self.in_proj.weight, tokens_cm)
         else:
-            xz = (self.in_proj.weight @ hidden_states.permute(2, 0, 1).reshape(dim, batch * seqlen))
-            xz = xz.view(-1, batch, seqlen).transpose(0, 1)
+            # token-major input (e.g. a channels-last map flattened to (b, l, c)): X^T enters the GEMM as a transposed operand,
+            # no "d (b l)" copy (mamba_simple.py:201-205 materialises it)
+            flat = hidden_states.reshape(batch * seqlen, dim)
+            xz = (self.in_proj.weight @ flat.t()).view(-1, batch, seqlen).transpose(0, 1)
         if self.in_proj.bias is not None:
             xz = xz + self.in_proj.bias.to(dtype=xz.dtype)[:, None]
         o_1 = o_2 = o_3 = None

@@ -630,11 +630,12 @@ def _out_proj(out_z, weight, bias):
 
 
 def _out_proj_autograd(total, weight, bias):
-    """Plain-autograd flavour of _out_proj for the v2/v3 branch (requirements/mamba_simple.py:270): (b, d, l) -> (b, l, e)."""
-    out = torch.matmul(weight, total)
+    """Plain-autograd flavour of _out_proj for the v2/v3 branch (requirements/mamba_simple.py:270): (b, d, l) -> (b, l, e), token-major
+    contiguous (the transposed operand goes into the GEMM as it is): reshaped to (b, e, H, W) by the caller it is a channels-last map."""
+    out = torch.matmul(total.transpose(1, 2), weight.t())
     if bias is not None:
-        out = out + bias.to(out.dtype)[:, None]
-    return out.transpose(1, 2)
+        out = out + bias.to(out.dtype)
+    return out
 
 
 def _out_proj_bwd(dout, out_z, weight, has_bias):
