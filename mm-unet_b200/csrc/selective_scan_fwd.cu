@@ -21,6 +21,7 @@
 #include "scan3_fwd.cuh"
 #include "tma_map.cuh"
 #include "scan4.cuh"
+#include "scan5_fwd.cuh"
 #include "scan_tiles.cuh"
 
 namespace mmu {
@@ -616,6 +617,61 @@ template <typename IN_T> int run_fwd4(const mmu_scan_fwd_params *p, cudaStream_t
     return rev ? launch_fwd4<IN_T, true, false>(a, st) : launch_fwd4<IN_T, false, false>(a, st);
 }
 
+
+// ---- v5 host side (scan5_fwd.cuh): wide fp32 problems, lane rings --------------------------------------------------------------
+// warps per CTA: the B/C tiles are per batch element, so bigger CTAs amortise them; one CTA per SM in a single wave where possible
+int plan_fwd5(int B, int D) {
+    const int forced = env_int("MMU_V5_W", 0);
+    if (forced == 2 || forced == 4 || forced == 6) return forced;
+    for (int W : {6, 4}) {
+        if (D % (4 * W) == 0 && B * (D / (4 * W)) >= 96) return W;
+    }
+    return D % 16 == 0 ? 4 : (D % 24 == 0 ? 6 : 2);
+}
+
+bool fwd5_eligible(const mmu_scan_fwd_params *p) {
+    if (env_int("MMU_RING", 0) == 0 || p->dtype != MMU_F32) return false;   // opt-in: measured slower than v3 (profiles/r2_v5_lane_ring.md)
+    if (p->order != MMU_ORDER_ROWMAJOR) return false;
+    const int xs = p->x_stride ? p->x_stride : MMU_STATE_STRIDE;
+    if (xs % 8 != 0) return false;
+    if (p->x && reinterpret_cast<uintptr_t>(p->x) % 16 != 0) return false;
+    if (p->seqlen < 256) return false;
+    if ((int64_t)p->batch * ((p->dim + 3) / 4) < env_int("MMU_V5_MIN_WARPS", 296)) return false;   // rows / 4 warps walk the whole sequence
+    return fwd3_eligible<float>(p);
+}
+
+template <int W> int launch_fwd5(const Fwd3Args &a, bool rev, cudaStream_t st) {
+    using Cfg = Fwd5Cfg<W>;
+    dim3 grid((a.D + Cfg::R - 1) / Cfg::R, a.B), block(Cfg::NT);
+    auto k = rev ? scan5_fwd_kernel<W, true> : scan5_fwd_kernel<W, false>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
+    k<<<grid, block, Cfg::smem_bytes, st>>>(a);
+    count_launch();
+    return check_launch("selective_scan_fwd(v5)");
+}
+
+int run_fwd5(const mmu_scan_fwd_params *p, cudaStream_t st) {
+    Fwd3Args a{};
+    make_ordmap(a.ord, MMU_ORDER_ROWMAJOR, 0, 0, 0, p->seqlen);
+    a.u = p->u, a.delta = p->delta, a.z = p->z, a.Bm = p->B, a.Cm = p->C;
+    a.A = p->A, a.Dv = p->D, a.dbias = p->delta_bias;
+    a.out = p->out, a.ysave = p->z ? p->y : nullptr, a.x = p->x, a.last_state = p->last_state;
+    a.u_bs = p->u_bs, a.u_ds = p->u_ds, a.dl_bs = p->delta_bs, a.dl_ds = p->delta_ds;
+    a.z_bs = p->z_bs, a.z_ds = p->z_ds, a.o_bs = p->out_bs, a.o_ds = p->out_ds, a.y_bs = p->y_bs, a.y_ds = p->y_ds;
+    a.B_bs = p->B_bs, a.B_ns = p->B_ns, a.C_bs = p->C_bs, a.C_ns = p->C_ns;
+    a.B = p->batch, a.D = p->dim, a.L = p->seqlen, a.N = p->dstate;
+    const int xs = p->x_stride ? p->x_stride : MMU_STATE_STRIDE;
+    a.nseg = 1, a.cps = xs / 8, a.nchunks = (p->seqlen + 127) / 128;      // cps: saved-state stride in 8-token blocks
+    a.nx = (p->seqlen + xs - 1) / xs;
+    a.softplus = p->delta_softplus;
+    const bool rev = p->reverse != 0;
+    switch (plan_fwd5(p->batch, p->dim)) {
+        case 6: return launch_fwd5<6>(a, rev, st);
+        case 4: return launch_fwd5<4>(a, rev, st);
+        default: return launch_fwd5<2>(a, rev, st);
+    }
+}
+
 template <typename IN_T> struct HasV3 { static constexpr bool value = false; };
 template <> struct HasV3<float> { static constexpr bool value = true; };
 template <> struct HasV3<__nv_bfloat16> { static constexpr bool value = true; };
@@ -629,6 +685,9 @@ template <typename IN_T> int run_fwd(const mmu_scan_fwd_params *p, cudaStream_t 
             return set_error(MMU_ERR_UNSUPPORTED, "selective_scan_fwd: scan order %d (H=%d W=%d nslices=%d) cannot be fused for this problem "
                              "(see mmu_scan_order_fusable); permute with mmu_scan_order_gather / _scatter", p->order, p->order_h, p->order_w, p->order_ns);
         if constexpr (HasV3<IN_T>::value) return run_fwd3<IN_T>(p, st);
+    }
+    if constexpr (sizeof(IN_T) == 4) {
+        if (fwd5_eligible(p)) return run_fwd5(p, st);
     }
     if constexpr (HasV3<IN_T>::value) {
         if (fwd4_eligible<IN_T>(p)) return run_fwd4<IN_T>(p, st);

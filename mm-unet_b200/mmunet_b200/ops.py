@@ -629,13 +629,38 @@ def _out_proj(out_z, weight, bias):
     return out.transpose(1, 2)
 
 
+class _OutProjTokenMajorFn(torch.autograd.Function):
+    """out_proj of the v2/v3 branch (requirements/mamba_simple.py:270): (b, d, l) -> (b, l, e) token-major.  Plain autograd would hand
+    `total` a gradient that is a transposed VIEW of (b, l, d); each of the three directions' backward then makes it contiguous
+    (three transpose copies of (b, d, l), 1.45 ms each at L = 65 536).  Here the gradient comes out of the GEMM as (b, d, l)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, total, weight, bias):
+        weight, bias = _cast_proj(weight, bias)
+        if weight.dtype != total.dtype:
+            weight = weight.to(total.dtype)
+        ctx.save_for_backward(total, weight)
+        ctx.has_bias = bias is not None
+        out = torch.matmul(total.transpose(1, 2), weight.t())
+        if bias is not None:
+            out = out + bias.to(out.dtype)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        total, weight = ctx.saved_tensors
+        dout_t = dout.to(weight.dtype).transpose(1, 2)                               # (b, e, l) view of the token-major gradient
+        dtotal = torch.matmul(weight.t(), dout_t)                                    # (b, d, l) contiguous
+        dweight = torch.bmm(dout_t, total.transpose(1, 2)).sum(0)                    # (e, d)
+        return dtotal, dweight, (dout_t.sum((0, 2)) if ctx.has_bias else None)
+
+
 def _out_proj_autograd(total, weight, bias):
-    """Plain-autograd flavour of _out_proj for the v2/v3 branch (requirements/mamba_simple.py:270): (b, d, l) -> (b, l, e), token-major
-    contiguous (the transposed operand goes into the GEMM as it is): reshaped to (b, e, H, W) by the caller it is a channels-last map."""
-    out = torch.matmul(total.transpose(1, 2), weight.t())
-    if bias is not None:
-        out = out + bias.to(out.dtype)
-    return out
+    """(b, d, l) -> (b, l, e), token-major contiguous (the transposed operand goes into the GEMM as it is): reshaped to
+    (b, e, H, W) by the caller it is a channels-last map."""
+    return _OutProjTokenMajorFn.apply(total, weight, bias)
 
 
 def _out_proj_bwd(dout, out_z, weight, has_bias):

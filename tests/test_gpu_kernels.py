@@ -287,6 +287,49 @@ def test_scan_v4_xz_strided_layout(monkeypatch):
     run_scan_case(2, 128, 264, 16, xz_layout=True, reverse=True)
 
 
+V5_SHAPES = [(2, 64, 256, 16), (1, 128, 1024, 16), (2, 130, 392, 16), (1, 96, 520, 8), (3, 70, 264, 5), (2, 24, 2048, 16),
+             (1, 48, 4096, 16)]
+
+
+@pytest.mark.parametrize("w", ["2", "4", "6"])
+@pytest.mark.parametrize("shape", V5_SHAPES)
+def test_scan_v5_lane_ring_forward(w, shape, monkeypatch):
+    """The lane-ring forward (csrc/scan5_fwd.cuh, opt-in MMU_RING=1: measured slower than v3, profiles/r2_v5_lane_ring.md) against
+    the C oracle - outputs, last state, and (through the v3 backward, which reads the states it saved) every gradient; ragged
+    lengths, d_state < 16, row counts that are not a multiple of the CTA's rows, both directions, all CTA widths."""
+    monkeypatch.setenv("MMU_RING", "1")
+    monkeypatch.setenv("MMU_V5_MIN_WARPS", "1")
+    monkeypatch.setenv("MMU_V5_W", w)
+    n0 = _lib.launch_count()
+    run_scan_case(*shape)
+    assert _lib.launch_count() - n0 >= 2
+    run_scan_case(*shape, reverse=True)
+
+
+@pytest.mark.parametrize("flags", [dict(has_z=False), dict(has_D=False, has_bias=False), dict(has_z=False, has_D=False, has_bias=False)])
+def test_scan_v5_optional_inputs_and_strided_rows(flags, monkeypatch):
+    monkeypatch.setenv("MMU_RING", "1")
+    monkeypatch.setenv("MMU_V5_MIN_WARPS", "1")
+    run_scan_case(2, 72, 520, 16, softplus=False, **flags)
+    run_scan_case(3, 64, 512, 16, xz_layout=True, **flags)
+
+
+def test_scan_v5_matches_v3_at_config2(monkeypatch):
+    """BASELINE config 2 through both forward kernels: same outputs and saved states (fp32 rounding apart)."""
+    cpu, gpu = make_scan_inputs(8, 384, 4096, 16)
+    args = tuple(gpu[k] for k in ("u", "delta", "A", "B", "C", "D", "z", "delta_bias"))
+    res = {}
+    for ring in ("0", "1"):
+        monkeypatch.setenv("MMU_RING", ring)
+        _lib.reload_knobs()
+        n0 = _lib.launch_count()
+        out, st, last = ops.selective_scan_fwd(*args, True, return_last_state=True)
+        assert _lib.launch_count() - n0 == 1
+        res[ring] = (out.float().cpu(), st.x.cpu(), st.y.float().cpu(), last.cpu())
+    for a, b, name in zip(res["1"], res["0"], ("out", "x", "y", "last_state")):
+        check(name, a, b.numpy(), 1e-3, 2e-3)
+
+
 @pytest.mark.parametrize("B,D,L,N", [(2, 20, 264, 64), (1, 9, 136, 40), (2, 6, 2048, 32), (1, 128, 512, 64)])
 @pytest.mark.parametrize("reverse", [False, True])
 def test_scan_wide_state_runs_on_fast_kernels(B, D, L, N, reverse):
