@@ -331,4 +331,335 @@ __global__ void __launch_bounds__(32 * W, Fwd5Cfg<W>::kMinBlocks) scan5_fwd_kern
     epilogue(NC - 1);
 }
 
+
+// ================================================================================================================================
+// Warp-specialised form of the lane-ring forward.  ncu of the kernel above (profiles/r2_v5_lane_ring.md): the 16 steps of a round
+// run at 0.57 instructions per clock and scheduler where two ring warps share a scheduler, but the uniform bulk phase is 40 % of
+// the round and the four schedulers of an SM carry 2, 2, 1, 1 ring warps (rows / 4 warps cannot be split further).  Here a ring
+// warp does NOTHING but steps; a HELPER warp per ring warp does every element-wise phase for it one round ahead / two rounds
+// behind, through double-buffered lane slots (twice the warps per SM for the same work):
+//   helper, round k:  softplus / delta*u / D*u of chunk k+1 -> stage[(k+1)&1], yin[(k+1)&1];   gate + store of chunk k-2 from
+//                     yout[(k-2)&1];  saved states of chunk k-2 from xbuf[(k-2)%3];  cp.async of u, delta (chunk k+2), z (chunk k-1)
+//                     into its landing slots and of its share of the B/C tile k+1;
+//   ring, round k:    16 steps on stage[k&1] / yin[k&1], finished y -> yout[(k-1)&1] at the lane's transition, states leaving the
+//                     blocks 7 and 15 of a chunk (stride-64 saved states) -> xbuf[chunk%3].
+// One __syncthreads per round orders everything.  The two rings of a warp are interleaved over the lanes (lane = 2 j + ring): the two
+// lanes in transition at a step then sit in the same quarter-warp and their predicated 16-byte accesses are one wavefront.
+// Saved-state stride 64 only (xs8 == 8); other strides use the kernel above.
+template <int WR> struct Fwd5sCfg {
+    static constexpr int T = kS3T, LPR = 16, CH = LPR * T, NRT = 32 * WR, NT = 2 * NRT, NRP = 2 * WR, R = 4 * WR;
+    using Tl = BcTile<LPR>;
+    static constexpr int kTiles = 3;
+    static constexpr int kTileBytes = kTiles * Tl::kBytes;
+    static constexpr int kLandBytes = 3 * 2 * 2 * NRT * 16;    // u | delta | z : [tensor][row][quad][ring thread] x 16 B
+    static constexpr int kStageBytes = 2 * 8 * NRT * 16;       // [parity][delta x4 | delta*u x4][ring thread]
+    static constexpr int kYBytes = 2 * 4 * NRT * 16;           // yin and yout, each [parity][quad][ring thread]
+    static constexpr int kXBytes = 3 * 16 * NRP * 2 * 8;       // [chunk % 3][state][ring][block 7 | block 15] float2
+    static constexpr int kABytes = NRP * 16 * 8;
+    static constexpr size_t smem_bytes = (size_t)kTileBytes + kLandBytes + kStageBytes + 2 * kYBytes + kXBytes + kABytes;
+};
+
+// predicated 8-byte shared-memory load INTO the given register pair (it keeps its value where pred is false).  The compiler's own
+// form of "if (p) acc = *ptr" on accumulators that FFMA2 chains are still updating is a load into temporaries plus predicated moves
+// (16 per step for the y accumulators); a 16-byte form needs an aligned register quad and gets the same moves.
+__device__ __forceinline__ void lds64_if(bool pred, const void *ptr, float2 &v) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p ld.shared.v2.f32 {%0, %1}, [%2];\n\t}"
+                 : "+f"(v.x), "+f"(v.y)
+                 : "r"(smem_u32(ptr)), "r"((int)pred)
+                 : "memory");
+}
+
+template <int WR, bool REV>
+__global__ void __launch_bounds__(64 * WR, 1) scan5s_fwd_kernel(const __grid_constant__ Fwd3Args p) {
+    using Cfg = Fwd5sCfg<WR>;
+    using Tl = typename Cfg::Tl;
+    constexpr int T = Cfg::T, LPR = Cfg::LPR, CH = Cfg::CH, NRT = Cfg::NRT, NRP = Cfg::NRP, R = Cfg::R;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int j = lane >> 1, ring = lane & 1;               // interleaved rings
+    const bool helper = warp >= WR;
+    const int rw = helper ? warp - WR : warp;               // the ring warp I am / I serve
+    const int rt = rw * 32 + lane;                          // ring-thread slot
+    const int rp = rw * 2 + ring;
+    const int b = blockIdx.y, row0 = blockIdx.x * R;
+    const int D = p.D, L = p.L, N = p.N;
+    const int NC = (L + CH - 1) / CH;
+    const bool has_z = p.z != nullptr, sp = p.softplus != 0;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *s_tile = smem_raw;
+    unsigned char *s_land = s_tile + Cfg::kTileBytes;
+    float4 *s_stage = reinterpret_cast<float4 *>(s_land + Cfg::kLandBytes);                                  // [2][8][NRT]
+    float4 *s_yin = reinterpret_cast<float4 *>(s_land + Cfg::kLandBytes + Cfg::kStageBytes);                 // [2][4][NRT]
+    float4 *s_yout = s_yin + 2 * 4 * NRT;                                                                    // [2][4][NRT]
+    float2 *s_x = reinterpret_cast<float2 *>(s_yout + 2 * 4 * NRT);                                          // [3][16][NRP][2]
+    float2 *s_A = s_x + 3 * 16 * NRP * 2;                                                                    // [NRP][16]
+
+    for (int i = tid; i < (int)((Cfg::smem_bytes - Cfg::kABytes) / 16); i += Cfg::NT) reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < NRP * 16; i += Cfg::NT) {
+        const int g = i >> 4, n = i & 15;
+        float a[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int row = row0 + 2 * g + r;
+            a[r] = (row < D && n < N) ? p.A[(int64_t)row * N + n] * kLog2e : 0.f;
+        }
+        s_A[i] = make_float2(a[0], a[1]);
+    }
+    __syncthreads();
+
+    if (helper) {
+        // ===================================== helper warp: every element-wise phase of ring warp rw ==================================
+        const int htid = tid - NRT;
+        const int rowA = row0 + 2 * rp;
+        const bool rok[2] = {rowA < D, rowA + 1 < D};
+        constexpr int STEP = REV ? -CH : CH;
+        const int mo0 = REV ? L - T - T * j : T * j;        // memory index of the lane's 8 tokens in chunk 0
+        const float *u_p[2], *d_p[2], *z_p[2];              // stand on the chunk whose copy is issued next
+        float *o_p[2], *y_p[2];                             // stand on the chunk stored next
+        float bias[2], Dsk[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int row = min(rowA + r, D - 1);
+            u_p[r] = reinterpret_cast<const float *>(p.u) + (int64_t)b * p.u_bs + (int64_t)row * p.u_ds + mo0;
+            d_p[r] = reinterpret_cast<const float *>(p.delta) + (int64_t)b * p.dl_bs + (int64_t)row * p.dl_ds + mo0;
+            z_p[r] = has_z ? reinterpret_cast<const float *>(p.z) + (int64_t)b * p.z_bs + (int64_t)row * p.z_ds + mo0 : nullptr;
+            o_p[r] = reinterpret_cast<float *>(p.out) + (int64_t)b * p.o_bs + (int64_t)row * p.o_ds + mo0;
+            y_p[r] = p.ysave == nullptr ? nullptr : reinterpret_cast<float *>(p.ysave) + (int64_t)b * p.y_bs + (int64_t)row * p.y_ds + mo0;
+            bias[r] = p.dbias != nullptr ? p.dbias[row] : 0.f;
+            Dsk[r] = p.Dv != nullptr ? p.Dv[row] : 0.f;
+        }
+        const float *B_b = reinterpret_cast<const float *>(p.Bm) + (int64_t)b * p.B_bs;
+        const float *C_b = reinterpret_cast<const float *>(p.Cm) + (int64_t)b * p.C_bs;
+        const unsigned s_tile_u32 = smem_u32(s_tile);
+        const unsigned s_land_u32 = smem_u32(s_land) + rt * 16;
+        const unsigned char *s_land_t = s_land + rt * 16;
+        auto issue_ud = [&](int c) {
+            if (c * CH + T * j < L) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        cp_async16(s_land_u32 + ((0 * 2 + r) * 2 + q) * NRT * 16, u_p[r] + q * 4);
+                        cp_async16(s_land_u32 + ((1 * 2 + r) * 2 + q) * NRT * 16, d_p[r] + q * 4);
+                    }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) u_p[r] += STEP, d_p[r] += STEP;
+        };
+        auto issue_z = [&](int c) {
+            if (!has_z) return;
+            if (c * CH + T * j < L) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) cp_async16(s_land_u32 + ((2 * 2 + r) * 2 + q) * NRT * 16, z_p[r] + q * 4);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) z_p[r] += STEP;
+        };
+        auto load_land = [&](int which, int r, float (&v)[T]) {
+            uint4 q[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) q[k] = *reinterpret_cast<const uint4 *>(s_land_t + ((which * 2 + r) * 2 + k) * NRT * 16);
+            float e[8];
+            Raw8<float>::unpack(q, e);
+            order8<REV>(e, v);
+        };
+        issue_ud(0);
+        tile_async_f32<LPR, NRT, REV, true>(s_tile_u32, B_b, C_b, p.B_ns, p.C_ns, N, 0, L, htid);
+        cp_async_commit();
+
+        for (int k = -1; k <= NC + 1; ++k) {
+            cp_async_wait_all();
+            __syncthreads();
+            // ---- softplus(delta + bias), delta*u, D*u of chunk k+1 -------------------------------------------------------------------
+            const int cp = k + 1;
+            if (cp <= NC) {
+                float4 *st = s_stage + (cp & 1) * 8 * NRT + rt, *yi = s_yin + (cp & 1) * 4 * NRT + rt;
+                if (cp < NC) {
+                    const bool ok = cp * CH + T * j < L;
+                    float uu[2][T], dd[2][T];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        load_land(0, r, uu[r]);
+                        load_land(1, r, dd[r]);
+#pragma unroll
+                        for (int i = 0; i < T; ++i) {
+                            const float xx = dd[r][i] + bias[r];
+                            const float v = sp ? softplus3(xx) : xx;
+                            dd[r][i] = (ok && rok[r]) ? v : 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int i0 = 2 * q, i1 = 2 * q + 1;
+                        st[q * NRT] = make_float4(dd[0][i0], dd[1][i0], dd[0][i1], dd[1][i1]);
+                        st[(4 + q) * NRT] = make_float4(dd[0][i0] * uu[0][i0], dd[1][i0] * uu[1][i0], dd[0][i1] * uu[0][i1], dd[1][i1] * uu[1][i1]);
+                        yi[q * NRT] = make_float4(Dsk[0] * uu[0][i0], Dsk[1] * uu[1][i0], Dsk[0] * uu[0][i1], Dsk[1] * uu[1][i1]);
+                    }
+                } else {                // the drain round reads an all-zero stage (delta = 0: a = 1, b = 0)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) st[q * NRT] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) yi[q * NRT] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            if (k + 2 < NC) issue_ud(k + 2);
+            // ---- gate + store of chunk k-2 ----------------------------------------------------------------------------------------------
+            const int ce = k - 2;
+            if (ce >= 0) {
+                const bool ok = ce * CH + T * j < L;
+                const float4 *yo = s_yout + (ce & 1) * 4 * NRT + rt;
+                float ya[2][T];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 v = yo[q * NRT];
+                    ya[0][2 * q] = v.x, ya[1][2 * q] = v.y, ya[0][2 * q + 1] = v.z, ya[1][2 * q + 1] = v.w;
+                }
+                if (ok) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        if (!rok[r]) continue;
+                        if (y_p[r] != nullptr) store8<float, REV>(y_p[r], ya[r]);
+                        if (has_z) {
+                            float zz[T];
+                            load_land(2, r, zz);
+#pragma unroll
+                            for (int i = 0; i < T; ++i) ya[r][i] *= zz[i] * sigmoid3(zz[i]);
+                        }
+                        store8<float, REV>(o_p[r], ya[r]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    o_p[r] += STEP;
+                    if (y_p[r] != nullptr) y_p[r] += STEP;
+                }
+                // saved states: my float4 of the ring warp's 2 rings x {block 7, block 15} x 2 rows x 16 states
+                if (p.x != nullptr || (p.last_state != nullptr && ce == NC - 1)) {
+                    const int xr = lane >> 4, slot = (lane >> 3) & 1, r = (lane >> 2) & 1, quad = lane & 3;
+                    const int rpx = rw * 2 + xr, row = row0 + 2 * rpx + r, kx = 2 * ce + slot;
+                    const float2 *sx = s_x + (((ce % 3) * 16 + 4 * quad) * NRP + rpx) * 2 + slot;
+                    float v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 t = sx[i * NRP * 2];
+                        v[i] = r ? t.y : t.x;
+                    }
+                    if (row < D) {
+                        if (p.x != nullptr && kx < p.nx) {
+                            float *xp = p.x + (((int64_t)b * D + row) * p.nx + kx) * N + 4 * quad;
+                            if (N == 16) {
+                                *reinterpret_cast<float4 *>(xp) = make_float4(v[0], v[1], v[2], v[3]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    if (4 * quad + i < N) xp[i] = v[i];
+                            }
+                        }
+                        if (p.last_state != nullptr && ce == NC - 1 && slot == 1) {     // blocks past L pass the final state through
+                            float *lp = p.last_state + ((int64_t)b * D + row) * N + 4 * quad;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                if (4 * quad + i < N) lp[i] = v[i];
+                        }
+                    }
+                }
+            }
+            if (k - 1 >= 0 && k - 1 < NC) issue_z(k - 1);
+            if (k + 1 >= 1 && k + 1 < NC)
+                tile_async_f32<LPR, NRT, REV, true>(s_tile_u32 + (unsigned)((k + 1) % Cfg::kTiles) * Tl::kBytes, B_b, C_b, p.B_ns, p.C_ns, N, (k + 1) * CH, L, htid);
+            cp_async_commit();
+        }
+        return;
+    }
+
+    // ========================================= ring warp: nothing but steps =========================================================
+    const int qa = REV ? 2 * (LPR - 1 - j) : 2 * j;         // my 8 tokens inside a tile row (memory order): two adjacent quads
+    const float2 *s_A_rp = s_A + rp * 16;
+    const int src_lane = 2 * ((j + 15) & 15) + ring;        // ring predecessor
+    const bool xsave = (j & 7) == 7;                        // my block ends a 64-token group: its leaving state is a saved state
+    float2 dl[T], dlu[T], ya[T];
+#pragma unroll
+    for (int i = 0; i < T; ++i) dl[i] = dlu[i] = ya[i] = make_float2(0.f, 0.f);
+    float2 hout = make_float2(0.f, 0.f);
+    float2 a[2][T], bb[2][T];
+    float Cn[2][T];
+
+    for (int k = -1; k <= NC + 1; ++k) {
+        __syncthreads();
+        if (k < 0 || k > NC) continue;
+        const unsigned char *tb_cur = s_tile + (k % Cfg::kTiles) * Tl::kBytes + Tl::quad_off(qa);
+        const unsigned char *tb_prev = s_tile + ((k + Cfg::kTiles - 1) % Cfg::kTiles) * Tl::kBytes + Tl::quad_off(qa);
+        const float4 *st = s_stage + (k & 1) * 8 * NRT + tid, *yi = s_yin + (k & 1) * 4 * NRT + tid;
+        float4 *yo = s_yout + ((k & 1) ^ 1) * 4 * NRT + tid;
+        float2 *sx_cur = s_x + ((k % 3) * 16 * NRP + rp) * 2 + (j >> 3), *sx_prev = s_x + (((k + 2) % 3) * 16 * NRP + rp) * 2 + (j >> 3);
+
+#define MMU_S5_PREP(s_, an, bn, cn, WITH_CHAIN, ac, bc, cc)                                                                            \
+        {                                                                                                                              \
+            if ((s_) == j) {                                                                                                           \
+                _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                                                        \
+                    const float4 v = st[q * NRT], w = st[(4 + q) * NRT];                                                               \
+                    dl[2 * q] = make_float2(v.x, v.y), dl[2 * q + 1] = make_float2(v.z, v.w);                                          \
+                    dlu[2 * q] = make_float2(w.x, w.y), dlu[2 * q + 1] = make_float2(w.z, w.w);                                        \
+                }                                                                                                                      \
+            }                                                                                                                          \
+            const int n_ = ((s_) - j) & 15;                                                                                            \
+            const unsigned char *rowB = ((s_) >= j ? tb_cur : tb_prev) + n_ * Tl::kRowBytes, *rowC = rowB + 16 * Tl::kRowBytes;        \
+            const float2 A2 = s_A_rp[n_];                                                                                              \
+            float Bn[T];                                                                                                               \
+            {                                                                                                                          \
+                const float4 b0 = *reinterpret_cast<const float4 *>(rowB), b1 = *reinterpret_cast<const float4 *>(rowB + 16);          \
+                const float eb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};                                                  \
+                order8<REV>(eb, Bn);                                                                                                   \
+                const float4 c0 = *reinterpret_cast<const float4 *>(rowC), c1 = *reinterpret_cast<const float4 *>(rowC + 16);          \
+                const float ec[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};                                                  \
+                order8<REV>(ec, cn);                                                                                                   \
+            }                                                                                                                          \
+            _Pragma("unroll") for (int i = 0; i < T; ++i) {                                                                            \
+                an[i] = ex2(fmul2(dl[i], A2));                                                                                         \
+                bn[i] = fmul2(dlu[i], splat(Bn[i]));                                                                                   \
+                if (WITH_CHAIN) {                                                                                                      \
+                    h = ffma2(ac[i], h, bc[i]);                                                                                        \
+                    ya[i] = ffma2(h, splat(cc[i]), ya[i]);                                                                             \
+                }                                                                                                                      \
+            }                                                                                                                          \
+        }
+        float2 h = make_float2(0.f, 0.f);
+        MMU_S5_PREP(0, a[0], bb[0], Cn[0], false, a[0], bb[0], Cn[0])
+        // one step: (transition) -> predecessor's state -> recurrence of step s_ interleaved with the operands of step s_ + 1.
+        // The step loop is NOT unrolled beyond the cur / nxt pair: one copy of the code keeps delta, delta*u and y in fixed registers,
+        // so the predicated transition loads land in them directly (the fully unrolled form split their live ranges and paid ~50
+        // predicated moves per step), and the round fits the instruction cache.
+#define MMU_S5_STEP(s_, cur, nxt, PREP)                                                                                                \
+        {                                                                                                                              \
+            if ((s_) == j) {   /* first step of my chunk k: the finished y of chunk k-1 goes out, D*u of chunk k comes in */            \
+                _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                                                        \
+                    yo[q * NRT] = make_float4(ya[2 * q].x, ya[2 * q].y, ya[2 * q + 1].x, ya[2 * q + 1].y);                             \
+                    const float4 v = yi[q * NRT];                                                                                      \
+                    ya[2 * q] = make_float2(v.x, v.y), ya[2 * q + 1] = make_float2(v.z, v.w);                                          \
+                }                                                                                                                      \
+            }                                                                                                                          \
+            h = make_float2(__shfl_sync(0xffffffffu, hout.x, src_lane), __shfl_sync(0xffffffffu, hout.y, src_lane));                   \
+            if (PREP) {                                                                                                                \
+                MMU_S5_PREP((s_) + 1, a[nxt], bb[nxt], Cn[nxt], true, a[cur], bb[cur], Cn[cur])                                        \
+            } else {                                                                                                                   \
+                _Pragma("unroll") for (int i = 0; i < T; ++i) {                                                                        \
+                    h = ffma2(a[cur][i], h, bb[cur][i]);                                                                               \
+                    ya[i] = ffma2(h, splat(Cn[cur][i]), ya[i]);                                                                        \
+                }                                                                                                                      \
+            }                                                                                                                          \
+            hout = h;                                                                                                                  \
+            if (xsave) ((s_) >= j ? sx_cur : sx_prev)[(((s_) - j) & 15) * NRP * 2] = h;                                                \
+        }
+#pragma unroll 1
+        for (int s = 0; s < 16; s += 2) {
+            MMU_S5_STEP(s, 0, 1, true)
+            MMU_S5_STEP(s + 1, 1, 0, s + 2 < 16)
+        }
+#undef MMU_S5_STEP
+#undef MMU_S5_PREP
+    }
+}
+
 }  // namespace mmu

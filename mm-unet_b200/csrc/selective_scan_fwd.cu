@@ -650,6 +650,16 @@ template <int W> int launch_fwd5(const Fwd3Args &a, bool rev, cudaStream_t st) {
     return check_launch("selective_scan_fwd(v5)");
 }
 
+template <int WR> int launch_fwd5s(const Fwd3Args &a, bool rev, cudaStream_t st) {
+    using Cfg = Fwd5sCfg<WR>;
+    dim3 grid((a.D + Cfg::R - 1) / Cfg::R, a.B), block(Cfg::NT);
+    auto k = rev ? scan5s_fwd_kernel<WR, true> : scan5s_fwd_kernel<WR, false>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
+    k<<<grid, block, Cfg::smem_bytes, st>>>(a);
+    count_launch();
+    return check_launch("selective_scan_fwd(v5s)");
+}
+
 int run_fwd5(const mmu_scan_fwd_params *p, cudaStream_t st) {
     Fwd3Args a{};
     make_ordmap(a.ord, MMU_ORDER_ROWMAJOR, 0, 0, 0, p->seqlen);
@@ -665,6 +675,13 @@ int run_fwd5(const mmu_scan_fwd_params *p, cudaStream_t st) {
     a.nx = (p->seqlen + xs - 1) / xs;
     a.softplus = p->delta_softplus;
     const bool rev = p->reverse != 0;
+    if (xs == 64 && env_int("MMU_V5_SPEC", 1) != 0) {     // warp-specialised form: ring warps + helper warps
+        switch (plan_fwd5(p->batch, p->dim)) {
+            case 6: return launch_fwd5s<6>(a, rev, st);
+            case 4: return launch_fwd5s<4>(a, rev, st);
+            default: return launch_fwd5s<2>(a, rev, st);
+        }
+    }
     switch (plan_fwd5(p->batch, p->dim)) {
         case 6: return launch_fwd5<6>(a, rev, st);
         case 4: return launch_fwd5<4>(a, rev, st);

@@ -13,9 +13,11 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True, with_stack=True) as p:
     tr.step(x, y)
     torch.cuda.synchronize()
-ka = p.key_averages(group_by_input_shape=True, group_by_stack_n=6)
+ka = p.key_averages(group_by_input_shape=True, group_by_stack_n=12)
 rows = [k for k in ka if k.self_device_time_total > 0 and k.key.startswith("aten::")]
 rows.sort(key=lambda k: -k.self_device_time_total)
-for k in rows[:45]:
-    st = [s for s in k.stack if "mmunet_b200" in s][:3]
-    print(f"{k.self_device_time_total/1e3:8.3f} ms {k.count:4d} x  {k.key:34s} {str(k.input_shapes)[:90]}  {' <- '.join(s.split('mmunet_b200/')[-1][:60] for s in st)}")
+for k in rows[:110]:
+    if not any(t in k.key for t in ("copy_", "sum", "add", "mul", "fill", "zero", "clone", "contiguous", "amax", "to")):
+        continue
+    st = [s for s in k.stack if ".py" in s and "torch/" not in s][:4]
+    print(f"{k.self_device_time_total/1e3:8.3f} ms {k.count:4d} x  {k.key:22s} {str(k.input_shapes)[:70]}  {' <- '.join(s.split('/')[-1][:50] for s in st)}")
