@@ -1,377 +1,63 @@
-// Selective scan forward, v5 "lane ring" kernel (fp32 I/O, dstate <= 16, seqlen % 8 == 0, 16-byte aligned rows, one segment).
-// Math: SURVEY.md Appendix A; replaces selective_scan_fwd_kernel (selective_scan_fwd_kernel.cuh:67-303).
+// Selective scan forward, v5 "lane ring" kernel (fp32 I/O, dstate <= 16, seqlen % 8 == 0, 16-byte aligned rows, one segment, saved
+// states every 64 tokens).  Math: SURVEY.md Appendix A; replaces selective_scan_fwd_kernel (selective_scan_fwd_kernel.cuh:67-303).
 //
 // v3 (scan3_fwd.cuh) closes the chunk-level recurrence with a cross-lane Kogge-Stone scan of (prod a, h) plus a fix-up
 // y_i += C_i Pc_i hs: 130 issue slots per (lane, state), 50 of them the scan, 23 the products it needs.  Here the lanes of a
 // row pair form a RING that works as a systolic pipeline instead:
-//   * 16 lanes (half a warp) own the 16 eight-token blocks of a 128-token chunk of a row pair (two rows packed in FFMA2 halves);
+//   * 16 lanes own the 16 eight-token blocks of a 128-token chunk of a row pair (two rows packed in the FFMA2 halves);
 //   * at step tau lane j works on item q = tau - j: chunk q / 16, state q % 16.  The state entering its block is what lane j-1
 //     produced one step earlier (one SHFL.IDX per packed half); lane 0 receives lane 15's result, which is exactly the state
 //     leaving the previous chunk for the same n - the ring carries the recurrence across chunks with no special case;
 //   * so every lane runs the TRUE recurrence h = a h + delta u B, y += C h: no aggregates, no scan, no fix-up, one MUFU.EX2 per
 //     (row, token, state), ~50 issue slots per (lane, state) for the recurrence itself.
-// The price is that the lanes of a ring sit in two different chunks at any time (lane j enters chunk k at step 16k + j), so the
-// per-(row, token) quantities cannot simply be reloaded by the whole warp at a chunk boundary:
-//   * once per ROUND of 16 steps a uniform bulk phase does the element-wise work for all lanes - softplus(delta + bias),
-//     delta*u and D*u of chunk k into a lane-private shared-memory stage; gate + store of chunk k-2; saved states of chunk k-2 -
-//     and issues the cp.async copies of chunk k+1 (lane-private landing slots, B/C tile into a 3-deep ring of tiles);
-//   * a lane picks its new delta / delta*u up from the stage at ITS transition step (8 predicated LDS.128), and swaps its y
-//     accumulators with the stage's D*u there (the slot then holds the finished y until the bulk phase two rounds later).
-// Work per warp is fixed by the problem (rows / 4 warps, each walking the whole sequence), so this kernel is for wide problems;
-// narrow ones stay on v3, which can cut the sequence into segments.  MUFU is the limiter: 16 ex2 per step = 128 clk of the
-// SM sub-partition's MUFU unit, against ~110 issue slots.
+// The price: the lanes of a ring sit in two different chunks at any time (lane j enters chunk k at step 16k + j), so the
+// per-(row, token) quantities cannot simply be reloaded by the whole warp at a chunk boundary.  A lane picks its new delta /
+// delta*u up from a shared-memory stage at ITS transition step (predicated loads), and leaves a snapshot of its y accumulators
+// there.  Work per warp is fixed by the problem (rows / 4 ring warps, each walking the whole sequence), so this kernel is for
+// wide problems; narrow ones stay on v3, which can cut the sequence into segments.
+//
+// Warp specialisation.  A first version (git history: b08aac9) let every warp do its own element-wise work in a uniform "bulk"
+// phase once per round of 16 steps: 195 us at BASELINE config 2 against v3's 172 us - ncu showed the steps running at 0.57
+// instructions per clock and scheduler, but the bulk phase taking 40 % of the round and the schedulers of an SM carrying 2, 2, 1, 1
+// ring warps.  Here a ring warp does NOTHING but steps; a HELPER warp per ring warp does every element-wise phase for it one round
+// ahead / two rounds behind, through double-buffered lane slots (twice the warps per SM for the same work):
+//   helper, round k:  gate + store of chunk k-2 from the y snapshots yout[(k-2)&1] (y of a chunk = difference of consecutive
+//                     snapshots + D*u: the ring lanes never reset their accumulators - a reload would cost 4 loads + 16 predicated
+//                     moves per step);  saved states of chunk k-2 from xbuf[(k-2)%3];  softplus / delta*u / D*u of chunk k+1 ->
+//                     stage[(k+1)&1], du[(k+1)%3];  cp.async of u, delta (chunk k+2), z (chunk k-1) into its landing slots and of
+//                     its share of the B/C tile k+1 (3-deep ring of tiles);
+//   ring, round k:    16 steps on stage[k&1]; y snapshot -> yout[(k-1)&1] at the lane's transition; the states leaving blocks 7
+//                     and 15 of a chunk (stride-64 saved states) -> xbuf[chunk%3].
+// One __syncthreads per round orders everything.  The two rings of a warp are interleaved over the lanes (lane = 2 j + ring): the
+// two lanes in transition at a step then sit in the same quarter-warp and their predicated 16-byte accesses are one wavefront.
+// The step loop is a runtime loop over step PAIRS (operand double buffer): fully unrolled, ptxas split the live ranges of delta,
+// delta*u and y across the 16 copies and paid ~50 predicated moves per step.
+// Measured (B200, fp32, profiles/r2_v5_lane_ring.md): config 2 (B8 D384 L4096) 154 us vs v3 172 us; B16 D128 L 4k / 16k / 64k
+// 115 / 416 / 1627 us vs 138 / 516 / 2034 us.  Time per round is ~3.2 us with 4 ring warps per CTA and ~4.4 us with 6 (170-register
+// cap at 384 threads, and 6 ring warps sit 2, 2, 1, 1 on the four schedulers), independent of the number of CTAs up to one per SM.
 #pragma once
 #include "scan3.cuh"
 #include "scan3_fwd.cuh"
 
 namespace mmu {
 
-template <int W> struct Fwd5Cfg {
-    static constexpr int T = kS3T, LPR = 16, CH = LPR * T, NT = 32 * W, NRP = 2 * W, R = 4 * W;
-    using Tl = BcTile<LPR>;
-    static constexpr int kTiles = 3;
-    static constexpr int kTileBytes = kTiles * Tl::kBytes;
-    static constexpr int kLandBytes = 3 * 2 * 2 * NT * 16;     // u | delta | z : [tensor][row][quad][thread] x 16 B
-    static constexpr int kStageBytes = 8 * NT * 16;            // delta (4 quads of float2 pairs) | delta*u (4 quads)
-    static constexpr int kYBytes = 4 * NT * 16;                // D*u of the chunk a lane is about to enter / y of the chunk it left
-    static constexpr int kXBytes = 2 * 16 * NT * 8;            // states leaving my block: [chunk parity][state][thread] float2
-    static constexpr int kABytes = NRP * 16 * 8;               // A*log2e of (row A, row B)
-    static constexpr size_t smem_bytes = (size_t)kTileBytes + kLandBytes + kStageBytes + kYBytes + kXBytes + kABytes;
-    static constexpr int kMinBlocks = smem_bytes * 2 <= 227 * 1024 ? 2 : 1;
-};
-
-template <int W, bool REV>
-__global__ void __launch_bounds__(32 * W, Fwd5Cfg<W>::kMinBlocks) scan5_fwd_kernel(const __grid_constant__ Fwd3Args p) {
-    using Cfg = Fwd5Cfg<W>;
-    using Tl = typename Cfg::Tl;
-    constexpr int T = Cfg::T, LPR = Cfg::LPR, CH = Cfg::CH, NT = Cfg::NT, NRP = Cfg::NRP, R = Cfg::R;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int j = lane & 15, ring = lane >> 4, rp = warp * 2 + ring;
-    const int b = blockIdx.y, row0 = blockIdx.x * R;
-    const int D = p.D, L = p.L, N = p.N;
-    const int NC = (L + CH - 1) / CH;
-    const bool has_z = p.z != nullptr, sp = p.softplus != 0;
-    const int xs8 = p.cps;                                  // saved-state stride in 8-token blocks (host: x_stride / 8)
-
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char *s_tile = smem_raw;
-    unsigned char *s_land = s_tile + Cfg::kTileBytes;
-    float4 *s_stage = reinterpret_cast<float4 *>(s_land + Cfg::kLandBytes);                    // [8][NT]
-    float4 *s_y = reinterpret_cast<float4 *>(s_land + Cfg::kLandBytes + Cfg::kStageBytes);     // [4][NT]
-    float2 *s_x = reinterpret_cast<float2 *>(s_land + Cfg::kLandBytes + Cfg::kStageBytes + Cfg::kYBytes);   // [2][16][NT]
-    float2 *s_A = s_x + 2 * 16 * NT;                                                           // [NRP][16]
-
-    for (int i = tid; i < (int)((Cfg::smem_bytes - Cfg::kABytes) / 16); i += NT) reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = tid; i < NRP * 16; i += NT) {
-        const int g = i >> 4, n = i & 15;
-        float a[2];
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int row = row0 + 2 * g + r;
-            a[r] = (row < D && n < N) ? p.A[(int64_t)row * N + n] * kLog2e : 0.f;
-        }
-        s_A[i] = make_float2(a[0], a[1]);
-    }
-
-    // ---- my two rows ------------------------------------------------------------------------------------------------------------
-    const int rowA = row0 + 2 * rp;
-    constexpr int STEP = REV ? -CH : CH;
-    const int mo0 = REV ? L - T - T * j : T * j;            // memory index of my 8 tokens in chunk 0
-    bool row_ok[2];
-    const float *u_p[2], *d_p[2], *z_p[2];                  // my 8 tokens of the chunk whose copy is issued next
-    float *o_p[2], *y_p[2];                                 // my 8 tokens of the chunk stored next
-    float bias[2], Dsk[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        row_ok[r] = rowA + r < D;
-        const int row = min(rowA + r, D - 1);
-        u_p[r] = reinterpret_cast<const float *>(p.u) + (int64_t)b * p.u_bs + (int64_t)row * p.u_ds + mo0;
-        d_p[r] = reinterpret_cast<const float *>(p.delta) + (int64_t)b * p.dl_bs + (int64_t)row * p.dl_ds + mo0;
-        z_p[r] = has_z ? reinterpret_cast<const float *>(p.z) + (int64_t)b * p.z_bs + (int64_t)row * p.z_ds + mo0 : nullptr;
-        o_p[r] = reinterpret_cast<float *>(p.out) + (int64_t)b * p.o_bs + (int64_t)row * p.o_ds + mo0;
-        y_p[r] = p.ysave == nullptr ? nullptr : reinterpret_cast<float *>(p.ysave) + (int64_t)b * p.y_bs + (int64_t)row * p.y_ds + mo0;
-        bias[r] = p.dbias != nullptr ? p.dbias[row] : 0.f;
-        Dsk[r] = p.Dv != nullptr ? p.Dv[row] : 0.f;
-    }
-    const float *B_b = reinterpret_cast<const float *>(p.Bm) + (int64_t)b * p.B_bs;
-    const float *C_b = reinterpret_cast<const float *>(p.Cm) + (int64_t)b * p.C_bs;
-
-    const int qa = REV ? 2 * (LPR - 1 - j) : 2 * j;         // my 8 tokens inside a tile row (memory order): two adjacent quads
-    const unsigned s_tile_u32 = smem_u32(s_tile);
-    const unsigned s_land_u32 = smem_u32(s_land) + tid * 16;
-    const unsigned char *s_land_t = s_land + tid * 16;
-    const float2 *s_A_rp = s_A + rp * 16;
-    const int src_lane = (lane & 16) | ((j + 15) & 15);     // ring predecessor
-
-    auto issue_tile = [&](int c) {
-        tile_async_f32<LPR, NT, REV, true>(s_tile_u32 + (unsigned)(c % Cfg::kTiles) * Tl::kBytes, B_b, C_b, p.B_ns, p.C_ns, N, c * CH, L, tid);
-    };
-    auto issue_ud = [&](int c) {             // u and delta of chunk c (the prefetch pointers stand on it), then advance them
-        if (c * CH + T * j < L) {
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    cp_async16(s_land_u32 + ((0 * 2 + r) * 2 + q) * NT * 16, u_p[r] + q * 4);
-                    cp_async16(s_land_u32 + ((1 * 2 + r) * 2 + q) * NT * 16, d_p[r] + q * 4);
-                }
-        }
-#pragma unroll
-        for (int r = 0; r < 2; ++r) u_p[r] += STEP, d_p[r] += STEP;
-    };
-    auto issue_z = [&](int c) {
-        if (!has_z) return;
-        if (c * CH + T * j < L) {
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-                for (int q = 0; q < 2; ++q) cp_async16(s_land_u32 + ((2 * 2 + r) * 2 + q) * NT * 16, z_p[r] + q * 4);
-        }
-#pragma unroll
-        for (int r = 0; r < 2; ++r) z_p[r] += STEP;
-    };
-    auto load_elem = [&](int which, int r, float (&v)[T]) {
-        uint4 q[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) q[k] = *reinterpret_cast<const uint4 *>(s_land_t + ((which * 2 + r) * 2 + k) * NT * 16);
-        float e[8];
-        Raw8<float>::unpack(q, e);
-        order8<REV>(e, v);
-    };
-    // gate + store of chunk c (its y sits in my s_y slot, its z in my landing slot); saved states of chunk c from s_x[c & 1]
-    auto epilogue = [&](int c) {
-        const bool ok = c * CH + T * j < L;
-        float2 ya[T];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 v = s_y[q * NT + tid];
-            ya[2 * q] = make_float2(v.x, v.y), ya[2 * q + 1] = make_float2(v.z, v.w);
-        }
-        float zz[2][T];
-        if (has_z) load_elem(2, 0, zz[0]), load_elem(2, 1, zz[1]);
-        if (ok) {
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                if (row_ok[r]) {
-                    float yv[T];
-#pragma unroll
-                    for (int i = 0; i < T; ++i) yv[i] = r ? ya[i].y : ya[i].x;
-                    if (y_p[r] != nullptr) store8<float, REV>(y_p[r], yv);
-                    if (has_z) {
-#pragma unroll
-                        for (int i = 0; i < T; ++i) yv[i] *= zz[r][i] * sigmoid3(zz[r][i]);
-                    }
-                    store8<float, REV>(o_p[r], yv);
-                }
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            o_p[r] += STEP;
-            if (y_p[r] != nullptr) y_p[r] += STEP;
-        }
-        const int blk = c * LPR + j;                         // my 8-token block; the state leaving it is h after token 8*blk + 7
-        if (blk < p.nx * xs8 && (p.x != nullptr || p.last_state != nullptr)) {
-            const float2 *sx = s_x + (c & 1) * 16 * NT + tid;
-            float hx[2][16];
-#pragma unroll
-            for (int n = 0; n < 16; ++n) {
-                const float2 v = sx[n * NT];
-                hx[0][n] = v.x, hx[1][n] = v.y;
-            }
-            const bool savex = p.x != nullptr && (blk + 1) % xs8 == 0;   // (blocks past L pass the final state through, as v3's tail)
-            const bool lastb = p.last_state != nullptr && blk == L / T - 1;
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                if (!row_ok[r]) continue;
-                if (savex) {
-                    float *xp = p.x + (((int64_t)b * D + rowA + r) * p.nx + ((blk + 1) / xs8 - 1)) * N;
-                    if (N == 16) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            reinterpret_cast<float4 *>(xp)[q] = make_float4(hx[r][4 * q], hx[r][4 * q + 1], hx[r][4 * q + 2], hx[r][4 * q + 3]);
-                    } else {
-#pragma unroll
-                        for (int n = 0; n < 16; ++n)
-                            if (n < N) xp[n] = hx[r][n];
-                    }
-                }
-                if (lastb) {
-                    float *lp = p.last_state + ((int64_t)b * D + rowA + r) * N;
-#pragma unroll
-                    for (int n = 0; n < 16; ++n)
-                        if (n < N) lp[n] = hx[r][n];
-                }
-            }
-        }
-    };
-
-    __syncthreads();                        // zero fill and tables visible before the first copies land
-    issue_tile(0);
-    issue_ud(0);
-    cp_async_commit();
-
-    // ---- registers that live across steps -----------------------------------------------------------------------------------------
-    float2 dl[T], dlu[T], ya[T];            // delta, delta*u, y of the chunk I am in (.x = row A, .y = row B)
-#pragma unroll
-    for (int i = 0; i < T; ++i) dl[i] = dlu[i] = ya[i] = make_float2(0.f, 0.f);
-    float2 hout = make_float2(0.f, 0.f);    // state leaving my block in the previous step
-    float2 a[2][T], bb[2][T];               // a_i and delta_i u_i B_i of the current / next step
-    float Cn[2][T];
-
-    for (int k = 0; k <= NC; ++k) {
-        // ================= bulk phase of round k =====================================================================================
-        cp_async_wait_all();
-        __syncthreads();                    // tile k, my landing slots; every warp has left round k-1 (tile (k+1) % 3 is free)
-        float2 yinit[T];
-        if (k < NC) {
-            const bool ok = k * CH + T * j < L;
-            float uu[2][T], dd[2][T];
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                load_elem(0, r, uu[r]);
-                load_elem(1, r, dd[r]);
-#pragma unroll
-                for (int i = 0; i < T; ++i) {
-                    const float xx = dd[r][i] + bias[r];
-                    const float v = sp ? softplus3(xx) : xx;
-                    dd[r][i] = (ok && row_ok[r]) ? v : 0.f;
-                    uu[r][i] = (ok && row_ok[r]) ? uu[r][i] : 0.f;
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int i0 = 2 * q, i1 = 2 * q + 1;
-                s_stage[q * NT + tid] = make_float4(dd[0][i0], dd[1][i0], dd[0][i1], dd[1][i1]);
-                s_stage[(4 + q) * NT + tid] = make_float4(dd[0][i0] * uu[0][i0], dd[1][i0] * uu[1][i0], dd[0][i1] * uu[0][i1], dd[1][i1] * uu[1][i1]);
-            }
-#pragma unroll
-            for (int i = 0; i < T; ++i) yinit[i] = make_float2(Dsk[0] * uu[0][i], Dsk[1] * uu[1][i]);
-            if (k + 1 < NC) issue_ud(k + 1);
-        } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) s_stage[q * NT + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < T; ++i) yinit[i] = make_float2(0.f, 0.f);
-        }
-        if (k >= 2) epilogue(k - 2);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) s_y[q * NT + tid] = make_float4(yinit[2 * q].x, yinit[2 * q].y, yinit[2 * q + 1].x, yinit[2 * q + 1].y);
-        if (k >= 1 && k - 1 < NC) issue_z(k - 1);
-        if (k + 1 < NC) issue_tile(k + 1);
-        cp_async_commit();
-
-        // ================= the 16 steps of round k ==================================================================================
-        const unsigned char *tb_cur = s_tile + (k % Cfg::kTiles) * Tl::kBytes + Tl::quad_off(qa);
-        const unsigned char *tb_prev = s_tile + ((k + Cfg::kTiles - 1) % Cfg::kTiles) * Tl::kBytes + Tl::quad_off(qa);
-        float2 *sx_cur = s_x + (k & 1) * 16 * NT + tid, *sx_prev = s_x + ((k & 1) ^ 1) * 16 * NT + tid;
-
-        // operands of step s (delta / delta*u picked up from the stage when the step is my first of chunk k), interleaved with the
-        // recurrence of the step before it (WITH_CHAIN): a_i, b_i of step s do not depend on the chain, so MUFU latency hides under it
-#define MMU_S5_PREP(s_, an, bn, cn, WITH_CHAIN, ac, bc, cc)                                                                            \
-        {                                                                                                                              \
-            if ((s_) == j) {                                                                                                           \
-                _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                                                        \
-                    const float4 v = s_stage[q * NT + tid], w = s_stage[(4 + q) * NT + tid];                                           \
-                    dl[2 * q] = make_float2(v.x, v.y), dl[2 * q + 1] = make_float2(v.z, v.w);                                          \
-                    dlu[2 * q] = make_float2(w.x, w.y), dlu[2 * q + 1] = make_float2(w.z, w.w);                                        \
-                }                                                                                                                      \
-            }                                                                                                                          \
-            const int n_ = ((s_) - j) & 15;                                                                                            \
-            const unsigned char *rowB = ((s_) >= j ? tb_cur : tb_prev) + n_ * Tl::kRowBytes, *rowC = rowB + 16 * Tl::kRowBytes;        \
-            const float2 A2 = s_A_rp[n_];                                                                                              \
-            float Bn[T];                                                                                                               \
-            {                                                                                                                          \
-                const float4 b0 = *reinterpret_cast<const float4 *>(rowB), b1 = *reinterpret_cast<const float4 *>(rowB + 16);          \
-                const float eb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};                                                  \
-                order8<REV>(eb, Bn);                                                                                                   \
-                const float4 c0 = *reinterpret_cast<const float4 *>(rowC), c1 = *reinterpret_cast<const float4 *>(rowC + 16);          \
-                const float ec[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};                                                  \
-                order8<REV>(ec, cn);                                                                                                   \
-            }                                                                                                                          \
-            _Pragma("unroll") for (int i = 0; i < T; ++i) {                                                                            \
-                an[i] = ex2(fmul2(dl[i], A2));                                                                                         \
-                bn[i] = fmul2(dlu[i], splat(Bn[i]));                                                                                   \
-                if (WITH_CHAIN) {                                                                                                      \
-                    h = ffma2(ac[i], h, bc[i]);                                                                                        \
-                    ya[i] = ffma2(h, splat(cc[i]), ya[i]);                                                                             \
-                }                                                                                                                      \
-            }                                                                                                                          \
-        }
-        float2 h = make_float2(0.f, 0.f);
-        MMU_S5_PREP(0, a[0], bb[0], Cn[0], false, a[0], bb[0], Cn[0])
-#pragma unroll
-        for (int s = 0; s < 16; ++s) {
-            const int cur = s & 1, nxt = cur ^ 1;
-            if (s == j) {                   // first step of my chunk: the slot holds D*u of the new chunk; leave the finished y there
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 v = s_y[q * NT + tid];
-                    s_y[q * NT + tid] = make_float4(ya[2 * q].x, ya[2 * q].y, ya[2 * q + 1].x, ya[2 * q + 1].y);
-                    ya[2 * q] = make_float2(v.x, v.y), ya[2 * q + 1] = make_float2(v.z, v.w);
-                }
-            }
-            h = make_float2(__shfl_sync(0xffffffffu, hout.x, src_lane), __shfl_sync(0xffffffffu, hout.y, src_lane));
-            if (s < 15) {
-                MMU_S5_PREP(s + 1, a[nxt], bb[nxt], Cn[nxt], true, a[cur], bb[cur], Cn[cur])
-            } else {
-#pragma unroll
-                for (int i = 0; i < T; ++i) {
-                    h = ffma2(a[cur][i], h, bb[cur][i]);
-                    ya[i] = ffma2(h, splat(Cn[cur][i]), ya[i]);
-                }
-            }
-            hout = h;
-            (s >= j ? sx_cur : sx_prev)[((s - j) & 15) * NT] = h;
-        }
-#undef MMU_S5_PREP
-    }
-    // the last chunk: every lane has left it (its y was swapped out in round NC)
-    cp_async_wait_all();
-    epilogue(NC - 1);
-}
-
-
-// ================================================================================================================================
-// Warp-specialised form of the lane-ring forward.  ncu of the kernel above (profiles/r2_v5_lane_ring.md): the 16 steps of a round
-// run at 0.57 instructions per clock and scheduler where two ring warps share a scheduler, but the uniform bulk phase is 40 % of
-// the round and the four schedulers of an SM carry 2, 2, 1, 1 ring warps (rows / 4 warps cannot be split further).  Here a ring
-// warp does NOTHING but steps; a HELPER warp per ring warp does every element-wise phase for it one round ahead / two rounds
-// behind, through double-buffered lane slots (twice the warps per SM for the same work):
-//   helper, round k:  softplus / delta*u / D*u of chunk k+1 -> stage[(k+1)&1], yin[(k+1)&1];   gate + store of chunk k-2 from
-//                     yout[(k-2)&1];  saved states of chunk k-2 from xbuf[(k-2)%3];  cp.async of u, delta (chunk k+2), z (chunk k-1)
-//                     into its landing slots and of its share of the B/C tile k+1;
-//   ring, round k:    16 steps on stage[k&1] / yin[k&1], finished y -> yout[(k-1)&1] at the lane's transition, states leaving the
-//                     blocks 7 and 15 of a chunk (stride-64 saved states) -> xbuf[chunk%3].
-// One __syncthreads per round orders everything.  The two rings of a warp are interleaved over the lanes (lane = 2 j + ring): the two
-// lanes in transition at a step then sit in the same quarter-warp and their predicated 16-byte accesses are one wavefront.
-// Saved-state stride 64 only (xs8 == 8); other strides use the kernel above.
-template <int WR> struct Fwd5sCfg {
+template <int WR> struct Fwd5Cfg {
     static constexpr int T = kS3T, LPR = 16, CH = LPR * T, NRT = 32 * WR, NT = 2 * NRT, NRP = 2 * WR, R = 4 * WR;
     using Tl = BcTile<LPR>;
     static constexpr int kTiles = 3;
     static constexpr int kTileBytes = kTiles * Tl::kBytes;
     static constexpr int kLandBytes = 3 * 2 * 2 * NRT * 16;    // u | delta | z : [tensor][row][quad][ring thread] x 16 B
     static constexpr int kStageBytes = 2 * 8 * NRT * 16;       // [parity][delta x4 | delta*u x4][ring thread]
-    static constexpr int kYBytes = 2 * 4 * NRT * 16;           // yin and yout, each [parity][quad][ring thread]
+    static constexpr int kDuBytes = 3 * 4 * NRT * 16;          // D*u of chunks k-2 .. k+1 (helper private): [chunk % 3][quad][ring thread]
+    static constexpr int kYBytes = 2 * 4 * NRT * 16;           // y accumulator snapshots: [parity][quad][ring thread]
     static constexpr int kXBytes = 3 * 16 * NRP * 2 * 8;       // [chunk % 3][state][ring][block 7 | block 15] float2
     static constexpr int kABytes = NRP * 16 * 8;
-    static constexpr size_t smem_bytes = (size_t)kTileBytes + kLandBytes + kStageBytes + 2 * kYBytes + kXBytes + kABytes;
+    static constexpr size_t smem_bytes = (size_t)kTileBytes + kLandBytes + kStageBytes + kDuBytes + kYBytes + kXBytes + kABytes;
 };
 
-// predicated 8-byte shared-memory load INTO the given register pair (it keeps its value where pred is false).  The compiler's own
-// form of "if (p) acc = *ptr" on accumulators that FFMA2 chains are still updating is a load into temporaries plus predicated moves
-// (16 per step for the y accumulators); a 16-byte form needs an aligned register quad and gets the same moves.
-__device__ __forceinline__ void lds64_if(bool pred, const void *ptr, float2 &v) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p ld.shared.v2.f32 {%0, %1}, [%2];\n\t}"
-                 : "+f"(v.x), "+f"(v.y)
-                 : "r"(smem_u32(ptr)), "r"((int)pred)
-                 : "memory");
-}
-
 template <int WR, bool REV>
-__global__ void __launch_bounds__(64 * WR, 1) scan5s_fwd_kernel(const __grid_constant__ Fwd3Args p) {
-    using Cfg = Fwd5sCfg<WR>;
+__global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_constant__ Fwd3Args p) {
+    using Cfg = Fwd5Cfg<WR>;
     using Tl = typename Cfg::Tl;
     constexpr int T = Cfg::T, LPR = Cfg::LPR, CH = Cfg::CH, NRT = Cfg::NRT, NRP = Cfg::NRP, R = Cfg::R;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -389,8 +75,8 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5s_fwd_kernel(const __grid_con
     unsigned char *s_tile = smem_raw;
     unsigned char *s_land = s_tile + Cfg::kTileBytes;
     float4 *s_stage = reinterpret_cast<float4 *>(s_land + Cfg::kLandBytes);                                  // [2][8][NRT]
-    float4 *s_yin = reinterpret_cast<float4 *>(s_land + Cfg::kLandBytes + Cfg::kStageBytes);                 // [2][4][NRT]
-    float4 *s_yout = s_yin + 2 * 4 * NRT;                                                                    // [2][4][NRT]
+    float4 *s_du = reinterpret_cast<float4 *>(s_land + Cfg::kLandBytes + Cfg::kStageBytes);                  // [3][4][NRT]
+    float4 *s_yout = s_du + 3 * 4 * NRT;                                                                     // [2][4][NRT]
     float2 *s_x = reinterpret_cast<float2 *>(s_yout + 2 * 4 * NRT);                                          // [3][16][NRP][2]
     float2 *s_A = s_x + 3 * 16 * NRP * 2;                                                                    // [NRP][16]
 
@@ -465,6 +151,9 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5s_fwd_kernel(const __grid_con
             Raw8<float>::unpack(q, e);
             order8<REV>(e, v);
         };
+        float4 ysnap[4];                                    // the lane's y accumulators when it left the previous chunk
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ysnap[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         issue_ud(0);
         tile_async_f32<LPR, NRT, REV, true>(s_tile_u32, B_b, C_b, p.B_ns, p.C_ns, N, 0, L, htid);
         cp_async_commit();
@@ -472,49 +161,17 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5s_fwd_kernel(const __grid_con
         for (int k = -1; k <= NC + 1; ++k) {
             cp_async_wait_all();
             __syncthreads();
-            // ---- softplus(delta + bias), delta*u, D*u of chunk k+1 -------------------------------------------------------------------
-            const int cp = k + 1;
-            if (cp <= NC) {
-                float4 *st = s_stage + (cp & 1) * 8 * NRT + rt, *yi = s_yin + (cp & 1) * 4 * NRT + rt;
-                if (cp < NC) {
-                    const bool ok = cp * CH + T * j < L;
-                    float uu[2][T], dd[2][T];
-#pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        load_land(0, r, uu[r]);
-                        load_land(1, r, dd[r]);
-#pragma unroll
-                        for (int i = 0; i < T; ++i) {
-                            const float xx = dd[r][i] + bias[r];
-                            const float v = sp ? softplus3(xx) : xx;
-                            dd[r][i] = (ok && rok[r]) ? v : 0.f;
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int i0 = 2 * q, i1 = 2 * q + 1;
-                        st[q * NRT] = make_float4(dd[0][i0], dd[1][i0], dd[0][i1], dd[1][i1]);
-                        st[(4 + q) * NRT] = make_float4(dd[0][i0] * uu[0][i0], dd[1][i0] * uu[1][i0], dd[0][i1] * uu[0][i1], dd[1][i1] * uu[1][i1]);
-                        yi[q * NRT] = make_float4(Dsk[0] * uu[0][i0], Dsk[1] * uu[1][i0], Dsk[0] * uu[0][i1], Dsk[1] * uu[1][i1]);
-                    }
-                } else {                // the drain round reads an all-zero stage (delta = 0: a = 1, b = 0)
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) st[q * NRT] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) yi[q * NRT] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-            if (k + 2 < NC) issue_ud(k + 2);
-            // ---- gate + store of chunk k-2 ----------------------------------------------------------------------------------------------
+            // ---- gate + store of chunk k-2 (before the prologue below overwrites its D*u slot: (k+1) % 3 == (k-2) % 3) ---------------------
             const int ce = k - 2;
             if (ce >= 0) {
                 const bool ok = ce * CH + T * j < L;
-                const float4 *yo = s_yout + (ce & 1) * 4 * NRT + rt;
+                const float4 *yo = s_yout + (ce & 1) * 4 * NRT + rt, *du = s_du + (ce % 3) * 4 * NRT + rt;
                 float ya[2][T];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 v = yo[q * NRT];
-                    ya[0][2 * q] = v.x, ya[1][2 * q] = v.y, ya[0][2 * q + 1] = v.z, ya[1][2 * q + 1] = v.w;
+                for (int q = 0; q < 4; ++q) {      // the ring lanes never reset their accumulators: y of the chunk = difference of snapshots
+                    const float4 v = yo[q * NRT], w = du[q * NRT], o = ysnap[q];
+                    ya[0][2 * q] = v.x - o.x + w.x, ya[1][2 * q] = v.y - o.y + w.y, ya[0][2 * q + 1] = v.z - o.z + w.z, ya[1][2 * q + 1] = v.w - o.w + w.w;
+                    ysnap[q] = v;
                 }
                 if (ok) {
 #pragma unroll
@@ -566,6 +223,37 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5s_fwd_kernel(const __grid_con
                     }
                 }
             }
+            // ---- softplus(delta + bias), delta*u, D*u of chunk k+1 -------------------------------------------------------------------
+            const int cp = k + 1;
+            if (cp <= NC) {
+                float4 *st = s_stage + (cp & 1) * 8 * NRT + rt, *yi = s_du + (cp % 3) * 4 * NRT + rt;
+                if (cp < NC) {
+                    const bool ok = cp * CH + T * j < L;
+                    float uu[2][T], dd[2][T];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        load_land(0, r, uu[r]);
+                        load_land(1, r, dd[r]);
+#pragma unroll
+                        for (int i = 0; i < T; ++i) {
+                            const float xx = dd[r][i] + bias[r];
+                            const float v = sp ? softplus3(xx) : xx;
+                            dd[r][i] = (ok && rok[r]) ? v : 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int i0 = 2 * q, i1 = 2 * q + 1;
+                        st[q * NRT] = make_float4(dd[0][i0], dd[1][i0], dd[0][i1], dd[1][i1]);
+                        st[(4 + q) * NRT] = make_float4(dd[0][i0] * uu[0][i0], dd[1][i0] * uu[1][i0], dd[0][i1] * uu[0][i1], dd[1][i1] * uu[1][i1]);
+                        yi[q * NRT] = make_float4(Dsk[0] * uu[0][i0], Dsk[1] * uu[1][i0], Dsk[0] * uu[0][i1], Dsk[1] * uu[1][i1]);
+                    }
+                } else {                // the drain round reads an all-zero stage (delta = 0: a = 1, b = 0)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) st[q * NRT] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            if (k + 2 < NC) issue_ud(k + 2);
             if (k - 1 >= 0 && k - 1 < NC) issue_z(k - 1);
             if (k + 1 >= 1 && k + 1 < NC)
                 tile_async_f32<LPR, NRT, REV, true>(s_tile_u32 + (unsigned)((k + 1) % Cfg::kTiles) * Tl::kBytes, B_b, C_b, p.B_ns, p.C_ns, N, (k + 1) * CH, L, htid);
@@ -591,7 +279,7 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5s_fwd_kernel(const __grid_con
         if (k < 0 || k > NC) continue;
         const unsigned char *tb_cur = s_tile + (k % Cfg::kTiles) * Tl::kBytes + Tl::quad_off(qa);
         const unsigned char *tb_prev = s_tile + ((k + Cfg::kTiles - 1) % Cfg::kTiles) * Tl::kBytes + Tl::quad_off(qa);
-        const float4 *st = s_stage + (k & 1) * 8 * NRT + tid, *yi = s_yin + (k & 1) * 4 * NRT + tid;
+        const float4 *st = s_stage + (k & 1) * 8 * NRT + tid;
         float4 *yo = s_yout + ((k & 1) ^ 1) * 4 * NRT + tid;
         float2 *sx_cur = s_x + ((k % 3) * 16 * NRP + rp) * 2 + (j >> 3), *sx_prev = s_x + (((k + 2) % 3) * 16 * NRP + rp) * 2 + (j >> 3);
 
@@ -633,12 +321,10 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5s_fwd_kernel(const __grid_con
         // predicated moves per step), and the round fits the instruction cache.
 #define MMU_S5_STEP(s_, cur, nxt, PREP)                                                                                                \
         {                                                                                                                              \
-            if ((s_) == j) {   /* first step of my chunk k: the finished y of chunk k-1 goes out, D*u of chunk k comes in */            \
-                _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                                                        \
+            if ((s_) == j) {   /* first step of my chunk k: snapshot of the y accumulators (they are never reset: the helper takes */   \
+                               /* differences of consecutive snapshots - a reload would cost 4 loads + 16 predicated moves per step) */ \
+                _Pragma("unroll") for (int q = 0; q < 4; ++q)                                                                          \
                     yo[q * NRT] = make_float4(ya[2 * q].x, ya[2 * q].y, ya[2 * q + 1].x, ya[2 * q + 1].y);                             \
-                    const float4 v = yi[q * NRT];                                                                                      \
-                    ya[2 * q] = make_float2(v.x, v.y), ya[2 * q + 1] = make_float2(v.z, v.w);                                          \
-                }                                                                                                                      \
             }                                                                                                                          \
             h = make_float2(__shfl_sync(0xffffffffu, hout.x, src_lane), __shfl_sync(0xffffffffu, hout.y, src_lane));                   \
             if (PREP) {                                                                                                                \

@@ -618,46 +618,45 @@ template <typename IN_T> int run_fwd4(const mmu_scan_fwd_params *p, cudaStream_t
 }
 
 
-// ---- v5 host side (scan5_fwd.cuh): wide fp32 problems, lane rings --------------------------------------------------------------
-// warps per CTA: the B/C tiles are per batch element, so bigger CTAs amortise them; one CTA per SM in a single wave where possible
+// ---- v5 host side (scan5_fwd.cuh): wide fp32 problems, lane rings ----------------------------------------------------------------
+// Ring warps per CTA.  A CTA's time is fixed by the sequence length and its width (measured per 128-token round: ~3.2 us with 4 ring
+// warps, ~4.4 us with 6, ~6.2 us with 2 warps at two CTAs per SM), so the plan minimises waves x time per round; the B/C tiles are per
+// batch element, so a CTA never spans two.
 int plan_fwd5(int B, int D) {
     const int forced = env_int("MMU_V5_W", 0);
     if (forced == 2 || forced == 4 || forced == 6) return forced;
-    for (int W : {6, 4}) {
-        if (D % (4 * W) == 0 && B * (D / (4 * W)) >= 96) return W;
+    int best = 4;
+    double best_cost = 1e30;
+    for (int W : {4, 6, 2}) {
+        const int ctas = B * ((D + 4 * W - 1) / (4 * W)), slots = W == 2 ? 296 : 148;
+        const double cost = (double)((ctas + slots - 1) / slots) * (W == 4 ? 3.2 : (W == 6 ? 4.4 : 6.2));
+        if (cost < best_cost - 1e-9) best_cost = cost, best = W;
     }
-    return D % 16 == 0 ? 4 : (D % 24 == 0 ? 6 : 2);
+    return best;
 }
 
 bool fwd5_eligible(const mmu_scan_fwd_params *p) {
-    if (env_int("MMU_RING", 0) == 0 || p->dtype != MMU_F32) return false;   // opt-in: measured slower than v3 (profiles/r2_v5_lane_ring.md)
+    if (env_int("MMU_RING", 1) == 0 || p->dtype != MMU_F32) return false;
     if (p->order != MMU_ORDER_ROWMAJOR) return false;
     const int xs = p->x_stride ? p->x_stride : MMU_STATE_STRIDE;
-    if (xs % 8 != 0) return false;
+    if (xs != 64) return false;
     if (p->x && reinterpret_cast<uintptr_t>(p->x) % 16 != 0) return false;
-    if (p->seqlen < 256) return false;
-    if ((int64_t)p->batch * ((p->dim + 3) / 4) < env_int("MMU_V5_MIN_WARPS", 296)) return false;   // rows / 4 warps walk the whole sequence
+    // rows / 4 ring warps walk the whole sequence: below ~1 300 rows v3 (which is latency bound too, but per row pair) is faster
+    // (scripts/probe_v5_thresh.py: B8 D128 L4096 v3 105 us / ring 113 us, B4 D384 136 / 113 us); short sequences pay the three
+    // fill / drain rounds
+    if (p->seqlen < 512) return false;
+    if ((int64_t)p->batch * ((p->dim + 3) / 4) < env_int("MMU_V5_MIN_WARPS", 320)) return false;
     return fwd3_eligible<float>(p);
 }
 
-template <int W> int launch_fwd5(const Fwd3Args &a, bool rev, cudaStream_t st) {
-    using Cfg = Fwd5Cfg<W>;
+template <int WR> int launch_fwd5(const Fwd3Args &a, bool rev, cudaStream_t st) {
+    using Cfg = Fwd5Cfg<WR>;
     dim3 grid((a.D + Cfg::R - 1) / Cfg::R, a.B), block(Cfg::NT);
-    auto k = rev ? scan5_fwd_kernel<W, true> : scan5_fwd_kernel<W, false>;
+    auto k = rev ? scan5_fwd_kernel<WR, true> : scan5_fwd_kernel<WR, false>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
     k<<<grid, block, Cfg::smem_bytes, st>>>(a);
     count_launch();
     return check_launch("selective_scan_fwd(v5)");
-}
-
-template <int WR> int launch_fwd5s(const Fwd3Args &a, bool rev, cudaStream_t st) {
-    using Cfg = Fwd5sCfg<WR>;
-    dim3 grid((a.D + Cfg::R - 1) / Cfg::R, a.B), block(Cfg::NT);
-    auto k = rev ? scan5s_fwd_kernel<WR, true> : scan5s_fwd_kernel<WR, false>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
-    k<<<grid, block, Cfg::smem_bytes, st>>>(a);
-    count_launch();
-    return check_launch("selective_scan_fwd(v5s)");
 }
 
 int run_fwd5(const mmu_scan_fwd_params *p, cudaStream_t st) {
@@ -670,18 +669,10 @@ int run_fwd5(const mmu_scan_fwd_params *p, cudaStream_t st) {
     a.z_bs = p->z_bs, a.z_ds = p->z_ds, a.o_bs = p->out_bs, a.o_ds = p->out_ds, a.y_bs = p->y_bs, a.y_ds = p->y_ds;
     a.B_bs = p->B_bs, a.B_ns = p->B_ns, a.C_bs = p->C_bs, a.C_ns = p->C_ns;
     a.B = p->batch, a.D = p->dim, a.L = p->seqlen, a.N = p->dstate;
-    const int xs = p->x_stride ? p->x_stride : MMU_STATE_STRIDE;
-    a.nseg = 1, a.cps = xs / 8, a.nchunks = (p->seqlen + 127) / 128;      // cps: saved-state stride in 8-token blocks
-    a.nx = (p->seqlen + xs - 1) / xs;
+    a.nseg = 1, a.cps = 0, a.nchunks = (p->seqlen + 127) / 128;
+    a.nx = (p->seqlen + MMU_STATE_STRIDE - 1) / MMU_STATE_STRIDE;
     a.softplus = p->delta_softplus;
     const bool rev = p->reverse != 0;
-    if (xs == 64 && env_int("MMU_V5_SPEC", 1) != 0) {     // warp-specialised form: ring warps + helper warps
-        switch (plan_fwd5(p->batch, p->dim)) {
-            case 6: return launch_fwd5s<6>(a, rev, st);
-            case 4: return launch_fwd5s<4>(a, rev, st);
-            default: return launch_fwd5s<2>(a, rev, st);
-        }
-    }
     switch (plan_fwd5(p->batch, p->dim)) {
         case 6: return launch_fwd5<6>(a, rev, st);
         case 4: return launch_fwd5<4>(a, rev, st);

@@ -84,10 +84,4 @@ for (B, D, L, dt) in shapes:
     if mode in ("bwd", "all"):
         line += " grads rel " + " ".join(f"{float((a - b).abs().max() / (b.abs().max() + 1e-30)):.1e}" for a, b in zip(ref[("b", 1)], ref[("b", 0)]))
     print(line, flush=True)
-    if mode != "bwd":
-        setv(1, MMU_V5_SPEC=0)
-        out, xs, _ = ops.selective_scan_fwd(u, delta, A, Bm, Cm, Dp, z, bias, True)
-        tf = timeit(lambda: ops.selective_scan_fwd(u, delta, A, Bm, Cm, Dp, z, bias, True), warm=3, it=20)
-        print(f"    unspecialised ring: fwd {tf:.0f} us  | out vs v3 abs {float((out.float() - ref[0]).abs().max()):.2e}", flush=True)
-        setv(1, MMU_V5_SPEC=1)
 

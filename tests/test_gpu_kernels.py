@@ -294,9 +294,10 @@ V5_SHAPES = [(2, 64, 256, 16), (1, 128, 1024, 16), (2, 130, 392, 16), (1, 96, 52
 @pytest.mark.parametrize("w", ["2", "4", "6"])
 @pytest.mark.parametrize("shape", V5_SHAPES)
 def test_scan_v5_lane_ring_forward(w, shape, monkeypatch):
-    """The lane-ring forward (csrc/scan5_fwd.cuh, opt-in MMU_RING=1: measured slower than v3, profiles/r2_v5_lane_ring.md) against
-    the C oracle - outputs, last state, and (through the v3 backward, which reads the states it saved) every gradient; ragged
-    lengths, d_state < 16, row counts that are not a multiple of the CTA's rows, both directions, all CTA widths."""
+    """The lane-ring forward (csrc/scan5_fwd.cuh: ring warps + helper warps; the default for wide fp32 problems) against the C
+    oracle - outputs, last state, and (through the v3 backward, which reads the states it saved) every gradient; ragged lengths,
+    d_state < 16, row counts that are not a multiple of the CTA's rows, both directions, all CTA widths.  MMU_V5_MIN_WARPS=1
+    forces it onto problems far below its selection threshold."""
     monkeypatch.setenv("MMU_RING", "1")
     monkeypatch.setenv("MMU_V5_MIN_WARPS", "1")
     monkeypatch.setenv("MMU_V5_W", w)
@@ -315,7 +316,8 @@ def test_scan_v5_optional_inputs_and_strided_rows(flags, monkeypatch):
 
 
 def test_scan_v5_matches_v3_at_config2(monkeypatch):
-    """BASELINE config 2 through both forward kernels: same outputs and saved states (fp32 rounding apart)."""
+    """BASELINE config 2 through both forward kernels (MMU_RING=0: v3 everywhere): same outputs and saved states, fp32 rounding
+    apart - the ring's y is a difference of running accumulator snapshots, hence the absolute part of the tolerance."""
     cpu, gpu = make_scan_inputs(8, 384, 4096, 16)
     args = tuple(gpu[k] for k in ("u", "delta", "A", "B", "C", "D", "z", "delta_bias"))
     res = {}
