@@ -41,23 +41,28 @@
 
 namespace mmu {
 
-template <int WR> struct Fwd5Cfg {
+template <typename IN_T, int WR> struct Fwd5Cfg {
     static constexpr int T = kS3T, LPR = 16, CH = LPR * T, NRT = 32 * WR, NT = 2 * NRT, NRP = 2 * WR, R = 4 * WR;
+    static constexpr bool kF32 = sizeof(IN_T) == 4;
+    static constexpr int NQ = Raw8<IN_T>::kQuads;
     using Tl = BcTile<LPR>;
     static constexpr int kTiles = 3;
     static constexpr int kTileBytes = kTiles * Tl::kBytes;
-    static constexpr int kLandBytes = 3 * 2 * 2 * NRT * 16;    // u | delta | z : [tensor][row][quad][ring thread] x 16 B
+    static constexpr int kRawBytes = kF32 ? 0 : 2 * (2 * 16 * CH * 2);     // 2-byte B/C rows as they sit in memory, double buffered
+    static constexpr int kLandBytes = 3 * 2 * NQ * NRT * 16;   // u | delta | z : [tensor][row][quad][ring thread] x 16 B
     static constexpr int kStageBytes = 2 * 8 * NRT * 16;       // [parity][delta x4 | delta*u x4][ring thread]
     static constexpr int kDuBytes = 3 * 4 * NRT * 16;          // D*u of chunks k-2 .. k+1 (helper private): [chunk % 3][quad][ring thread]
     static constexpr int kYBytes = 2 * 4 * NRT * 16;           // y accumulator snapshots: [parity][quad][ring thread]
     static constexpr int kXBytes = 3 * 16 * NRP * 2 * 8;       // [chunk % 3][state][ring][block 7 | block 15] float2
     static constexpr int kABytes = NRP * 16 * 8;
-    static constexpr size_t smem_bytes = (size_t)kTileBytes + kLandBytes + kStageBytes + kDuBytes + kYBytes + kXBytes + kABytes;
+    static constexpr size_t smem_bytes = (size_t)kTileBytes + kRawBytes + kLandBytes + kStageBytes + kDuBytes + kYBytes + kXBytes + kABytes;
 };
 
-template <int WR, bool REV>
+template <typename IN_T, int WR, bool REV>
 __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_constant__ Fwd3Args p) {
-    using Cfg = Fwd5Cfg<WR>;
+    using Cfg = Fwd5Cfg<IN_T, WR>;
+    constexpr bool kF32 = Cfg::kF32;
+    constexpr int NQ = Cfg::NQ, EPQ = 16 / (int)sizeof(IN_T);
     using Tl = typename Cfg::Tl;
     constexpr int T = Cfg::T, LPR = Cfg::LPR, CH = Cfg::CH, NRT = Cfg::NRT, NRP = Cfg::NRP, R = Cfg::R;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -73,7 +78,8 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_cons
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *s_tile = smem_raw;
-    unsigned char *s_land = s_tile + Cfg::kTileBytes;
+    unsigned char *s_rawbc = s_tile + Cfg::kTileBytes;      // 2-byte inputs only
+    unsigned char *s_land = s_rawbc + Cfg::kRawBytes;
     float4 *s_stage = reinterpret_cast<float4 *>(s_land + Cfg::kLandBytes);                                  // [2][8][NRT]
     float4 *s_du = reinterpret_cast<float4 *>(s_land + Cfg::kLandBytes + Cfg::kStageBytes);                  // [3][4][NRT]
     float4 *s_yout = s_du + 3 * 4 * NRT;                                                                     // [2][4][NRT]
@@ -100,23 +106,23 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_cons
         const bool rok[2] = {rowA < D, rowA + 1 < D};
         constexpr int STEP = REV ? -CH : CH;
         const int mo0 = REV ? L - T - T * j : T * j;        // memory index of the lane's 8 tokens in chunk 0
-        const float *u_p[2], *d_p[2], *z_p[2];              // stand on the chunk whose copy is issued next
-        float *o_p[2], *y_p[2];                             // stand on the chunk stored next
+        const IN_T *u_p[2], *d_p[2], *z_p[2];               // stand on the chunk whose copy is issued next
+        IN_T *o_p[2], *y_p[2];                              // stand on the chunk stored next
         float bias[2], Dsk[2];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int row = min(rowA + r, D - 1);
-            u_p[r] = reinterpret_cast<const float *>(p.u) + (int64_t)b * p.u_bs + (int64_t)row * p.u_ds + mo0;
-            d_p[r] = reinterpret_cast<const float *>(p.delta) + (int64_t)b * p.dl_bs + (int64_t)row * p.dl_ds + mo0;
-            z_p[r] = has_z ? reinterpret_cast<const float *>(p.z) + (int64_t)b * p.z_bs + (int64_t)row * p.z_ds + mo0 : nullptr;
-            o_p[r] = reinterpret_cast<float *>(p.out) + (int64_t)b * p.o_bs + (int64_t)row * p.o_ds + mo0;
-            y_p[r] = p.ysave == nullptr ? nullptr : reinterpret_cast<float *>(p.ysave) + (int64_t)b * p.y_bs + (int64_t)row * p.y_ds + mo0;
+            u_p[r] = reinterpret_cast<const IN_T *>(p.u) + (int64_t)b * p.u_bs + (int64_t)row * p.u_ds + mo0;
+            d_p[r] = reinterpret_cast<const IN_T *>(p.delta) + (int64_t)b * p.dl_bs + (int64_t)row * p.dl_ds + mo0;
+            z_p[r] = has_z ? reinterpret_cast<const IN_T *>(p.z) + (int64_t)b * p.z_bs + (int64_t)row * p.z_ds + mo0 : nullptr;
+            o_p[r] = reinterpret_cast<IN_T *>(p.out) + (int64_t)b * p.o_bs + (int64_t)row * p.o_ds + mo0;
+            y_p[r] = p.ysave == nullptr ? nullptr : reinterpret_cast<IN_T *>(p.ysave) + (int64_t)b * p.y_bs + (int64_t)row * p.y_ds + mo0;
             bias[r] = p.dbias != nullptr ? p.dbias[row] : 0.f;
             Dsk[r] = p.Dv != nullptr ? p.Dv[row] : 0.f;
         }
-        const float *B_b = reinterpret_cast<const float *>(p.Bm) + (int64_t)b * p.B_bs;
-        const float *C_b = reinterpret_cast<const float *>(p.Cm) + (int64_t)b * p.C_bs;
-        const unsigned s_tile_u32 = smem_u32(s_tile);
+        const IN_T *B_b = reinterpret_cast<const IN_T *>(p.Bm) + (int64_t)b * p.B_bs;
+        const IN_T *C_b = reinterpret_cast<const IN_T *>(p.Cm) + (int64_t)b * p.C_bs;
+        const unsigned s_tile_u32 = smem_u32(s_tile), s_raw_u32 = smem_u32(s_rawbc);
         const unsigned s_land_u32 = smem_u32(s_land) + rt * 16;
         const unsigned char *s_land_t = s_land + rt * 16;
         auto issue_ud = [&](int c) {
@@ -124,9 +130,9 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_cons
 #pragma unroll
                 for (int r = 0; r < 2; ++r)
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        cp_async16(s_land_u32 + ((0 * 2 + r) * 2 + q) * NRT * 16, u_p[r] + q * 4);
-                        cp_async16(s_land_u32 + ((1 * 2 + r) * 2 + q) * NRT * 16, d_p[r] + q * 4);
+                    for (int q = 0; q < NQ; ++q) {
+                        cp_async16(s_land_u32 + ((0 * 2 + r) * NQ + q) * NRT * 16, u_p[r] + q * EPQ);
+                        cp_async16(s_land_u32 + ((1 * 2 + r) * NQ + q) * NRT * 16, d_p[r] + q * EPQ);
                     }
             }
 #pragma unroll
@@ -138,25 +144,47 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_cons
 #pragma unroll
                 for (int r = 0; r < 2; ++r)
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) cp_async16(s_land_u32 + ((2 * 2 + r) * 2 + q) * NRT * 16, z_p[r] + q * 4);
+                    for (int q = 0; q < NQ; ++q) cp_async16(s_land_u32 + ((2 * 2 + r) * NQ + q) * NRT * 16, z_p[r] + q * EPQ);
             }
 #pragma unroll
             for (int r = 0; r < 2; ++r) z_p[r] += STEP;
         };
         auto load_land = [&](int which, int r, float (&v)[T]) {
-            uint4 q[2];
+            uint4 q[NQ];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) q[k] = *reinterpret_cast<const uint4 *>(s_land_t + ((which * 2 + r) * 2 + k) * NRT * 16);
+            for (int k = 0; k < NQ; ++k) q[k] = *reinterpret_cast<const uint4 *>(s_land_t + ((which * 2 + r) * NQ + k) * NRT * 16);
             float e[8];
-            Raw8<float>::unpack(q, e);
+            Raw8<IN_T>::unpack(q, e);
             order8<REV>(e, v);
         };
         float4 ysnap[4];                                    // the lane's y accumulators when it left the previous chunk
 #pragma unroll
         for (int q = 0; q < 4; ++q) ysnap[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // B/C tile of chunk c.  fp32: cp.async straight into tile c % 3.  2-byte inputs: the raw rows go to raw[c & 1] and are widened
+        // into tile c % 3 by the helpers ONE ROUND LATER (widen_tile), so a tile is requested two rounds before its first use.
+        auto issue_tile = [&](int c) {
+            if constexpr (kF32) {
+                tile_async_f32<LPR, NRT, REV, true>(s_tile_u32 + (unsigned)(c % Cfg::kTiles) * Tl::kBytes, reinterpret_cast<const float *>(B_b),
+                                                    reinterpret_cast<const float *>(C_b), p.B_ns, p.C_ns, N, c * CH, L, htid);
+            } else {
+                raw_async_bf16<LPR, NRT, REV, true>(s_raw_u32 + (unsigned)(c & 1) * (Cfg::kRawBytes / 2), reinterpret_cast<const __nv_bfloat16 *>(B_b),
+                                                    reinterpret_cast<const __nv_bfloat16 *>(C_b), p.B_ns, p.C_ns, N, c * CH, L, htid);
+            }
+        };
+        auto widen_tile = [&](int c) {
+            if constexpr (!kF32) widen_bf16_tile<LPR, NRT, true>(s_tile + (c % Cfg::kTiles) * Tl::kBytes, s_rawbc + (c & 1) * (Cfg::kRawBytes / 2), htid);
+        };
         issue_ud(0);
-        tile_async_f32<LPR, NRT, REV, true>(s_tile_u32, B_b, C_b, p.B_ns, p.C_ns, N, 0, L, htid);
+        issue_tile(0);
         cp_async_commit();
+        if constexpr (!kF32) {      // the raw tile of chunk 0 has to be widened before round 0: one extra start-up round trip
+            cp_async_wait_all();
+            // (helpers only: named barrier 1)
+            asm volatile("bar.sync 1, %0;" ::"r"(NRT) : "memory");
+            widen_tile(0);
+            if (NC > 1) issue_tile(1);
+            cp_async_commit();
+        }
 
         for (int k = -1; k <= NC + 1; ++k) {
             cp_async_wait_all();
@@ -177,14 +205,14 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_cons
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {
                         if (!rok[r]) continue;
-                        if (y_p[r] != nullptr) store8<float, REV>(y_p[r], ya[r]);
+                        if (y_p[r] != nullptr) store8<IN_T, REV>(y_p[r], ya[r]);
                         if (has_z) {
                             float zz[T];
                             load_land(2, r, zz);
 #pragma unroll
                             for (int i = 0; i < T; ++i) ya[r][i] *= zz[i] * sigmoid3(zz[i]);
                         }
-                        store8<float, REV>(o_p[r], ya[r]);
+                        store8<IN_T, REV>(o_p[r], ya[r]);
                     }
                 }
 #pragma unroll
@@ -255,8 +283,12 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_cons
             }
             if (k + 2 < NC) issue_ud(k + 2);
             if (k - 1 >= 0 && k - 1 < NC) issue_z(k - 1);
-            if (k + 1 >= 1 && k + 1 < NC)
-                tile_async_f32<LPR, NRT, REV, true>(s_tile_u32 + (unsigned)((k + 1) % Cfg::kTiles) * Tl::kBytes, B_b, C_b, p.B_ns, p.C_ns, N, (k + 1) * CH, L, htid);
+            if constexpr (kF32) {
+                if (k + 1 >= 1 && k + 1 < NC) issue_tile(k + 1);
+            } else {                // raw[(k+1)&1] landed before this round's barrier; raw[k&1] was widened last round
+                if (k + 1 >= 1 && k + 1 < NC) widen_tile(k + 1);
+                if (k + 2 >= 2 && k + 2 < NC) issue_tile(k + 2);
+            }
             cp_async_commit();
         }
         return;

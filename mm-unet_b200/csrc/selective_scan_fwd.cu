@@ -618,7 +618,7 @@ template <typename IN_T> int run_fwd4(const mmu_scan_fwd_params *p, cudaStream_t
 }
 
 
-// ---- v5 host side (scan5_fwd.cuh): wide fp32 problems, lane rings ----------------------------------------------------------------
+// ---- v5 host side (scan5_fwd.cuh): wide problems (fp32 / bf16), lane rings ----------------------------------------------------------------
 // Ring warps per CTA.  A CTA's time is fixed by the sequence length and its width (measured per 128-token round: ~3.2 us with 4 ring
 // warps, ~4.4 us with 6, ~6.2 us with 2 warps at two CTAs per SM), so the plan minimises waves x time per round; the B/C tiles are per
 // batch element, so a CTA never spans two.
@@ -635,8 +635,8 @@ int plan_fwd5(int B, int D) {
     return best;
 }
 
-bool fwd5_eligible(const mmu_scan_fwd_params *p) {
-    if (env_int("MMU_RING", 1) == 0 || p->dtype != MMU_F32) return false;
+template <typename IN_T> bool fwd5_eligible(const mmu_scan_fwd_params *p) {
+    if (env_int("MMU_RING", 1) == 0) return false;
     if (p->order != MMU_ORDER_ROWMAJOR) return false;
     const int xs = p->x_stride ? p->x_stride : MMU_STATE_STRIDE;
     if (xs != 64) return false;
@@ -646,20 +646,20 @@ bool fwd5_eligible(const mmu_scan_fwd_params *p) {
     // fill / drain rounds
     if (p->seqlen < 512) return false;
     if ((int64_t)p->batch * ((p->dim + 3) / 4) < env_int("MMU_V5_MIN_WARPS", 320)) return false;
-    return fwd3_eligible<float>(p);
+    return fwd3_eligible<IN_T>(p);
 }
 
-template <int WR> int launch_fwd5(const Fwd3Args &a, bool rev, cudaStream_t st) {
-    using Cfg = Fwd5Cfg<WR>;
+template <typename IN_T, int WR> int launch_fwd5(const Fwd3Args &a, bool rev, cudaStream_t st) {
+    using Cfg = Fwd5Cfg<IN_T, WR>;
     dim3 grid((a.D + Cfg::R - 1) / Cfg::R, a.B), block(Cfg::NT);
-    auto k = rev ? scan5_fwd_kernel<WR, true> : scan5_fwd_kernel<WR, false>;
+    auto k = rev ? scan5_fwd_kernel<IN_T, WR, true> : scan5_fwd_kernel<IN_T, WR, false>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
     k<<<grid, block, Cfg::smem_bytes, st>>>(a);
     count_launch();
     return check_launch("selective_scan_fwd(v5)");
 }
 
-int run_fwd5(const mmu_scan_fwd_params *p, cudaStream_t st) {
+template <typename IN_T> int run_fwd5(const mmu_scan_fwd_params *p, cudaStream_t st) {
     Fwd3Args a{};
     make_ordmap(a.ord, MMU_ORDER_ROWMAJOR, 0, 0, 0, p->seqlen);
     a.u = p->u, a.delta = p->delta, a.z = p->z, a.Bm = p->B, a.Cm = p->C;
@@ -674,9 +674,9 @@ int run_fwd5(const mmu_scan_fwd_params *p, cudaStream_t st) {
     a.softplus = p->delta_softplus;
     const bool rev = p->reverse != 0;
     switch (plan_fwd5(p->batch, p->dim)) {
-        case 6: return launch_fwd5<6>(a, rev, st);
-        case 4: return launch_fwd5<4>(a, rev, st);
-        default: return launch_fwd5<2>(a, rev, st);
+        case 6: return launch_fwd5<IN_T, 6>(a, rev, st);
+        case 4: return launch_fwd5<IN_T, 4>(a, rev, st);
+        default: return launch_fwd5<IN_T, 2>(a, rev, st);
     }
 }
 
@@ -694,8 +694,8 @@ template <typename IN_T> int run_fwd(const mmu_scan_fwd_params *p, cudaStream_t 
                              "(see mmu_scan_order_fusable); permute with mmu_scan_order_gather / _scatter", p->order, p->order_h, p->order_w, p->order_ns);
         if constexpr (HasV3<IN_T>::value) return run_fwd3<IN_T>(p, st);
     }
-    if constexpr (sizeof(IN_T) == 4) {
-        if (fwd5_eligible(p)) return run_fwd5(p, st);
+    if constexpr (HasV3<IN_T>::value) {
+        if (fwd5_eligible<IN_T>(p)) return run_fwd5<IN_T>(p, st);
     }
     if constexpr (HasV3<IN_T>::value) {
         if (fwd4_eligible<IN_T>(p)) return run_fwd4<IN_T>(p, st);
