@@ -637,6 +637,9 @@ int plan_fwd5(int B, int D) {
 
 template <typename IN_T> bool fwd5_eligible(const mmu_scan_fwd_params *p) {
     if (env_int("MMU_RING", 1) == 0) return false;
+    // 2-byte I/O: the ring is latency bound and gains nothing from the halved bytes, v3 does (B16 D128 L65536 bf16: 1 809 -> 1 689 us,
+    // config 2 bf16 no change), and its one 200 KB CTA per SM keeps the other directions' kernels of a v3 Mamba off the SM: opt-in
+    if (sizeof(IN_T) != 4 && env_int("MMU_RING_BF16", 0) == 0) return false;
     if (p->order != MMU_ORDER_ROWMAJOR) return false;
     const int xs = p->x_stride ? p->x_stride : MMU_STATE_STRIDE;
     if (xs != 64) return false;

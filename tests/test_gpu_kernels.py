@@ -315,6 +315,21 @@ def test_scan_v5_optional_inputs_and_strided_rows(flags, monkeypatch):
     run_scan_case(3, 64, 512, 16, xz_layout=True, **flags)
 
 
+@pytest.mark.parametrize("w", ["2", "4", "6"])
+@pytest.mark.parametrize("reverse", [False, True])
+def test_scan_v5_bf16(w, reverse, monkeypatch):
+    """bf16 I/O through the ring (opt-in, MMU_RING_BF16=1: v3 is as fast for 2-byte I/O): the helpers widen the raw B/C rows into the
+    fp32 tile one round after they landed."""
+    monkeypatch.setenv("MMU_RING", "1")
+    monkeypatch.setenv("MMU_RING_BF16", "1")
+    monkeypatch.setenv("MMU_V5_MIN_WARPS", "1")
+    monkeypatch.setenv("MMU_V5_W", w)
+    run_scan_case(2, 128, 1024, 16, dtype=torch.bfloat16, reverse=reverse)
+    run_scan_case(1, 66, 776, 16, dtype=torch.bfloat16, reverse=reverse)
+    run_scan_case(3, 64, 512, 16, dtype=torch.bfloat16, reverse=reverse, xz_layout=True)
+    run_scan_case(2, 40, 136, 7, dtype=torch.bfloat16, reverse=reverse)
+
+
 def test_scan_v5_matches_v3_at_config2(monkeypatch):
     """BASELINE config 2 through both forward kernels (MMU_RING=0: v3 everywhere): same outputs and saved states, fp32 rounding
     apart - the ring's y is a difference of running accumulator snapshots, hence the absolute part of the tolerance."""
