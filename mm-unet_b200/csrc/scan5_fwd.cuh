@@ -39,6 +39,10 @@
 #include "scan3.cuh"
 #include "scan3_fwd.cuh"
 
+#ifndef MMU_S5_WHATIF
+#define MMU_S5_WHATIF 0      // timing probe only (wrong results): half of the exponentials skipped
+#endif
+
 namespace mmu {
 
 template <typename IN_T, int WR> struct Fwd5Cfg {
@@ -337,7 +341,7 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_cons
                 order8<REV>(ec, cn);                                                                                                   \
             }                                                                                                                          \
             _Pragma("unroll") for (int i = 0; i < T; ++i) {                                                                            \
-                an[i] = ex2(fmul2(dl[i], A2));                                                                                         \
+                an[i] = (MMU_S5_WHATIF && (i & 1)) ? fmul2(dl[i], A2) : ex2(fmul2(dl[i], A2));                                         \
                 bn[i] = fmul2(dlu[i], splat(Bn[i]));                                                                                   \
                 if (WITH_CHAIN) {                                                                                                      \
                     h = ffma2(ac[i], h, bc[i]);                                                                                        \
