@@ -12,8 +12,8 @@
 //     (row, token, state), ~50 issue slots per (lane, state) for the recurrence itself.
 // The price: the lanes of a ring sit in two different chunks at any time (lane j enters chunk k at step 16k + j), so the
 // per-(row, token) quantities cannot simply be reloaded by the whole warp at a chunk boundary.  A lane picks its new delta /
-// delta*u up from a shared-memory stage at ITS transition step (predicated loads), and leaves a snapshot of its y accumulators
-// there.  Work per warp is fixed by the problem (rows / 4 ring warps, each walking the whole sequence), so this kernel is for
+// delta*u up from a shared-memory stage at ITS transition step (predicated loads), and swaps its y accumulators with the D*u
+// of the new chunk there.  Work per warp is fixed by the problem (rows / 4 ring warps, each walking the whole sequence), so this kernel is for
 // wide problems; narrow ones stay on v3, which can cut the sequence into segments.
 //
 // Warp specialisation.  A first version (git history: b08aac9) let every warp do its own element-wise work in a uniform "bulk"
@@ -21,13 +21,11 @@
 // instructions per clock and scheduler, but the bulk phase taking 40 % of the round and the schedulers of an SM carrying 2, 2, 1, 1
 // ring warps.  Here a ring warp does NOTHING but steps; a HELPER warp per ring warp does every element-wise phase for it one round
 // ahead / two rounds behind, through double-buffered lane slots (twice the warps per SM for the same work):
-//   helper, round k:  gate + store of chunk k-2 from the y snapshots yout[(k-2)&1] (y of a chunk = difference of consecutive
-//                     snapshots + D*u: the ring lanes never reset their accumulators - a reload would cost 4 loads + 16 predicated
-//                     moves per step);  saved states of chunk k-2 from xbuf[(k-2)%3];  softplus / delta*u / D*u of chunk k+1 ->
-//                     stage[(k+1)&1], du[(k+1)%3];  cp.async of u, delta (chunk k+2), z (chunk k-1) into its landing slots and of
-//                     its share of the B/C tile k+1 (3-deep ring of tiles);
-//   ring, round k:    16 steps on stage[k&1]; y snapshot -> yout[(k-1)&1] at the lane's transition; the states leaving blocks 7
-//                     and 15 of a chunk (stride-64 saved states) -> xbuf[chunk%3].
+//   helper, round k:  gate + store of chunk k-2 from yout[(k-2)&1];  saved states of chunk k-2 from xbuf[(k-2)%3];  softplus /
+//                     delta*u / D*u of chunk k+1 -> stage[(k+1)&1], du[(k+1)&1];  cp.async of u, delta (chunk k+2), z (chunk k-1)
+//                     into its landing slots and of its share of the B/C tile k+1 (3-deep ring of tiles);
+//   ring, round k:    16 steps on stage[k&1]; at the lane's transition the finished y -> yout[(k-1)&1] and D*u of the new chunk
+//                     <- du[k&1]; the states leaving blocks 7 and 15 of a chunk (stride-64 saved states) -> xbuf[chunk%3].
 // One __syncthreads per round orders everything.  The two rings of a warp are interleaved over the lanes (lane = 2 j + ring): the
 // two lanes in transition at a step then sit in the same quarter-warp and their predicated 16-byte accesses are one wavefront.
 // The step loop is a runtime loop over step PAIRS (operand double buffer): fully unrolled, ptxas split the live ranges of delta,
@@ -55,8 +53,8 @@ template <typename IN_T, int WR> struct Fwd5Cfg {
     static constexpr int kRawBytes = kF32 ? 0 : 2 * (2 * 16 * CH * 2);     // 2-byte B/C rows as they sit in memory, double buffered
     static constexpr int kLandBytes = 3 * 2 * NQ * NRT * 16;   // u | delta | z : [tensor][row][quad][ring thread] x 16 B
     static constexpr int kStageBytes = 2 * 8 * NRT * 16;       // [parity][delta x4 | delta*u x4][ring thread]
-    static constexpr int kDuBytes = 3 * 4 * NRT * 16;          // D*u of chunks k-2 .. k+1 (helper private): [chunk % 3][quad][ring thread]
-    static constexpr int kYBytes = 2 * 4 * NRT * 16;           // y accumulator snapshots: [parity][quad][ring thread]
+    static constexpr int kDuBytes = 2 * 4 * NRT * 16;          // D*u of the chunk a lane is about to enter: [parity][quad][ring thread]
+    static constexpr int kYBytes = 2 * 4 * NRT * 16;           // finished y of the chunk a lane left: [parity][quad][ring thread]
     static constexpr int kXBytes = 3 * 16 * NRP * 2 * 8;       // [chunk % 3][state][ring][block 7 | block 15] float2
     static constexpr int kABytes = NRP * 16 * 8;
     static constexpr size_t smem_bytes = (size_t)kTileBytes + kRawBytes + kLandBytes + kStageBytes + kDuBytes + kYBytes + kXBytes + kABytes;
@@ -85,8 +83,8 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_cons
     unsigned char *s_rawbc = s_tile + Cfg::kTileBytes;      // 2-byte inputs only
     unsigned char *s_land = s_rawbc + Cfg::kRawBytes;
     float4 *s_stage = reinterpret_cast<float4 *>(s_land + Cfg::kLandBytes);                                  // [2][8][NRT]
-    float4 *s_du = reinterpret_cast<float4 *>(s_land + Cfg::kLandBytes + Cfg::kStageBytes);                  // [3][4][NRT]
-    float4 *s_yout = s_du + 3 * 4 * NRT;                                                                     // [2][4][NRT]
+    float4 *s_du = reinterpret_cast<float4 *>(s_land + Cfg::kLandBytes + Cfg::kStageBytes);                  // [2][4][NRT]
+    float4 *s_yout = s_du + 2 * 4 * NRT;                                                                     // [2][4][NRT]
     float2 *s_x = reinterpret_cast<float2 *>(s_yout + 2 * 4 * NRT);                                          // [3][16][NRP][2]
     float2 *s_A = s_x + 3 * 16 * NRP * 2;                                                                    // [NRP][16]
 
@@ -161,9 +159,6 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_cons
             Raw8<IN_T>::unpack(q, e);
             order8<REV>(e, v);
         };
-        float4 ysnap[4];                                    // the lane's y accumulators when it left the previous chunk
-#pragma unroll
-        for (int q = 0; q < 4; ++q) ysnap[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         // B/C tile of chunk c.  fp32: cp.async straight into tile c % 3.  2-byte inputs: the raw rows go to raw[c & 1] and are widened
         // into tile c % 3 by the helpers ONE ROUND LATER (widen_tile), so a tile is requested two rounds before its first use.
         auto issue_tile = [&](int c) {
@@ -193,17 +188,16 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_cons
         for (int k = -1; k <= NC + 1; ++k) {
             cp_async_wait_all();
             __syncthreads();
-            // ---- gate + store of chunk k-2 (before the prologue below overwrites its D*u slot: (k+1) % 3 == (k-2) % 3) ---------------------
+            // ---- gate + store of chunk k-2 ------------------------------------------------------------------------------------------------
             const int ce = k - 2;
             if (ce >= 0) {
                 const bool ok = ce * CH + T * j < L;
-                const float4 *yo = s_yout + (ce & 1) * 4 * NRT + rt, *du = s_du + (ce % 3) * 4 * NRT + rt;
+                const float4 *yo = s_yout + (ce & 1) * 4 * NRT + rt;
                 float ya[2][T];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {      // the ring lanes never reset their accumulators: y of the chunk = difference of snapshots
-                    const float4 v = yo[q * NRT], w = du[q * NRT], o = ysnap[q];
-                    ya[0][2 * q] = v.x - o.x + w.x, ya[1][2 * q] = v.y - o.y + w.y, ya[0][2 * q + 1] = v.z - o.z + w.z, ya[1][2 * q + 1] = v.w - o.w + w.w;
-                    ysnap[q] = v;
+                for (int q = 0; q < 4; ++q) {
+                    const float4 v = yo[q * NRT];
+                    ya[0][2 * q] = v.x, ya[1][2 * q] = v.y, ya[0][2 * q + 1] = v.z, ya[1][2 * q + 1] = v.w;
                 }
                 if (ok) {
 #pragma unroll
@@ -258,7 +252,7 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_cons
             // ---- softplus(delta + bias), delta*u, D*u of chunk k+1 -------------------------------------------------------------------
             const int cp = k + 1;
             if (cp <= NC) {
-                float4 *st = s_stage + (cp & 1) * 8 * NRT + rt, *yi = s_du + (cp % 3) * 4 * NRT + rt;
+                float4 *st = s_stage + (cp & 1) * 8 * NRT + rt, *yi = s_du + (cp & 1) * 4 * NRT + rt;
                 if (cp < NC) {
                     const bool ok = cp * CH + T * j < L;
                     float uu[2][T], dd[2][T];
@@ -283,6 +277,8 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_cons
                 } else {                // the drain round reads an all-zero stage (delta = 0: a = 1, b = 0)
 #pragma unroll
                     for (int q = 0; q < 8; ++q) st[q * NRT] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) yi[q * NRT] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
             if (k + 2 < NC) issue_ud(k + 2);
@@ -315,7 +311,7 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_cons
         if (k < 0 || k > NC) continue;
         const unsigned char *tb_cur = s_tile + (k % Cfg::kTiles) * Tl::kBytes + Tl::quad_off(qa);
         const unsigned char *tb_prev = s_tile + ((k + Cfg::kTiles - 1) % Cfg::kTiles) * Tl::kBytes + Tl::quad_off(qa);
-        const float4 *st = s_stage + (k & 1) * 8 * NRT + tid;
+        const float4 *st = s_stage + (k & 1) * 8 * NRT + tid, *yi = s_du + (k & 1) * 4 * NRT + tid;
         float4 *yo = s_yout + ((k & 1) ^ 1) * 4 * NRT + tid;
         float2 *sx_cur = s_x + ((k % 3) * 16 * NRP + rp) * 2 + (j >> 3), *sx_prev = s_x + (((k + 2) % 3) * 16 * NRP + rp) * 2 + (j >> 3);
 
@@ -357,10 +353,15 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_cons
         // predicated moves per step), and the round fits the instruction cache.
 #define MMU_S5_STEP(s_, cur, nxt, PREP)                                                                                                \
         {                                                                                                                              \
-            if ((s_) == j) {   /* first step of my chunk k: snapshot of the y accumulators (they are never reset: the helper takes */   \
-                               /* differences of consecutive snapshots - a reload would cost 4 loads + 16 predicated moves per step) */ \
-                _Pragma("unroll") for (int q = 0; q < 4; ++q)                                                                          \
+            if ((s_) == j) {   /* first step of my chunk k: the finished y of chunk k-1 goes out, D*u of chunk k comes in.  (Leaving  */  \
+                               /* the accumulators running and letting the helper take differences of snapshots saves the reload:  */  \
+                               /* 115 instead of 117 us at B16 D128 L4096, nothing at config 2 - not worth an error term that      */  \
+                               /* grows with the number of chunks.)                                                                */  \
+                _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                                                        \
                     yo[q * NRT] = make_float4(ya[2 * q].x, ya[2 * q].y, ya[2 * q + 1].x, ya[2 * q + 1].y);                             \
+                    const float4 v = yi[q * NRT];                                                                                      \
+                    ya[2 * q] = make_float2(v.x, v.y), ya[2 * q + 1] = make_float2(v.z, v.w);                                          \
+                }                                                                                                                      \
             }                                                                                                                          \
             h = make_float2(__shfl_sync(0xffffffffu, hout.x, src_lane), __shfl_sync(0xffffffffu, hout.y, src_lane));                   \
             if (PREP) {                                                                                                                \
