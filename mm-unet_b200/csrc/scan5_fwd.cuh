@@ -60,8 +60,11 @@ template <typename IN_T, int WR> struct Fwd5Cfg {
     static constexpr size_t smem_bytes = (size_t)kTileBytes + kRawBytes + kLandBytes + kStageBytes + kDuBytes + kYBytes + kXBytes + kABytes;
 };
 
-template <typename IN_T, int WR, bool REV>
+// ORD: fused scan order (as scan3_fwd_kernel; the host selects it for TWOROW only) - the helpers gather the gate z and scatter out through p.ord
+// (ord_issue8 / ord_store8 in scan3.cuh); everything the ring warps touch stays in scan order.  Never together with REV.
+template <typename IN_T, int WR, bool REV, bool ORD = false>
 __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_constant__ Fwd3Args p) {
+    static_assert(!ORD || !REV, "ordered gate / output: forward direction only");
     using Cfg = Fwd5Cfg<IN_T, WR>;
     constexpr bool kF32 = Cfg::kF32;
     constexpr int NQ = Cfg::NQ, EPQ = 16 / (int)sizeof(IN_T);
@@ -116,8 +119,9 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_cons
             const int row = min(rowA + r, D - 1);
             u_p[r] = reinterpret_cast<const IN_T *>(p.u) + (int64_t)b * p.u_bs + (int64_t)row * p.u_ds + mo0;
             d_p[r] = reinterpret_cast<const IN_T *>(p.delta) + (int64_t)b * p.dl_bs + (int64_t)row * p.dl_ds + mo0;
-            z_p[r] = has_z ? reinterpret_cast<const IN_T *>(p.z) + (int64_t)b * p.z_bs + (int64_t)row * p.z_ds + mo0 : nullptr;
-            o_p[r] = reinterpret_cast<IN_T *>(p.out) + (int64_t)b * p.o_bs + (int64_t)row * p.o_ds + mo0;
+            // ORD: row bases (the token offset goes through the index map); else the lane's 8 tokens of chunk 0
+            z_p[r] = has_z ? reinterpret_cast<const IN_T *>(p.z) + (int64_t)b * p.z_bs + (int64_t)row * p.z_ds + (ORD ? 0 : mo0) : nullptr;
+            o_p[r] = reinterpret_cast<IN_T *>(p.out) + (int64_t)b * p.o_bs + (int64_t)row * p.o_ds + (ORD ? 0 : mo0);
             y_p[r] = p.ysave == nullptr ? nullptr : reinterpret_cast<IN_T *>(p.ysave) + (int64_t)b * p.y_bs + (int64_t)row * p.y_ds + mo0;
             bias[r] = p.dbias != nullptr ? p.dbias[row] : 0.f;
             Dsk[r] = p.Dv != nullptr ? p.Dv[row] : 0.f;
@@ -142,6 +146,14 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_cons
         };
         auto issue_z = [&](int c) {
             if (!has_z) return;
+            if constexpr (ORD) {
+                if (c * CH + T * j < L) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r)
+                        ord_issue8<IN_T>(p.ord, c * CH + T * j, z_p[r], s_land_u32 + ((2 * 2 + r) * NQ) * NRT * 16, s_land_u32 + ((2 * 2 + r) * NQ + NQ - 1) * NRT * 16);
+                }
+                return;
+            }
             if (c * CH + T * j < L) {
 #pragma unroll
                 for (int r = 0; r < 2; ++r)
@@ -206,16 +218,26 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_cons
                         if (y_p[r] != nullptr) store8<IN_T, REV>(y_p[r], ya[r]);
                         if (has_z) {
                             float zz[T];
-                            load_land(2, r, zz);
+                            if constexpr (ORD) {
+                                uint4 q[NQ];
+#pragma unroll
+                                for (int kq = 0; kq < NQ; ++kq) q[kq] = *reinterpret_cast<const uint4 *>(s_land_t + ((2 * 2 + r) * NQ + kq) * NRT * 16);
+                                float e[8];
+                                Raw8<IN_T>::unpack(q, e);
+                                ord_to_tokens(p.ord, ce * CH + T * j, e, zz);
+                            } else {
+                                load_land(2, r, zz);
+                            }
 #pragma unroll
                             for (int i = 0; i < T; ++i) ya[r][i] *= zz[i] * sigmoid3(zz[i]);
                         }
-                        store8<IN_T, REV>(o_p[r], ya[r]);
+                        if constexpr (ORD) ord_store8<IN_T>(p.ord, ce * CH + T * j, o_p[r], ya[r]);
+                        else store8<IN_T, REV>(o_p[r], ya[r]);
                     }
                 }
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
-                    o_p[r] += STEP;
+                    if (!ORD) o_p[r] += STEP;
                     if (y_p[r] != nullptr) y_p[r] += STEP;
                 }
                 // saved states: my float4 of the ring warp's 2 rings x {block 7, block 15} x 2 rows x 16 states

@@ -637,10 +637,14 @@ int plan_fwd5(int B, int D) {
 
 template <typename IN_T> bool fwd5_eligible(const mmu_scan_fwd_params *p) {
     if (env_int("MMU_RING", 1) == 0) return false;
+    // fused scan orders: two-row only (two 16-byte pieces per lane and row).  nslices is eight 4-byte pieces per lane and row in the
+    // helpers' loads and stores and measured 187 us against v3's 179 us at config 2 (plain order: 158 us)
+    if (p->order != MMU_ORDER_ROWMAJOR &&
+        (p->order != MMU_ORDER_TWOROW || p->reverse || !ordmap_fusable(p->order, p->order_h, p->order_w, p->order_ns, p->seqlen)))
+        return false;
     // 2-byte I/O: the ring is latency bound and gains nothing from the halved bytes, v3 does (B16 D128 L65536 bf16: 1 809 -> 1 689 us,
     // config 2 bf16 no change), and its one 200 KB CTA per SM keeps the other directions' kernels of a v3 Mamba off the SM: opt-in
     if (sizeof(IN_T) != 4 && env_int("MMU_RING_BF16", 0) == 0) return false;
-    if (p->order != MMU_ORDER_ROWMAJOR) return false;
     const int xs = p->x_stride ? p->x_stride : MMU_STATE_STRIDE;
     if (xs != 64) return false;
     if (p->x && reinterpret_cast<uintptr_t>(p->x) % 16 != 0) return false;
@@ -655,7 +659,8 @@ template <typename IN_T> bool fwd5_eligible(const mmu_scan_fwd_params *p) {
 template <typename IN_T, int WR> int launch_fwd5(const Fwd3Args &a, bool rev, cudaStream_t st) {
     using Cfg = Fwd5Cfg<IN_T, WR>;
     dim3 grid((a.D + Cfg::R - 1) / Cfg::R, a.B), block(Cfg::NT);
-    auto k = rev ? scan5_fwd_kernel<IN_T, WR, true> : scan5_fwd_kernel<IN_T, WR, false>;
+    auto k = a.ord.kind != MMU_ORDER_ROWMAJOR ? scan5_fwd_kernel<IN_T, WR, false, true>
+                                             : (rev ? scan5_fwd_kernel<IN_T, WR, true> : scan5_fwd_kernel<IN_T, WR, false>);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
     k<<<grid, block, Cfg::smem_bytes, st>>>(a);
     count_launch();
@@ -664,7 +669,7 @@ template <typename IN_T, int WR> int launch_fwd5(const Fwd3Args &a, bool rev, cu
 
 template <typename IN_T> int run_fwd5(const mmu_scan_fwd_params *p, cudaStream_t st) {
     Fwd3Args a{};
-    make_ordmap(a.ord, MMU_ORDER_ROWMAJOR, 0, 0, 0, p->seqlen);
+    make_ordmap(a.ord, p->order, p->order_h, p->order_w, p->order_ns, p->seqlen);
     a.u = p->u, a.delta = p->delta, a.z = p->z, a.Bm = p->B, a.Cm = p->C;
     a.A = p->A, a.Dv = p->D, a.dbias = p->delta_bias;
     a.out = p->out, a.ysave = p->z ? p->y : nullptr, a.x = p->x, a.last_state = p->last_state;
@@ -695,7 +700,10 @@ template <typename IN_T> int run_fwd(const mmu_scan_fwd_params *p, cudaStream_t 
         if (!ok)
             return set_error(MMU_ERR_UNSUPPORTED, "selective_scan_fwd: scan order %d (H=%d W=%d nslices=%d) cannot be fused for this problem "
                              "(see mmu_scan_order_fusable); permute with mmu_scan_order_gather / _scatter", p->order, p->order_h, p->order_w, p->order_ns);
-        if constexpr (HasV3<IN_T>::value) return run_fwd3<IN_T>(p, st);
+        if constexpr (HasV3<IN_T>::value) {
+            if (fwd5_eligible<IN_T>(p)) return run_fwd5<IN_T>(p, st);
+            return run_fwd3<IN_T>(p, st);
+        }
     }
     if constexpr (HasV3<IN_T>::value) {
         if (fwd5_eligible<IN_T>(p)) return run_fwd5<IN_T>(p, st);

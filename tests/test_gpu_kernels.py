@@ -652,6 +652,39 @@ def test_scan_order_golden_and_errors():
 # ---------------------------------------------------------------------------------------------------------------
 # scan order fused into the conv / scan kernels' addressing (requirements/mamba_simple.py:245-263, MMUNet.py:68-121, 178-183)
 # ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("order,B,D", [((3, 32, 64, 1), 1, 128), ((3, 9, 64, 1), 3, 20), ((3, 64, 64, 1), 2, 40)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_scan_v5_fused_scan_order(order, B, D, dtype, monkeypatch):
+    """The ring forward with MMConv's two-row scan order fused (its helper warps gather z and scatter out through idx(l)) against the
+    same kernel on explicitly gathered tensors: identical arithmetic, bit-equal results (an odd tail row included).  nslices stays on
+    v3 (eight 4-byte pieces per lane in the helpers: measured slower)."""
+    monkeypatch.setenv("MMU_RING", "1")
+    monkeypatch.setenv("MMU_RING_BF16", "1")
+    monkeypatch.setenv("MMU_V5_MIN_WARPS", "1")
+    kind, H, W, ns = order
+    L, N = H * W, 16
+    if not ops.order_fusable(order, N, dtype):
+        pytest.skip("not fusable for this dtype")
+    gth = lambda t: ops.scan_order_gather(t, kind, H, W, ns)
+    sct = lambda t: ops.scan_order_scatter(t, kind, H, W, ns)
+    g = torch.Generator().manual_seed(5)
+    u, z = (torch.randn(B, D, L, generator=g).to(DEV, dtype) for _ in range(2))
+    delta = (0.5 * torch.rand(B, D, L, generator=g)).to(DEV, dtype)
+    A = (-0.5 * torch.rand(D, N, generator=g)).to(DEV)
+    Bm, Cm = (torch.randn(B, 1, N, L, generator=g).to(DEV, dtype) for _ in range(2))
+    Dp, bias = torch.randn(D, generator=g).to(DEV), (0.5 * torch.rand(D, generator=g)).to(DEV)
+    n0 = _lib.launch_count()
+    o_f, st_f, l_f = ops.selective_scan_fwd(u, delta, A, Bm, Cm, Dp, z, bias, True, return_last_state=True, order=order)
+    assert _lib.launch_count() - n0 == 1
+    o_e, st_e, l_e = ops.selective_scan_fwd(u, delta, A, Bm, Cm, Dp, gth(z), bias, True, return_last_state=True)
+    assert torch.equal(o_f, sct(o_e)) and torch.equal(l_f, l_e) and torch.equal(st_f.y, st_e.y) and torch.equal(st_f.x, st_e.x)
+    monkeypatch.setenv("MMU_RING", "0")
+    o_3, st_3, _ = ops.selective_scan_fwd(u, delta, A, Bm, Cm, Dp, z, bias, True, order=order)
+    tol = dict(rtol=1e-3, atol=2e-3) if dtype == torch.float32 else dict(rtol=2e-2, atol=5e-2)
+    torch.testing.assert_close(o_f.float(), o_3.float(), **tol)
+    torch.testing.assert_close(st_f.x, st_3.x, rtol=1e-3, atol=2e-3)
+
+
 FUSED_ORDERS = [((2, 1, 512, 16), 2, 8), ((2, 1, 1024, 64), 1, 72), ((2, 1, 4096, 32), 2, 6), ((3, 8, 16, 1), 2, 6), ((3, 6, 8, 1), 1, 2),
                 ((3, 5, 8, 1), 2, 6), ((3, 32, 64, 1), 1, 128)]
 
