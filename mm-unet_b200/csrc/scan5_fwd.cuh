@@ -1,5 +1,5 @@
-// Selective scan forward, v5 "lane ring" kernel (fp32 I/O, dstate <= 16, seqlen % 8 == 0, 16-byte aligned rows, one segment, saved
-// states every 64 tokens).  Math: SURVEY.md Appendix A; replaces selective_scan_fwd_kernel (selective_scan_fwd_kernel.cuh:67-303).
+// Selective scan forward, v5 "lane ring" kernel (fp32 / bf16 I/O, dstate <= 16, seqlen % 8 == 0, 16-byte aligned rows, one segment,
+// saved states every 64 tokens; plain, flipped (REV) or fused two-row (ORD) scan order).  Math: SURVEY.md Appendix A; replaces selective_scan_fwd_kernel (selective_scan_fwd_kernel.cuh:67-303).
 //
 // v3 (scan3_fwd.cuh) closes the chunk-level recurrence with a cross-lane Kogge-Stone scan of (prod a, h) plus a fix-up
 // y_i += C_i Pc_i hs: 130 issue slots per (lane, state), 50 of them the scan, 23 the products it needs.  Here the lanes of a
@@ -13,8 +13,8 @@
 // The price: the lanes of a ring sit in two different chunks at any time (lane j enters chunk k at step 16k + j), so the
 // per-(row, token) quantities cannot simply be reloaded by the whole warp at a chunk boundary.  A lane picks its new delta /
 // delta*u up from a shared-memory stage at ITS transition step (predicated loads), and swaps its y accumulators with the D*u
-// of the new chunk there.  Work per warp is fixed by the problem (rows / 4 ring warps, each walking the whole sequence), so this kernel is for
-// wide problems; narrow ones stay on v3, which can cut the sequence into segments.
+// of the new chunk there.  Work per warp is fixed by the problem (rows / 4 ring warps, each walking the whole sequence), so this
+// kernel is for wide problems; narrow ones stay on v3, which can cut the sequence into segments.
 //
 // Warp specialisation.  A first version (git history: b08aac9) let every warp do its own element-wise work in a uniform "bulk"
 // phase once per round of 16 steps: 195 us at BASELINE config 2 against v3's 172 us - ncu showed the steps running at 0.57
@@ -30,9 +30,10 @@
 // two lanes in transition at a step then sit in the same quarter-warp and their predicated 16-byte accesses are one wavefront.
 // The step loop is a runtime loop over step PAIRS (operand double buffer): fully unrolled, ptxas split the live ranges of delta,
 // delta*u and y across the 16 copies and paid ~50 predicated moves per step.
-// Measured (B200, fp32, profiles/r2_v5_lane_ring.md): config 2 (B8 D384 L4096) 154 us vs v3 172 us; B16 D128 L 4k / 16k / 64k
-// 115 / 416 / 1627 us vs 138 / 516 / 2034 us.  Time per round is ~3.2 us with 4 ring warps per CTA and ~4.4 us with 6 (170-register
-// cap at 384 threads, and 6 ring warps sit 2, 2, 1, 1 on the four schedulers), independent of the number of CTAs up to one per SM.
+// Measured (B200, fp32, profiles/r2_v5_lane_ring.md): config 2 (B8 D384 L4096) 154-159 us vs v3 172 us; B16 D128 L 4k / 16k / 64k
+// 117 / 433 / 1627 us vs 138 / 516 / 2034 us.  Time per round is ~3.2 us with 4 ring warps per CTA and ~4.4 us with 6 (6 ring warps
+// sit 2, 2, 1, 1 on the four schedulers), independent of the number of CTAs up to one per SM.  2-byte I/O gains nothing over v3
+// (latency bound): opt-in.
 #pragma once
 #include "scan3.cuh"
 #include "scan3_fwd.cuh"
