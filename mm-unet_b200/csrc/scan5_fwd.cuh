@@ -63,9 +63,14 @@ template <typename IN_T, int WR> struct Fwd5Cfg {
 
 // ORD: fused scan order (as scan3_fwd_kernel; the host selects it for TWOROW only) - the helpers gather the gate z and scatter out through p.ord
 // (ord_issue8 / ord_store8 in scan3.cuh); everything the ring warps touch stays in scan order.  Never together with REV.
-template <typename IN_T, int WR, bool REV, bool ORD = false>
+// ORD == 2: NSLICES for 4-byte elements with 8 / 16 / 32 slices and L % 128 == 0, through a transposition in the z landing slots: a
+// chunk of a row is 128 / ns consecutive elements in each of the ns slices, i.e. 32 sixteen-byte pieces - two per lane, as in the plain
+// order - which the lanes read / write at their logical tokens' positions (the generic element-wise form of ord_issue8 / ord_store8,
+// eight 4-byte pieces per lane and row, measured 187 us at config 2 against 158 us for the plain order).
+template <typename IN_T, int WR, bool REV, int ORD = 0>
 __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_constant__ Fwd3Args p) {
     static_assert(!ORD || !REV, "ordered gate / output: forward direction only");
+    static_assert(ORD != 2 || sizeof(IN_T) == 4, "tiled nslices: 4-byte elements");
     using Cfg = Fwd5Cfg<IN_T, WR>;
     constexpr bool kF32 = Cfg::kF32;
     constexpr int NQ = Cfg::NQ, EPQ = 16 / (int)sizeof(IN_T);
@@ -132,6 +137,17 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_cons
         const unsigned s_tile_u32 = smem_u32(s_tile), s_raw_u32 = smem_u32(s_rawbc);
         const unsigned s_land_u32 = smem_u32(s_land) + rt * 16;
         const unsigned char *s_land_t = s_land + rt * 16;
+        // tiled nslices (ORD == 2): 16-byte piece pc (0..31) of a chunk = slice pc / pps, quad pc % pps of its 128 / ns elements
+        [[maybe_unused]] const int ns_sh = p.ord.ns_shift;
+        [[maybe_unused]] auto ns_piece_off = [&](int pc, int c) {
+            return (int64_t)(pc >> (5 - ns_sh)) * p.ord.Ls + ((c * CH) >> ns_sh) + 4 * (pc & ((32 >> ns_sh) - 1));
+        };
+        // landing-slot address (tensor z, row r) of the element that holds token i of my 8 logical tokens
+        [[maybe_unused]] auto ns_elem = [&](int r, int i) {
+            const int t = T * j + i, sl = t & ((1 << ns_sh) - 1), jj = t >> ns_sh;
+            const int pc = (sl << (5 - ns_sh)) + (jj >> 2);
+            return reinterpret_cast<float *>(s_land + ((2 * 2 + r) * NQ + (pc & 1)) * NRT * 16 + (rw * 32 + 2 * (pc >> 1) + ring) * 16) + (jj & 3);
+        };
         auto issue_ud = [&](int c) {
             if (c * CH + T * j < L) {
 #pragma unroll
@@ -147,7 +163,13 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_cons
         };
         auto issue_z = [&](int c) {
             if (!has_z) return;
-            if constexpr (ORD) {
+            if constexpr (ORD == 2) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) cp_async16(s_land_u32 + ((2 * 2 + r) * NQ + q) * NRT * 16, z_p[r] + ns_piece_off(2 * j + q, c));
+                return;
+            } else if constexpr (ORD == 1) {
                 if (c * CH + T * j < L) {
 #pragma unroll
                     for (int r = 0; r < 2; ++r)
@@ -212,14 +234,38 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_cons
                     const float4 v = yo[q * NRT];
                     ya[0][2 * q] = v.x, ya[1][2 * q] = v.y, ya[0][2 * q + 1] = v.z, ya[1][2 * q + 1] = v.w;
                 }
-                if (ok) {
+                if constexpr (ORD == 2) {       // every lane runs the whole sequence: the __syncwarp()s are warp-wide
+                    float zz[2][T];
+                    if (has_z) {
+#pragma unroll
+                        for (int r = 0; r < 2; ++r)
+#pragma unroll
+                            for (int i = 0; i < T; ++i) zz[r][i] = *ns_elem(r, i);
+                    }
+                    __syncwarp();               // z has been read: the slots now stage the output
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        if (rok[r] && y_p[r] != nullptr) store8<IN_T, REV>(y_p[r], ya[r]);
+#pragma unroll
+                        for (int i = 0; i < T; ++i) *ns_elem(r, i) = has_z ? ya[r][i] * (zz[r][i] * sigmoid3(zz[r][i])) : ya[r][i];
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        if (!rok[r]) continue;
+#pragma unroll
+                        for (int q = 0; q < 2; ++q)
+                            *reinterpret_cast<uint4 *>(o_p[r] + ns_piece_off(2 * j + q, ce)) = *reinterpret_cast<const uint4 *>(s_land_t + ((2 * 2 + r) * NQ + q) * NRT * 16);
+                    }
+                    __syncwarp();               // before the next chunk's z lands in the slots
+                } else if (ok) {
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {
                         if (!rok[r]) continue;
                         if (y_p[r] != nullptr) store8<IN_T, REV>(y_p[r], ya[r]);
                         if (has_z) {
                             float zz[T];
-                            if constexpr (ORD) {
+                            if constexpr (ORD == 1) {
                                 uint4 q[NQ];
 #pragma unroll
                                 for (int kq = 0; kq < NQ; ++kq) q[kq] = *reinterpret_cast<const uint4 *>(s_land_t + ((2 * 2 + r) * NQ + kq) * NRT * 16);
@@ -232,7 +278,7 @@ __global__ void __launch_bounds__(64 * WR, 1) scan5_fwd_kernel(const __grid_cons
 #pragma unroll
                             for (int i = 0; i < T; ++i) ya[r][i] *= zz[i] * sigmoid3(zz[i]);
                         }
-                        if constexpr (ORD) ord_store8<IN_T>(p.ord, ce * CH + T * j, o_p[r], ya[r]);
+                        if constexpr (ORD == 1) ord_store8<IN_T>(p.ord, ce * CH + T * j, o_p[r], ya[r]);
                         else store8<IN_T, REV>(o_p[r], ya[r]);
                     }
                 }

@@ -637,11 +637,14 @@ int plan_fwd5(int B, int D) {
 
 template <typename IN_T> bool fwd5_eligible(const mmu_scan_fwd_params *p) {
     if (env_int("MMU_RING", 1) == 0) return false;
-    // fused scan orders: two-row only (two 16-byte pieces per lane and row).  nslices is eight 4-byte pieces per lane and row in the
-    // helpers' loads and stores and measured 187 us against v3's 179 us at config 2 (plain order: 158 us)
-    if (p->order != MMU_ORDER_ROWMAJOR &&
-        (p->order != MMU_ORDER_TWOROW || p->reverse || !ordmap_fusable(p->order, p->order_h, p->order_w, p->order_ns, p->seqlen)))
-        return false;
+    // fused scan orders: two-row (two 16-byte pieces per lane and row) and, tiled through the landing slots, fp32 nslices (the
+    // element-wise form - eight 4-byte pieces per lane and row - measured 187 us against v3's 179 us at config 2; plain order 158 us)
+    if (p->order != MMU_ORDER_ROWMAJOR) {
+        if (p->order == MMU_ORDER_FLIP || p->reverse || !ordmap_fusable(p->order, p->order_h, p->order_w, p->order_ns, p->seqlen)) return false;
+        if (p->order == MMU_ORDER_NSLICES &&        // tiled through the landing slots: 4-byte elements, 8 / 16 / 32 slices, whole chunks
+            (sizeof(IN_T) != 4 || (p->order_ns != 8 && p->order_ns != 16 && p->order_ns != 32) || p->seqlen % 128 != 0))
+            return false;
+    }
     // 2-byte I/O: the ring is latency bound and gains nothing from the halved bytes, v3 does (B16 D128 L65536 bf16: 1 809 -> 1 689 us,
     // config 2 bf16 no change), and its one 200 KB CTA per SM keeps the other directions' kernels of a v3 Mamba off the SM: opt-in
     if (sizeof(IN_T) != 4 && env_int("MMU_RING_BF16", 0) == 0) return false;
@@ -659,8 +662,11 @@ template <typename IN_T> bool fwd5_eligible(const mmu_scan_fwd_params *p) {
 template <typename IN_T, int WR> int launch_fwd5(const Fwd3Args &a, bool rev, cudaStream_t st) {
     using Cfg = Fwd5Cfg<IN_T, WR>;
     dim3 grid((a.D + Cfg::R - 1) / Cfg::R, a.B), block(Cfg::NT);
-    auto k = a.ord.kind != MMU_ORDER_ROWMAJOR ? scan5_fwd_kernel<IN_T, WR, false, true>
-                                             : (rev ? scan5_fwd_kernel<IN_T, WR, true> : scan5_fwd_kernel<IN_T, WR, false>);
+    auto k = rev ? scan5_fwd_kernel<IN_T, WR, true> : scan5_fwd_kernel<IN_T, WR, false>;
+    if (a.ord.kind == MMU_ORDER_TWOROW) k = scan5_fwd_kernel<IN_T, WR, false, 1>;
+    if constexpr (sizeof(IN_T) == 4) {
+        if (a.ord.kind == MMU_ORDER_NSLICES) k = scan5_fwd_kernel<IN_T, WR, false, 2>;
+    }
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
     k<<<grid, block, Cfg::smem_bytes, st>>>(a);
     count_launch();

@@ -652,12 +652,13 @@ def test_scan_order_golden_and_errors():
 # ---------------------------------------------------------------------------------------------------------------
 # scan order fused into the conv / scan kernels' addressing (requirements/mamba_simple.py:245-263, MMUNet.py:68-121, 178-183)
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("order,B,D", [((3, 32, 64, 1), 1, 128), ((3, 9, 64, 1), 3, 20), ((3, 64, 64, 1), 2, 40)])
+@pytest.mark.parametrize("order,B,D", [((3, 32, 64, 1), 1, 128), ((3, 9, 64, 1), 3, 20), ((3, 64, 64, 1), 2, 40),
+                                       ((2, 1, 1024, 16), 2, 24), ((2, 1, 4096, 32), 2, 8), ((2, 1, 2048, 8), 1, 70)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_scan_v5_fused_scan_order(order, B, D, dtype, monkeypatch):
-    """The ring forward with MMConv's two-row scan order fused (its helper warps gather z and scatter out through idx(l)) against the
-    same kernel on explicitly gathered tensors: identical arithmetic, bit-equal results (an odd tail row included).  nslices stays on
-    v3 (eight 4-byte pieces per lane in the helpers: measured slower)."""
+    """The ring forward with a scan order fused (its helper warps gather z and scatter out through idx(l)) against the same kernel on
+    explicitly gathered tensors: identical arithmetic, bit-equal results.  MMConv's two-row order (an odd tail row included) and, for
+    fp32, nslices with 8 / 16 / 32 slices (transposed through the helpers' landing slots)."""
     monkeypatch.setenv("MMU_RING", "1")
     monkeypatch.setenv("MMU_RING_BF16", "1")
     monkeypatch.setenv("MMU_V5_MIN_WARPS", "1")
